@@ -1,0 +1,202 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+Run once in the build container (``python tests/golden/make_golden.py``); needs /root/reference.
+Nothing on the GPU box ever imports this file's outputs' generator -- only the ``.npz`` fixtures travel.
+
+How the reference is executed (nothing from it is written into this repo):
+  * ``vit_unet/torch/model.py`` is read from /root/reference and exec'd as an in-memory module;
+  * ``skimage`` (imported by ``functions.py:2``, absent here) is replaced by an empty stub module;
+  * the two constructor defects that make ``HViT_UNet`` unconstructible at HEAD are patched IN MEMORY
+    (SURVEY.md section 8(c)):  ``model.py:78-79`` (PatchEncoder reads ``self.preprocessing`` before it
+    exists; the conv it would build is never applied)  and  ``model.py:309`` (6-argument call to a
+    4-argument constructor + ``self.dtype`` never set);
+  * ``PatchEncoder.positions`` is device-agnostic here because no CUDA device exists in this container.
+
+Weights are NOT drawn from torch's default init stream (that would couple fixtures to module
+construction order); every tensor of the state_dict is filled from ``fill_state_dict`` below, keyed by
+its name, so the oracle / the CUDA module can load the identical weights from the same function.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+# ----------------------------------------------------------------------------- shared helpers
+def _seed_of(name: str, salt: int) -> int:
+    return int.from_bytes(hashlib.sha256(f"{salt}:{name}".encode()).digest()[:4], "little")
+
+
+def fill_state_dict(sd: dict, salt: int = 0) -> dict:
+    """Deterministic, name-keyed weights (same function used by tests for the oracle and the CUDA path).
+
+    Scales are chosen so activations stay O(1) and every term matters: linear/conv weights
+    ~ U(-1,1)/sqrt(fan_in), biases small, LN/BN affine near (1, 0) but not equal, BN running stats
+    non-trivial so eval-mode BN is not the identity, head-mixing matrix dense.
+    """
+    out = {}
+    for name, t in sd.items():
+        g = torch.Generator().manual_seed(_seed_of(name, salt))
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros_like(t)
+            continue
+        u = torch.rand(t.shape, generator=g, dtype=torch.float32) * 2 - 1
+        if name.endswith("running_var"):
+            v = 0.75 + 0.5 * (u * 0.5 + 0.5)            # U(0.75, 1.25)
+            # softmax maps are ~1/N: scale so normalisation is not swamped by eps nor explosive
+            v = v * 1e-3
+        elif name.endswith("running_mean"):
+            v = 0.01 * u
+        elif "position_embedding" in name:
+            v = 0.5 * u
+        elif ".LN" in name and name.endswith("weight"):
+            v = 1.0 + 0.2 * u
+        elif ".LN" in name and name.endswith("bias"):
+            v = 0.1 * u
+        elif "var_norm.weight" in name:
+            v = 1.0 + 0.3 * u
+        elif "var_norm.bias" in name:
+            v = 0.002 * u
+        elif "reatten_matrix.weight" in name:
+            v = u / t.shape[1] ** 0.5
+        elif name.endswith("bias"):
+            v = 0.05 * u
+        else:   # conv / linear weights
+            fan_in = int(np.prod(t.shape[1:])) if t.dim() > 1 else int(t.shape[0])
+            v = u / fan_in ** 0.5
+        out[name] = v.to(t.dtype).reshape(t.shape)
+    return out
+
+
+def make_input(B: int, C: int, S: int, seed: int = 0):
+    """Synthetic denoising pair in the reference's input range (run_denoising.py:54, dataset.py:65)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    clean = torch.rand(B, C, S, S, generator=g)
+    noisy = (clean + 0.1 * torch.randn(B, C, S, S, generator=g)).clamp(0, 1)
+    return ((noisy - 0.456) / 0.224).contiguous(), clean.contiguous()
+
+
+# configs: name -> (variant, ctor kwargs, batch).  "tiny" ones are fully stored; 224^2 ones subsampled.
+CONFIGS = {
+    "tiny_head": ("head", dict(depth=2, depth_te=1, size_bottleneck=1, preprocessing="conv", im_size=32,
+                               patch_size=16, num_channels=3, hidden_dim=32, num_heads=4,
+                               attn_drop=0.0, proj_drop=0.0, linear_drop=0), 2),
+    "tiny_head_te2": ("head", dict(depth=1, depth_te=2, size_bottleneck=2, preprocessing="conv", im_size=48,
+                                   patch_size=8, num_channels=3, hidden_dim=16, num_heads=2,
+                                   attn_drop=0.0, proj_drop=0.0, linear_drop=0), 3),
+    "tiny_head_1ch": ("head", dict(depth=2, depth_te=1, size_bottleneck=1, preprocessing="conv", im_size=64,
+                                   patch_size=32, num_channels=1, hidden_dim=32, num_heads=8,
+                                   attn_drop=0.0, proj_drop=0.0, linear_drop=0), 2),
+    "lite_head": ("head", dict(depth=2, depth_te=1, size_bottleneck=2, preprocessing="conv", im_size=224,
+                               patch_size=16, num_channels=3, hidden_dim=64, num_heads=4,
+                               attn_drop=0.0, proj_drop=0.0, linear_drop=0), 1),
+    "base_head": ("head", dict(depth=2, depth_te=2, size_bottleneck=2, preprocessing="conv", im_size=224,
+                               patch_size=32, num_channels=3, hidden_dim=128, num_heads=8,
+                               attn_drop=0.0, proj_drop=0.0, linear_drop=0), 2),
+}
+
+
+def load_reference_module():
+    src_path = os.path.join(REF, "vit_unet/torch/model.py")
+    src = open(src_path).read()
+    # in-memory fixes (see module docstring); each must match exactly once
+    fixes = [
+        ("        if self.preprocessing == \"conv\":\n"
+         "            self.conv2d = torch.nn.Conv2d(self.num_channels, self.num_channels, 3, padding = 'same')\n"
+         "        self.position_embedding",
+         "        self.position_embedding"),
+        ("PatchEncoder(self.depth,self.num_patches,self.patch_size,self.num_channels,self.preprocessing,self.dtype)",
+         "PatchEncoder(self.im_size,self.patch_size,self.num_channels)"),
+        ('device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")', 'device = torch.device("cpu")'),
+        ("from .functions import softmax_top", "softmax_top = None  # unused by any caller (model.py:5)"),
+    ]
+    for old, new in fixes:
+        assert src.count(old) == 1, f"reference drifted; cannot apply in-memory fix for: {old[:50]}..."
+        src = src.replace(old, new)
+    mod = types.ModuleType("_reference_vit_unet_model")
+    mod.__file__ = src_path
+    exec(compile(src, src_path, "exec"), mod.__dict__)
+    return mod
+
+
+def run_case(model, x, y, train: bool):
+    """eval forward, and (train=True) a train-mode fwd+bwd with L1 loss and dropout p=0."""
+    res = {}
+    model.eval()
+    with torch.no_grad():
+        res["eval_out"] = model(x).detach().clone()
+    if train:
+        model.train()
+        model.zero_grad(set_to_none=True)
+        xin = x.clone().requires_grad_(True)
+        out = model(xin)
+        loss = torch.nn.functional.l1_loss(out, y)
+        loss.backward()
+        res["train_out"] = out.detach().clone()
+        res["loss"] = loss.detach().clone()
+        res["dx"] = xin.grad.detach().clone()
+        res["grads"] = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        res["buffers_after"] = {k: b.detach().clone() for k, b in model.named_buffers()}
+    return res
+
+
+def _sub(t: torch.Tensor, n: int = 4096) -> np.ndarray:
+    """Deterministic strided subsample of a flattened tensor (keeps fixtures small)."""
+    f = t.reshape(-1)
+    if f.numel() <= n:
+        return f.numpy().copy()
+    step = f.numel() // n
+    return f[::step][:n].numpy().copy()
+
+
+def pack(res: dict, full: bool) -> dict:
+    out = {}
+    for k in ("eval_out", "train_out", "dx"):
+        if k in res:
+            t = res[k]
+            out[k + "_sum"] = np.float64(t.double().sum().item())
+            out[k + "_abs"] = np.float64(t.double().abs().sum().item())
+            out[k] = t.numpy().copy() if full else _sub(t)
+    if "loss" in res:
+        out["loss"] = np.float64(res["loss"].item())
+        for name, g in res["grads"].items():
+            out["g_norm:" + name] = np.float64(g.double().norm().item())
+            out["g:" + name] = g.numpy().copy() if (full and g.numel() <= 8192) else _sub(g, 512)
+        for name, b in res["buffers_after"].items():
+            out["buf:" + name] = b.numpy().copy()
+    return out
+
+
+def main():
+    sys.modules.setdefault("skimage", types.ModuleType("skimage"))
+    ref = load_reference_module()
+    import contextlib
+    import io
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    for name, (variant, kw, B) in CONFIGS.items():
+        with contextlib.redirect_stdout(io.StringIO()):      # ctor prints the architecture table
+            model = ref.HViT_UNet(**kw)
+        model.load_state_dict(fill_state_dict(model.state_dict()))
+        x, y = make_input(B, kw["num_channels"], kw["im_size"])
+        full = name.startswith("tiny")
+        res = run_case(model, x, y, train=True)
+        out = pack(res, full)
+        out["n_params"] = np.int64(sum(p.numel() for p in model.parameters()))
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: params={out['n_params']} loss={out['loss']:.6f} -> {path} "
+              f"({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    main()
