@@ -1,0 +1,148 @@
+/* vit_unet_b200.h -- C ABI of the B200-native ViT-UNet forward/backward kernels.
+ *
+ * Plain C: pointers, sizes, POD descriptors.  No torch types.  Every pointer is a DEVICE pointer unless
+ * the name ends in _host.  Every launch goes to the cudaStream_t passed as `stream` (a torch
+ * `current_stream().cuda_stream` value works); nothing here synchronises the device or allocates.
+ * All functions return 0 on success; non-zero = VU_ERR_*; vu_last_error() returns the text.
+ *
+ * The reference has no native layer: each entry point below replaces the ATen op
+ * sequence the reference's Python issues at the cited lines of /root/reference/vit_unet/torch/model.py.
+ *
+ * Layout vocabulary ("patch layout p"):  a (B, C, H, W) image stored as tokens (B, N, C*p*p) with
+ * token r*(W/p)+c and feature ch*p*p+i*p+j  <->  pixel (ch, r*p+i, c*p+j)   [model.py:8-35].
+ * p == 0 means plain NCHW.  Every level of the network is the same image in a different patch layout.
+ */
+#ifndef VIT_UNET_B200_H
+#define VIT_UNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VU_OK 0
+#define VU_ERR_ARG 1      /* bad shape / unsupported configuration */
+#define VU_ERR_CUDA 2     /* CUDA runtime error (text in vu_last_error) */
+#define VU_ERR_UNSUPPORTED 3
+
+int vu_version(void);                 /* ABI version, bumped on any signature change */
+const char* vu_last_error(void);      /* thread-local text of the last non-zero return */
+int vu_device_sm_count(int device);   /* 148 on B200 */
+
+/* ---------------------------------------------------------------- layout (model.py:8-53, :84-91) */
+/* out[layout p_out] = in[layout p_in]; patch / unpatch / downsampling / upsampling in one permutation. */
+int vu_repatch(const float* in, float* out, int B, int C, int H, int W, int p_in, int p_out, void* stream);
+/* PatchEncoder: out[p_out] = in[p_in] + table[p_table] (table has no batch dim). model.py:84-91,
+ * ViT_UNet.ipynb c16:L31-40 */
+int vu_pe_fwd(const float* in, int p_in, const float* table, int p_table, float* out, int p_out,
+              int B, int C, int H, int W, void* stream);
+/* dtable[p_table] (+)= sum_b dout[b][p_out] */
+int vu_pe_bwd_table(const float* dout, int p_out, float* dtable, int p_table,
+                    int B, int C, int H, int W, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- 3x3 convs (model.py:137-139,152-154,428) */
+/* nconv (1..3) bias-optional 3x3 C->C convs sharing one input.  Zero padding at the borders of
+ * `border_p`-sized patches (border_p == 0: image borders).  w: [nconv][C][C][3][3], bias: [nconv][C] or NULL.
+ * x is read in layout p_x; out_k written in layout p_out. */
+int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const float* bias, int nconv,
+                   float* out0, float* out1, float* out2, int p_out, int border_p,
+                   int B, int C, int H, int W, void* stream);
+/* dx[p_dx] (+)= sum_k conv_transpose(dy_k[p_dy], w_k) */
+int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const float* dy2, int p_dy,
+                        const float* w, int nconv, float* dx, int p_dx, int border_p,
+                        int B, int C, int H, int W, int accumulate, void* stream);
+/* dw[nconv][C][C][3][3] += ..., dbias[nconv][C] += ... (atomic accumulation: caller zeroes) */
+int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, const float* dy1, const float* dy2,
+                          int p_dy, int nconv, float* dw, float* dbias, int border_p,
+                          int B, int C, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- GEMM (model.py:155,161,162; :103,106) */
+enum { VU_ACT_NONE = 0, VU_ACT_GELU = 1, VU_ACT_GELU_BWD = 2 };
+enum { VU_PREC_FP32 = 0, VU_PREC_TF32 = 1 };   /* FP32: CUDA-core FMA; TF32: tcgen05 tensor cores */
+
+typedef struct vu_gemm_desc {
+  const float* A; const float* B; float* C;
+  const float* bias;      /* [N] added to every row, or NULL */
+  const float* residual;  /* same indexing as C (ldr), added after activation/dropout, or NULL */
+  const float* aux_in;    /* VU_ACT_GELU_BWD: pre-activation, same indexing as C (ldaux) */
+  float* aux_out;         /* VU_ACT_GELU: pre-activation written here (ldaux), or NULL */
+  int M, N, K;
+  int trans_a;            /* 0: A(m,k)=A[m*lda+k]   1: A(m,k)=A[k*lda+m] */
+  int trans_b;            /* 0: B(k,n)=B[k*ldb+n]   1: B(k,n)=B[n*ldb+k]  (nn.Linear weight layout) */
+  int64_t lda, ldb, ldc, ldr, ldaux;
+  int batch_outer, batch_inner;               /* batch z = zo*batch_inner + zi */
+  int64_t sAo, sAi, sBo, sBi, sCo, sCi;       /* element strides; residual/aux use the C strides */
+  float alpha;            /* C = act(alpha*A.B + bias) [dropout] + residual */
+  int act;
+  int accumulate;         /* 1: C += result (no act/residual allowed with split_k>1) */
+  int split_k;            /* >1: K is split, partials atomically added into C (caller zeroes C unless accumulate) */
+  float drop_p;           /* >0: inverted dropout on act(...) keyed by (drop_seed, drop_stream, m*N+n) */
+  uint64_t drop_seed; uint32_t drop_stream;
+  int precision;          /* VU_PREC_* */
+} vu_gemm_desc;
+
+int vu_gemm(const vu_gemm_desc* d_host, void* stream);
+/* out[n] (+)= sum_m X[m*ld+n]   (bias gradients) */
+int vu_colsum(const float* X, int64_t M, int N, int64_t ld, float* out, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- Re-Attention core (model.py:155-161) */
+/* maps are (B, h, N, ld) fp32 with ld >= N, ld % 4 == 0 */
+/* in place: P[r, :N] = softmax(scale * S[r, :N]) for r in rows, pad columns zeroed. */
+int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scale, void* stream);
+/* train-mode BatchNorm statistics of M_h = sum_g W[h,g]*drop(P_g) + b[h] over (B,N,N):
+ * sums[2h] (double, caller zeroes) += { sum(M_h - c_h), sum((M_h - c_h)^2) }, c_h = b[h] + sum_g W[h,g]/N */
+int vu_reattn_stats(const float* P, int B, int h, int N, int ld, const float* W, const float* bconv,
+                    float drop_p, uint64_t seed, uint32_t stream_id, double* sums, void* stream);
+/* fold conv1x1 + BatchNorm into one affine:  fold[h*h + h] = {alpha'[h][g], beta'[h]};
+ * saved[2h] = {mean_h, invstd_h}.  train=1: batch statistics from `sums` (+ running-stat update,
+ * momentum, unbiased variance, num_batches_tracked += 1); train=0: running statistics. model.py:136,159 */
+int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, int N, const float* W, const float* bconv,
+                          const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          int64_t* num_batches_tracked, float eps, float momentum, int train,
+                          float* fold, float* saved, void* stream);
+/* A_h = sum_g alpha'[h,g]*drop(P_g) + beta'[h] */
+int vu_reattn_mix(const float* P, float* A, const float* fold, int B, int h, int N, int ld,
+                  float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
+/* BN-backward reductions: red[2h] (double, caller zeroes) += { sum dA_h, sum dA_h * Ahat_h } */
+int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, const float* W,
+                         const float* bconv, const float* saved, float drop_p, uint64_t seed,
+                         uint32_t stream_id, double* red, void* stream);
+/* in place dA -> dS (gradient of the pre-softmax scores), plus parameter gradients (atomic, caller zeroes
+ * or accumulates): dW[h*h], dbconv[h], dgamma[h], dbeta[h]. */
+int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, int N, int ld, const float* W,
+                       const float* bconv, const float* gamma, const float* saved, const double* red,
+                       int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id,
+                       float* dW, float* dbconv, float* dgamma, float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------- LayerNorm over (N,D) (model.py:193-196,204,206) */
+/* stats[b] = {mean, rstd} over the n = N*D elements of image b */
+int vu_ln_stats(const float* x, int B, int64_t n, float eps, float* stats, void* stream);
+int vu_ln_apply(const float* x, const float* stats, const float* w, const float* b, float* out,
+                int B, int64_t n, void* stream);
+/* dx = LN backward; dw/db += (atomic; caller zeroes or accumulates: the README variant shares one LN) */
+int vu_ln_bwd(const float* g, const float* x, const float* stats, const float* w, float* dx,
+              float* dw, float* db, float* scratch /* 2*B floats */, int B, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- losses (run_denoising.py:80, README.md:91-101) */
+enum { VU_LOSS_L1 = 0, VU_LOSS_MSE = 1, VU_LOSS_DICE = 2 };
+/* sums[4] (double, zeroed here): L1 {sum|d|}, MSE {sum d^2}, DICE {sum xy, sum x, sum y}; loss[0] = the scalar */
+int vu_loss_fwd(int kind, const float* pred, const float* target, int64_t n, double* sums, float* loss,
+                void* stream);
+/* dpred = gscale[0] * dloss/dpred  (gscale: device scalar, the upstream gradient) */
+int vu_loss_bwd(int kind, const float* pred, const float* target, int64_t n, const double* sums,
+                const float* gscale, float* dpred, void* stream);
+
+/* ---------------------------------------------------------------- misc */
+/* out = in * keep / (1-p), keep from the same Philox stream the GEMM epilogue uses (index = flat element) */
+int vu_dropout(const float* in, float* out, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream);
+/* y = a*x + b*y elementwise */
+int vu_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);
+/* fused AdamW over one flat parameter buffer (torch.optim.AdamW semantics; run_denoising.py:81) */
+int vu_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+             float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIT_UNET_B200_H */

@@ -1,0 +1,325 @@
+"""Per-kernel parity: every C-ABI entry point against the plain fp32 PyTorch op it replaces (run on CPU so
+the check does not depend on cuBLAS/cuDNN TF32 settings).  Tolerances: 1e-5-class relative for the FP32 path."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vit_unet_oracle as O          # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vit_unet_b200 import ops as _ops
+    return _ops
+
+
+def _close(a, b, rtol=2e-5, atol_rel=2e-6, name=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    scale = max(b.abs().max().item(), 1e-30)
+    err = (a - b).abs().max().item()
+    assert err <= rtol * scale + atol_rel * scale, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+
+# ------------------------------------------------------------------------------------------------ layout
+@pytest.mark.parametrize("C,S,p_in,p_out", [(3, 32, 0, 16), (3, 32, 16, 8), (3, 32, 8, 16), (3, 64, 32, 0),
+                                             (1, 64, 16, 4), (3, 28, 0, 7), (3, 28, 14, 7), (2, 24, 12, 0)])
+def test_repatch(ops, C, S, p_in, p_out):
+    B = 3
+    img = _rand(B, C, S, S)
+    src = img if p_in == 0 else O.patchify(img, p_in)
+    exp = img if p_out == 0 else O.patchify(img, p_out)
+    out = torch.empty(exp.shape, device="cuda")
+    ops.repatch(src.contiguous().cuda(), out, B, C, S, S, p_in, p_out)
+    assert torch.equal(out.cpu(), exp)            # pure permutation: bit exact
+
+
+def test_pe_fwd_and_table_grad(ops):
+    B, C, S, p, pt = 3, 3, 32, 16, 4
+    img = _rand(B, C, S, S)
+    table = _rand((S // pt) ** 2, C * pt * pt, seed=1)
+    exp = O.patchify(O.unpatchify(O.patchify(img, pt) + table, C), p)
+    out = torch.empty(exp.shape, device="cuda")
+    ops.pe_fwd(img.cuda(), 0, table.cuda(), pt, out, p, B, C, S, S)
+    assert torch.equal(out.cpu(), exp)
+    dout = _rand(*exp.shape, seed=2)
+    dt = torch.empty_like(table, device="cuda")
+    ops.pe_bwd_table(dout.cuda(), p, dt, pt, B, C, S, S)
+    exp_dt = O.patchify(O.unpatchify(dout, C), pt).sum(0)
+    _close(dt, exp_dt, name="dtable")
+
+
+# ------------------------------------------------------------------------------------------------ convs
+@pytest.mark.parametrize("C,S,p", [(3, 32, 16), (3, 32, 4), (1, 32, 8), (3, 28, 7)])
+@pytest.mark.parametrize("nconv", [1, 2, 3])
+def test_patch_conv_fwd_bwd(ops, C, S, p, nconv):
+    B = 2
+    img = _rand(B, C, S, S)
+    x = O.patchify(img, p).contiguous()
+    N, D = x.shape[1], x.shape[2]
+    ws = [_rand(C, C, 3, 3, seed=10 + k, scale=0.5) for k in range(nconv)]
+    xr = x.clone().requires_grad_(True)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    ys = [F.conv2d(xr.reshape(B * N, C, p, p), w, padding=1).reshape(B, N, D) for w in wr]
+    outs = [torch.empty(B, N, D, device="cuda") for _ in range(nconv)]
+    wcat = torch.cat([w.reshape(-1) for w in ws]).cuda()
+    ops.conv3x3_fwd(x.cuda(), p, wcat, None, outs, p, p, B, C, S, S)
+    for o, y in zip(outs, ys):
+        _close(o, y, name="conv fwd")
+    dys = [_rand(B, N, D, seed=20 + k) for k in range(nconv)]
+    sum((y * d).sum() for y, d in zip(ys, dys)).backward()
+    dx = torch.empty(B, N, D, device="cuda")
+    ops.conv3x3_bwd_data([d.cuda() for d in dys], p, wcat, dx, p, p, B, C, S, S)
+    _close(dx, xr.grad, name="conv dx")
+    dw = torch.zeros(nconv * C * C * 9, device="cuda")
+    ops.conv3x3_bwd_weight(x.cuda(), p, [d.cuda() for d in dys], p, dw, None, p, B, C, S, S)
+    _close(dw, torch.cat([w.grad.reshape(-1) for w in wr]), rtol=1e-4, name="conv dw")
+
+
+@pytest.mark.parametrize("C,S,p", [(3, 32, 16), (1, 64, 32)])
+def test_image_conv_on_token_layout(ops, C, S, p):
+    """Reconstruction head: un-patch + 3x3 'same' conv with bias (model.py:425-428), reading tokens directly."""
+    B = 2
+    img = _rand(B, C, S, S).requires_grad_(True)
+    w = _rand(C, C, 3, 3, seed=3, scale=0.5).requires_grad_(True)
+    b = _rand(C, seed=4).requires_grad_(True)
+    y = F.conv2d(img, w, b, padding=1)
+    tok = O.patchify(img.detach(), p).contiguous()
+    out = torch.empty(B, C, S, S, device="cuda")
+    ops.conv3x3_fwd(tok.cuda(), p, w.detach().cuda(), b.detach().cuda(), [out], 0, 0, B, C, S, S)
+    _close(out, y, name="head conv")
+    dy = _rand(B, C, S, S, seed=5)
+    (y * dy).sum().backward()
+    dtok = torch.empty_like(tok, device="cuda")
+    ops.conv3x3_bwd_data([dy.cuda()], 0, w.detach().cuda(), dtok, p, 0, B, C, S, S)
+    _close(dtok, O.patchify(img.grad, p), name="head conv dx")
+    dw, db = torch.zeros(C * C * 9, device="cuda"), torch.zeros(C, device="cuda")
+    ops.conv3x3_bwd_weight(tok.cuda(), p, [dy.cuda()], 0, dw, db, 0, B, C, S, S)
+    _close(dw, w.grad.reshape(-1), rtol=1e-4, name="head conv dw")
+    _close(db, b.grad, rtol=1e-4, name="head conv db")
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(98, 3072, 3072), (392, 768, 768), (1568, 192, 192), (1568, 32, 192),
+                                    (130, 70, 50), (64, 24, 49), (49, 49, 384), (257, 129, 1030)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_plain(ops, M, N, K, ta, tb):
+    if M * N * K > 2e8 and (ta or not tb):
+        pytest.skip("large shape only in the nn.Linear orientation")
+    A = _rand(K, M, seed=1) if ta else _rand(M, K, seed=1)
+    Bm = _rand(N, K, seed=2) if tb else _rand(K, N, seed=2)
+    exp = (A.t() if ta else A).double() @ (Bm.t() if tb else Bm).double()
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(A.cuda(), Bm.cuda(), out, M, N, K, trans_a=ta, trans_b=tb, lda=A.shape[1], ldb=Bm.shape[1], ldc=N)
+    _close(out, exp, rtol=1e-5 * math.sqrt(K) / 4, name="gemm")
+
+
+def test_gemm_epilogues_and_batch(ops):
+    M, N, K = 100, 72, 40
+    A, W, bias, R = _rand(M, K, seed=1), _rand(N, K, seed=2), _rand(N, seed=3), _rand(M, N, seed=4)
+    pre = A @ W.t() * 0.5 + bias
+    out, aux = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    ops.gemm(A.cuda(), W.cuda(), out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, bias=bias.cuda(),
+             residual=R.cuda(), alpha=0.5, act=ops.ACT_GELU, aux_out=aux)
+    _close(aux, pre, name="aux")
+    _close(out, F.gelu(pre) + R, name="gelu+res")
+    # gelu backward epilogue
+    pr = pre.clone().requires_grad_(True)
+    F.gelu(pr).backward(torch.ones_like(pr))
+    ops.gemm(A.cuda(), W.cuda(), out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, act=ops.ACT_GELU_BWD, aux_in=aux)
+    _close(out, (A @ W.t()) * pr.grad, name="gelu bwd")
+    # split-K accumulate (weight-gradient shape)
+    dY, X = _rand(5000, 24, seed=5), _rand(5000, 56, seed=6)
+    dW = torch.ones(24, 56, device="cuda")
+    ops.gemm(dY.cuda(), X.cuda(), dW, 24, 56, 5000, trans_a=True, lda=24, ldb=56, ldc=56, accumulate=True, split_k=7)
+    _close(dW, dY.double().t() @ X.double() + 1, rtol=1e-4, name="splitk")
+    # head-strided batch: S[b,h] = q[b,:,h,:] k[b,:,h,:]^T
+    B, h, Nt, hd = 3, 4, 49, 12
+    D, ld = h * hd, 52
+    q, k = _rand(B, Nt, D, seed=7), _rand(B, Nt, D, seed=8)
+    S = torch.zeros(B, h, Nt, ld, device="cuda")
+    ops.gemm(q.cuda(), k.cuda(), S, Nt, Nt, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
+             sA=(Nt * D, hd), sB=(Nt * D, hd), sC=(h * Nt * ld, Nt * ld))
+    exp = torch.einsum("bihe,bjhe->bhij", q.reshape(B, Nt, h, hd), k.reshape(B, Nt, h, hd))
+    _close(S[..., :Nt], exp, name="batched qk")
+    assert torch.all(S[..., Nt:] == 0)
+
+
+def test_gemm_dropout_matches_standalone(ops):
+    M, N, K = 64, 48, 32
+    A, W = _rand(M, K, seed=1), _rand(N, K, seed=2)
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(A.cuda(), W.cuda(), out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, drop_p=0.3, drop_seed=1234,
+             drop_stream=5)
+    plain = (A @ W.t()).cuda()
+    exp = ops.dropout(plain, torch.empty_like(plain), 0.3, 1234, 5)
+    _close(out, exp, name="dropout epilogue")
+    frac = (exp == 0).float().mean().item()
+    assert 0.25 < frac < 0.35
+    assert torch.allclose(exp[exp != 0], plain[exp != 0] / 0.7, rtol=1e-6)
+
+
+def test_colsum(ops):
+    X = _rand(3001, 70, seed=3)
+    out = torch.ones(70, device="cuda")
+    ops.colsum(X.cuda(), 3001, 70, 70, out, accumulate=True)
+    _close(out, X.double().sum(0) + 1, rtol=1e-5, name="colsum")
+
+
+# ------------------------------------------------------------------------------------------------ re-attention
+def _reattn_ref(S, scale, W, b, gamma, beta, rm, rv, train, mask=None, p=0.0):
+    Pm = F.softmax(S * scale, dim=-1)
+    Pd = Pm if mask is None else Pm * mask / (1 - p)
+    h = S.shape[1]
+    M = F.conv2d(Pd, W.reshape(h, h, 1, 1), b)
+    A = F.batch_norm(M, rm, rv, gamma, beta, training=train, momentum=0.1, eps=1e-5)
+    return Pm, A
+
+
+@pytest.mark.parametrize("h,N", [(8, 49), (4, 196), (2, 30), (8, 70)])
+@pytest.mark.parametrize("train", [False, True])
+def test_reattn_forward_backward(ops, h, N, train):
+    B, ld = 3, (N + 3) // 4 * 4
+    scale = 0.37
+    S = _rand(B, h, N, N, seed=1, scale=3.0).requires_grad_(True)
+    W = _rand(h, h, seed=2, scale=0.6).requires_grad_(True)
+    b = _rand(h, seed=3, scale=0.01).requires_grad_(True)
+    gamma = (1 + _rand(h, seed=4, scale=0.3)).requires_grad_(True)
+    beta = _rand(h, seed=5, scale=0.01).requires_grad_(True)
+    rm, rv = _rand(h, seed=6, scale=0.01), (1 + _rand(h, seed=7, scale=0.3)) * 1e-3
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    Pm_ref, A_ref = _reattn_ref(S, scale, W, b, gamma, beta, rm_ref, rv_ref, train)
+    dA = _rand(B, h, N, N, seed=8)
+    (A_ref * dA).sum().backward()
+
+    Sd = torch.zeros(B, h, N, ld, device="cuda"); Sd[..., :N] = S.detach().cuda()
+    ops.softmax_rows(Sd, B * h * N, N, ld, scale)
+    _close(Sd[..., :N], Pm_ref, name="softmax")
+    Wd, bd, gd, btd = W.detach().cuda(), b.detach().cuda(), gamma.detach().cuda(), beta.detach().cuda()
+    rmd, rvd = rm.clone().cuda(), rv.clone().cuda()
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    sums = torch.zeros(2 * h, dtype=torch.float64, device="cuda") if train else None
+    if train:
+        ops.reattn_stats(Sd, B, h, N, ld, Wd, bd, 0.0, 0, 0, sums)
+    fold, saved = torch.empty(h * h + h, device="cuda"), torch.empty(2 * h, device="cuda")
+    ops.reattn_bn_finalize(sums, B * N * N, h, N, Wd, bd, gd, btd, rmd, rvd, nbt, 1e-5, 0.1, train, fold, saved)
+    A = torch.empty_like(Sd)
+    ops.reattn_mix(Sd, A, fold, B, h, N, ld, 0.0, 0, 0)
+    _close(A[..., :N], A_ref, rtol=2e-4, name="mixed map")
+    assert torch.all(A[..., N:] == 0)
+    if train:
+        _close(rmd, rm_ref, rtol=1e-5, name="running_mean")
+        _close(rvd, rv_ref, rtol=1e-4, name="running_var")
+        assert nbt.item() == 1
+    # backward
+    dAd = torch.zeros(B, h, N, ld, device="cuda"); dAd[..., :N] = dA.cuda()
+    red = torch.zeros(2 * h, dtype=torch.float64, device="cuda")
+    ops.reattn_bwd_reduce(Sd, dAd, B, h, N, ld, Wd, bd, saved, 0.0, 0, 0, red)
+    dW, dbc, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"),
+                        torch.zeros(h, device="cuda"), torch.zeros(h, device="cuda"))
+    ops.reattn_bwd_rows(Sd, dAd, B, h, N, ld, Wd, bd, gd, saved, red, train, scale, 0.0, 0, 0, dW, dbc, dg, dbt)
+    # dAd now holds dL/d(raw scores)
+    _close(dAd[..., :N], S.grad, rtol=5e-4, name="dS")
+    _close(dW.reshape(h, h), W.grad, rtol=5e-4, name="dW mix")
+    _close(dg, gamma.grad, rtol=5e-4, name="dgamma")
+    _close(dbt, beta.grad, rtol=5e-4, name="dbeta")
+    if not train:
+        _close(dbc, b.grad, rtol=5e-4, name="dbias mix")
+    else:   # BN removes the mean: the true gradient is 0; ours must be tiny relative to |dM| mass
+        assert dbc.abs().max().item() <= 1e-3 * max(1.0, W.grad.abs().max().item() * N)
+
+
+def test_reattn_dropout_consistency(ops):
+    """The Philox mask is identical in stats / mix / backward: compare against torch with the mask read back."""
+    B, h, N, p = 2, 4, 33, 0.2
+    ld = 36
+    scale = 0.5
+    S = _rand(B, h, N, N, seed=1, scale=2.0).requires_grad_(True)
+    W = _rand(h, h, seed=2, scale=0.6).requires_grad_(True)
+    b = _rand(h, seed=3, scale=0.01).requires_grad_(True)
+    gamma = (1 + _rand(h, seed=4, scale=0.3)).requires_grad_(True)
+    beta = _rand(h, seed=5, scale=0.01).requires_grad_(True)
+    ones = torch.ones(B, h, N, ld, device="cuda")
+    keep = ops.dropout(ones, torch.empty_like(ones), p, 99, 6)          # same (seed, stream, flat index) keying
+    mask = (keep[..., :N] != 0).float().cpu()
+    assert 0.7 < mask.mean().item() < 0.9
+    Pm_ref, A_ref = _reattn_ref(S, scale, W, b, gamma, beta, torch.zeros(h), torch.ones(h), True, mask, p)
+    dA = _rand(B, h, N, N, seed=8)
+    (A_ref * dA).sum().backward()
+    Sd = torch.zeros(B, h, N, ld, device="cuda"); Sd[..., :N] = S.detach().cuda()
+    ops.softmax_rows(Sd, B * h * N, N, ld, scale)
+    Wd, bd, gd, btd = W.detach().cuda(), b.detach().cuda(), gamma.detach().cuda(), beta.detach().cuda()
+    sums = torch.zeros(2 * h, dtype=torch.float64, device="cuda")
+    ops.reattn_stats(Sd, B, h, N, ld, Wd, bd, p, 99, 6, sums)
+    fold, saved = torch.empty(h * h + h, device="cuda"), torch.empty(2 * h, device="cuda")
+    ops.reattn_bn_finalize(sums, B * N * N, h, N, Wd, bd, gd, btd, torch.zeros(h, device="cuda"),
+                           torch.ones(h, device="cuda"), None, 1e-5, 0.1, True, fold, saved)
+    A = torch.empty_like(Sd)
+    ops.reattn_mix(Sd, A, fold, B, h, N, ld, p, 99, 6)
+    _close(A[..., :N], A_ref, rtol=2e-4, name="mixed map (dropout)")
+    dAd = torch.zeros(B, h, N, ld, device="cuda"); dAd[..., :N] = dA.cuda()
+    red = torch.zeros(2 * h, dtype=torch.float64, device="cuda")
+    ops.reattn_bwd_reduce(Sd, dAd, B, h, N, ld, Wd, bd, saved, p, 99, 6, red)
+    dW, dbc, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"),
+                        torch.zeros(h, device="cuda"), torch.zeros(h, device="cuda"))
+    ops.reattn_bwd_rows(Sd, dAd, B, h, N, ld, Wd, bd, gd, saved, red, True, scale, p, 99, 6, dW, dbc, dg, dbt)
+    _close(dAd[..., :N], S.grad, rtol=5e-4, name="dS (dropout)")
+    _close(dW.reshape(h, h), W.grad, rtol=5e-4, name="dW mix (dropout)")
+
+
+# ------------------------------------------------------------------------------------------------ layer norm
+@pytest.mark.parametrize("B,N,D", [(3, 49, 3072), (2, 16, 48), (5, 7, 9)])
+def test_layernorm(ops, B, N, D):
+    x = (_rand(B, N, D, seed=1) * 2 + 0.3).requires_grad_(True)
+    w = (1 + _rand(N, D, seed=2, scale=0.2)).requires_grad_(True)
+    b = _rand(N, D, seed=3, scale=0.1).requires_grad_(True)
+    y = F.layer_norm(x, (N, D), w, b, 1e-5)
+    g = _rand(B, N, D, seed=4)
+    (y * g).sum().backward()
+    n = N * D
+    stats = torch.empty(B, 2, device="cuda")
+    xd = x.detach().cuda()
+    ops.ln_stats(xd, B, n, 1e-5, stats)
+    out = torch.empty_like(xd)
+    ops.ln_apply(xd, stats, w.detach().cuda(), b.detach().cuda(), out, B, n)
+    _close(out, y, name="ln fwd")
+    dx, dw, db = torch.empty_like(xd), torch.zeros(N, D, device="cuda"), torch.zeros(N, D, device="cuda")
+    ops.ln_bwd(g.cuda(), xd, stats, w.detach().cuda(), dx, dw, db, torch.empty(B, 2, device="cuda"), B, n)
+    _close(dx, x.grad, rtol=1e-4, name="ln dx")
+    _close(dw, w.grad, rtol=1e-5, name="ln dw")
+    _close(db, b.grad, rtol=1e-5, name="ln db")
+
+
+# ------------------------------------------------------------------------------------------------ losses / optimizer
+@pytest.mark.parametrize("kind", ["l1", "mse", "dice"])
+def test_losses(kind):
+    import vit_unet_b200 as vu
+    pred = _rand(4, 3, 32, 32, seed=1).requires_grad_(True)
+    tgt = (_rand(4, 3, 32, 32, seed=2) > 0).float() if kind == "dice" else _rand(4, 3, 32, 32, seed=2)
+    ref = {"l1": F.l1_loss, "mse": F.mse_loss, "dice": O.dice_loss}[kind](pred, tgt)
+    (ref * 1.7).backward()
+    pc = pred.detach().cuda().requires_grad_(True)
+    got = {"l1": vu.l1_loss, "mse": vu.mse_loss, "dice": vu.dice_loss}[kind](pc, tgt.cuda())
+    (got * 1.7).backward()
+    _close(got, ref, name="loss")
+    _close(pc.grad, pred.grad, name="dloss")
+
+
+def test_adamw(ops):
+    p0, g = _rand(1000, seed=1), _rand(1000, seed=2)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-2, weight_decay=0.05)
+    pd, m, v = p0.clone().cuda(), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+    for step in range(1, 4):
+        pr.grad = g * step
+        opt.step()
+        ops.adamw(pd, (g * step).cuda(), m, v, 1e-2, 0.9, 0.999, 1e-8, 0.05, step)
+    _close(pd, pr, rtol=1e-5, name="adamw")

@@ -1,0 +1,239 @@
+"""End-to-end parity of the CUDA ViT-UNet (through the nn.Module / C-ABI path) against the CPU oracle and the
+golden vectors produced by the reference's own model.py.
+
+FP32 path tolerance: outputs within 1e-5 relative (north_star); gradients within 1e-4 of the gradient's max
+(they sum O(1e5) fp32 terms in a different order than ATen does).
+"""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from make_golden import CONFIGS, fill_state_dict, make_input, pack, run_case   # noqa: E402
+from oracle import vit_unet_oracle as O                                          # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _pair(variant, kw):
+    import vit_unet_b200 as vu
+    if variant == "head":
+        ref, net = _quiet(O.HViT_UNet, **kw), _quiet(vu.HViT_UNet, **kw)
+    else:
+        ref, net = _quiet(O.ViT_UNet, **kw), _quiet(vu.ViT_UNet, **kw)
+    sd = fill_state_dict(ref.state_dict())
+    ref.load_state_dict(sd)
+    net.load_state_dict(sd)            # identical keys and shapes, or this raises
+    return ref, net.to("cuda")
+
+
+def _compare(ref, net, x, y, out_tol=1e-5, grad_tol=1e-4):
+    import vit_unet_b200 as vu
+    ref.eval(); net.eval()
+    with torch.no_grad():
+        eo, en = ref(x), net(x.cuda())
+    assert en.shape == eo.shape
+    assert _rel(en, eo) <= out_tol, ("eval out", _rel(en, eo))
+    ref.train(); net.train()
+    ref.zero_grad(); net.zero_grad()
+    xr = x.clone().requires_grad_(True)
+    xn = x.clone().cuda().requires_grad_(True)
+    lr = torch.nn.functional.l1_loss(ref(xr), y); lr.backward()
+    out_n = net(xn)
+    ln = vu.l1_loss(out_n, y.cuda()); ln.backward()
+    assert abs(lr.item() - ln.item()) <= out_tol * abs(lr.item()) + 1e-7
+    assert _rel(xn.grad, xr.grad) <= grad_tol, ("dx", _rel(xn.grad, xr.grad))
+    gr = dict(ref.named_parameters())
+    worst = ("", 0.0)
+    for n, p in net.named_parameters():
+        assert p.grad is not None, n
+        r = _rel(p.grad, gr[n].grad)
+        if gr[n].grad.abs().max() < 1e-12:      # e.g. reatten_matrix.bias under train-mode BN: exactly 0 in theory
+            assert p.grad.abs().max().item() < 1e-6, n
+            continue
+        if r > worst[1]:
+            worst = (n, r)
+    assert worst[1] <= grad_tol, worst
+    br = dict(ref.named_buffers())
+    for n, b in net.named_buffers():
+        if b.dtype == torch.int64:
+            assert b.item() == br[n].item(), n
+        else:
+            assert _rel(b, br[n]) <= 1e-4, (n, _rel(b, br[n]))
+    return out_n
+
+
+@pytest.mark.parametrize("name", ["tiny_head", "tiny_head_te2", "tiny_head_1ch"])
+def test_tiny_configs_match_oracle(name):
+    variant, kw, B = CONFIGS[name]
+    ref, net = _pair(variant, kw)
+    x, y = make_input(B, kw["num_channels"], kw["im_size"])
+    _compare(ref, net, x, y)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_matches_reference_golden(name):
+    """CUDA path vs vectors produced by executing the reference's model.py (tests/golden/make_golden.py)."""
+    import vit_unet_b200 as vu
+    variant, kw, B = CONFIGS[name]
+    gold = np.load(os.path.join(GOLD, f"{name}.npz"))
+    net = _quiet(vu.HViT_UNet, **kw)
+    assert sum(p.numel() for p in net.parameters()) == int(gold["n_params"])
+    net.load_state_dict(fill_state_dict(net.state_dict()))
+    net.to("cuda")
+    x, y = make_input(B, kw["num_channels"], kw["im_size"])
+
+    class _Wrap(torch.nn.Module):       # run_case drives a CPU-style module; hop to the device at the boundary
+        def __init__(self, m): super().__init__(); self.m = m
+        def forward(self, t): return self.m(t.cuda()).cpu()
+    got = pack(run_case(_Wrap(net), x, y, train=True), full=name.startswith("tiny"))
+    for k in gold.files:
+        if k == "n_params":
+            continue
+        kk = k.replace("g:", "g:m.").replace("g_norm:", "g_norm:m.").replace("buf:", "buf:m.")
+        g, o = gold[k], got[kk]
+        scale = max(np.abs(g).max(), 1e-30)
+        tol = 1e-5 if k in ("eval_out", "train_out", "loss", "eval_out_sum", "train_out_sum") else 2e-4
+        if "reatten_matrix.bias" in k:      # true gradient is 0 under train-mode BN; both sides hold round-off
+            assert np.abs(o).max() < 1e-5
+            continue
+        assert np.abs(o - g).max() <= tol * scale + 1e-7, (k, float(np.abs(o - g).max()), float(scale))
+
+
+@pytest.mark.parametrize("preset,B", [("lite", 1), ("base", 2)])
+def test_presets_match_oracle(preset, B):
+    import vit_unet_b200 as vu
+    ref = _quiet(O.get_vit_unet, preset, variant="head", attn_drop=0.0, proj_drop=0.0)
+    net = _quiet(vu.get_vit_unet, preset)
+    net.engine.g.attn_drop = net.engine.g.proj_drop = 0.0      # parity is defined with dropout off
+    sd = fill_state_dict(ref.state_dict())
+    ref.load_state_dict(sd); net.load_state_dict(sd)
+    net.to("cuda")
+    x, y = make_input(B, 3, 224)
+    _compare(ref, net, x, y)
+
+
+@pytest.mark.parametrize("preset", ["lite", "base"])
+def test_readme_variant_matches_oracle(preset):
+    import vit_unet_b200 as vu
+    cfg = O.PRESETS[preset]
+    kw = dict(depth=cfg["depth"], depth_te=cfg["depth_te"], size_bottleneck=cfg["size_bottleneck"],
+              preprocessing="conv", num_patches=(224 // cfg["patch_size"]) ** 2, patch_size=cfg["patch_size"],
+              num_channels=3, hidden_dim=cfg["hidden_dim"], num_heads=cfg["num_heads"], attn_drop=0.0,
+              proj_drop=0.0, linear_drop=0)
+    ref, net = _pair("readme", kw)
+    n_params = {"lite": 3_387_568, "base": 36_613_036}[preset]        # README.md:16,34
+    assert sum(p.numel() for p in net.parameters()) == n_params
+    x, y = make_input(1, 3, 224)
+    _compare(ref, net, x, y)
+
+
+def test_readme_variant_tiny_none_preprocessing():
+    kw = dict(depth=1, depth_te=1, size_bottleneck=1, preprocessing="none", num_patches=4, patch_size=8,
+              num_channels=3, hidden_dim=16, num_heads=2, attn_drop=0.0, proj_drop=0.0, linear_drop=0)
+    ref, net = _pair("readme", kw)
+    x, y = make_input(2, 3, 16)
+    _compare(ref, net, x, y)
+
+
+def test_psnr_delta_on_reconstruction():
+    """north_star acceptance: PSNR of the CUDA reconstruction vs the oracle's differs by < 0.01 dB."""
+    variant, kw, B = CONFIGS["lite_head"]
+    ref, net = _pair(variant, kw)
+    x, clean = make_input(2, 3, 224, seed=5)
+    ref.eval(); net.eval()
+    with torch.no_grad():
+        a, b = ref(x), net(x.cuda()).cpu()
+
+    def psnr(o):
+        return 10 * torch.log10(4.0 / ((o - clean) ** 2).flatten(1).mean(1))
+    assert (psnr(a) - psnr(b)).abs().max().item() < 0.01
+
+
+def test_dropout_train_mode_runs_and_is_seeded():
+    import vit_unet_b200 as vu
+    _, kw, _ = CONFIGS["tiny_head"]
+    kw = dict(kw, attn_drop=0.2, proj_drop=0.2)
+    net = _quiet(vu.HViT_UNet, **kw).to("cuda")
+    x, y = make_input(2, 3, 32)
+    net.train()
+    torch.manual_seed(7); a = net(x.cuda())
+    torch.manual_seed(7); b = net(x.cuda())
+    torch.manual_seed(8); c = net(x.cuda())
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    vu.l1_loss(a, y.cuda()).backward()
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters())
+    net.eval()
+    with torch.no_grad():
+        assert torch.equal(net(x.cuda()), net(x.cuda()))
+
+
+def test_dropout_gradients_match_finite_differences():
+    """With dropout ON the masks cannot match torch's RNG; check backward against central differences of the
+    CUDA forward itself (same seed => same masks)."""
+    import vit_unet_b200 as vu
+    kw = dict(depth=1, depth_te=1, size_bottleneck=1, preprocessing="conv", im_size=16, patch_size=8,
+              num_channels=3, hidden_dim=16, num_heads=2, attn_drop=0.25, proj_drop=0.25, linear_drop=0)
+    net = _quiet(vu.HViT_UNet, **kw)
+    net.load_state_dict(fill_state_dict(net.state_dict()))
+    net.to("cuda").train()
+    x, y = make_input(2, 3, 16)
+    x, y = x.cuda(), y.cuda()
+
+    def loss():
+        torch.manual_seed(11)
+        return vu.mse_loss(net(x), y)
+    net.zero_grad(); loss().backward()
+    p = dict(net.named_parameters())["Encoders.0.FeedForward.net.3.bias"]
+    q = dict(net.named_parameters())["Encoders.0.ReAttn.proj.bias"]
+    for prm, idx in ((p, 5), (q, 17)):
+        g = prm.grad.view(-1)[idx].item()
+        with torch.no_grad():
+            eps = 1e-2
+            prm.view(-1)[idx] += eps; lp = loss().item()
+            prm.view(-1)[idx] -= 2 * eps; lm = loss().item()
+            prm.view(-1)[idx] += eps
+        fd = (lp - lm) / (2 * eps)
+        assert abs(fd - g) <= 5e-2 * max(abs(g), abs(fd)) + 1e-6, (fd, g)
+
+
+def test_boundary_errors_and_state_dict():
+    import vit_unet_b200 as vu
+    with pytest.raises(ValueError):
+        vu.get_vit_unet("huge")
+    with pytest.raises(AssertionError):
+        _quiet(vu.HViT_UNet, 3, 1, 1, "conv", 224, 16, 3, 64, 4, 0., 0., 0)
+    net = _quiet(vu.get_vit_unet, "lite")
+    ref = _quiet(O.get_vit_unet, "lite")
+    assert list(net.state_dict().keys()) == list(ref.state_dict().keys())
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 224, 224))            # CPU tensor: no fallback
+    net.to("cuda")
+    with pytest.raises(AssertionError):
+        net(torch.zeros(1, 3, 100, 100, device="cuda"))
+
+
+def test_drop_in_module_path():
+    import vit_unet.torch.model as models            # run_denoising.py:2
+    m = _quiet(models.get_vit_unet, "lite").to("cuda")
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)  # run_denoising.py:81
+    crit = torch.nn.MSELoss()                         # run_denoising.py:80 (plain torch loss on our output)
+    x, y = make_input(2, 3, 224)
+    out = m(x.cuda())
+    loss = crit(out, y.cuda()); loss.backward(); opt.step()
+    assert out.shape == (2, 3, 224, 224) and torch.isfinite(loss)

@@ -1,0 +1,127 @@
+// Shared device/host helpers for the vit_unet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/vit_unet_b200.h"
+
+namespace vu {
+
+// ------------------------------------------------------------------ host-side error plumbing
+void set_error(const std::string& s);
+int fail_arg(const char* fn, const char* what);
+int check_launch(const char* fn);     // cudaPeekAtLastError -> VU_ERR_CUDA
+int sm_count();
+
+#define VU_REQUIRE(cond, fn, msg) do { if (!(cond)) return vu::fail_arg(fn, msg); } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------ patch-layout addressing
+// Offset (inside one image of C*H*W floats) of pixel (c, y, x) in patch layout p (p == 0: NCHW).
+// reference: patch()/unflatten()/unpatch(), model.py:8-35.
+struct Layout {
+  int C, H, W, p, gw, pp;   // gw = W/p, pp = p*p
+  __host__ __device__ Layout() {}
+  __host__ __device__ Layout(int C_, int H_, int W_, int p_) : C(C_), H(H_), W(W_), p(p_) {
+    gw = p ? W / p : 1; pp = p * p;
+  }
+  __device__ __forceinline__ int64_t at(int c, int y, int x) const {
+    if (p == 0) return ((int64_t)c * H + y) * W + x;
+    int r = y / p, q = x / p;
+    int i = y - r * p, j = x - q * p;
+    return ((int64_t)(r * gw + q) * C + c) * pp + i * p + j;
+  }
+  // inverse: linear pixel index (channel 0 plane ordering of this layout) -> (y, x).
+  // pix enumerates (token, i, j) for p>0 and (y, x) for p==0.
+  __device__ __forceinline__ void pixel(int64_t pix, int& y, int& x) const {
+    if (p == 0) { y = (int)(pix / W); x = (int)(pix - (int64_t)y * W); return; }
+    int n = (int)(pix / pp); int rem = (int)(pix - (int64_t)n * pp);
+    int i = rem / p, j = rem - i * p;
+    int r = n / gw, q = n - r * gw;
+    y = r * p + i; x = q * p + j;
+  }
+  // offset of channel-0 value for linear pixel index pix, and stride between channels
+  __device__ __forceinline__ int64_t base_of(int64_t pix) const {
+    if (p == 0) return pix;
+    int64_t n = pix / pp; int64_t rem = pix - n * pp;
+    return n * C * pp + rem;
+  }
+  __device__ __forceinline__ int64_t cstride() const { return p == 0 ? (int64_t)H * W : pp; }
+};
+
+// ------------------------------------------------------------------ Philox4x32-10 (counter-based RNG)
+// keyed by (seed, stream id); counter = element index / 4.  Same generator in every kernel that
+// needs the mask of a given element, so masks never have to be stored.
+struct Philox {
+  __device__ __forceinline__ static uint4 gen(uint64_t seed, uint32_t stream, uint64_t ctr) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0x5eed5eedu;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+  // keep-probability test for one element index; thresh = p * 2^32 (drop if r < thresh)
+  __device__ __forceinline__ static bool keep(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thresh) {
+    uint4 r = gen(seed, stream, idx >> 2);
+    uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+    return v >= thresh;
+  }
+};
+static inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0; if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+
+// ------------------------------------------------------------------ reductions
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum of NV values per thread (double), result valid in thread 0. blockDim.x <= 1024.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* >= NV*32 doubles */) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double t = lane < nw ? smem[i * 32 + lane] : 0.0;
+      v[i] = warp_sum(t);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float gelu_exact(float x) {          // torch.nn.GELU() default (erf form)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_exact_grad(float x) {
+  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+}  // namespace vu

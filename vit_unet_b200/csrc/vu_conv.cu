@@ -1,0 +1,255 @@
+// 3x3 C->C convolutions of the ViT-UNet path, evaluated directly on the patch layouts:
+//   * q/k/v convs: every token is a (C,p,p) image, zero padded at the PATCH border (model.py:137-139,152-154)
+//   * PatchEncoder conv (README variant) and the reconstruction conv: whole-image 'same' conv (model.py:428)
+// One thread per pixel, all C output channels of all fused convs in registers; the 9*C input taps come from
+// L1 (each input float is reused 9*C*nconv times), so HBM sees one read of x and one write per output.
+#include "vu_common.cuh"
+
+namespace vu {
+
+struct ConvGeom {
+  Layout lin, lout;      // storage layouts of the tensor(s) read / written
+  int bp;                // border patch (0: image)
+  int fast;              // lin.p == bp: taps are at fixed offsets inside the patch
+  int64_t per_image, npix_total;   // C*H*W ; B*H*W
+};
+
+__device__ __forceinline__ void tap_setup(const ConvGeom& g, int y, int x, int& iy, int& ix, int& limy, int& limx) {
+  if (g.bp) { iy = y % g.bp; ix = x % g.bp; limy = g.bp; limx = g.bp; }
+  else { iy = y; ix = x; limy = g.lin.H; limx = g.lin.W; }
+}
+
+// forward: out_k[co] = bias_k[co] + sum_{ci,ky,kx} x[ci](y+ky-1, x+kx-1) * w_k[co][ci][ky][kx]
+template <int C, int NCONV>
+__global__ void __launch_bounds__(256)
+conv3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2, ConvGeom g) {
+  __shared__ float sw[NCONV * C * C * 9];
+  __shared__ float sb[NCONV * C];
+  for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < NCONV * C; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int64_t hw = (int64_t)g.lin.H * g.lin.W;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.npix_total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t / hw; int64_t pix = t - b * hw;
+    int y, xx; g.lout.pixel(pix, y, xx);
+    int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
+    const float* xb = x + b * g.per_image;
+    float v[C][9];
+    const int64_t cs = g.lin.cstride();
+    if (g.fast) {
+      int64_t base = g.lin.at(0, y, xx);
+      int rs = g.bp ? g.bp : g.lin.W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          bool ok = (unsigned)(iy + ky - 1) < (unsigned)limy && (unsigned)(ix + kx - 1) < (unsigned)limx;
+#pragma unroll
+          for (int ci = 0; ci < C; ++ci)
+            v[ci][ky * 3 + kx] = ok ? __ldg(xb + base + ci * cs + (ky - 1) * rs + (kx - 1)) : 0.f;
+        }
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          bool ok = (unsigned)(iy + ky - 1) < (unsigned)limy && (unsigned)(ix + kx - 1) < (unsigned)limx;
+          int64_t off = ok ? g.lin.at(0, y + ky - 1, xx + kx - 1) : 0;
+#pragma unroll
+          for (int ci = 0; ci < C; ++ci) v[ci][ky * 3 + kx] = ok ? __ldg(xb + off + ci * cs) : 0.f;
+        }
+    }
+    int64_t obase = b * g.per_image + g.lout.base_of(pix);
+    const int64_t ocs = g.lout.cstride();
+#pragma unroll
+    for (int k = 0; k < NCONV; ++k) {
+      float* op = k == 0 ? o0 : (k == 1 ? o1 : o2);
+#pragma unroll
+      for (int co = 0; co < C; ++co) {
+        float acc = sb[k * C + co];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci)
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) acc = fmaf(v[ci][tp], sw[((k * C + co) * C + ci) * 9 + tp], acc);
+        op[obase + co * ocs] = acc;
+      }
+    }
+  }
+}
+
+// backward data: dx[ci](y,x) = sum_k sum_co sum_{ky,kx} dy_k[co](y-ky+1, x-kx+1) * w_k[co][ci][ky][kx]
+template <int C, int NCONV>
+__global__ void __launch_bounds__(256)
+conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ d1, const float* __restrict__ d2,
+                        const float* __restrict__ w, float* __restrict__ dx, ConvGeom g, int accumulate) {
+  __shared__ float sw[NCONV * C * C * 9];
+  for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int64_t hw = (int64_t)g.lin.H * g.lin.W;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.npix_total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t / hw; int64_t pix = t - b * hw;
+    int y, xx; g.lout.pixel(pix, y, xx);
+    int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
+    float acc[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) acc[ci] = 0.f;
+    const int64_t cs = g.lin.cstride();
+    int64_t base = g.fast ? g.lin.at(0, y, xx) : 0;
+    int rs = g.bp ? g.bp : g.lin.W;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        // source pixel (y - ky + 1, x - kx + 1)
+        bool ok = (unsigned)(iy - ky + 1) < (unsigned)limy && (unsigned)(ix - kx + 1) < (unsigned)limx;
+        if (!ok) continue;
+        int64_t off = g.fast ? base + (1 - ky) * rs + (1 - kx) : g.lin.at(0, y - ky + 1, xx - kx + 1);
+#pragma unroll
+        for (int k = 0; k < NCONV; ++k) {
+          const float* dp = (k == 0 ? d0 : (k == 1 ? d1 : d2)) + b * g.per_image + off;
+#pragma unroll
+          for (int co = 0; co < C; ++co) {
+            float dv = __ldg(dp + co * cs);
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) acc[ci] = fmaf(dv, sw[((k * C + co) * C + ci) * 9 + ky * 3 + kx], acc[ci]);
+          }
+        }
+      }
+    int64_t obase = b * g.per_image + g.lout.base_of(pix);
+    const int64_t ocs = g.lout.cstride();
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+      float* p = dx + obase + ci * ocs;
+      *p = accumulate ? *p + acc[ci] : acc[ci];
+    }
+  }
+}
+
+// backward weights.  grid.y = nconv*C enumerates (k, co); each thread keeps the C*9 partial sums of that
+// output channel plus the bias sum, pixels are grid-strided in x's own layout order.
+// Here g.lin describes x, g.lout describes dy.
+template <int C>
+__global__ void __launch_bounds__(256)
+conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ d0, const float* __restrict__ d1,
+                          const float* __restrict__ d2, float* __restrict__ dw, float* __restrict__ dbias,
+                          ConvGeom g) {
+  const int k = blockIdx.y / C, co = blockIdx.y % C;
+  const float* dy = k == 0 ? d0 : (k == 1 ? d1 : d2);
+  float acc[C * 9 + 1];
+#pragma unroll
+  for (int i = 0; i < C * 9 + 1; ++i) acc[i] = 0.f;
+  const int64_t hw = (int64_t)g.lin.H * g.lin.W;
+  const int64_t cs = g.lin.cstride(), dcs = g.lout.cstride();
+  const int rs = g.bp ? g.bp : g.lin.W;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.npix_total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t / hw; int64_t pix = t - b * hw;
+    int y, xx; g.lin.pixel(pix, y, xx);
+    int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
+    float dv = __ldg(dy + b * g.per_image + g.lout.at(co, y, xx));
+    acc[C * 9] += dv;
+    const float* xb = x + b * g.per_image;
+    int64_t base = g.lin.base_of(pix);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        bool ok = (unsigned)(iy + ky - 1) < (unsigned)limy && (unsigned)(ix + kx - 1) < (unsigned)limx;
+        if (!ok) continue;
+        int64_t off = g.fast ? base + (ky - 1) * rs + (kx - 1) : g.lin.at(0, y + ky - 1, xx + kx - 1);
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) acc[ci * 9 + ky * 3 + kx] = fmaf(dv, __ldg(xb + off + ci * cs), acc[ci * 9 + ky * 3 + kx]);
+      }
+  }
+  __shared__ float red[C * 9 + 1][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < C * 9 + 1; ++i) {
+    float v = warp_sum(acc[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < C * 9 + 1) {
+    float s = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += red[threadIdx.x][wv];
+    if (threadIdx.x < C * 9) atomicAdd(dw + ((int64_t)(k * C + co) * C) * 9 + threadIdx.x, s);
+    else if (dbias) atomicAdd(dbias + k * C + co, s);
+  }
+}
+
+static int make_geom(const char* fn, ConvGeom& g, int p_in, int p_out, int border_p, int B, int C, int H, int W) {
+  VU_REQUIRE(B > 0 && H > 0 && W > 0, fn, "empty shape");
+  VU_REQUIRE(C >= 1 && C <= 4, fn, "num_channels must be 1..4");
+  auto ok = [&](int p) { return p == 0 || (p > 0 && H % p == 0 && W % p == 0); };
+  VU_REQUIRE(ok(p_in) && ok(p_out) && ok(border_p), fn, "patch size must divide the image height and width");
+  g.lin = Layout(C, H, W, p_in); g.lout = Layout(C, H, W, p_out);
+  g.bp = border_p; g.fast = (p_in == border_p);
+  g.per_image = (int64_t)C * H * W; g.npix_total = (int64_t)B * H * W;
+  return VU_OK;
+}
+
+}  // namespace vu
+
+#define VU_DISPATCH_C(C, ...)                  \
+  switch (C) {                                 \
+    case 1: { constexpr int CC = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int CC = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int CC = 3; __VA_ARGS__; } break; \
+    default: { constexpr int CC = 4; __VA_ARGS__; } break; \
+  }
+
+extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const float* bias, int nconv,
+                              float* out0, float* out1, float* out2, int p_out, int border_p,
+                              int B, int C, int H, int W, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_conv3x3_fwd";
+  VU_REQUIRE(x && w && out0 && nconv >= 1 && nconv <= 3, fn, "null pointer or nconv outside 1..3");
+  VU_REQUIRE((nconv < 2 || out1) && (nconv < 3 || out2), fn, "missing output pointer");
+  ConvGeom g; int rc = make_geom(fn, g, p_x, p_out, border_p, B, C, H, W); if (rc) return rc;
+  int threads = 256;
+  int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
+  cudaStream_t s = as_stream(stream);
+  VU_DISPATCH_C(C,
+    if (nconv == 1) conv3x3_fwd_kernel<CC, 1><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
+    else if (nconv == 2) conv3x3_fwd_kernel<CC, 2><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
+    else conv3x3_fwd_kernel<CC, 3><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g));
+  return check_launch(fn);
+}
+
+extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const float* dy2, int p_dy,
+                                   const float* w, int nconv, float* dx, int p_dx, int border_p,
+                                   int B, int C, int H, int W, int accumulate, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_conv3x3_bwd_data";
+  VU_REQUIRE(dy0 && w && dx && nconv >= 1 && nconv <= 3, fn, "null pointer or nconv outside 1..3");
+  VU_REQUIRE((nconv < 2 || dy1) && (nconv < 3 || dy2), fn, "missing gradient pointer");
+  ConvGeom g; int rc = make_geom(fn, g, p_dy, p_dx, border_p, B, C, H, W); if (rc) return rc;
+  int threads = 256;
+  int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
+  cudaStream_t s = as_stream(stream);
+  VU_DISPATCH_C(C,
+    if (nconv == 1) conv3x3_bwd_data_kernel<CC, 1><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);
+    else if (nconv == 2) conv3x3_bwd_data_kernel<CC, 2><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);
+    else conv3x3_bwd_data_kernel<CC, 3><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate));
+  return check_launch(fn);
+}
+
+extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, const float* dy1,
+                                     const float* dy2, int p_dy, int nconv, float* dw, float* dbias,
+                                     int border_p, int B, int C, int H, int W, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_conv3x3_bwd_weight";
+  VU_REQUIRE(x && dy0 && dw && nconv >= 1 && nconv <= 3, fn, "null pointer or nconv outside 1..3");
+  VU_REQUIRE((nconv < 2 || dy1) && (nconv < 3 || dy2), fn, "missing gradient pointer");
+  ConvGeom g; int rc = make_geom(fn, g, p_x, p_dy, border_p, B, C, H, W); if (rc) return rc;
+  int threads = 256;
+  int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 8), (int64_t)sm_count() * 2);
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, nconv * C);
+  cudaStream_t s = as_stream(stream);
+  VU_DISPATCH_C(C, conv3x3_bwd_weight_kernel<CC><<<grid, threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g));
+  return check_launch(fn);
+}

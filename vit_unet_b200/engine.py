@@ -1,0 +1,392 @@
+"""Forward / backward schedule of the ViT-UNet hot path on the CUDA kernels.
+
+This is the host side of the path: a fixed sequence of C-ABI launches per block (no tracing compiler, no
+autograd graph inside the network -- the whole model is ONE autograd node, see model.py).  Reference order of
+operations: HViT_UNet.forward (model.py:372-435) -> ReAttentionTransformerEncoder.forward (:201-207) ->
+ReAttention.forward (:150-164) / SkipConnection.forward (:244-259) / FeedForward (:95-110).
+
+Activations are fp32 token tensors (B, N_l, D_l) in the patch layout of their level; N_l * D_l = C*H*W at every
+level, so "downsampling"/"upsampling" are permutations (vu_repatch).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+_PRECISION = {"value": ops.PREC_FP32}
+
+
+def set_precision(mode: str) -> None:
+    """'fp32': CUDA-core FMA everywhere (1e-5 parity).  'tf32': tcgen05 tensor cores for the contractions."""
+    _PRECISION["value"] = {"fp32": ops.PREC_FP32, "tf32": ops.PREC_TF32}[mode]
+
+
+def get_precision() -> str:
+    return "tf32" if _PRECISION["value"] == ops.PREC_TF32 else "fp32"
+
+
+@dataclass
+class Geometry:
+    C: int
+    S: int                 # square image side
+    p0: int
+    depth: int
+    depth_te: int
+    n_bottleneck: int
+    heads: int
+    hidden: int
+    shared_ln: bool        # README variant: one LN per block used twice (ViT_UNet.ipynb c27)
+    pe_conv: bool          # README variant applies conv2d in the PatchEncoder (ViT_UNet.ipynb c16:L32-33)
+    table_p: int           # patch size the position table is indexed at (p0: model.py:80-82; p0/2^depth: c16)
+    out_conv: bool
+    attn_drop: float = 0.0
+    proj_drop: float = 0.0
+    linear_drop: float = 0.0
+
+    def p(self, l): return self.p0 // (2 ** l)
+    def N(self, l): return (self.S // self.p(l)) ** 2
+    def D(self, l): return self.C * self.p(l) ** 2
+    def Hd(self, l): return self.hidden // (2 ** l)
+
+    def schedule(self):
+        """Forward order of blocks: ('block', prefix, level) / ('down', l) / ('up', l) / ('skip', prefix, level)."""
+        s = []
+        i = 0
+        for l in range(self.depth):
+            for _ in range(self.depth_te):
+                s.append(("block", f"Encoders.{i}.", l)); i += 1
+            s.append(("down", l))
+        for i in range(self.n_bottleneck):
+            s.append(("block", f"BottleNeck.{i}.", self.depth))
+        i = 0
+        for lv in range(self.depth):
+            l = self.depth - lv
+            for _ in range(self.depth_te):
+                s.append(("block", f"Decoders.{i}.", l)); i += 1
+            s.append(("up", l))
+            s.append(("skip", f"SkipConnections.{lv}.", l - 1))
+        return s
+
+    def param_order(self, names: List[str]) -> List[str]:
+        """Parameter names in forward-execution order (backward finishes them in exactly the reverse order, so
+        a flat gradient buffer in this order becomes ready as a growing suffix -> contiguous all-reduce buckets)."""
+        groups = ["PE."]
+        for st in self.schedule():
+            if st[0] in ("block", "skip"):
+                groups.append(st[1])
+        groups.append("conv2d.")
+        out = []
+        for gname in groups:
+            out += [n for n in names if n.startswith(gname) and n not in out]
+        assert sorted(out) == sorted(names), "parameter naming drifted from the schedule"
+        return out
+
+
+def _empty(shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+class Engine:
+    """Runs the schedule.  `P` maps state_dict-style names to CUDA tensors (parameters and BN buffers)."""
+
+    def __init__(self, geom: Geometry):
+        self.g = geom
+        self.sched = geom.schedule()
+        self.on_grads_ready = None     # callback(first_param_index) used by the data-parallel wrapper
+
+    # ------------------------------------------------------------------------------------------- helpers
+    def _gemm_tokens(self, A, W, out, M, N, K, **kw):
+        """out[M,N] = A[M,K] @ W[N,K]^T (+epilogue): the nn.Linear shape."""
+        return ops.gemm(A, W, out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, precision=_PRECISION["value"], **kw)
+
+    # ------------------------------------------------------------------------------------------- attention
+    def _attn_fwd(self, P, pre, xq, xkv, l, B, train, seed, sid, residual, saved):
+        g = self.g
+        N, D, h, p = g.N(l), g.D(l), g.heads, g.p(l)
+        hd, ld = D // h, ops.pad4(N)
+        prec = _PRECISION["value"]
+        wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
+        q, k, v = _empty((B, N, D), xq), _empty((B, N, D), xq), _empty((B, N, D), xq)
+        if xq is xkv:
+            wcat = torch.cat([wq.reshape(-1), wk.reshape(-1), wv.reshape(-1)])
+            ops.conv3x3_fwd(xq, p, wcat, None, [q, k, v], p, p, B, g.C, g.S, g.S)
+        else:
+            ops.conv3x3_fwd(xq, p, wq.contiguous(), None, [q], p, p, B, g.C, g.S, g.S)
+            wcat = torch.cat([wk.reshape(-1), wv.reshape(-1)])
+            ops.conv3x3_fwd(xkv, p, wcat, None, [k, v], p, p, B, g.C, g.S, g.S)
+        Pm = _empty((B, h, N, ld), xq)
+        ops.gemm(q, k, Pm, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
+                 sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
+        scale = float(hd) ** -0.5
+        ops.softmax_rows(Pm, B * h * N, N, ld, scale)
+        Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
+        bm = P[pre + "reatten_matrix.bias"]
+        adrop = g.attn_drop if train else 0.0
+        sums = None
+        if train:
+            sums = torch.zeros(2 * h, dtype=torch.float64, device=xq.device)
+            ops.reattn_stats(Pm, B, h, N, ld, Wm, bm, adrop, seed, sid, sums)
+        fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
+        ops.reattn_bn_finalize(sums, B * N * N, h, N, Wm, bm, P[pre + "var_norm.weight"], P[pre + "var_norm.bias"],
+                               P[pre + "var_norm.running_mean"], P[pre + "var_norm.running_var"],
+                               P.get(pre + "var_norm.num_batches_tracked"), 1e-5, 0.1, train, fold, bn_saved)
+        A = _empty((B, h, N, ld), xq)
+        ops.reattn_mix(Pm, A, fold, B, h, N, ld, adrop, seed, sid)
+        O = _empty((B, N, D), xq)
+        ops.gemm(A, v, O, N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B, batch_inner=h,
+                 sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
+        del A
+        y = _empty((B, N, D), xq)
+        pdrop = g.proj_drop if train else 0.0
+        self._gemm_tokens(O, P[pre + "proj.weight"], y, B * N, D, D, bias=P[pre + "proj.bias"],
+                          residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
+        if saved is not None:
+            saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, seed=seed, sid=sid,
+                         adrop=adrop, pdrop=pdrop, train=train)
+        return y
+
+    def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):
+        """dy: grad of proj output (pre-residual).  Accumulates into dxq_acc / dxkv_acc (may be the same tensor)."""
+        g = self.g
+        N, D, h, p = g.N(l), g.D(l), g.heads, g.p(l)
+        hd, ld = D // h, ops.pad4(N)
+        prec = _PRECISION["value"]
+        M = B * N
+        q, k, v, Pm, O = sv["q"], sv["k"], sv["v"], sv["Pm"], sv["O"]
+        seed, sid, adrop, pdrop, train = sv["seed"], sv["sid"], sv["adrop"], sv["pdrop"], sv["train"]
+        if pdrop > 0:
+            dyd = ops.dropout(dy, torch.empty_like(dy), pdrop, seed, sid + 1)
+        else:
+            dyd = dy
+        Wp = P[pre + "proj.weight"]
+        # proj: dO = dyd @ Wp ; dWp = dyd^T @ O ; dbp = colsum(dyd)
+        dO = _empty((B, N, D), dy)
+        ops.gemm(dyd, Wp, dO, M, D, D, trans_b=False, lda=D, ldb=D, ldc=D, precision=prec)
+        self._wgrad(dyd, O, G[pre + "proj.weight"], M, D, D)
+        ops.colsum(dyd, M, D, D, G[pre + "proj.bias"], accumulate=True)
+        del dyd
+        # recompute the mixed map, then dV = A^T dO ; dA = dO V^T
+        Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
+        bm = P[pre + "reatten_matrix.bias"]
+        A = _empty((B, h, N, ld), dy)
+        ops.reattn_mix(Pm, A, sv["fold"], B, h, N, ld, adrop, seed, sid)
+        dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
+        ops.gemm(A, dO, dv, N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B,
+                 batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
+        dA = A   # reuse the buffer: A is dead once dV is formed
+        ops.gemm(dO, v, dA, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
+                 sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
+        del dO
+        red = torch.zeros(2 * h, dtype=torch.float64, device=dy.device)
+        ops.reattn_bwd_reduce(Pm, dA, B, h, N, ld, Wm, bm, sv["bn"], adrop, seed, sid, red)
+        scale = float(hd) ** -0.5
+        ops.reattn_bwd_rows(Pm, dA, B, h, N, ld, Wm, bm, P[pre + "var_norm.weight"], sv["bn"], red, train, scale,
+                            adrop, seed, sid, G[pre + "reatten_matrix.weight"], G[pre + "reatten_matrix.bias"],
+                            G[pre + "var_norm.weight"], G[pre + "var_norm.bias"])
+        dS = dA
+        # dQ = dS K ; dK = dS^T Q
+        ops.gemm(dS, k, dq, N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B, batch_inner=h,
+                 sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
+        ops.gemm(dS, q, dk, N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B,
+                 batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
+        del dS, dA
+        wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
+        xq, xkv = sv["xq"], sv["xkv"]
+        C, S = g.C, g.S
+        nw = wq.numel()
+        if xq is xkv:
+            wcat = torch.cat([wq.reshape(-1), wk.reshape(-1), wv.reshape(-1)])
+            ops.conv3x3_bwd_data([dq, dk, dv], p, wcat, dxq_acc, p, p, B, C, S, S, accumulate=True)
+            dw = torch.zeros(3 * nw, dtype=torch.float32, device=dy.device)
+            ops.conv3x3_bwd_weight(xq, p, [dq, dk, dv], p, dw, None, p, B, C, S, S)
+            G[pre + "qconv2d.weight"].view(-1).add_(dw[:nw])
+            G[pre + "kconv2d.weight"].view(-1).add_(dw[nw:2 * nw])
+            G[pre + "vconv2d.weight"].view(-1).add_(dw[2 * nw:])
+        else:
+            ops.conv3x3_bwd_data([dq], p, wq.contiguous(), dxq_acc, p, p, B, C, S, S, accumulate=True)
+            wcat = torch.cat([wk.reshape(-1), wv.reshape(-1)])
+            ops.conv3x3_bwd_data([dk, dv], p, wcat, dxkv_acc, p, p, B, C, S, S, accumulate=True)
+            ops.conv3x3_bwd_weight(xq, p, [dq], p, G[pre + "qconv2d.weight"], None, p, B, C, S, S)
+            dw = torch.zeros(2 * nw, dtype=torch.float32, device=dy.device)
+            ops.conv3x3_bwd_weight(xkv, p, [dk, dv], p, dw, None, p, B, C, S, S)
+            G[pre + "kconv2d.weight"].view(-1).add_(dw[:nw])
+            G[pre + "vconv2d.weight"].view(-1).add_(dw[nw:])
+
+    def _wgrad(self, dY, X, dW, M, N, K):
+        """dW[N,K] += dY[M,N]^T @ X[M,K]; split over the (long) token dimension for parallelism."""
+        tiles = ((N + 127) // 128) * ((K + 127) // 128)
+        split = max(1, min(64, (2 * 148) // max(tiles, 1), M // 512))
+        ops.gemm(dY, X, dW, N, K, M, trans_a=True, trans_b=False, lda=N, ldb=K, ldc=K, accumulate=True,
+                 split_k=split, precision=_PRECISION["value"])
+
+    # ------------------------------------------------------------------------------------------- block
+    def _ln_names(self, pre):
+        if self.g.shared_ln:
+            return pre + "LN.", pre + "LN."
+        return pre + "LN1.", pre + "LN2."
+
+    def _block_fwd(self, P, pre, x, l, B, train, seed, sid, saved):
+        g = self.g
+        N, D, Hd = g.N(l), g.D(l), g.Hd(l)
+        n, M = N * D, B * N
+        ln1, ln2 = self._ln_names(pre)
+        sv_attn = {} if saved is not None else None
+        y1 = self._attn_fwd(P, pre + "ReAttn.", x, x, l, B, train, seed, sid, x, sv_attn)
+        st1 = _empty((B, 2), x)
+        ops.ln_stats(y1, B, n, 1e-5, st1)
+        x1 = _empty((B, N, D), x)
+        ops.ln_apply(y1, st1, P[ln1 + "weight"], P[ln1 + "bias"], x1, B, n)
+        if train and g.linear_drop > 0:
+            raise NotImplementedError("linear_drop > 0 is not implemented on the CUDA path (all presets use 0)")
+        pre_act, act = _empty((M, Hd), x), _empty((M, Hd), x)
+        self._gemm_tokens(x1, P[pre + "FeedForward.net.0.weight"], act, M, Hd, D,
+                          bias=P[pre + "FeedForward.net.0.bias"], act=ops.ACT_GELU, aux_out=pre_act, ldaux=Hd)
+        y2 = _empty((B, N, D), x)
+        self._gemm_tokens(act, P[pre + "FeedForward.net.3.weight"], y2, M, D, Hd,
+                          bias=P[pre + "FeedForward.net.3.bias"], residual=x1)
+        st2 = _empty((B, 2), x)
+        ops.ln_stats(y2, B, n, 1e-5, st2)
+        x2 = _empty((B, N, D), x)
+        ops.ln_apply(y2, st2, P[ln2 + "weight"], P[ln2 + "bias"], x2, B, n)
+        if saved is not None:
+            saved.update(attn=sv_attn, y1=y1, st1=st1, x1=x1, pre_act=pre_act, act=act, y2=y2, st2=st2)
+        return x2
+
+    def _block_bwd(self, P, G, pre, dx2, l, B, sv):
+        g = self.g
+        N, D, Hd = g.N(l), g.D(l), g.Hd(l)
+        n, M = N * D, B * N
+        prec = _PRECISION["value"]
+        ln1, ln2 = self._ln_names(pre)
+        scratch = _empty((B, 2), dx2)
+        dy2 = torch.empty_like(dx2)
+        ops.ln_bwd(dx2, sv["y2"], sv["st2"], P[ln2 + "weight"], dy2, G[ln2 + "weight"], G[ln2 + "bias"], scratch, B, n)
+        W1, W2 = P[pre + "FeedForward.net.0.weight"], P[pre + "FeedForward.net.3.weight"]
+        # FF2: dpre = (dy2 @ W2) * gelu'(pre) ; dW2 = dy2^T act ; db2 = colsum(dy2)
+        dpre = _empty((M, Hd), dx2)
+        ops.gemm(dy2, W2, dpre, M, Hd, D, trans_b=False, lda=D, ldb=Hd, ldc=Hd, act=ops.ACT_GELU_BWD,
+                 aux_in=sv["pre_act"], ldaux=Hd, precision=prec)
+        self._wgrad(dy2, sv["act"], G[pre + "FeedForward.net.3.weight"], M, D, Hd)
+        ops.colsum(dy2, M, D, D, G[pre + "FeedForward.net.3.bias"], accumulate=True)
+        # FF1: dx1 = dpre @ W1 + dy2 ; dW1 = dpre^T x1 ; db1 = colsum(dpre)
+        dx1 = torch.empty_like(dx2)
+        ops.gemm(dpre, W1, dx1, M, D, Hd, trans_b=False, lda=Hd, ldb=D, ldc=D, residual=dy2, precision=prec)
+        self._wgrad(dpre, sv["x1"], G[pre + "FeedForward.net.0.weight"], M, Hd, D)
+        ops.colsum(dpre, M, Hd, Hd, G[pre + "FeedForward.net.0.bias"], accumulate=True)
+        del dy2, dpre
+        dy1 = torch.empty_like(dx2)
+        ops.ln_bwd(dx1, sv["y1"], sv["st1"], P[ln1 + "weight"], dy1, G[ln1 + "weight"], G[ln1 + "bias"], scratch, B, n)
+        del dx1
+        # residual: dx = dy1 + (attention path); conv backward accumulates into dy1 in place
+        self._attn_bwd(P, G, pre + "ReAttn.", dy1, l, B, sv["attn"], dy1, dy1)
+        return dy1
+
+    # ------------------------------------------------------------------------------------------- network
+    def forward(self, P: Dict[str, torch.Tensor], X: torch.Tensor, train: bool, save: bool, seed: int = 0):
+        g = self.g
+        B = X.shape[0]
+        C, S = g.C, g.S
+        saved: Optional[dict] = {"steps": [], "B": B} if save else None
+        src = X
+        if g.pe_conv:
+            src = torch.empty_like(X)
+            ops.conv3x3_fwd(X, 0, P["PE.conv2d.weight"].contiguous(), P["PE.conv2d.bias"], [src], 0, 0, B, C, S, S)
+        x = _empty((B, g.N(0), g.D(0)), X)
+        ops.pe_fwd(src, 0, P["PE.position_embedding.weight"], g.table_p, x, g.p0, B, C, S, S)
+        if save:
+            saved["X"] = X
+        skips = {}
+        sid = 0
+        for st in self.sched:
+            kind = st[0]
+            sv = {} if save else None
+            if kind == "block":
+                _, pre, l = st
+                x = self._block_fwd(P, pre, x, l, B, train, seed, sid, sv)
+                sid += 2
+            elif kind == "down":
+                l = st[1]
+                skips[l] = x
+                y = _empty((B, g.N(l + 1), g.D(l + 1)), x)
+                x = ops.repatch(x, y, B, C, S, S, g.p(l), g.p(l + 1))
+            elif kind == "up":
+                l = st[1]
+                y = _empty((B, g.N(l - 1), g.D(l - 1)), x)
+                x = ops.repatch(x, y, B, C, S, S, g.p(l), g.p(l - 1))
+            else:
+                _, pre, l = st
+                enc = skips[l]
+                assert enc.shape == x.shape, "enc and dec not same shape"      # model.py:417
+                x = self._attn_fwd(P, pre, enc, x, l, B, train, seed, sid, None, sv)
+                sid += 2
+            if save:
+                saved["steps"].append(sv)
+        out = _empty((B, C, S, S), X)
+        if g.out_conv:
+            ops.conv3x3_fwd(x, g.p0, P["conv2d.weight"].contiguous(), P["conv2d.bias"], [out], 0, 0, B, C, S, S)
+        else:
+            ops.repatch(x, out, B, C, S, S, g.p0, 0)
+        if save:
+            saved["x_last"] = x
+        return out, saved
+
+    def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], saved: dict, dout: torch.Tensor,
+                 need_dx: bool):
+        """Fills G (zero-initialised gradient tensors keyed like P).  Returns dX or None."""
+        g = self.g
+        B, C, S = saved["B"], g.C, g.S
+        dx = _empty((B, g.N(0), g.D(0)), dout)
+        if g.out_conv:
+            w = P["conv2d.weight"].contiguous()
+            ops.conv3x3_bwd_data([dout], 0, w, dx, g.p0, 0, B, C, S, S)
+            ops.conv3x3_bwd_weight(saved["x_last"], g.p0, [dout], 0, G["conv2d.weight"], G["conv2d.bias"], 0, B, C, S, S)
+        else:
+            ops.repatch(dout, dx, B, C, S, S, 0, g.p0)
+        self._notify("conv2d.")
+        skip_grads = {}
+        for st, sv in zip(reversed(self.sched), reversed(saved["steps"])):
+            kind = st[0]
+            if kind == "block":
+                _, pre, l = st
+                dx = self._block_bwd(P, G, pre, dx, l, B, sv)
+                self._notify(pre)
+            elif kind == "down":
+                l = st[1]
+                y = _empty((B, g.N(l), g.D(l)), dx)
+                ops.repatch(dx, y, B, C, S, S, g.p(l + 1), g.p(l))
+                dx = ops.axpby(skip_grads.pop(l), y, 1.0, 1.0)
+            elif kind == "up":
+                l = st[1]
+                y = _empty((B, g.N(l), g.D(l)), dx)
+                dx = ops.repatch(dx, y, B, C, S, S, g.p(l - 1), g.p(l))
+            else:
+                _, pre, l = st
+                d_enc = torch.zeros_like(dx)
+                d_dec = torch.zeros_like(dx)
+                self._attn_bwd(P, G, pre, dx, l, B, sv, d_enc, d_dec)
+                skip_grads[l] = d_enc
+                dx = d_dec
+                self._notify(pre)
+        # PatchEncoder: tokens = patchify(src) + table
+        ops.pe_bwd_table(dx, g.p0, G["PE.position_embedding.weight"], g.table_p, B, C, S, S, accumulate=False)
+        dX = None
+        if g.pe_conv:
+            dsrc = _empty((B, C, S, S), dx)
+            ops.repatch(dx, dsrc, B, C, S, S, g.p0, 0)
+            ops.conv3x3_bwd_weight(saved["X"], 0, [dsrc], 0, G["PE.conv2d.weight"], G["PE.conv2d.bias"], 0, B, C, S, S)
+            if need_dx:
+                dX = _empty((B, C, S, S), dx)
+                ops.conv3x3_bwd_data([dsrc], 0, P["PE.conv2d.weight"].contiguous(), dX, 0, 0, B, C, S, S)
+        elif need_dx:
+            dX = _empty((B, C, S, S), dx)
+            ops.repatch(dx, dX, B, C, S, S, g.p0, 0)
+        self._notify("PE.")
+        return dX
+
+    def _notify(self, prefix: str):
+        if self.on_grads_ready is not None:
+            self.on_grads_ready(prefix)

@@ -1,0 +1,192 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is used only for device memory and streams.
+
+Every function validates device/dtype/contiguity, launches on ``torch.cuda.current_stream()`` and raises
+``VuError`` on failure.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, VuError, call
+
+ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2
+PREC_FP32, PREC_TF32 = 0, 1
+LOSS_KINDS = {"l1": 0, "mse": 1, "dice": 2}
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> int:
+    if not t.is_cuda:
+        raise VuError(f"{name}: tensor must live on a CUDA device (vit_unet_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise VuError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise VuError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _opt(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
+    return None if t is None else _chk(t, name, dtype)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+# ----------------------------------------------------------------------------------------- layout
+def repatch(x, out, B, Cc, H, W, p_in, p_out):
+    call("vu_repatch", _chk(x, "in"), _chk(out, "out"), B, Cc, H, W, p_in, p_out, _stream())
+    return out
+
+
+def pe_fwd(x, p_in, table, p_table, out, p_out, B, Cc, H, W):
+    call("vu_pe_fwd", _chk(x, "in"), p_in, _chk(table, "table"), p_table, _chk(out, "out"), p_out,
+         B, Cc, H, W, _stream())
+    return out
+
+
+def pe_bwd_table(dout, p_out, dtable, p_table, B, Cc, H, W, accumulate=False):
+    call("vu_pe_bwd_table", _chk(dout, "dout"), p_out, _chk(dtable, "dtable"), p_table, B, Cc, H, W,
+         int(accumulate), _stream())
+    return dtable
+
+
+# ----------------------------------------------------------------------------------------- convs
+def conv3x3_fwd(x, p_x, w, bias, outs, p_out, border_p, B, Cc, H, W):
+    n = len(outs)
+    ptrs = [_chk(o, f"out{i}") for i, o in enumerate(outs)] + [None] * (3 - n)
+    call("vu_conv3x3_fwd", _chk(x, "x"), p_x, _chk(w, "w"), _opt(bias, "bias"), n, ptrs[0], ptrs[1], ptrs[2],
+         p_out, border_p, B, Cc, H, W, _stream())
+    return outs
+
+
+def conv3x3_bwd_data(dys, p_dy, w, dx, p_dx, border_p, B, Cc, H, W, accumulate=False):
+    n = len(dys)
+    ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
+    call("vu_conv3x3_bwd_data", ptrs[0], ptrs[1], ptrs[2], p_dy, _chk(w, "w"), n, _chk(dx, "dx"), p_dx,
+         border_p, B, Cc, H, W, int(accumulate), _stream())
+    return dx
+
+
+def conv3x3_bwd_weight(x, p_x, dys, p_dy, dw, dbias, border_p, B, Cc, H, W):
+    n = len(dys)
+    ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
+    call("vu_conv3x3_bwd_weight", _chk(x, "x"), p_x, ptrs[0], ptrs[1], ptrs[2], p_dy, n, _chk(dw, "dw"),
+         _opt(dbias, "dbias"), border_p, B, Cc, H, W, _stream())
+
+
+# ----------------------------------------------------------------------------------------- GEMM
+def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
+         bias=None, residual=None, ldr=0, aux_in=None, aux_out=None, ldaux=0,
+         batch_outer=1, batch_inner=1, sA=(0, 0), sB=(0, 0), sC=(0, 0),
+         alpha=1.0, act=ACT_NONE, accumulate=False, split_k=1,
+         drop_p=0.0, drop_seed=0, drop_stream=0, precision=PREC_FP32):
+    """C = act(alpha * op(A) @ op(B) + bias) [dropout] + residual, batched over (outer, inner)."""
+    d = GemmDesc()
+    d.A, d.B, d.C = _chk(A, "A"), _chk(Bm, "B"), _chk(Cm, "C")
+    d.bias, d.residual = _opt(bias, "bias"), _opt(residual, "residual")
+    d.aux_in, d.aux_out = _opt(aux_in, "aux_in"), _opt(aux_out, "aux_out")
+    d.M, d.N, d.K = M, N, K
+    d.trans_a, d.trans_b = int(trans_a), int(trans_b)
+    d.lda, d.ldb, d.ldc, d.ldr, d.ldaux = lda, ldb, ldc, ldr or ldc, ldaux or ldc
+    d.batch_outer, d.batch_inner = batch_outer, batch_inner
+    d.sAo, d.sAi = sA
+    d.sBo, d.sBi = sB
+    d.sCo, d.sCi = sC
+    d.alpha, d.act, d.accumulate, d.split_k = alpha, act, int(accumulate), split_k
+    d.drop_p, d.drop_seed, d.drop_stream = drop_p, drop_seed, drop_stream
+    d.precision = precision
+    call("vu_gemm", C.byref(d), _stream())
+    return Cm
+
+
+def colsum(X, M, N, ld, out, accumulate=False):
+    call("vu_colsum", _chk(X, "X"), M, N, ld, _chk(out, "out"), int(accumulate), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------- re-attention
+def softmax_rows(S, rows, N, ld, scale):
+    call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream())
+
+
+def reattn_stats(P, B, h, N, ld, W, bconv, drop_p, seed, sid, sums):
+    call("vu_reattn_stats", _chk(P, "P"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"), drop_p, seed, sid,
+         _chk(sums, "sums", torch.float64), _stream())
+
+
+def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nbt, eps, momentum, train,
+                       fold, saved):
+    call("vu_reattn_bn_finalize", _opt(sums, "sums", torch.float64), count, h, N, _chk(W, "W"),
+         _chk(bconv, "bconv"), _chk(gamma, "gamma"), _chk(beta, "beta"), _chk(rmean, "running_mean"),
+         _chk(rvar, "running_var"), _opt(nbt, "num_batches_tracked", torch.int64), eps, momentum, int(train),
+         _chk(fold, "fold"), _chk(saved, "saved"), _stream())
+
+
+def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid):
+    call("vu_reattn_mix", _chk(P, "P"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream())
+
+
+def reattn_bwd_reduce(P, dA, B, h, N, ld, W, bconv, saved, drop_p, seed, sid, red):
+    call("vu_reattn_bwd_reduce", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
+         _chk(saved, "saved"), drop_p, seed, sid, _chk(red, "red", torch.float64), _stream())
+
+
+def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, red, train, scale, drop_p, seed, sid,
+                    dW, dbconv, dgamma, dbeta):
+    call("vu_reattn_bwd_rows", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
+         _chk(gamma, "gamma"), _chk(saved, "saved"), _opt(red, "red", torch.float64), int(train), scale,
+         drop_p, seed, sid, _chk(dW, "dW"), _chk(dbconv, "dbconv"), _chk(dgamma, "dgamma"),
+         _chk(dbeta, "dbeta"), _stream())
+
+
+# ----------------------------------------------------------------------------------------- layer norm
+def ln_stats(x, B, n, eps, stats):
+    call("vu_ln_stats", _chk(x, "x"), B, n, eps, _chk(stats, "stats"), _stream())
+
+
+def ln_apply(x, stats, w, b, out, B, n):
+    call("vu_ln_apply", _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(b, "b"), _chk(out, "out"), B, n,
+         _stream())
+
+
+def ln_bwd(g, x, stats, w, dx, dw, db, scratch, B, n):
+    call("vu_ln_bwd", _chk(g, "g"), _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(dx, "dx"),
+         _chk(dw, "dw"), _chk(db, "db"), _chk(scratch, "scratch"), B, n, _stream())
+
+
+# ----------------------------------------------------------------------------------------- losses / misc
+def loss_fwd(kind, pred, target, sums, loss):
+    call("vu_loss_fwd", LOSS_KINDS[kind], _chk(pred, "pred"), _chk(target, "target"), pred.numel(),
+         _chk(sums, "sums", torch.float64), _chk(loss, "loss"), _stream())
+
+
+def loss_bwd(kind, pred, target, sums, gscale, dpred):
+    call("vu_loss_bwd", LOSS_KINDS[kind], _chk(pred, "pred"), _chk(target, "target"), pred.numel(),
+         _chk(sums, "sums", torch.float64), _chk(gscale, "gscale"), _chk(dpred, "dpred"), _stream())
+
+
+def dropout(x, out, p, seed, sid):
+    call("vu_dropout", _chk(x, "in"), _chk(out, "out"), x.numel(), p, seed, sid, _stream())
+    return out
+
+
+def axpby(x, y, a, b):
+    call("vu_axpby", _chk(x, "x"), _chk(y, "y"), x.numel(), a, b, _stream())
+    return y
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+    call("vu_adamw", _chk(p, "p"), _chk(g, "g"), _chk(m, "m"), _chk(v, "v"), p.numel(), lr, beta1, beta2, eps,
+         wd, step, grad_scale, _stream())
+
+
+def sm_count(device: int = 0) -> int:
+    return _lib.load().vu_device_sm_count(device)
