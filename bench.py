@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of the ViT-UNet hot path: Base (depth_te=2, hidden 128, 8 heads, patch 32, 49 patches) denoising
+training step -- zero_grad + forward + L1 loss + backward (+ gradient all-reduce for N>1) -- on synthetic
+3x224x224 batches, images/s over all ranks (BASELINE.json metric, configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU PyTorch path (oracle port)
+
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for how every field is produced.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOPS_PER_IMAGE_FWD_BWD = 23.26e9      # Base, 2xMAC of the reference math, fwd+bwd = 3x fwd
+METRIC = "ViT-UNet Base 224^2 images/s fwd+bwd"
+BASE_KW = dict(depth=2, depth_te=2, size_bottleneck=2, preprocessing="conv", im_size=224, patch_size=32,
+               num_channels=3, hidden_dim=128, num_heads=8, attn_drop=0.2, proj_drop=0.2, linear_drop=0)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
+                    hbm=float(d.get("hbm_gbs", 6650.0)), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+def _synthetic(B, gen_seed=0):
+    """clean=rand, x=clamp(clean+0.1*randn,0,1) normalised like run_denoising.py:54."""
+    g = torch.Generator().manual_seed(gen_seed)
+    clean = torch.rand(B, 3, 224, 224, generator=g)
+    noisy = (clean + 0.1 * torch.randn(B, 3, 224, 224, generator=g)).clamp(0, 1)
+    return ((noisy - 0.456) / 0.224).contiguous(), clean.contiguous()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_env(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and "RANK" not in os.environ:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step_time(B, steps, warmup, threads):
+    """The reference's own CPU implementation of the path (oracle port of vit_unet/torch/model.py), train step with
+    L1 loss and the preset's dropout (0.2/0.2/0), all host threads.  Returns seconds per step."""
+    from oracle import vit_unet_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = O.get_vit_unet("base", variant="head")
+    m.train()
+    x, y = _synthetic(B)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        m.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.l1_loss(m(x), y)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), float(loss.item())
+
+
+def run_reference(args):
+    rank, world, _ = _dist_env(args)
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = args.cpu_batch
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    sec, _ = cpu_reference_step_time(B, steps, warmup, cores)
+    ips = B / sec
+    sample = f"Base train step (zero_grad+fwd+L1+bwd, dropout 0.2/0.2/0), batch {B}, fp32, {steps} timed + {warmup} warm-up"
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ViT_UNet Base denoising training step, L1 loss, 3x224x224 (BASELINE configs[2])",
+                       "batch_per_step": B, "where": "host CPU, oracle port of the reference (reference model.py is "
+                       "unconstructible at HEAD and has no build; SURVEY.md F2)"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import torch.distributed as dist
+    import vit_unet_b200 as vu
+    from vit_unet_b200 import _lib, ops
+    from vit_unet_b200.dp import DataParallel
+
+    rank, world, local = _dist_env(args)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    vu.set_precision(args.precision)
+    B = args.batch
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = vu.HViT_UNet(**BASE_KW)
+    net.to(dev).train()
+    model = DataParallel(net) if world > 1 else net
+    x_h, y_h = _synthetic(B, gen_seed=rank)
+    x_pin, y_pin = x_h.pin_memory(), y_h.pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    params = [p for p in net.parameters()]
+
+    def step(x, y):
+        for p in params:
+            p.grad = None
+        loss = vu.l1_loss(model(x), y)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, args.min_warmup)):
+        step(x_d, y_d)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs (value) ------------------------------------------------
+    prof = ops.KernelTimer() if args.kernel_timing else None
+    _lib.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ops.set_kernel_timer(prof)
+        ev0.record()
+        for _ in range(args.steps):
+            step(x_d, y_d)
+        ev1.record()
+        ops.set_kernel_timer(None)
+        barrier()
+    launches = _lib.launch_count()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- timed region 2: end to end through the public API with pinned HOST buffers (e2e) -----------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        xd = x_pin.to(dev, non_blocking=True)
+        yd = y_pin.to(dev, non_blocking=True)
+        loss = step(xd, yd)
+        loss_host = loss.item()                    # device -> host read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    roof = {"bound": "tensor", "achieved": None, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": None,
+            "traffic": None, "peak_source": peaks["src"]}
+    if prof is not None:
+        k = prof.summary()
+        top = k["top"]
+        roof.update({"kernel": top["name"], "achieved": top["tflops"], "frac": top["tflops"] / peaks["tflops"],
+                     "kernel_ms_per_step": top["ms"] / args.steps, "kernel_share_of_step": top["ms"] / ms,
+                     "launches_timed": top["launches"], "by_kernel": k["by_kernel"]})
+    roof["step_tflops"] = value / world * FLOPS_PER_IMAGE_FWD_BWD / 1e12
+    roof["step_frac"] = roof["step_tflops"] / peaks["tflops"]
+
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": "ViT_UNet Base denoising training step, L1 loss, 3x224x224 (BASELINE configs[2])",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "step": "zero_grad + forward + L1 loss + backward" + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
+                       "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)", "precision": args.precision,
+                       "l2": "per-step working set (saved activations + attention maps, GBs) >> 126 MB L2"},
+            "clocks": clocks.summary(), "roofline": roof,
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.nbytes + y_pin.nbytes),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": loss_host},
+            "gpu_launches": launches}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sec, _ = cpu_reference_step_time(args.cpu_batch, 2, 1, cores)
+        line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"oracle port of the reference, Base train step, batch {args.cpu_batch}, "
+                                          f"fp32, 2 timed + 1 warm-up steps, {cores} threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
+    ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-warmup", type=int, default=3, help="lower only for profiler runs (numbers under ncu are never bench values)")
+    ap.add_argument("--kernel-timing", type=int, default=1, help="CUDA-event timing of every GEMM launch (roofline)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""World-size-2 gloo test (CPU) of the data-parallel host logic: suffix bucketing of the flat gradient buffer
+and averaged all-reduce.  The kernels are not involved (they need a GPU); a fake backward fills the groups in
+the order the engine's schedule finishes them."""
+import contextlib
+import io
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vit_unet_b200 as vu
+        from vit_unet_b200.dp import DataParallel, _group_of
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = vu.HViT_UNet(depth=2, depth_te=2, size_bottleneck=1, preprocessing="conv", im_size=32,
+                               patch_size=16, num_channels=3, hidden_dim=32, num_heads=4, attn_drop=0.,
+                               proj_drop=0., linear_drop=0)
+        torch.manual_seed(100 + rank)                    # ranks start with DIFFERENT weights ...
+        for p in net.parameters():
+            p.data.normal_()
+        dpm = DataParallel(net, bucket_mb=0.5)           # ... and the wrapper broadcasts rank 0's
+        ref0 = [p.detach().clone() for p in net.parameters()]
+        gathered = [torch.empty_like(ref0[0]) for _ in range(world)]
+        dist.all_gather(gathered, ref0[0])
+        assert all(torch.equal(g, gathered[0]) for g in gathered)
+
+        b = dpm.bucketer
+        flat = torch.zeros(net._flat_numel)
+        b.begin(flat)
+        # fake backward: groups finish in reverse forward order, each rank writes rank-dependent values
+        order, seen = [], set()
+        for n in net._param_names:
+            g = _group_of(n)
+            if g not in seen:
+                seen.add(g); order.append(g)
+        starts = b.group_starts
+        ends = {g: (starts[order[i + 1]] if i + 1 < len(order) else net._flat_numel) for i, g in enumerate(order)}
+        for g in reversed(order):
+            flat[starts[g]:ends[g]] = float(rank + 1) * (1 + order.index(g))
+            b.on_ready(g)
+        b.finish()
+        exp = torch.zeros_like(flat)
+        for g in order:
+            exp[starts[g]:ends[g]] = (sum(range(1, world + 1)) / world) * (1 + order.index(g))
+        assert torch.allclose(flat, exp), "averaged gradients differ"
+        # buckets: contiguous, descending, cover the whole buffer exactly once, more than one of them
+        spans = b.launched
+        assert len(spans) > 1 and spans[0][1] == net._flat_numel and spans[-1][0] == 0
+        assert all(spans[i][0] == spans[i + 1][1] for i in range(len(spans) - 1))
+        assert order[0] == "PE." and order[-1] == "conv2d."
+        q.put((rank, "ok"))
+    except Exception as e:       # noqa: BLE001
+        q.put((rank, f"fail: {e!r}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

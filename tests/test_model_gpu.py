@@ -62,10 +62,13 @@ def _compare(ref, net, x, y, out_tol=1e-5, grad_tol=1e-4):
     worst = ("", 0.0)
     for n, p in net.named_parameters():
         assert p.grad is not None, n
-        r = _rel(p.grad, gr[n].grad)
-        if gr[n].grad.abs().max() < 1e-12:      # e.g. reatten_matrix.bias under train-mode BN: exactly 0 in theory
-            assert p.grad.abs().max().item() < 1e-6, n
+        if n.endswith("reatten_matrix.bias"):
+            # train-mode BN subtracts the batch mean, so d/d(conv bias) is exactly 0 in theory: both sides hold
+            # round-off only.  Require ours to be negligible against the mixing-weight gradient of the same layer.
+            wn = n.replace("reatten_matrix.bias", "reatten_matrix.weight")
+            assert p.grad.abs().max().item() <= 1e-4 * gr[wn].grad.abs().max().item() + 1e-9, n
             continue
+        r = _rel(p.grad, gr[n].grad)
         if r > worst[1]:
             worst = (n, r)
     assert worst[1] <= grad_tol, worst
@@ -110,7 +113,9 @@ def test_matches_reference_golden(name):
         scale = max(np.abs(g).max(), 1e-30)
         tol = 1e-5 if k in ("eval_out", "train_out", "loss", "eval_out_sum", "train_out_sum") else 2e-4
         if "reatten_matrix.bias" in k:      # true gradient is 0 under train-mode BN; both sides hold round-off
-            assert np.abs(o).max() < 1e-5
+            wk = kk.replace("reatten_matrix.bias", "reatten_matrix.weight")
+            if wk in got:
+                assert np.abs(o).max() <= 1e-4 * np.abs(got[wk]).max() + 1e-9, k
             continue
         assert np.abs(o - g).max() <= tol * scale + 1e-7, (k, float(np.abs(o - g).max()), float(scale))
 

@@ -69,6 +69,19 @@ _SPECIAL = {
 
 _lib = None
 
+# kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
+_KERNELS_PER_CALL = {"vu_ln_bwd": 2, "vu_loss_fwd": 2}
+_launches = 0
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
 
 def load() -> C.CDLL:
     """Load the shared library once; raise loudly if it is absent or has the wrong ABI."""
@@ -94,8 +107,10 @@ def load() -> C.CDLL:
 
 
 def call(name: str, *args) -> None:
+    global _launches
     lib = load()
     rc = getattr(lib, name)(*args)
+    _launches += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.vu_last_error()
         raise VuError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -83,7 +83,13 @@ class _ViTUNetFn(torch.autograd.Function):
         flat = torch.zeros(owner._flat_numel, dtype=torch.float32, device=dout.device)
         G = {n: flat[o:o + p.numel()].view(p.shape) for n, p, o in zip(names, params, owner._flat_offsets)}
         owner._last_flat_grad = flat
+        dp = owner._dp
+        if dp is not None:           # data parallel: all-reduce finished suffixes of `flat` while backward continues
+            dp.begin(flat)
+            owner.engine.on_grads_ready = dp.on_ready
         dX = owner.engine.backward(P, G, ctx.saved, dout.contiguous(), ctx.needs_input_grad[0])
+        if dp is not None:
+            dp.finish()
         ctx.saved = None
         return (dX, None, None) + tuple(G[n] for n in names)
 
@@ -100,6 +106,7 @@ class _ViTUNetBase(nn.Module):
             off += (pd[n].numel() + 3) // 4 * 4          # keep every view 16-byte aligned
         self._flat_numel = off
         self._last_flat_grad = None
+        self._dp = None
 
     def _build_blocks(self, depth, depth_te, size_bottleneck, N0, D0, C, hidden, heads, linear_drop, shared_ln,
                       dtype=None):

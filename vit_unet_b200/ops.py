@@ -82,6 +82,46 @@ def conv3x3_bwd_weight(x, p_x, dys, p_dy, dw, dbias, border_p, B, Cc, H, W):
          _opt(dbias, "dbias"), border_p, B, Cc, H, W, _stream())
 
 
+# ----------------------------------------------------------------------------------------- kernel timing
+class KernelTimer:
+    """CUDA-event timing of individual launches on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.records = []          # (name, flops, start_event, end_event)
+
+    def time(self, name, flops):
+        timer = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                self_inner.e1 = torch.cuda.Event(enable_timing=True)
+                self_inner.e0.record()
+
+            def __exit__(self_inner, *a):
+                self_inner.e1.record()
+                timer.records.append((name, flops, self_inner.e0, self_inner.e1))
+        return _Ctx()
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, flops, e0, e1 in self.records:
+            a = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            a["ms"] += e0.elapsed_time(e1); a["flops"] += flops; a["launches"] += 1
+        by = {k: {"ms": v["ms"], "launches": v["launches"],
+                  "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0} for k, v in agg.items()}
+        top_name = max(by, key=lambda k: by[k]["ms"])
+        return {"by_kernel": by, "top": dict(by[top_name], name=top_name)}
+
+
+_TIMER = {"t": None}
+
+
+def set_kernel_timer(t):
+    _TIMER["t"] = t
+
+
 # ----------------------------------------------------------------------------------------- GEMM
 def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
          bias=None, residual=None, ldr=0, aux_in=None, aux_out=None, ldaux=0,
@@ -103,7 +143,13 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
     d.alpha, d.act, d.accumulate, d.split_k = alpha, act, int(accumulate), split_k
     d.drop_p, d.drop_seed, d.drop_stream = drop_p, drop_seed, drop_stream
     d.precision = precision
-    call("vu_gemm", C.byref(d), _stream())
+    t = _TIMER["t"]
+    if t is not None:
+        kind = "gemm_tcgen05_tf32" if precision == PREC_TF32 else "gemm_simt_fp32"
+        with t.time(kind, 2.0 * M * N * K * batch_outer * batch_inner):
+            call("vu_gemm", C.byref(d), _stream())
+    else:
+        call("vu_gemm", C.byref(d), _stream())
     return Cm
 
 
