@@ -128,25 +128,47 @@ def load_reference_module():
     return mod
 
 
+def _fwd_bwd(model, x, y):
+    model.zero_grad(set_to_none=True)
+    xin = x.clone().requires_grad_(True)
+    out = model(xin)
+    loss = torch.nn.functional.l1_loss(out, y)
+    loss.backward()
+    return dict(out=out.detach().clone(), loss=loss.detach().clone(), dx=xin.grad.detach().clone(),
+                grads={k: p.grad.detach().clone() for k, p in model.named_parameters()})
+
+
 def run_case(model, x, y, train: bool):
-    """eval forward, and (train=True) a train-mode fwd+bwd with L1 loss and dropout p=0."""
+    """eval forward; eval-mode fwd+bwd (BatchNorm on running statistics: the well-conditioned gradient check);
+    train-mode fwd+bwd with L1 loss and dropout p=0 (batch statistics + running-stat update)."""
     res = {}
     model.eval()
     with torch.no_grad():
         res["eval_out"] = model(x).detach().clone()
     if train:
+        res["evg"] = _fwd_bwd(model, x, y)
         model.train()
-        model.zero_grad(set_to_none=True)
-        xin = x.clone().requires_grad_(True)
-        out = model(xin)
-        loss = torch.nn.functional.l1_loss(out, y)
-        loss.backward()
-        res["train_out"] = out.detach().clone()
-        res["loss"] = loss.detach().clone()
-        res["dx"] = xin.grad.detach().clone()
-        res["grads"] = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        res["trn"] = _fwd_bwd(model, x, y)
         res["buffers_after"] = {k: b.detach().clone() for k, b in model.named_buffers()}
     return res
+
+
+def conditioning(model, x, y):
+    """How far the fp32 model is from its own fp64 evaluation in TRAIN mode (max-relative errors).
+
+    Train-mode BatchNorm over near-uniform attention maps amplifies fp32 round-off by orders of magnitude per
+    block, so the reference's fp32 train-mode outputs/gradients are themselves only accurate to these figures;
+    tests use them as the yardstick for train-mode parity at full size (eval-mode parity stays at 1e-5)."""
+    import copy
+    m64 = copy.deepcopy(model).double()
+    model.train(); m64.train()
+    a = _fwd_bwd(model, x, y)
+    b = _fwd_bwd(m64, x.double(), y.double())
+
+    def rel(u, v):
+        return float(((u.double() - v).abs().max() / v.abs().max().clamp_min(1e-300)).item())
+    worst = max(rel(a["grads"][k], b["grads"][k]) for k in a["grads"] if not k.endswith("reatten_matrix.bias"))
+    return dict(cond_out=rel(a["out"], b["out"]), cond_dx=rel(a["dx"], b["dx"]), cond_grad=worst)
 
 
 def _sub(t: torch.Tensor, n: int = 4096) -> np.ndarray:
@@ -160,19 +182,26 @@ def _sub(t: torch.Tensor, n: int = 4096) -> np.ndarray:
 
 def pack(res: dict, full: bool) -> dict:
     out = {}
-    for k in ("eval_out", "train_out", "dx"):
-        if k in res:
-            t = res[k]
-            out[k + "_sum"] = np.float64(t.double().sum().item())
-            out[k + "_abs"] = np.float64(t.double().abs().sum().item())
-            out[k] = t.numpy().copy() if full else _sub(t)
-    if "loss" in res:
-        out["loss"] = np.float64(res["loss"].item())
-        for name, g in res["grads"].items():
-            out["g_norm:" + name] = np.float64(g.double().norm().item())
-            out["g:" + name] = g.numpy().copy() if (full and g.numel() <= 8192) else _sub(g, 512)
+
+    def put(key, t):
+        t = t.detach().cpu()
+        out[key + "_sum"] = np.float64(t.double().sum().item())
+        out[key] = t.numpy().copy() if full else _sub(t)
+    put("eval_out", res["eval_out"])
+    for tag in ("evg", "trn"):
+        if tag not in res:
+            continue
+        r = res[tag]
+        put(f"{tag}_out", r["out"])
+        put(f"{tag}_dx", r["dx"])
+        out[f"{tag}_loss"] = np.float64(r["loss"].item())
+        for name, g in r["grads"].items():
+            g = g.detach().cpu()
+            out[f"{tag}_gnorm:" + name] = np.float64(g.double().norm().item())
+            out[f"{tag}_g:" + name] = g.numpy().copy() if (full and g.numel() <= 8192) else _sub(g, 512)
+    if "buffers_after" in res:
         for name, b in res["buffers_after"].items():
-            out["buf:" + name] = b.numpy().copy()
+            out["buf:" + name] = b.detach().cpu().numpy().copy()
     return out
 
 
@@ -191,10 +220,14 @@ def main():
         full = name.startswith("tiny")
         res = run_case(model, x, y, train=True)
         out = pack(res, full)
+        model.load_state_dict(fill_state_dict(model.state_dict()))      # undo the running-stat update
+        for k, v in conditioning(model, x, y).items():
+            out[k] = np.float64(v)
         out["n_params"] = np.int64(sum(p.numel() for p in model.parameters()))
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **out)
-        print(f"{name}: params={out['n_params']} loss={out['loss']:.6f} -> {path} "
+        print(f"{name}: params={out['n_params']} loss={out['trn_loss']:.6f} cond(out/dx/grad)="
+              f"{out['cond_out']:.1e}/{out['cond_dx']:.1e}/{out['cond_grad']:.1e} -> {path} "
               f"({os.path.getsize(path) / 1024:.0f} KiB)")
 
 

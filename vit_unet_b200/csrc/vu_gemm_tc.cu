@@ -1,6 +1,384 @@
-// tcgen05 / TMEM / TMA tensor-core GEMM (TF32 inputs, FP32 accumulate).  Placeholder until the kernel lands:
-// reports "not handled" so vu_gemm uses the CUDA-core kernel.
+// Tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32, FP32 accumulate in TMEM) fed by TMA through an
+// mbarrier pipeline.  Same vu_gemm_desc contract (batch strides, transposes, fused epilogues, split-K) as the
+// CUDA-core kernel in vu_gemm_simt.cu, so every contraction of the ViT-UNet block -- QK^T / PV, proj,
+// FeedForward and all their data / weight gradients -- runs here when precision == VU_PREC_TF32.
+//
+// Operands stay FP32 in HBM; TMA (data type TFLOAT32) lands them in shared memory in the canonical
+// SWIZZLE_128B layouts the UMMA smem descriptors expect:
+//   K-major  operand (k contiguous in memory):  one box of {32 k, ROWS} per stage; row r at r*128 B, 8-row swizzle
+//            atoms 1024 B apart (SBO).  One MMA consumes 8 k = 32 B: descriptor start advances 32 B per k-step.
+//   MN-major operand (m or n contiguous):       ROWS/32 boxes of {32 mn, 32 k} per stage; each box is 32 k-rows of
+//            128 B; slabs 4096 B apart (LBO), 8-k groups 1024 B apart (SBO); start advances 1024 B per k-step.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global), each owning its TMEM lane quarter.
+// One 128 x BLOCK_N output tile per CTA; two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
 #include "vu_common.cuh"
+
 namespace vu {
-int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) { (void)d; (void)s; *handled = false; return VU_OK; }
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 32;          // floats per stage along K (= 128 bytes = one swizzle span)
+constexpr int TC_UMMA_K = 8;            // tf32: 32 bytes per MMA
+
+struct TcArgs {
+  float* C;
+  const float* bias; const float* residual; const float* aux_in; float* aux_out;
+  int M, N, K;
+  int64_t ldc, ldr, ldaux;
+  int batch_inner;
+  int64_t sCo, sCi;
+  float alpha; int act; int accumulate; int split_k; int k_per_split;
+  float drop_scale; uint32_t drop_thresh; uint64_t drop_seed; uint32_t drop_stream;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;          // LayoutType::SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor: F32 accumulate, TF32 x TF32, M=128
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
+  constexpr uint32_t A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 4;
+  constexpr uint32_t B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  int z = blockIdx.z, ks = 0;
+  if (g.split_k > 1) { ks = z % g.split_k; z /= g.split_k; }
+  const int zo = z / g.batch_inner, zi = z % g.batch_inner;
+  const int kbeg = ks * g.k_per_split;
+  const int kend = min(g.K, kbeg + g.k_per_split);
+  const int nkb = (kend - kbeg + TC_BLOCK_K - 1) / TC_BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        mbar_expect_tx(full_bar + s, A_BYTES + B_BYTES);
+        const int k0 = kbeg + kb * TC_BLOCK_K;
+        uint8_t* a_dst = sA + s * A_BYTES;
+        uint8_t* b_dst = sB + s * B_BYTES;
+        if (!A_MN) tma_load_4d(a_dst, &tmA, full_bar + s, k0, m0, zi, zo);
+        else {
+#pragma unroll
+          for (int sl = 0; sl < TC_BLOCK_M / 32; ++sl) tma_load_4d(a_dst + sl * 4096, &tmA, full_bar + s, m0 + sl * 32, k0, zi, zo);
+        }
+        if (!B_MN) tma_load_4d(b_dst, &tmB, full_bar + s, k0, n0, zi, zo);
+        else {
+#pragma unroll
+          for (int sl = 0; sl < BLOCK_N / 32; ++sl) tma_load_4d(b_dst + sl * 4096, &tmB, full_bar + s, n0 + sl * 32, k0, zi, zo);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_N, A_MN, B_MN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(full_bar + s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < TC_BLOCK_K / TC_UMMA_K; ++kk) {
+          const uint64_t ad = A_MN ? make_smem_desc(a_base + kk * 1024, 4096, 1024) : make_smem_desc(a_base + kk * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc(b_base + kk * 1024, 4096, 1024) : make_smem_desc(b_base + kk * 32, 16, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);                       // frees the smem slot once these MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full_bar);    // accumulator complete -> epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    const int64_t coff = zo * g.sCo + zi * g.sCi;
+    float* C = g.C + coff;
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const bool vec_ok = ((uintptr_t)C % 16 == 0) && (g.ldc % 4 == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+      uint32_t r[16];
+      if (nkb > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      if (m >= g.M) continue;
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const int n = n0 + c0 + j4;
+        if (n >= g.N) continue;
+        const int nv = min(4, g.N - n);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 + j]) * g.alpha;
+        if (g.split_k > 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nv) {
+              float t = v[j];
+              if (ks == 0) {
+                if (g.bias) t += g.bias[n + j];
+                if (g.residual) t += g.residual[coff + (int64_t)m * g.ldr + n + j];
+              }
+              atomicAdd(C + (int64_t)m * g.ldc + n + j, t);
+            }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nv) {
+            float t = v[j];
+            if (g.bias) t += g.bias[n + j];
+            if (g.act == VU_ACT_GELU) {
+              if (g.aux_out) g.aux_out[coff + (int64_t)m * g.ldaux + n + j] = t;
+              t = gelu_exact(t);
+            } else if (g.act == VU_ACT_GELU_BWD) {
+              t *= gelu_exact_grad(g.aux_in[coff + (int64_t)m * g.ldaux + n + j]);
+            }
+            if (g.drop_thresh) {
+              uint64_t idx = (uint64_t)z * g.M * g.N + (uint64_t)m * g.N + (n + j);
+              t = Philox::keep(g.drop_seed, g.drop_stream, idx, g.drop_thresh) ? t * g.drop_scale : 0.f;
+            }
+            if (g.residual) t += g.residual[coff + (int64_t)m * g.ldr + n + j];
+            v[j] = t;
+          }
+        }
+        float* dst = C + (int64_t)m * g.ldc + n;
+        if (vec_ok && nv == 4) {
+          float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nv) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 4-D view of one operand: (contiguous extent, rows extent [stride ld], inner batch [stride sI], outer batch [stride sO])
+static bool encode_operand(CUtensorMap* tm, const float* base, int64_t contig, int64_t rows, int64_t ld, int bi,
+                           int64_t sI, int bo, int64_t sO, int box_contig, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  if ((uintptr_t)base % 16 != 0 || ld % 4 != 0) return false;
+  if (bi > 1 && sI % 4 != 0) return false;
+  if (bo > 1 && sO % 4 != 0) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)contig, (cuuint64_t)rows, (cuuint64_t)(bi > 0 ? bi : 1), (cuuint64_t)(bo > 0 ? bo : 1)};
+  // unused batch dims still need a legal (multiple of 16 B, non-zero) stride
+  cuuint64_t st_i = (bi > 1 ? (cuuint64_t)sI : (cuuint64_t)ld * (cuuint64_t)rows) * 4;
+  cuuint64_t st_o = (bo > 1 ? (cuuint64_t)sO : (cuuint64_t)ld * (cuuint64_t)rows) * 4;
+  if (st_i == 0) st_i = 16; if (st_o == 0) st_o = 16;
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, st_i, st_o};
+  cuuint32_t box[4] = {(cuuint32_t)box_contig, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& g, bool a_mn, bool b_mn, int nbatch,
+                     cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BLOCK_M * TC_BLOCK_K * 4 + BLOCK_N * TC_BLOCK_K * 4) + 1024 + 256;
+  dim3 grid((unsigned)cdiv(g.N, BLOCK_N), (unsigned)cdiv(g.M, TC_BLOCK_M), (unsigned)(nbatch * g.split_k));
+  dim3 block(192);
+#define VU_TC_LAUNCH(AMN, BMN)                                                                                   \
+  do {                                                                                                            \
+    auto kfn = gemm_tf32_tc_kernel<BLOCK_N, STAGES, AMN, BMN>;                                                    \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set) {                                                                                              \
+      if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)       \
+        return check_launch("vu_gemm(tc attr)");                                                                  \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    kfn<<<grid, block, smem, s>>>(tmA, tmB, g);                                                                   \
+  } while (0)
+  if (!a_mn && !b_mn) VU_TC_LAUNCH(false, false);
+  else if (!a_mn && b_mn) VU_TC_LAUNCH(false, true);
+  else if (a_mn && b_mn) VU_TC_LAUNCH(true, true);
+  else VU_TC_LAUNCH(true, false);
+#undef VU_TC_LAUNCH
+  return check_launch("vu_gemm(tc)");
+}
+
+int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
+  *handled = false;
+  const bool a_mn = d.trans_a != 0;        // A(m,k) = A[k*lda + m]  -> m contiguous
+  const bool b_mn = d.trans_b == 0;        // B(k,n) = B[k*ldb + n]  -> n contiguous
+  const int bi = d.batch_inner > 0 ? d.batch_inner : 1, bo = d.batch_outer > 0 ? d.batch_outer : 1;
+  int block_n = d.N <= 32 ? 32 : (d.N <= 64 ? 64 : 128);
+  CUtensorMap tmA, tmB;
+  bool ok;
+  if (!a_mn) ok = encode_operand(&tmA, d.A, d.K, d.M, d.lda, bi, d.sAi, bo, d.sAo, TC_BLOCK_K, TC_BLOCK_M);
+  else ok = encode_operand(&tmA, d.A, d.M, d.K, d.lda, bi, d.sAi, bo, d.sAo, 32, TC_BLOCK_K);
+  if (!ok) return VU_OK;
+  if (!b_mn) ok = encode_operand(&tmB, d.B, d.K, d.N, d.ldb, bi, d.sBi, bo, d.sBo, TC_BLOCK_K, block_n);
+  else ok = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, 32, TC_BLOCK_K);
+  if (!ok) return VU_OK;
+
+  TcArgs g;
+  g.C = d.C; g.bias = d.bias; g.residual = d.residual; g.aux_in = d.aux_in; g.aux_out = d.aux_out;
+  g.M = d.M; g.N = d.N; g.K = d.K; g.ldc = d.ldc; g.ldr = d.ldr; g.ldaux = d.ldaux;
+  g.batch_inner = bi; g.sCo = d.sCo; g.sCi = d.sCi;
+  g.alpha = d.alpha; g.act = d.act; g.accumulate = d.accumulate;
+  g.split_k = d.split_k > 1 ? d.split_k : 1;
+  int kps = (int)cdiv(cdiv(g.K, g.split_k), TC_BLOCK_K) * TC_BLOCK_K;
+  g.k_per_split = kps;
+  g.split_k = (int)cdiv(g.K, kps);
+  g.drop_thresh = d.drop_p > 0.f ? drop_threshold(d.drop_p) : 0u;
+  g.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
+  g.drop_seed = d.drop_seed; g.drop_stream = d.drop_stream;
+  const int nbatch = bi * bo;
+  int rc;
+  if (block_n == 32) rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  else if (block_n == 64) rc = launch_tc<64, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  else rc = launch_tc<128, 3>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  *handled = true;
+  return rc;
+}
+
+}  // namespace vu
