@@ -154,21 +154,28 @@ def run_case(model, x, y, train: bool):
 
 
 def conditioning(model, x, y):
-    """How far the fp32 model is from its own fp64 evaluation in TRAIN mode (max-relative errors).
+    """How far the fp32 model is from its own fp64 evaluation (max-relative errors), per mode and per tensor.
 
     Train-mode BatchNorm over near-uniform attention maps amplifies fp32 round-off by orders of magnitude per
-    block, so the reference's fp32 train-mode outputs/gradients are themselves only accurate to these figures;
-    tests use them as the yardstick for train-mode parity at full size (eval-mode parity stays at 1e-5)."""
+    block, and some gradients (e.g. the q/k convs of the last decoder block) are differences of nearly equal
+    terms, so the reference's own fp32 numbers are only accurate to these figures.  Tests use them as the
+    yardstick: CUDA-vs-reference error <= base tolerance + 4 x (reference fp32-vs-fp64 error).
+    Returns {"evg_cond:out": .., "evg_cond:dx": .., "evg_cond:<param>": .., "trn_cond:...": ..}."""
     import copy
     m64 = copy.deepcopy(model).double()
-    model.train(); m64.train()
-    a = _fwd_bwd(model, x, y)
-    b = _fwd_bwd(m64, x.double(), y.double())
 
     def rel(u, v):
         return float(((u.double() - v).abs().max() / v.abs().max().clamp_min(1e-300)).item())
-    worst = max(rel(a["grads"][k], b["grads"][k]) for k in a["grads"] if not k.endswith("reatten_matrix.bias"))
-    return dict(cond_out=rel(a["out"], b["out"]), cond_dx=rel(a["dx"], b["dx"]), cond_grad=worst)
+    out = {}
+    for tag, train in (("evg", False), ("trn", True)):
+        model.train(train); m64.train(train)
+        a = _fwd_bwd(model, x, y)
+        b = _fwd_bwd(m64, x.double(), y.double())
+        out[f"{tag}_cond:out"] = rel(a["out"], b["out"])
+        out[f"{tag}_cond:dx"] = rel(a["dx"], b["dx"])
+        for k in a["grads"]:
+            out[f"{tag}_cond:{k}"] = rel(a["grads"][k], b["grads"][k])
+    return out
 
 
 def _sub(t: torch.Tensor, n: int = 4096) -> np.ndarray:
@@ -226,9 +233,9 @@ def main():
         out["n_params"] = np.int64(sum(p.numel() for p in model.parameters()))
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **out)
-        print(f"{name}: params={out['n_params']} loss={out['trn_loss']:.6f} cond(out/dx/grad)="
-              f"{out['cond_out']:.1e}/{out['cond_dx']:.1e}/{out['cond_grad']:.1e} -> {path} "
-              f"({os.path.getsize(path) / 1024:.0f} KiB)")
+        print(f"{name}: params={out['n_params']} loss={out['trn_loss']:.6f} cond eval(out/dx)="
+              f"{out['evg_cond:out']:.1e}/{out['evg_cond:dx']:.1e} train(out/dx)="
+              f"{out['trn_cond:out']:.1e}/{out['trn_cond:dx']:.1e} -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
 if __name__ == "__main__":

@@ -8,11 +8,14 @@
 //   K-major  operand (k contiguous in memory):  one box of {32 k, ROWS} per stage; row r at r*128 B, 8-row swizzle
 //            atoms 1024 B apart (SBO).  One MMA consumes 8 k = 32 B: descriptor start advances 32 B per k-step.
 //   MN-major operand (m or n contiguous):       ROWS/32 boxes of {32 mn, 32 k} per stage; each box is 32 k-rows of
-//            128 B; slabs 4096 B apart (LBO), 8-k groups 1024 B apart (SBO); start advances 1024 B per k-step.
+//            128 B.  For 32-bit MN-major operands the only legal layout is SWIZZLE_128B_BASE32B (32-byte swizzle
+//            atoms, TMA mode SWIZZLE_128B_ATOM_32B): slabs 4096 B apart (LBO), 4-k groups 512 B apart (SBO);
+//            start advances 1024 B (8 k-rows) per k-step.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global), each owning its TMEM lane quarter.
 // One 128 x BLOCK_N output tile per CTA; two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "vu_common.cuh"
 
@@ -31,6 +34,7 @@ struct TcArgs {
   int64_t sCo, sCi;
   float alpha; int act; int accumulate; int split_k; int k_per_split;
   float drop_scale; uint32_t drop_thresh; uint64_t drop_seed; uint32_t drop_stream;
+  uint32_t mn_lbo, mn_sbo;      // MN-major descriptor strides (bytes)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -99,13 +103,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;          // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B (16 B atoms), 1 = SWIZZLE_128B_BASE32B (32 B atoms)
   return d;
 }
 // cute::UMMA::InstrDescriptor: F32 accumulate, TF32 x TF32, M=128
@@ -187,8 +192,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
         for (int kk = 0; kk < TC_BLOCK_K / TC_UMMA_K; ++kk) {
-          const uint64_t ad = A_MN ? make_smem_desc(a_base + kk * 1024, 4096, 1024) : make_smem_desc(a_base + kk * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(b_base + kk * 1024, 4096, 1024) : make_smem_desc(b_base + kk * 32, 16, 1024);
+          const uint64_t ad = A_MN ? make_smem_desc(a_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(a_base + kk * 32, 16, 1024, 2);
+          const uint64_t bd = B_MN ? make_smem_desc(b_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(b_base + kk * 32, 16, 1024, 2);
           umma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar + s);                       // frees the smem slot once these MMAs retire
@@ -300,7 +305,7 @@ static EncodeTiledFn get_encode() {
 
 // 4-D view of one operand: (contiguous extent, rows extent [stride ld], inner batch [stride sI], outer batch [stride sO])
 static bool encode_operand(CUtensorMap* tm, const float* base, int64_t contig, int64_t rows, int64_t ld, int bi,
-                           int64_t sI, int bo, int64_t sO, int box_contig, int box_rows) {
+                           int64_t sI, int bo, int64_t sO, int box_contig, int box_rows, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   if ((uintptr_t)base % 16 != 0 || ld % 4 != 0) return false;
@@ -315,7 +320,9 @@ static bool encode_operand(CUtensorMap* tm, const float* base, int64_t contig, i
   cuuint32_t box[4] = {(cuuint32_t)box_contig, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -353,11 +360,11 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   int block_n = d.N <= 32 ? 32 : (d.N <= 64 ? 64 : 128);
   CUtensorMap tmA, tmB;
   bool ok;
-  if (!a_mn) ok = encode_operand(&tmA, d.A, d.K, d.M, d.lda, bi, d.sAi, bo, d.sAo, TC_BLOCK_K, TC_BLOCK_M);
-  else ok = encode_operand(&tmA, d.A, d.M, d.K, d.lda, bi, d.sAi, bo, d.sAo, 32, TC_BLOCK_K);
+  if (!a_mn) ok = encode_operand(&tmA, d.A, d.K, d.M, d.lda, bi, d.sAi, bo, d.sAo, TC_BLOCK_K, TC_BLOCK_M, false);
+  else ok = encode_operand(&tmA, d.A, d.M, d.K, d.lda, bi, d.sAi, bo, d.sAo, 32, TC_BLOCK_K, true);
   if (!ok) return VU_OK;
-  if (!b_mn) ok = encode_operand(&tmB, d.B, d.K, d.N, d.ldb, bi, d.sBi, bo, d.sBo, TC_BLOCK_K, block_n);
-  else ok = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, 32, TC_BLOCK_K);
+  if (!b_mn) ok = encode_operand(&tmB, d.B, d.K, d.N, d.ldb, bi, d.sBi, bo, d.sBo, TC_BLOCK_K, block_n, false);
+  else ok = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, 32, TC_BLOCK_K, true);
   if (!ok) return VU_OK;
 
   TcArgs g;
@@ -372,6 +379,9 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   g.drop_thresh = d.drop_p > 0.f ? drop_threshold(d.drop_p) : 0u;
   g.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
   g.drop_seed = d.drop_seed; g.drop_stream = d.drop_stream;
+  g.mn_lbo = 4096; g.mn_sbo = 512;
+  if (const char* e = getenv("VU_TC_MN_LBO")) g.mn_lbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("VU_TC_MN_SBO")) g.mn_sbo = (uint32_t)atoi(e);
   const int nbatch = bi * bo;
   int rc;
   if (block_n == 32) rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
