@@ -90,10 +90,11 @@ int vu_colsum(const float* X, int64_t M, int N, int64_t ld, float* out, int accu
 /* maps are (B, h, N, ld) fp32 with ld >= N, ld % 4 == 0 */
 /* in place: P[r, :N] = softmax(scale * S[r, :N]) for r in rows, pad columns zeroed. */
 int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scale, void* stream);
-/* train-mode BatchNorm statistics of M_h = sum_g W[h,g]*drop(P_g) + b[h] over (B,N,N):
- * sums[2h] (double, caller zeroes) += { sum(M_h - c_h), sum((M_h - c_h)^2) }, c_h = b[h] + sum_g W[h,g]/N */
-int vu_reattn_stats(const float* P, int B, int h, int N, int ld, const float* W, const float* bconv,
-                    float drop_p, uint64_t seed, uint32_t stream_id, double* sums, void* stream);
+/* train-mode moments of the dropped maps Pd_g = drop(P_g), centred at c = 1/N, over all (b,i,j):
+ * sums[h + h*h] (double, caller zeroes) += { s'_g = sum(Pd_g - c),  G'_{gg'} = sum (Pd_g - c)(Pd_g' - c) }.
+ * The BatchNorm batch statistics of M_h = sum_g W[h,g] Pd_g + b[h] follow in closed form (vu_reattn_bn_finalize). */
+int vu_reattn_stats(const float* P, int B, int h, int N, int ld, float drop_p, uint64_t seed, uint32_t stream_id,
+                    double* sums, void* stream);
 /* fold conv1x1 + BatchNorm into one affine:  fold[h*h + h] = {alpha'[h][g], beta'[h]};
  * saved[2h] = {mean_h, invstd_h}.  train=1: batch statistics from `sums` (+ running-stat update,
  * momentum, unbiased variance, num_batches_tracked += 1); train=0: running statistics. model.py:136,159 */
@@ -104,16 +105,19 @@ int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, int N, const
 /* A_h = sum_g alpha'[h,g]*drop(P_g) + beta'[h] */
 int vu_reattn_mix(const float* P, float* A, const float* fold, int B, int h, int N, int ld,
                   float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
-/* BN-backward reductions: red[2h] (double, caller zeroes) += { sum dA_h, sum dA_h * Ahat_h } */
-int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, const float* W,
-                         const float* bconv, const float* saved, float drop_p, uint64_t seed,
+/* backward reductions: red[h + h*h] (double, caller zeroes) += { s1_h = sum dA_h,  X'_{hg} = sum dA_h (Pd_g - c) } */
+int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, float drop_p, uint64_t seed,
                          uint32_t stream_id, double* red, void* stream);
-/* in place dA -> dS (gradient of the pre-softmax scores), plus parameter gradients (atomic, caller zeroes
- * or accumulates): dW[h*h], dbconv[h], dgamma[h], dbeta[h]. */
+/* closed-form parameter gradients from (red, sums): dW[h*h], dbconv[h], dgamma[h], dbeta[h] are ACCUMULATED
+ * (atomic; caller zeroes); coef[2h] = BatchNorm-backward means {mean dA_h, mean dA_h*Ahat_h} for vu_reattn_bwd_rows.
+ * sums may be NULL when train == 0. */
+int vu_reattn_bwd_params(const double* red, const double* sums, int B, int h, int N, const float* W,
+                         const float* bconv, const float* gamma, const float* saved, int train,
+                         float* coef, float* dW, float* dbconv, float* dgamma, float* dbeta, void* stream);
+/* in place dA -> dS (gradient of the pre-softmax scores) */
 int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, int N, int ld, const float* W,
-                       const float* bconv, const float* gamma, const float* saved, const double* red,
-                       int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id,
-                       float* dW, float* dbconv, float* dgamma, float* dbeta, void* stream);
+                       const float* bconv, const float* gamma, const float* saved, const float* coef,
+                       int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 
 /* ---------------------------------------------------------------- LayerNorm over (N,D) (model.py:193-196,204,206) */
 /* stats[b] = {mean, rstd} over the n = N*D elements of image b */

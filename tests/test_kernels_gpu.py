@@ -206,9 +206,9 @@ def test_reattn_forward_backward(ops, h, N, train):
     Wd, bd, gd, btd = W.detach().cuda(), b.detach().cuda(), gamma.detach().cuda(), beta.detach().cuda()
     rmd, rvd = rm.clone().cuda(), rv.clone().cuda()
     nbt = torch.zeros((), dtype=torch.int64, device="cuda")
-    sums = torch.zeros(2 * h, dtype=torch.float64, device="cuda") if train else None
+    sums = torch.zeros(h + h * h, dtype=torch.float64, device="cuda") if train else None
     if train:
-        ops.reattn_stats(Sd, B, h, N, ld, Wd, bd, 0.0, 0, 0, sums)
+        ops.reattn_stats(Sd, B, h, N, ld, 0.0, 0, 0, sums)
     fold, saved = torch.empty(h * h + h, device="cuda"), torch.empty(2 * h, device="cuda")
     ops.reattn_bn_finalize(sums, B * N * N, h, N, Wd, bd, gd, btd, rmd, rvd, nbt, 1e-5, 0.1, train, fold, saved)
     A = torch.empty_like(Sd)
@@ -221,11 +221,13 @@ def test_reattn_forward_backward(ops, h, N, train):
         assert nbt.item() == 1
     # backward
     dAd = torch.zeros(B, h, N, ld, device="cuda"); dAd[..., :N] = dA.cuda()
-    red = torch.zeros(2 * h, dtype=torch.float64, device="cuda")
-    ops.reattn_bwd_reduce(Sd, dAd, B, h, N, ld, Wd, bd, saved, 0.0, 0, 0, red)
+    red = torch.zeros(h + h * h, dtype=torch.float64, device="cuda")
+    ops.reattn_bwd_reduce(Sd, dAd, B, h, N, ld, 0.0, 0, 0, red)
     dW, dbc, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"),
                         torch.zeros(h, device="cuda"), torch.zeros(h, device="cuda"))
-    ops.reattn_bwd_rows(Sd, dAd, B, h, N, ld, Wd, bd, gd, saved, red, train, scale, 0.0, 0, 0, dW, dbc, dg, dbt)
+    coef = torch.empty(2 * h, device="cuda")
+    ops.reattn_bwd_params(red, sums, B, h, N, Wd, bd, gd, saved, train, coef, dW, dbc, dg, dbt)
+    ops.reattn_bwd_rows(Sd, dAd, B, h, N, ld, Wd, bd, gd, saved, coef, train, scale, 0.0, 0, 0)
     # dAd now holds dL/d(raw scores)
     _close(dAd[..., :N], S.grad, rtol=5e-4, name="dS")
     _close(dW.reshape(h, h), W.grad, rtol=5e-4, name="dW mix")
@@ -257,8 +259,8 @@ def test_reattn_dropout_consistency(ops):
     Sd = torch.zeros(B, h, N, ld, device="cuda"); Sd[..., :N] = S.detach().cuda()
     ops.softmax_rows(Sd, B * h * N, N, ld, scale)
     Wd, bd, gd, btd = W.detach().cuda(), b.detach().cuda(), gamma.detach().cuda(), beta.detach().cuda()
-    sums = torch.zeros(2 * h, dtype=torch.float64, device="cuda")
-    ops.reattn_stats(Sd, B, h, N, ld, Wd, bd, p, 99, 6, sums)
+    sums = torch.zeros(h + h * h, dtype=torch.float64, device="cuda")
+    ops.reattn_stats(Sd, B, h, N, ld, p, 99, 6, sums)
     fold, saved = torch.empty(h * h + h, device="cuda"), torch.empty(2 * h, device="cuda")
     ops.reattn_bn_finalize(sums, B * N * N, h, N, Wd, bd, gd, btd, torch.zeros(h, device="cuda"),
                            torch.ones(h, device="cuda"), None, 1e-5, 0.1, True, fold, saved)
@@ -266,11 +268,15 @@ def test_reattn_dropout_consistency(ops):
     ops.reattn_mix(Sd, A, fold, B, h, N, ld, p, 99, 6)
     _close(A[..., :N], A_ref, rtol=2e-4, name="mixed map (dropout)")
     dAd = torch.zeros(B, h, N, ld, device="cuda"); dAd[..., :N] = dA.cuda()
-    red = torch.zeros(2 * h, dtype=torch.float64, device="cuda")
-    ops.reattn_bwd_reduce(Sd, dAd, B, h, N, ld, Wd, bd, saved, p, 99, 6, red)
+    red = torch.zeros(h + h * h, dtype=torch.float64, device="cuda")
+    ops.reattn_bwd_reduce(Sd, dAd, B, h, N, ld, p, 99, 6, red)
     dW, dbc, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"),
                         torch.zeros(h, device="cuda"), torch.zeros(h, device="cuda"))
-    ops.reattn_bwd_rows(Sd, dAd, B, h, N, ld, Wd, bd, gd, saved, red, True, scale, p, 99, 6, dW, dbc, dg, dbt)
+    coef = torch.empty(2 * h, device="cuda")
+    ops.reattn_bwd_params(red, sums, B, h, N, Wd, bd, gd, saved, True, coef, dW, dbc, dg, dbt)
+    ops.reattn_bwd_rows(Sd, dAd, B, h, N, ld, Wd, bd, gd, saved, coef, True, scale, p, 99, 6)
+    _close(dg, gamma.grad, rtol=5e-4, name="dgamma (dropout)")
+    _close(dbt, beta.grad, rtol=5e-4, name="dbeta (dropout)")
     _close(dAd[..., :N], S.grad, rtol=5e-4, name="dS (dropout)")
     _close(dW.reshape(h, h), W.grad, rtol=5e-4, name="dW mix (dropout)")
 

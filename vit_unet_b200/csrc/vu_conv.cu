@@ -128,19 +128,22 @@ conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ 
   }
 }
 
-// backward weights.  grid.y = nconv*C enumerates (k, co); each thread keeps the C*9 partial sums of that
-// output channel plus the bias sum, pixels are grid-strided in x's own layout order.
-// Here g.lin describes x, g.lout describes dy.
-template <int C>
+// backward weights.  grid.y enumerates the fused convs k (WIDE: every thread keeps the C*C*9 + C partial sums
+// of one conv, so the 9*C taps of x are loaded once per conv) or (k, co) pairs (narrow fallback for C == 4).
+// Pixels are grid-strided in x's own layout order.  Here g.lin describes x, g.lout describes dy.
+template <int C, bool WIDE>
 __global__ void __launch_bounds__(256)
 conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ d0, const float* __restrict__ d1,
                           const float* __restrict__ d2, float* __restrict__ dw, float* __restrict__ dbias,
                           ConvGeom g) {
-  const int k = blockIdx.y / C, co = blockIdx.y % C;
+  constexpr int NCO = WIDE ? C : 1;
+  constexpr int NACC = NCO * (C * 9 + 1);
+  const int k = WIDE ? blockIdx.y : blockIdx.y / C;
+  const int co0 = WIDE ? 0 : blockIdx.y % C;
   const float* dy = k == 0 ? d0 : (k == 1 ? d1 : d2);
-  float acc[C * 9 + 1];
+  float acc[NACC];
 #pragma unroll
-  for (int i = 0; i < C * 9 + 1; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
   const int64_t hw = (int64_t)g.lin.H * g.lin.W;
   const int64_t cs = g.lin.cstride(), dcs = g.lout.cstride();
   const int rs = g.bp ? g.bp : g.lin.W;
@@ -149,8 +152,10 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
     int64_t b = t / hw; int64_t pix = t - b * hw;
     int y, xx; g.lin.pixel(pix, y, xx);
     int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
-    float dv = __ldg(dy + b * g.per_image + g.lout.at(co, y, xx));
-    acc[C * 9] += dv;
+    float dv[NCO];
+    const int64_t dbase = b * g.per_image + g.lout.at(co0, y, xx);
+#pragma unroll
+    for (int c = 0; c < NCO; ++c) { dv[c] = __ldg(dy + dbase + c * dcs); acc[c * (C * 9 + 1) + C * 9] += dv[c]; }
     const float* xb = x + b * g.per_image;
     int64_t base = g.lin.base_of(pix);
 #pragma unroll
@@ -161,21 +166,28 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
         if (!ok) continue;
         int64_t off = g.fast ? base + (ky - 1) * rs + (kx - 1) : g.lin.at(0, y + ky - 1, xx + kx - 1);
 #pragma unroll
-        for (int ci = 0; ci < C; ++ci) acc[ci * 9 + ky * 3 + kx] = fmaf(dv, __ldg(xb + off + ci * cs), acc[ci * 9 + ky * 3 + kx]);
+        for (int ci = 0; ci < C; ++ci) {
+          float xv = __ldg(xb + off + ci * cs);
+#pragma unroll
+          for (int c = 0; c < NCO; ++c)
+            acc[c * (C * 9 + 1) + ci * 9 + ky * 3 + kx] = fmaf(dv[c], xv, acc[c * (C * 9 + 1) + ci * 9 + ky * 3 + kx]);
+        }
       }
   }
-  __shared__ float red[C * 9 + 1][8];
+  __shared__ float red[NACC][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < C * 9 + 1; ++i) {
+  for (int i = 0; i < NACC; ++i) {
     float v = warp_sum(acc[i]);
     if (lane == 0) red[i][warp] = v;
   }
   __syncthreads();
-  if (threadIdx.x < C * 9 + 1) {
+  if (threadIdx.x < NACC) {
     float s = 0.f;
     for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += red[threadIdx.x][wv];
-    if (threadIdx.x < C * 9) atomicAdd(dw + ((int64_t)(k * C + co) * C) * 9 + threadIdx.x, s);
+    const int c = threadIdx.x / (C * 9 + 1), e = threadIdx.x % (C * 9 + 1);
+    const int co = co0 + c;
+    if (e < C * 9) atomicAdd(dw + ((int64_t)(k * C + co) * C) * 9 + e, s);
     else if (dbias) atomicAdd(dbias + k * C + co, s);
   }
 }
@@ -246,10 +258,11 @@ extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, 
   VU_REQUIRE((nconv < 2 || dy1) && (nconv < 3 || dy2), fn, "missing gradient pointer");
   ConvGeom g; int rc = make_geom(fn, g, p_x, p_dy, border_p, B, C, H, W); if (rc) return rc;
   int threads = 256;
-  int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 8), (int64_t)sm_count() * 2);
+  int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 4), (int64_t)sm_count() * 4);
   if (bx < 1) bx = 1;
-  dim3 grid(bx, nconv * C);
   cudaStream_t s = as_stream(stream);
-  VU_DISPATCH_C(C, conv3x3_bwd_weight_kernel<CC><<<grid, threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g));
+  VU_DISPATCH_C(C,
+    if (CC <= 3) conv3x3_bwd_weight_kernel<CC, (CC <= 3)><<<dim3(bx, nconv), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g);
+    else conv3x3_bwd_weight_kernel<CC, false><<<dim3(bx, nconv * C), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g));
   return check_launch(fn);
 }

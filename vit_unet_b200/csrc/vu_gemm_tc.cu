@@ -203,15 +203,18 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================================================== epilogue (warps 2..5)
+    // TMEM -> registers (one accumulator row per lane) -> shared-memory staging (the pipeline buffers are idle
+    // once the accumulator is complete) -> row-contiguous float4 global accesses: every load of residual / aux
+    // and every store of C is a fully coalesced 16 B-per-lane transaction.
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
     const int64_t coff = zo * g.sCo + zi * g.sCi;
     float* C = g.C + coff;
+    constexpr int LDS = BLOCK_N + 4;                      // padded staging row (floats)
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)q * 32 * LDS;
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const bool vec_ok = ((uintptr_t)C % 16 == 0) && (g.ldc % 4 == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
       uint32_t r[16];
@@ -222,58 +225,89 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = 0u;
       }
-      if (m >= g.M) continue;
 #pragma unroll
-      for (int j4 = 0; j4 < 16; j4 += 4) {
-        const int n = n0 + c0 + j4;
-        if (n >= g.N) continue;
-        const int nv = min(4, g.N - n);
-        float v[4];
+      for (int j4 = 0; j4 < 16; j4 += 4)
+        *reinterpret_cast<float4*>(stage + lane * LDS + c0 + j4) =
+            make_float4(__uint_as_float(r[j4]) * g.alpha, __uint_as_float(r[j4 + 1]) * g.alpha,
+                        __uint_as_float(r[j4 + 2]) * g.alpha, __uint_as_float(r[j4 + 3]) * g.alpha);
+    }
+    __syncwarp();
+    constexpr int LPR = BLOCK_N / 4;                      // lanes covering one output row
+    constexpr int RPI = 32 / LPR;                         // rows handled per iteration
+    const int cl = (lane % LPR) * 4;                      // this lane's 4 columns inside the tile
+    const int n = n0 + cl;
+    const int nv = min(4, g.N - n);                       // <= 0: nothing to do for this lane
+    const bool vec_c = ((uintptr_t)C % 16 == 0) && (g.ldc % 4 == 0) && nv == 4;
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g.bias && (g.split_k <= 1 || ks == 0)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j4 + j]) * g.alpha;
-        if (g.split_k > 1) {
+      for (int j = 0; j < 4; ++j) if (j < nv) bias4[j] = g.bias[n + j];
+    }
+    const bool vec_r = g.residual && ((uintptr_t)(g.residual + coff) % 16 == 0) && (g.ldr % 4 == 0) && nv == 4;
+    const float* axp = g.aux_in ? g.aux_in : g.aux_out;
+    const bool vec_x = axp && ((uintptr_t)(axp + coff) % 16 == 0) && (g.ldaux % 4 == 0) && nv == 4;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += RPI) {
+      const int row = r0 + lane / LPR;
+      const int m = m0 + q * 32 + row;
+      if (m >= g.M || nv <= 0) continue;
+      const float4 t4 = *reinterpret_cast<const float4*>(stage + row * LDS + cl);
+      float v[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
+      float* dst = C + (int64_t)m * g.ldc + n;
+      if (g.split_k > 1) {
+        if (g.residual && ks == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nv) {
-              float t = v[j];
-              if (ks == 0) {
-                if (g.bias) t += g.bias[n + j];
-                if (g.residual) t += g.residual[coff + (int64_t)m * g.ldr + n + j];
-              }
-              atomicAdd(C + (int64_t)m * g.ldc + n + j, t);
-            }
-          }
-          continue;
+          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += g.residual[coff + (int64_t)m * g.ldr + n + j];
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
+        continue;
+      }
+      if (g.act == VU_ACT_GELU) {
+        if (g.aux_out) {
+          float* ax = g.aux_out + coff + (int64_t)m * g.ldaux + n;
+          if (vec_x) *reinterpret_cast<float4*>(ax) = make_float4(v[0], v[1], v[2], v[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = v[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = gelu_exact(v[j]);
+      } else if (g.act == VU_ACT_GELU_BWD) {
+        const float* ax = g.aux_in + coff + (int64_t)m * g.ldaux + n;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec_x) { float4 t = *reinterpret_cast<const float4*>(ax); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) a[j] = ax[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] *= gelu_exact_grad(a[j]);
+      }
+      if (g.drop_thresh) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (j < nv) {
-            float t = v[j];
-            if (g.bias) t += g.bias[n + j];
-            if (g.act == VU_ACT_GELU) {
-              if (g.aux_out) g.aux_out[coff + (int64_t)m * g.ldaux + n + j] = t;
-              t = gelu_exact(t);
-            } else if (g.act == VU_ACT_GELU_BWD) {
-              t *= gelu_exact_grad(g.aux_in[coff + (int64_t)m * g.ldaux + n + j]);
-            }
-            if (g.drop_thresh) {
-              uint64_t idx = (uint64_t)z * g.M * g.N + (uint64_t)m * g.N + (n + j);
-              t = Philox::keep(g.drop_seed, g.drop_stream, idx, g.drop_thresh) ? t * g.drop_scale : 0.f;
-            }
-            if (g.residual) t += g.residual[coff + (int64_t)m * g.ldr + n + j];
-            v[j] = t;
-          }
+          uint64_t idx = (uint64_t)z * g.M * g.N + (uint64_t)m * g.N + (n + j);
+          v[j] = Philox::keep(g.drop_seed, g.drop_stream, idx, g.drop_thresh) ? v[j] * g.drop_scale : 0.f;
         }
-        float* dst = C + (int64_t)m * g.ldc + n;
-        if (vec_ok && nv == 4) {
-          float4 o = make_float4(v[0], v[1], v[2], v[3]);
-          if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-          *reinterpret_cast<float4*>(dst) = o;
-        } else {
+      }
+      if (g.residual) {
+        const float* rp = g.residual + coff + (int64_t)m * g.ldr + n;
+        if (vec_r) { float4 t = *reinterpret_cast<const float4*>(rp); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+        else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nv) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
+          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rp[j];
         }
+      }
+      if (vec_c) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+        *reinterpret_cast<float4*>(dst) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nv) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
       }
     }
   }

@@ -1,8 +1,14 @@
 // Re-Attention map kernels (DeepViT-style head mixing + BatchNorm over the attention maps):
 //   attn = softmax(q k^T * scale); attn = dropout(attn); attn = BN_h(Conv1x1_{h->h}(attn))   model.py:155-159
-// Maps are (B, h, N, ld) fp32.  The 1x1 conv + BatchNorm are folded into ONE h x h affine per position
-// (SURVEY.md F5); train-mode batch statistics come from a streamed reduction over all (b,i,j).
-// Attention dropout masks are regenerated from Philox in every kernel that needs them (never stored).
+// Maps are (B, h, N, ld) fp32, ld % 4 == 0.  The 1x1 conv + BatchNorm are folded into ONE h x h affine per position
+// (SURVEY.md F5).  Everything that is a reduction over all (b,i,j) positions is expressed through CENTRED moments
+// of the dropped maps Pd_g (centre c = 1/N, the exact mean of a softmax row):
+//     forward  (train):  s'_g = sum (Pd_g - c)            G'_{gg'} = sum (Pd_g - c)(Pd_g' - c)
+//     backward        :  s1_h = sum dA_h                  X'_{hg}  = sum dA_h (Pd_g - c)
+// from which the BatchNorm batch statistics, the BatchNorm backward means and ALL parameter gradients (mixing
+// matrix, conv bias, BN gamma/beta) follow in closed form (reattn_bwd_params_kernel) -- the big kernels only stream.
+// Every streaming kernel handles 4 consecutive keys per thread (float4) so that one Philox4x32 call yields the
+// dropout mask of the whole quad; masks are regenerated, never stored.
 #include "vu_common.cuh"
 
 namespace vu {
@@ -17,19 +23,11 @@ softmax_rows_kernel(float* __restrict__ S, int64_t rows, int N, int ld, float sc
   for (int64_t r = wid; r < rows; r += nw) {
     float* row = S + r * ld;
     float mx = -INFINITY;
-    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j] * sl2);
     mx = warp_max(mx);
-    // scale may be negative in principle; softmax(scale*s): shift by max of scale*s
-    float mxs = mx * sl2;
-    if (scale < 0.f) {
-      float mn = INFINITY;
-      for (int j = lane; j < N; j += 32) mn = fminf(mn, row[j]);
-      mn = -warp_max(-mn);
-      mxs = mn * sl2;
-    }
     float sum = 0.f;
     for (int j = lane; j < N; j += 32) {
-      float e = exp2f(fmaf(row[j], sl2, -mxs));
+      float e = exp2f(fmaf(row[j], sl2, -mx));
       row[j] = e; sum += e;
     }
     sum = warp_sum(sum);
@@ -39,67 +37,72 @@ softmax_rows_kernel(float* __restrict__ S, int64_t rows, int N, int ld, float sc
   }
 }
 
-// ------------------------------------------------------------------ per-position head vector helpers
-template <int H>
-struct HeadMix {
-  // load P_g(b,i,j) for all heads with the dropout mask applied
-  __device__ __forceinline__ static void load(const float* __restrict__ P, int64_t head_stride, int64_t off,
-                                              uint32_t thresh, float dscale, uint64_t seed, uint32_t stream,
-                                              int64_t flat_base, float (&p)[H]) {
-#pragma unroll
-    for (int g = 0; g < H; ++g) {
-      float v = __ldg(P + g * head_stride + off);
-      if (thresh) v = Philox::keep(seed, stream, (uint64_t)(flat_base + g * head_stride + off), thresh) ? v * dscale : 0.f;
-      p[g] = v;
-    }
-  }
+// ------------------------------------------------------------------ quad loader
+// P quad of head g at (b, i, j..j+3) with dropout applied and the centre subtracted; invalid (pad) lanes -> 0.
+struct QuadCtx {
+  uint32_t thresh; float dscale; uint64_t seed; uint32_t stream; float c; int N;
 };
+__device__ __forceinline__ float4 load_pd(const float* __restrict__ p, uint64_t flat_idx, const QuadCtx& q) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  if (q.thresh) {
+    uint4 rr = Philox::gen(q.seed, q.stream, flat_idx >> 2);
+    v.x = rr.x >= q.thresh ? v.x * q.dscale : 0.f; v.y = rr.y >= q.thresh ? v.y * q.dscale : 0.f;
+    v.z = rr.z >= q.thresh ? v.z * q.dscale : 0.f; v.w = rr.w >= q.thresh ? v.w * q.dscale : 0.f;
+  }
+  return v;
+}
+__device__ __forceinline__ void centre(float4& v, int j, const QuadCtx& q) {
+  v.x = j + 0 < q.N ? v.x - q.c : 0.f; v.y = j + 1 < q.N ? v.y - q.c : 0.f;
+  v.z = j + 2 < q.N ? v.z - q.c : 0.f; v.w = j + 3 < q.N ? v.w - q.c : 0.f;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float sum4(const float4& a) { return (a.x + a.y) + (a.z + a.w); }
 
-// sums[h] += sum (M_h - c_h), sums[H+h] += sum (M_h - c_h)^2,  M_h = sum_g W[h][g] Pd_g + b_h
+// ------------------------------------------------------------------ forward statistics (train)
+// sums[g] += sum (Pd_g - c);  sums[H + g*H + g'] += sum (Pd_g - c)(Pd_g' - c)   (g' >= g filled, mirrored later)
 template <int H>
 __global__ void __launch_bounds__(256)
-reattn_stats_kernel(const float* __restrict__ P, int B, int N, int ld, const float* __restrict__ W,
-                    const float* __restrict__ bconv, uint32_t thresh, float dscale, uint64_t seed, uint32_t stream,
-                    double* __restrict__ sums) {
-  __shared__ float sW[H * H];
-  __shared__ float sc[H];
-  __shared__ double red[2 * H * 32];
-  for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = W[i];
-  __syncthreads();
-  if (threadIdx.x < H) {
-    float rs = 0.f;
-    for (int g = 0; g < H; ++g) rs += sW[threadIdx.x * H + g];
-    sc[threadIdx.x] = rs / (float)N;       // M_h - b_h - rowsum/N : shift keeps the sums well conditioned
-  }
-  __syncthreads();
+reattn_stats_kernel(const float* __restrict__ P, int B, int N, int ld, QuadCtx q, double* __restrict__ sums) {
+  constexpr int NV = H + H * (H + 1) / 2;
+  __shared__ double red[NV * 32];
+  const int ld4 = ld >> 2;
   const int64_t head_stride = (int64_t)N * ld, img_stride = head_stride * H;
-  const int64_t per_img = (int64_t)N * N, total = per_img * B;
-  float s1[H], s2[H];
+  const int64_t per_img4 = (int64_t)N * ld4, total = per_img4 * B;
+  float acc[NV];
 #pragma unroll
-  for (int h = 0; h < H; ++h) { s1[h] = 0.f; s2[h] = 0.f; }
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = t / per_img; int64_t r = t - b * per_img;
-    int i = (int)(r / N), j = (int)(r - (int64_t)i * N);
-    int64_t off = (int64_t)i * ld + j;
-    float p[H];
-    HeadMix<H>::load(P + b * img_stride, head_stride, off, thresh, dscale, seed, stream, b * img_stride, p);
+    int64_t b = t / per_img4; int64_t r = t - b * per_img4;
+    int j = (int)(r % ld4) * 4;
+    int64_t off = b * img_stride + r * 4;
+    float4 p[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
-      float m = -sc[h];
+    for (int g = 0; g < H; ++g) { p[g] = load_pd(P + off + g * head_stride, (uint64_t)(off + g * head_stride), q); centre(p[g], j, q); }
+    int k = H;
 #pragma unroll
-      for (int g = 0; g < H; ++g) m = fmaf(sW[h * H + g], p[g], m);
-      s1[h] += m; s2[h] = fmaf(m, m, s2[h]);
+    for (int g = 0; g < H; ++g) {
+      acc[g] += sum4(p[g]);
+#pragma unroll
+      for (int g2 = g; g2 < H; ++g2) { acc[k] += dot4(p[g], p[g2]); ++k; }
     }
   }
-  double v[2 * H];
+  double v[NV];
 #pragma unroll
-  for (int h = 0; h < H; ++h) { v[h] = s1[h]; v[H + h] = s2[h]; }
-  block_sum<2 * H>(v, red);
+  for (int i = 0; i < NV; ++i) v[i] = acc[i];
+  block_sum<NV>(v, red);
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < 2 * H; ++i) atomicAdd(sums + i, v[i]);
+    int k = H;
+    for (int g = 0; g < H; ++g) {
+      atomicAdd(sums + g, v[g]);
+      for (int g2 = g; g2 < H; ++g2) {
+        atomicAdd(sums + H + g * H + g2, v[k]);
+        if (g2 != g) atomicAdd(sums + H + g2 * H + g, v[k]);
+        ++k;
+      }
+    }
   }
-  (void)bconv;
 }
 
 // one block: statistics -> folded affine + saved (mean, invstd) + running-stat update
@@ -113,11 +116,16 @@ __global__ void reattn_bn_finalize_kernel(const double* __restrict__ sums, doubl
   if (h < H) {
     float mean, var;
     if (train) {
-      float rs = 0.f;
-      for (int g = 0; g < H; ++g) rs += W[h * H + g];
-      double c = (double)bconv[h] + (double)(rs / (float)N);
-      double m1 = sums[h] / count, m2 = sums[H + h] / count;
-      double dmean = c + m1, dvar = m2 - m1 * m1;
+      // M_h - c_h = sum_g W_hg (Pd_g - c),  c_h = b_h + c * sum_g W_hg
+      double rs = 0, m1 = 0, m2 = 0;
+      for (int g = 0; g < H; ++g) {
+        rs += (double)W[h * H + g];
+        m1 += (double)W[h * H + g] * sums[g];
+        for (int g2 = 0; g2 < H; ++g2) m2 += (double)W[h * H + g] * (double)W[h * H + g2] * sums[H + g * H + g2];
+      }
+      m1 /= count; m2 /= count;
+      double c_h = (double)bconv[h] + rs / (double)N;
+      double dmean = c_h + m1, dvar = m2 - m1 * m1;
       if (dvar < 0) dvar = 0;
       mean = (float)dmean; var = (float)dvar;
       double unbiased = count > 1 ? dvar * (count / (count - 1.0)) : dvar;
@@ -126,9 +134,7 @@ __global__ void reattn_bn_finalize_kernel(const double* __restrict__ sums, doubl
     } else {
       mean = rmean[h]; var = rvar[h];
     }
-    float invstd = rsqrtf(var + eps);
-    // torch computes 1/sqrt in fp32 as well; use the correctly rounded form for parity
-    invstd = 1.0f / sqrtf(var + eps);
+    float invstd = 1.0f / sqrtf(var + eps);
     float a = gamma[h] * invstd;
     for (int g = 0; g < H; ++g) fold[h * H + g] = a * W[h * H + g];
     fold[H * H + h] = a * (bconv[h] - mean) + beta[h];
@@ -141,7 +147,7 @@ __global__ void reattn_bn_finalize_kernel(const double* __restrict__ sums, doubl
 template <int H>
 __global__ void __launch_bounds__(256)
 reattn_mix_kernel(const float* __restrict__ P, float* __restrict__ A, const float* __restrict__ fold,
-                  int B, int N, int ld, uint32_t thresh, float dscale, uint64_t seed, uint32_t stream) {
+                  int B, int N, int ld, QuadCtx q) {
   __shared__ float sF[H * H + H];
   for (int i = threadIdx.x; i < H * H + H; i += blockDim.x) sF[i] = fold[i];
   __syncthreads();
@@ -151,20 +157,10 @@ reattn_mix_kernel(const float* __restrict__ P, float* __restrict__ A, const floa
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = t / per_img4; int64_t r = t - b * per_img4;      // r = i*ld4 + j4
     int j = (int)(r % ld4) * 4;
-    int64_t off = r * 4;
+    int64_t off = b * img_stride + r * 4;
     float4 p[H];
 #pragma unroll
-    for (int g = 0; g < H; ++g) {
-      float4 v = *reinterpret_cast<const float4*>(P + b * img_stride + g * head_stride + off);
-      if (thresh) {
-        // element index is a multiple of 4 -> one Philox call covers the quad
-        uint64_t idx = (uint64_t)(b * img_stride + g * head_stride + off);
-        uint4 rr = Philox::gen(seed, stream, idx >> 2);
-        v.x = rr.x >= thresh ? v.x * dscale : 0.f; v.y = rr.y >= thresh ? v.y * dscale : 0.f;
-        v.z = rr.z >= thresh ? v.z * dscale : 0.f; v.w = rr.w >= thresh ? v.w * dscale : 0.f;
-      }
-      p[g] = v;
-    }
+    for (int g = 0; g < H; ++g) p[g] = load_pd(P + off + g * head_stride, (uint64_t)(off + g * head_stride), q);
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       float bb = sF[H * H + h];
@@ -177,77 +173,114 @@ reattn_mix_kernel(const float* __restrict__ P, float* __restrict__ A, const floa
       if (j + 3 >= N) {      // keep the pad columns at zero
         if (j + 0 >= N) a.x = 0.f; if (j + 1 >= N) a.y = 0.f; if (j + 2 >= N) a.z = 0.f; if (j + 3 >= N) a.w = 0.f;
       }
-      *reinterpret_cast<float4*>(A + b * img_stride + h * head_stride + off) = a;
+      *reinterpret_cast<float4*>(A + off + h * head_stride) = a;
     }
   }
 }
 
-// red[h] += sum dA_h ; red[H+h] += sum dA_h * Ahat_h ;  Ahat_h = (M_h - mean_h) * invstd_h
+// ------------------------------------------------------------------ backward reductions
+// red[h] += sum dA_h ;  red[H + h*H + g] += sum dA_h (Pd_g - c)
 template <int H>
 __global__ void __launch_bounds__(256)
-reattn_bwd_reduce_kernel(const float* __restrict__ P, const float* __restrict__ dA, int B, int N, int ld,
-                         const float* __restrict__ W, const float* __restrict__ bconv, const float* __restrict__ saved,
-                         uint32_t thresh, float dscale, uint64_t seed, uint32_t stream, double* __restrict__ out) {
-  __shared__ float sW[H * H];
-  __shared__ float sOff[H], sInv[H];
-  __shared__ double red[2 * H * 32];
-  for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = W[i];
-  if (threadIdx.x < H) { sOff[threadIdx.x] = bconv[threadIdx.x] - saved[threadIdx.x]; sInv[threadIdx.x] = saved[H + threadIdx.x]; }
-  __syncthreads();
+reattn_bwd_reduce_kernel(const float* __restrict__ P, const float* __restrict__ dA, int B, int N, int ld, QuadCtx q,
+                         double* __restrict__ out) {
+  constexpr int NV = H + H * H;
+  __shared__ double red[NV * 32];
+  const int ld4 = ld >> 2;
   const int64_t head_stride = (int64_t)N * ld, img_stride = head_stride * H;
-  const int64_t per_img = (int64_t)N * N, total = per_img * B;
-  float s1[H], s2[H];
+  const int64_t per_img4 = (int64_t)N * ld4, total = per_img4 * B;
+  float acc[NV];
 #pragma unroll
-  for (int h = 0; h < H; ++h) { s1[h] = 0.f; s2[h] = 0.f; }
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = t / per_img; int64_t r = t - b * per_img;
-    int i = (int)(r / N), j = (int)(r - (int64_t)i * N);
-    int64_t off = (int64_t)i * ld + j;
-    float p[H];
-    HeadMix<H>::load(P + b * img_stride, head_stride, off, thresh, dscale, seed, stream, b * img_stride, p);
+    int64_t b = t / per_img4; int64_t r = t - b * per_img4;
+    int j = (int)(r % ld4) * 4;
+    int64_t off = b * img_stride + r * 4;
+    float4 p[H];
+#pragma unroll
+    for (int g = 0; g < H; ++g) { p[g] = load_pd(P + off + g * head_stride, (uint64_t)(off + g * head_stride), q); centre(p[g], j, q); }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      float m = sOff[h];
+      float4 d = *reinterpret_cast<const float4*>(dA + off + h * head_stride);
+      if (j + 3 >= N) { if (j + 0 >= N) d.x = 0.f; if (j + 1 >= N) d.y = 0.f; if (j + 2 >= N) d.z = 0.f; if (j + 3 >= N) d.w = 0.f; }
+      acc[h] += sum4(d);
 #pragma unroll
-      for (int g = 0; g < H; ++g) m = fmaf(sW[h * H + g], p[g], m);
-      float ah = m * sInv[h];
-      float d = __ldg(dA + b * img_stride + h * head_stride + off);
-      s1[h] += d; s2[h] = fmaf(d, ah, s2[h]);
+      for (int g = 0; g < H; ++g) acc[H + h * H + g] += dot4(d, p[g]);
     }
   }
-  double v[2 * H];
+  double v[NV];
 #pragma unroll
-  for (int h = 0; h < H; ++h) { v[h] = s1[h]; v[H + h] = s2[h]; }
-  block_sum<2 * H>(v, red);
+  for (int i = 0; i < NV; ++i) v[i] = acc[i];
+  block_sum<NV>(v, red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < 2 * H; ++i) atomicAdd(out + i, v[i]);
+    for (int i = 0; i < NV; ++i) atomicAdd(out + i, v[i]);
   }
 }
 
-// One warp walks whole rows (b, i) for all heads:
-//   dM_h  = k_h (dA_h - m1_h - Ahat_h m2_h)          (train)   |   k_h dA_h   (eval),  k_h = gamma_h invstd_h
+// One block.  From the backward reductions (red) and the forward centred moments (sums) derive
+//   coef[h] = m1_h = mean(dA_h), coef[H+h] = m2_h = mean(dA_h * Ahat_h)      (train; zero in eval)
+// and accumulate the parameter gradients dW[h][g], dbconv[h], dgamma[h], dbeta[h].
+__global__ void reattn_bwd_params_kernel(const double* __restrict__ red, const double* __restrict__ sums, double count,
+                                         int H, int N, const float* __restrict__ W, const float* __restrict__ bconv,
+                                         const float* __restrict__ gamma, const float* __restrict__ saved, int train,
+                                         float* __restrict__ coef, float* __restrict__ dW, float* __restrict__ dbconv,
+                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int h = threadIdx.x;
+  if (h >= H) return;
+  const double c = 1.0 / (double)N;
+  const double mean = saved[h], invstd = saved[H + h], k_h = (double)gamma[h] * invstd;
+  const double s1 = red[h];
+  double rs = 0, wx = 0;
+  for (int g = 0; g < H; ++g) { rs += (double)W[h * H + g]; wx += (double)W[h * H + g] * red[H + h * H + g]; }
+  const double c_h = (double)bconv[h] + c * rs;         // value of M_h when every Pd_g equals its centre
+  double delta = mean - c_h;                            // M_h - mean = sum_g W_hg (Pd_g - c) - delta
+  if (train) {                                          // batch statistics: delta is the centred mean, exactly
+    delta = 0;
+    for (int g = 0; g < H; ++g) delta += (double)W[h * H + g] * sums[g];
+    delta /= count;
+  }
+  // s2 = sum dA_h * Ahat_h = invstd * ( sum_g W_hg X'_hg - delta * s1 )
+  const double s2 = invstd * (wx - delta * s1);
+  atomicAdd(dgamma + h, (float)s2);
+  atomicAdd(dbeta + h, (float)s1);
+  if (train) {
+    const double m1 = s1 / count, m2 = s2 / count;
+    coef[h] = (float)m1; coef[H + h] = (float)m2;
+    // dW_hg = sum dM_h Pd_g = sum dM_h (Pd_g - c)      (sum dM_h == 0 under batch statistics)
+    //       = k_h [ X'_hg - m1 s'_g - m2 invstd ( sum_g' W_hg' G'_g'g - delta s'_g ) ]
+    for (int g = 0; g < H; ++g) {
+      double wg = 0;
+      for (int g2 = 0; g2 < H; ++g2) wg += (double)W[h * H + g2] * sums[H + g2 * H + g];
+      double v = k_h * (red[H + h * H + g] - m1 * sums[g] - m2 * invstd * (wg - delta * sums[g]));
+      atomicAdd(dW + h * H + g, (float)v);
+    }
+    // dbconv_h = sum dM_h = 0 exactly: nothing to add
+  } else {
+    coef[h] = 0.f; coef[H + h] = 0.f;
+    // eval: dM_h = k_h dA_h  ->  dW_hg = k_h (X'_hg + c s1),  dbconv_h = k_h s1
+    for (int g = 0; g < H; ++g) atomicAdd(dW + h * H + g, (float)(k_h * (red[H + h * H + g] + c * s1)));
+    if (dbconv) atomicAdd(dbconv + h, (float)(k_h * s1));
+  }
+}
+
+// One warp walks whole rows (b, i) for all heads, 4 keys per lane:
+//   dM_h  = k_h (dA_h - m1_h - Ahat_h m2_h)   (train)   |   k_h dA_h   (eval)
 //   dPd_g = sum_h W[h][g] dM_h ;  dP_g = keep_g dPd_g / (1-p)
 //   r_g   = sum_j dP_g P_g ;       dS_g = scale * P_g (dP_g - r_g)           (written over dA)
-//   dW[h][g] += dM_h Pd_g ; dbconv[h] += dM_h ; dgamma[h] = sum dA_h Ahat_h ; dbeta[h] = sum dA_h
 template <int H>
 __global__ void __launch_bounds__(128)
 reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int B, int N, int ld,
                        const float* __restrict__ W, const float* __restrict__ bconv, const float* __restrict__ gamma,
-                       const float* __restrict__ saved, const double* __restrict__ red, double count, int train,
-                       float scale, uint32_t thresh, float dscale, uint64_t seed, uint32_t stream,
-                       float* __restrict__ dW, float* __restrict__ dbconv, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta) {
+                       const float* __restrict__ saved, const float* __restrict__ coef, int train, float scale,
+                       QuadCtx q) {
   __shared__ float sW[H * H];
   __shared__ float sOff[H], sInv[H], sK[H], sM1[H], sM2[H];
-  __shared__ float sAcc[H * H + H];
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = W[i];
-  for (int i = threadIdx.x; i < H * H + H; i += blockDim.x) sAcc[i] = 0.f;
   if (threadIdx.x < H) {
     int h = threadIdx.x;
     sOff[h] = bconv[h] - saved[h]; sInv[h] = saved[H + h]; sK[h] = gamma[h] * saved[H + h];
-    sM1[h] = (train && red) ? (float)(red[h] / count) : 0.f;
-    sM2[h] = (train && red) ? (float)(red[H + h] / count) : 0.f;
+    sM1[h] = train ? coef[h] : 0.f; sM2[h] = train ? coef[H + h] : 0.f;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -255,89 +288,70 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int 
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t head_stride = (int64_t)N * ld, img_stride = head_stride * H;
   const int64_t rows = (int64_t)B * N;
-  float aW[H][H], aB[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) { aB[h] = 0.f;
-#pragma unroll
-    for (int g = 0; g < H; ++g) aW[h][g] = 0.f; }
-
   for (int64_t r = wid; r < rows; r += nw) {
     int64_t b = r / N; int i = (int)(r - b * N);
-    const float* Pb = P + b * img_stride + (int64_t)i * ld;
-    float* Db = dA + b * img_stride + (int64_t)i * ld;
+    const int64_t row_off = b * img_stride + (int64_t)i * ld;
     float rg[H];
 #pragma unroll
     for (int g = 0; g < H; ++g) rg[g] = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      float p[H], pd[H], dm[H];
-      bool keep[H];
+    for (int j = lane * 4; j < ld; j += 128) {
+      float4 p[H], pd[H], dm[H];
+      uint4 keep[H];
 #pragma unroll
       for (int g = 0; g < H; ++g) {
-        p[g] = Pb[g * head_stride + j];
-        keep[g] = thresh ? Philox::keep(seed, stream, (uint64_t)(b * img_stride + g * head_stride + (int64_t)i * ld + j), thresh) : true;
-        pd[g] = keep[g] ? p[g] * dscale : 0.f;
+        p[g] = *reinterpret_cast<const float4*>(P + row_off + g * head_stride + j);
+        pd[g] = p[g];
+        keep[g] = make_uint4(1, 1, 1, 1);
+        if (q.thresh) {
+          uint4 rr = Philox::gen(q.seed, q.stream, (uint64_t)(row_off + g * head_stride + j) >> 2);
+          keep[g] = make_uint4(rr.x >= q.thresh, rr.y >= q.thresh, rr.z >= q.thresh, rr.w >= q.thresh);
+          pd[g].x = keep[g].x ? p[g].x * q.dscale : 0.f; pd[g].y = keep[g].y ? p[g].y * q.dscale : 0.f;
+          pd[g].z = keep[g].z ? p[g].z * q.dscale : 0.f; pd[g].w = keep[g].w ? p[g].w * q.dscale : 0.f;
+        }
       }
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        float d = Db[h * head_stride + j];
-        float t = d;
+        float4 d = *reinterpret_cast<const float4*>(dA + row_off + h * head_stride + j);
+        float4 t = d;
         if (train) {
-          float m = sOff[h];
+          float4 m = make_float4(sOff[h], sOff[h], sOff[h], sOff[h]);
 #pragma unroll
-          for (int g = 0; g < H; ++g) m = fmaf(sW[h * H + g], pd[g], m);
-          t = d - sM1[h] - (m * sInv[h]) * sM2[h];
+          for (int g = 0; g < H; ++g) {
+            float w = sW[h * H + g];
+            m.x = fmaf(w, pd[g].x, m.x); m.y = fmaf(w, pd[g].y, m.y); m.z = fmaf(w, pd[g].z, m.z); m.w = fmaf(w, pd[g].w, m.w);
+          }
+          const float a2 = sInv[h] * sM2[h], a1 = sM1[h];
+          t.x = d.x - a1 - m.x * a2; t.y = d.y - a1 - m.y * a2; t.z = d.z - a1 - m.z * a2; t.w = d.w - a1 - m.w * a2;
         }
-        dm[h] = sK[h] * t;
-        aB[h] += dm[h];
-#pragma unroll
-        for (int g = 0; g < H; ++g) aW[h][g] = fmaf(dm[h], pd[g], aW[h][g]);
+        const float kh = sK[h];
+        dm[h] = make_float4(kh * t.x, kh * t.y, kh * t.z, kh * t.w);
       }
 #pragma unroll
       for (int g = 0; g < H; ++g) {
-        float dpd = 0.f;
+        float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int h = 0; h < H; ++h) dpd = fmaf(sW[h * H + g], dm[h], dpd);
-        float dp = keep[g] ? dpd * dscale : 0.f;
-        rg[g] = fmaf(dp, p[g], rg[g]);
-        Db[g * head_stride + j] = dp;
+        for (int h = 0; h < H; ++h) {
+          float w = sW[h * H + g];
+          dp.x = fmaf(w, dm[h].x, dp.x); dp.y = fmaf(w, dm[h].y, dp.y); dp.z = fmaf(w, dm[h].z, dp.z); dp.w = fmaf(w, dm[h].w, dp.w);
+        }
+        dp.x = (keep[g].x && j + 0 < N) ? dp.x * q.dscale : 0.f; dp.y = (keep[g].y && j + 1 < N) ? dp.y * q.dscale : 0.f;
+        dp.z = (keep[g].z && j + 2 < N) ? dp.z * q.dscale : 0.f; dp.w = (keep[g].w && j + 3 < N) ? dp.w * q.dscale : 0.f;
+        rg[g] += dot4(dp, p[g]);
+        *reinterpret_cast<float4*>(dA + row_off + g * head_stride + j) = dp;
       }
     }
 #pragma unroll
     for (int g = 0; g < H; ++g) rg[g] = warp_sum(rg[g]);
-    for (int j = lane; j < N; j += 32) {
+    for (int j = lane * 4; j < ld; j += 128) {
 #pragma unroll
       for (int g = 0; g < H; ++g) {
-        float pv = Pb[g * head_stride + j];
-        float dp = Db[g * head_stride + j];
-        Db[g * head_stride + j] = scale * pv * (dp - rg[g]);
+        float4 pv = *reinterpret_cast<const float4*>(P + row_off + g * head_stride + j);
+        float4 dp = *reinterpret_cast<const float4*>(dA + row_off + g * head_stride + j);
+        float4 o;
+        o.x = scale * pv.x * (dp.x - rg[g]); o.y = scale * pv.y * (dp.y - rg[g]);
+        o.z = scale * pv.z * (dp.z - rg[g]); o.w = scale * pv.w * (dp.w - rg[g]);   // pad columns: P == 0 -> 0
+        *reinterpret_cast<float4*>(dA + row_off + g * head_stride + j) = o;
       }
-    }
-    for (int j = N + lane; j < ld; j += 32) {
-#pragma unroll
-      for (int g = 0; g < H; ++g) Db[g * head_stride + j] = 0.f;
-    }
-  }
-  // parameter gradients: warp -> block (smem atomics) -> global atomics
-#pragma unroll
-  for (int h = 0; h < H; ++h) {
-#pragma unroll
-    for (int g = 0; g < H; ++g) {
-      float v = warp_sum(aW[h][g]);
-      if (lane == 0) atomicAdd(&sAcc[h * H + g], v);
-    }
-    float v = warp_sum(aB[h]);
-    if (lane == 0) atomicAdd(&sAcc[H * H + h], v);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < H * H + H; i += blockDim.x) {
-    if (i < H * H) atomicAdd(dW + i, sAcc[i]);
-    else if (dbconv) atomicAdd(dbconv + (i - H * H), sAcc[i]);
-  }
-  if (blockIdx.x == 0 && threadIdx.x < H) {
-    int h = threadIdx.x;
-    if (red) {     // BN affine gradients come straight from the two reductions
-      atomicAdd(dgamma + h, (float)red[H + h]);
-      atomicAdd(dbeta + h, (float)red[h]);
     }
   }
 }
@@ -346,6 +360,12 @@ static int grid_for(int64_t work_items, int threads, int per_sm) {
   int64_t b = cdiv(work_items, threads);
   int64_t cap = (int64_t)sm_count() * per_sm;
   return (int)std::max<int64_t>(1, std::min(b, cap));
+}
+static QuadCtx make_ctx(float drop_p, uint64_t seed, uint32_t stream_id, int N) {
+  QuadCtx q;
+  q.thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  q.dscale = 1.f / (1.f - drop_p); q.seed = seed; q.stream = stream_id; q.c = 1.0f / (float)N; q.N = N;
+  return q;
 }
 
 }  // namespace vu
@@ -358,6 +378,7 @@ static int grid_for(int64_t work_items, int threads, int per_sm) {
     case 8: { constexpr int HH = 8; __VA_ARGS__; } break;           \
     default: return vu::fail_arg(fn, "num_heads must be 1, 2, 4 or 8"); \
   }
+#define VU_MAP_ARGS_OK(P) ((P) && B > 0 && N > 0 && ld >= N && ld % 4 == 0 && ((uintptr_t)(P) % 16 == 0))
 
 extern "C" int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scale, void* stream) {
   using namespace vu;
@@ -368,15 +389,15 @@ extern "C" int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scal
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_stats(const float* P, int B, int h, int N, int ld, const float* W, const float* bconv,
-                               float drop_p, uint64_t seed, uint32_t stream_id, double* sums, void* stream) {
+extern "C" int vu_reattn_stats(const float* P, int B, int h, int N, int ld, float drop_p, uint64_t seed,
+                               uint32_t stream_id, double* sums, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_stats";
-  VU_REQUIRE(P && W && bconv && sums && B > 0 && N > 0 && ld >= N && ld % 4 == 0, fn, "bad arguments");
+  VU_REQUIRE(VU_MAP_ARGS_OK(P) && sums, fn, "bad arguments (maps need ld % 4 == 0 and 16-byte alignment)");
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
-  uint32_t th = drop_p > 0.f ? drop_threshold(drop_p) : 0u; float ds = 1.f / (1.f - drop_p);
-  int blocks = grid_for((int64_t)B * N * N, 256 * 4, 8);
-  VU_DISPATCH_H(h, fn, reattn_stats_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, B, N, ld, W, bconv, th, ds, seed, stream_id, sums));
+  QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);
+  VU_DISPATCH_H(h, fn, reattn_stats_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, B, N, ld, q, sums));
   return check_launch(fn);
 }
 
@@ -399,40 +420,48 @@ extern "C" int vu_reattn_mix(const float* P, float* A, const float* fold, int B,
                              float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_mix";
-  VU_REQUIRE(P && A && fold && B > 0 && N > 0 && ld >= N && ld % 4 == 0, fn, "bad arguments");
-  VU_REQUIRE(((uintptr_t)P % 16 == 0) && ((uintptr_t)A % 16 == 0), fn, "maps must be 16-byte aligned");
+  VU_REQUIRE(VU_MAP_ARGS_OK(P) && A && fold && ((uintptr_t)A % 16 == 0), fn, "bad arguments");
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
-  uint32_t th = drop_p > 0.f ? drop_threshold(drop_p) : 0u; float ds = 1.f / (1.f - drop_p);
+  QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256, 16);
-  VU_DISPATCH_H(h, fn, reattn_mix_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, A, fold, B, N, ld, th, ds, seed, stream_id));
+  VU_DISPATCH_H(h, fn, reattn_mix_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, A, fold, B, N, ld, q));
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, const float* W,
-                                    const float* bconv, const float* saved, float drop_p, uint64_t seed,
-                                    uint32_t stream_id, double* red, void* stream) {
+extern "C" int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, float drop_p,
+                                    uint64_t seed, uint32_t stream_id, double* red, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_bwd_reduce";
-  VU_REQUIRE(P && dA && W && bconv && saved && red && B > 0 && N > 0 && ld >= N, fn, "bad arguments");
-  uint32_t th = drop_p > 0.f ? drop_threshold(drop_p) : 0u; float ds = 1.f / (1.f - drop_p);
-  int blocks = grid_for((int64_t)B * N * N, 256 * 4, 8);
-  VU_DISPATCH_H(h, fn, reattn_bwd_reduce_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, dA, B, N, ld, W, bconv, saved, th, ds, seed, stream_id, red));
+  VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA && red && ((uintptr_t)dA % 16 == 0), fn, "bad arguments");
+  QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);
+  VU_DISPATCH_H(h, fn, reattn_bwd_reduce_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, dA, B, N, ld, q, red));
+  return check_launch(fn);
+}
+
+extern "C" int vu_reattn_bwd_params(const double* red, const double* sums, int B, int h, int N, const float* W,
+                                    const float* bconv, const float* gamma, const float* saved, int train,
+                                    float* coef, float* dW, float* dbconv, float* dgamma, float* dbeta, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_reattn_bwd_params";
+  VU_REQUIRE(red && W && bconv && gamma && saved && coef && dW && dgamma && dbeta, fn, "null pointer");
+  VU_REQUIRE(!train || sums, fn, "train mode needs the forward moments");
+  VU_REQUIRE(h >= 1 && h <= 32 && B > 0 && N > 0, fn, "bad shape");
+  reattn_bwd_params_kernel<<<1, 32, 0, as_stream(stream)>>>(red, sums, (double)B * N * N, h, N, W, bconv, gamma, saved,
+                                                            train, coef, dW, dbconv, dgamma, dbeta);
   return check_launch(fn);
 }
 
 extern "C" int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, int N, int ld, const float* W,
-                                  const float* bconv, const float* gamma, const float* saved, const double* red,
-                                  int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id,
-                                  float* dW, float* dbconv, float* dgamma, float* dbeta, void* stream) {
+                                  const float* bconv, const float* gamma, const float* saved, const float* coef,
+                                  int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_bwd_rows";
-  VU_REQUIRE(P && dA_dS && W && bconv && gamma && saved && dW && dgamma && dbeta, fn, "null pointer");
-  VU_REQUIRE(B > 0 && N > 0 && ld >= N, fn, "bad shape");
-  VU_REQUIRE(!train || red, fn, "train mode needs the BN reductions");
-  uint32_t th = drop_p > 0.f ? drop_threshold(drop_p) : 0u; float ds = 1.f / (1.f - drop_p);
-  int blocks = grid_for((int64_t)B * N * 32, 128, 8);
-  double count = (double)B * N * N;
+  VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA_dS && W && bconv && gamma && saved && ((uintptr_t)dA_dS % 16 == 0), fn, "bad arguments");
+  VU_REQUIRE(!train || coef, fn, "train mode needs the BN-backward coefficients");
+  QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  int blocks = grid_for((int64_t)B * N * 32, 128, 12);
   VU_DISPATCH_H(h, fn, reattn_bwd_rows_kernel<HH><<<blocks, 128, 0, as_stream(stream)>>>(
-      P, dA_dS, B, N, ld, W, bconv, gamma, saved, red, count, train, scale, th, ds, seed, stream_id, dW, dbconv, dgamma, dbeta));
+      P, dA_dS, B, N, ld, W, bconv, gamma, saved, coef, train, scale, q));
   return check_launch(fn);
 }

@@ -128,8 +128,8 @@ class Engine:
         adrop = g.attn_drop if train else 0.0
         sums = None
         if train:
-            sums = torch.zeros(2 * h, dtype=torch.float64, device=xq.device)
-            ops.reattn_stats(Pm, B, h, N, ld, Wm, bm, adrop, seed, sid, sums)
+            sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device)
+            ops.reattn_stats(Pm, B, h, N, ld, adrop, seed, sid, sums)
         fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
         ops.reattn_bn_finalize(sums, B * N * N, h, N, Wm, bm, P[pre + "var_norm.weight"], P[pre + "var_norm.bias"],
                                P[pre + "var_norm.running_mean"], P[pre + "var_norm.running_var"],
@@ -145,7 +145,7 @@ class Engine:
         self._gemm_tokens(O, P[pre + "proj.weight"], y, B * N, D, D, bias=P[pre + "proj.bias"],
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
-            saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, seed=seed, sid=sid,
+            saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums, seed=seed, sid=sid,
                          adrop=adrop, pdrop=pdrop, train=train)
         return y
 
@@ -181,12 +181,15 @@ class Engine:
         ops.gemm(dO, v, dA, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
                  sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
         del dO
-        red = torch.zeros(2 * h, dtype=torch.float64, device=dy.device)
-        ops.reattn_bwd_reduce(Pm, dA, B, h, N, ld, Wm, bm, sv["bn"], adrop, seed, sid, red)
+        red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
+        ops.reattn_bwd_reduce(Pm, dA, B, h, N, ld, adrop, seed, sid, red)
+        coef = _empty((2 * h,), dy)
+        gamma = P[pre + "var_norm.weight"]
+        ops.reattn_bwd_params(red, sv["sums"], B, h, N, Wm, bm, gamma, sv["bn"], train, coef,
+                              G[pre + "reatten_matrix.weight"], G[pre + "reatten_matrix.bias"],
+                              G[pre + "var_norm.weight"], G[pre + "var_norm.bias"])
         scale = float(hd) ** -0.5
-        ops.reattn_bwd_rows(Pm, dA, B, h, N, ld, Wm, bm, P[pre + "var_norm.weight"], sv["bn"], red, train, scale,
-                            adrop, seed, sid, G[pre + "reatten_matrix.weight"], G[pre + "reatten_matrix.bias"],
-                            G[pre + "var_norm.weight"], G[pre + "var_norm.bias"])
+        ops.reattn_bwd_rows(Pm, dA, B, h, N, ld, Wm, bm, gamma, sv["bn"], coef, train, scale, adrop, seed, sid)
         dS = dA
         # dQ = dS K ; dK = dS^T Q
         ops.gemm(dS, k, dq, N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B, batch_inner=h,

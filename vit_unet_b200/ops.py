@@ -163,9 +163,8 @@ def softmax_rows(S, rows, N, ld, scale):
     call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream())
 
 
-def reattn_stats(P, B, h, N, ld, W, bconv, drop_p, seed, sid, sums):
-    call("vu_reattn_stats", _chk(P, "P"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"), drop_p, seed, sid,
-         _chk(sums, "sums", torch.float64), _stream())
+def reattn_stats(P, B, h, N, ld, drop_p, seed, sid, sums):
+    call("vu_reattn_stats", _chk(P, "P"), B, h, N, ld, drop_p, seed, sid, _chk(sums, "sums", torch.float64), _stream())
 
 
 def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nbt, eps, momentum, train,
@@ -180,17 +179,22 @@ def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid):
     call("vu_reattn_mix", _chk(P, "P"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream())
 
 
-def reattn_bwd_reduce(P, dA, B, h, N, ld, W, bconv, saved, drop_p, seed, sid, red):
-    call("vu_reattn_bwd_reduce", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
-         _chk(saved, "saved"), drop_p, seed, sid, _chk(red, "red", torch.float64), _stream())
+def reattn_bwd_reduce(P, dA, B, h, N, ld, drop_p, seed, sid, red):
+    call("vu_reattn_bwd_reduce", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, drop_p, seed, sid,
+         _chk(red, "red", torch.float64), _stream())
 
 
-def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, red, train, scale, drop_p, seed, sid,
-                    dW, dbconv, dgamma, dbeta):
+def reattn_bwd_params(red, sums, B, h, N, W, bconv, gamma, saved, train, coef, dW, dbconv, dgamma, dbeta):
+    call("vu_reattn_bwd_params", _chk(red, "red", torch.float64), _opt(sums, "sums", torch.float64), B, h, N,
+         _chk(W, "W"), _chk(bconv, "bconv"), _chk(gamma, "gamma"), _chk(saved, "saved"), int(train),
+         _chk(coef, "coef"), _chk(dW, "dW"), _chk(dbconv, "dbconv"), _chk(dgamma, "dgamma"), _chk(dbeta, "dbeta"),
+         _stream())
+
+
+def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid):
     call("vu_reattn_bwd_rows", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
-         _chk(gamma, "gamma"), _chk(saved, "saved"), _opt(red, "red", torch.float64), int(train), scale,
-         drop_p, seed, sid, _chk(dW, "dW"), _chk(dbconv, "dbconv"), _chk(dgamma, "dgamma"),
-         _chk(dbeta, "dbeta"), _stream())
+         _chk(gamma, "gamma"), _chk(saved, "saved"), _chk(coef, "coef"), int(train), scale, drop_p, seed, sid,
+         _stream())
 
 
 # ----------------------------------------------------------------------------------------- layer norm
