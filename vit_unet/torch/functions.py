@@ -14,8 +14,11 @@ def psnr(model, dataloader, data_range=None):
             x = batch['x'].to('cuda').float()
             y = batch['y'].to('cuda').float()
             out = model(x)
-            # skimage.metrics.peak_signal_noise_ratio: data_range from dtype (float -> 2.0 span [-1,1]) unless given
-            dr = 2.0 if data_range is None else float(data_range)
+            # skimage.metrics.peak_signal_noise_ratio on float images: data_range = 1 if min(y) >= 0 else 2
             mse = ((out - y) ** 2).flatten(1).mean(dim=1)
+            if data_range is None:
+                dr = torch.where(y.flatten(1).min(dim=1).values >= 0, 1.0, 2.0)
+            else:
+                dr = torch.full_like(mse, float(data_range))
             score.append((10.0 * torch.log10(dr * dr / mse)).cpu())
     return np.asarray(torch.cat(score).numpy())

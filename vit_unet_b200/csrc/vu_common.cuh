@@ -35,19 +35,19 @@ struct Layout {
     return ((int64_t)(r * gw + q) * C + c) * pp + i * p + j;
   }
   // inverse: linear pixel index (channel 0 plane ordering of this layout) -> (y, x).
-  // pix enumerates (token, i, j) for p>0 and (y, x) for p==0.
-  __device__ __forceinline__ void pixel(int64_t pix, int& y, int& x) const {
-    if (p == 0) { y = (int)(pix / W); x = (int)(pix - (int64_t)y * W); return; }
-    int n = (int)(pix / pp); int rem = (int)(pix - (int64_t)n * pp);
+  // pix enumerates (token, i, j) for p>0 and (y, x) for p==0.  (pix < H*W always fits 32 bits.)
+  __device__ __forceinline__ void pixel(uint32_t pix, int& y, int& x) const {
+    if (p == 0) { y = (int)(pix / (uint32_t)W); x = (int)(pix - (uint32_t)y * W); return; }
+    int n = (int)(pix / (uint32_t)pp); int rem = (int)(pix - (uint32_t)n * pp);
     int i = rem / p, j = rem - i * p;
     int r = n / gw, q = n - r * gw;
     y = r * p + i; x = q * p + j;
   }
   // offset of channel-0 value for linear pixel index pix, and stride between channels
-  __device__ __forceinline__ int64_t base_of(int64_t pix) const {
+  __device__ __forceinline__ int64_t base_of(uint32_t pix) const {
     if (p == 0) return pix;
-    int64_t n = pix / pp; int64_t rem = pix - n * pp;
-    return n * C * pp + rem;
+    uint32_t n = pix / (uint32_t)pp; uint32_t rem = pix - n * pp;
+    return (int64_t)n * C * pp + rem;
   }
   __device__ __forceinline__ int64_t cstride() const { return p == 0 ? (int64_t)H * W : pp; }
 };

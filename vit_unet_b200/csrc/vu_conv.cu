@@ -29,13 +29,12 @@ conv3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < NCONV * C; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int64_t hw = (int64_t)g.lin.H * g.lin.W;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.npix_total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = t / hw; int64_t pix = t - b * hw;
+  const uint32_t hw = (uint32_t)(g.lin.H * g.lin.W), total = (uint32_t)g.npix_total;     // host checks < 2^31
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t b = t / hw, pix = t - b * hw;
     int y, xx; g.lout.pixel(pix, y, xx);
     int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
-    const float* xb = x + b * g.per_image;
+    const float* xb = x + (int64_t)b * g.per_image;
     float v[C][9];
     const int64_t cs = g.lin.cstride();
     if (g.fast) {
@@ -61,7 +60,7 @@ conv3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
           for (int ci = 0; ci < C; ++ci) v[ci][ky * 3 + kx] = ok ? __ldg(xb + off + ci * cs) : 0.f;
         }
     }
-    int64_t obase = b * g.per_image + g.lout.base_of(pix);
+    int64_t obase = (int64_t)b * g.per_image + g.lout.base_of(pix);
     const int64_t ocs = g.lout.cstride();
 #pragma unroll
     for (int k = 0; k < NCONV; ++k) {
@@ -87,10 +86,9 @@ conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ 
   __shared__ float sw[NCONV * C * C * 9];
   for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const int64_t hw = (int64_t)g.lin.H * g.lin.W;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.npix_total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = t / hw; int64_t pix = t - b * hw;
+  const uint32_t hw = (uint32_t)(g.lin.H * g.lin.W), total = (uint32_t)g.npix_total;     // host checks < 2^31
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t b = t / hw, pix = t - b * hw;
     int y, xx; g.lout.pixel(pix, y, xx);
     int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
     float acc[C];
@@ -109,7 +107,7 @@ conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ 
         int64_t off = g.fast ? base + (1 - ky) * rs + (1 - kx) : g.lin.at(0, y - ky + 1, xx - kx + 1);
 #pragma unroll
         for (int k = 0; k < NCONV; ++k) {
-          const float* dp = (k == 0 ? d0 : (k == 1 ? d1 : d2)) + b * g.per_image + off;
+          const float* dp = (k == 0 ? d0 : (k == 1 ? d1 : d2)) + (int64_t)b * g.per_image + off;
 #pragma unroll
           for (int co = 0; co < C; ++co) {
             float dv = __ldg(dp + co * cs);
@@ -118,7 +116,7 @@ conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ 
           }
         }
       }
-    int64_t obase = b * g.per_image + g.lout.base_of(pix);
+    int64_t obase = (int64_t)b * g.per_image + g.lout.base_of(pix);
     const int64_t ocs = g.lout.cstride();
 #pragma unroll
     for (int ci = 0; ci < C; ++ci) {
@@ -144,19 +142,18 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
   float acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-  const int64_t hw = (int64_t)g.lin.H * g.lin.W;
+  const uint32_t hw = (uint32_t)(g.lin.H * g.lin.W), total = (uint32_t)g.npix_total;     // host checks < 2^31
   const int64_t cs = g.lin.cstride(), dcs = g.lout.cstride();
   const int rs = g.bp ? g.bp : g.lin.W;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < g.npix_total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = t / hw; int64_t pix = t - b * hw;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t b = t / hw, pix = t - b * hw;
     int y, xx; g.lin.pixel(pix, y, xx);
     int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
     float dv[NCO];
-    const int64_t dbase = b * g.per_image + g.lout.at(co0, y, xx);
+    const int64_t dbase = (int64_t)b * g.per_image + g.lout.at(co0, y, xx);
 #pragma unroll
     for (int c = 0; c < NCO; ++c) { dv[c] = __ldg(dy + dbase + c * dcs); acc[c * (C * 9 + 1) + C * 9] += dv[c]; }
-    const float* xb = x + b * g.per_image;
+    const float* xb = x + (int64_t)b * g.per_image;
     int64_t base = g.lin.base_of(pix);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
@@ -194,6 +191,7 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
 
 static int make_geom(const char* fn, ConvGeom& g, int p_in, int p_out, int border_p, int B, int C, int H, int W) {
   VU_REQUIRE(B > 0 && H > 0 && W > 0, fn, "empty shape");
+  VU_REQUIRE((int64_t)B * H * W < (int64_t)1 << 31, fn, "B*H*W must be below 2^31 pixels per call");
   VU_REQUIRE(C >= 1 && C <= 4, fn, "num_channels must be 1..4");
   auto ok = [&](int p) { return p == 0 || (p > 0 && H % p == 0 && W % p == 0); };
   VU_REQUIRE(ok(p_in) && ok(p_out) && ok(border_p), fn, "patch size must divide the image height and width");

@@ -144,8 +144,26 @@ class _ViTUNetBase(nn.Module):
         P = {n: p.detach() for n, p in pd.items()}
         P.update(self._buffer_dict())
         seed = int(torch.empty((), dtype=torch.int64).random_().item()) if self.training else 0
-        out, _ = self.engine.forward(P, X, train=self.training, save=False, seed=seed)
+        B = X.shape[0]
+        chunk = self._eval_chunk(B)
+        if self.training or chunk >= B:
+            out, _ = self.engine.forward(P, X, train=self.training, save=False, seed=seed)
+            return out
+        # inference: images are independent (BatchNorm uses running statistics), so the batch is processed in
+        # slices that keep the transient attention maps (2 x B*h*N^2 floats at the finest level) within budget
+        out = torch.empty_like(X)
+        for s0 in range(0, B, chunk):
+            o, _ = self.engine.forward(P, X[s0:s0 + chunk], train=False, save=False, seed=seed)
+            out[s0:s0 + chunk] = o
         return out
+
+    map_budget_bytes = 16 << 30       # transient attention-map budget for no-grad inference (HBM is 180 GB)
+
+    def _eval_chunk(self, B: int) -> int:
+        g = self.engine.g
+        n = g.N(g.depth)
+        per_image = 2 * g.heads * n * ((n + 3) // 4 * 4) * 4
+        return max(1, min(B, self.map_budget_bytes // per_image))
 
     def flat_grad(self):
         """The flat fp32 gradient buffer of the last backward (forward-execution parameter order)."""
