@@ -310,7 +310,7 @@ def test_inference_batch_slicing_is_exact():
     x, _ = make_input(7, 3, 32)
     with torch.no_grad():
         full = net(x.cuda())
-        net.map_budget_bytes = 3 * net._eval_chunk(1) and 2 * 2 * 4 * 64 * 64 * 4 * 3    # room for 3 images
+        net.map_budget_bytes = 3 * (2 * 4 * 64 * 64 * 4)     # room for 3 images: 2 maps x h=4 x N=64 x ld=64 floats
         assert net._eval_chunk(7) == 3
         sliced = net(x.cuda())
     assert torch.equal(full, sliced)
