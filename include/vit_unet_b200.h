@@ -95,6 +95,9 @@ int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scale, void* st
  * The BatchNorm batch statistics of M_h = sum_g W[h,g] Pd_g + b[h] follow in closed form (vu_reattn_bn_finalize). */
 int vu_reattn_stats(const float* P, int B, int h, int N, int ld, float drop_p, uint64_t seed, uint32_t stream_id,
                     double* sums, void* stream);
+/* fused train-mode pass: in-place softmax of every head + the moments above in ONE read of S / write of P */
+int vu_softmax_stats(float* S, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
+                     uint32_t stream_id, double* sums, void* stream);
 /* fold conv1x1 + BatchNorm into one affine:  fold[h*h + h] = {alpha'[h][g], beta'[h]};
  * saved[2h] = {mean_h, invstd_h}.  train=1: batch statistics from `sums` (+ running-stat update,
  * momentum, unbiased variance, num_batches_tracked += 1); train=0: running statistics. model.py:136,159 */
@@ -108,6 +111,9 @@ int vu_reattn_mix(const float* P, float* A, const float* fold, int B, int h, int
 /* backward reductions: red[h + h*h] (double, caller zeroes) += { s1_h = sum dA_h,  X'_{hg} = sum dA_h (Pd_g - c) } */
 int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, float drop_p, uint64_t seed,
                          uint32_t stream_id, double* red, void* stream);
+/* fused backward pass: A = mix(P) (as vu_reattn_mix) AND the reductions of vu_reattn_bwd_reduce, one read of P, dA */
+int vu_reattn_mix_reduce(const float* P, const float* dA, float* A, const float* fold, int B, int h, int N, int ld,
+                         float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream);
 /* closed-form parameter gradients from (red, sums): dW[h*h], dbconv[h], dgamma[h], dbeta[h] are ACCUMULATED
  * (atomic; caller zeroes); coef[2h] = BatchNorm-backward means {mean dA_h, mean dA_h*Ahat_h} for vu_reattn_bwd_rows.
  * sums may be NULL when train == 0. */
@@ -120,13 +126,14 @@ int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, int N, int ld
                        int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 
 /* ---------------------------------------------------------------- LayerNorm over (N,D) (model.py:193-196,204,206) */
-/* stats[b] = {mean, rstd} over the n = N*D elements of image b */
-int vu_ln_stats(const float* x, int B, int64_t n, float eps, float* stats, void* stream);
+#define VU_LN_SPLIT 8      /* CTAs cooperating on one image's statistics */
+/* stats[b] = {mean, rstd} over the n = N*D elements of image b; scratch: 2*VU_LN_SPLIT*B floats */
+int vu_ln_stats(const float* x, int B, int64_t n, float eps, float* stats, float* scratch, void* stream);
 int vu_ln_apply(const float* x, const float* stats, const float* w, const float* b, float* out,
                 int B, int64_t n, void* stream);
 /* dx = LN backward; dw/db += (atomic; caller zeroes or accumulates: the README variant shares one LN) */
 int vu_ln_bwd(const float* g, const float* x, const float* stats, const float* w, float* dx,
-              float* dw, float* db, float* scratch /* 2*B floats */, int B, int64_t n, void* stream);
+              float* dw, float* db, float* scratch /* (2 + 2*VU_LN_SPLIT)*B floats */, int B, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------- losses (run_denoising.py:80, README.md:91-101) */
 enum { VU_LOSS_L1 = 0, VU_LOSS_MSE = 1, VU_LOSS_DICE = 2 };

@@ -298,7 +298,7 @@ def test_layernorm(ops, B, N, D):
     ops.ln_apply(xd, stats, w.detach().cuda(), b.detach().cuda(), out, B, n)
     _close(out, y, name="ln fwd")
     dx, dw, db = torch.empty_like(xd), torch.zeros(N, D, device="cuda"), torch.zeros(N, D, device="cuda")
-    ops.ln_bwd(g.cuda(), xd, stats, w.detach().cuda(), dx, dw, db, torch.empty(B, 2, device="cuda"), B, n)
+    ops.ln_bwd(g.cuda(), xd, stats, w.detach().cuda(), dx, dw, db, torch.empty(B, ops.LN_SCRATCH, device="cuda"), B, n)
     _close(dx, x.grad, rtol=1e-4, name="ln dx")
     _close(dw, w.grad, rtol=1e-5, name="ln dw")
     _close(db, b.grad, rtol=1e-5, name="ln db")
@@ -329,3 +329,26 @@ def test_adamw(ops):
         opt.step()
         ops.adamw(pd, (g * step).cuda(), m, v, 1e-2, 0.9, 0.999, 1e-8, 0.05, step)
     _close(pd, pr, rtol=1e-5, name="adamw")
+
+
+@pytest.mark.parametrize("h,N,p", [(8, 49, 0.0), (4, 70, 0.25), (2, 196, 0.1)])
+def test_reattn_fused_passes_match_separate_kernels(ops, h, N, p):
+    """vu_softmax_stats == softmax_rows + reattn_stats;  vu_reattn_mix_reduce == reattn_mix + reattn_bwd_reduce."""
+    B, ld, scale = 3, (N + 3) // 4 * 4, 0.41
+    S = torch.zeros(B, h, N, ld, device="cuda"); S[..., :N] = _rand(B, h, N, N, seed=1, scale=3.0).cuda()
+    P1, P2 = S.clone(), S.clone()
+    s1 = torch.zeros(h + h * h, dtype=torch.float64, device="cuda"); s2 = torch.zeros_like(s1)
+    ops.softmax_rows(P1, B * h * N, N, ld, scale)
+    ops.reattn_stats(P1, B, h, N, ld, p, 5, 2, s1)
+    ops.softmax_stats(P2, B, h, N, ld, scale, p, 5, 2, s2)
+    assert torch.equal(P1, P2)
+    _close(s2, s1, rtol=1e-6, name="fused moments")
+    fold = _rand(h * h + h, seed=2).cuda()
+    dA = torch.zeros(B, h, N, ld, device="cuda"); dA[..., :N] = _rand(B, h, N, N, seed=3).cuda()
+    A1, A2 = torch.empty_like(P1), torch.empty_like(P1)
+    r1 = torch.zeros(h + h * h, dtype=torch.float64, device="cuda"); r2 = torch.zeros_like(r1)
+    ops.reattn_mix(P1, A1, fold, B, h, N, ld, p, 5, 2)
+    ops.reattn_bwd_reduce(P1, dA, B, h, N, ld, p, 5, 2, r1)
+    ops.reattn_mix_reduce(P1, dA, A2, fold, B, h, N, ld, p, 5, 2, r2)
+    assert torch.equal(A1, A2)
+    _close(r2, r1, rtol=1e-6, name="fused reductions")

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitunet_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class VuError(RuntimeError):
@@ -46,13 +46,15 @@ SIGNATURES = {
     "vu_gemm": [C.POINTER(GemmDesc), _p],
     "vu_colsum": [_p, _l, _i, _l, _p, _i, _p],
     "vu_softmax_rows": [_p, _l, _i, _i, _f, _p],
+    "vu_softmax_stats": [_p, _i, _i, _i, _i, _f, _f, _u64, _u32, _p, _p],
+    "vu_reattn_mix_reduce": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_stats": [_p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bn_finalize": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p],
     "vu_reattn_mix": [_p, _p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p],
     "vu_reattn_bwd_reduce": [_p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bwd_params": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "vu_reattn_bwd_rows": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _f, _u64, _u32, _p],
-    "vu_ln_stats": [_p, _i, _l, _f, _p, _p],
+    "vu_ln_stats": [_p, _i, _l, _f, _p, _p, _p],
     "vu_ln_apply": [_p, _p, _p, _p, _p, _i, _l, _p],
     "vu_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p],
     "vu_loss_fwd": [_i, _p, _p, _l, _p, _p, _p],
@@ -70,7 +72,8 @@ _SPECIAL = {
 _lib = None
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
-_KERNELS_PER_CALL = {"vu_ln_bwd": 2, "vu_loss_fwd": 2}
+_KERNELS_PER_CALL = {"vu_ln_bwd": 3, "vu_ln_stats": 2, "vu_loss_fwd": 2}
+LN_SPLIT = 8
 _launches = 0
 
 

@@ -12,9 +12,8 @@
 //            atoms, TMA mode SWIZZLE_128B_ATOM_32B): slabs 4096 B apart (LBO), 4-k groups 512 B apart (SBO);
 //            start advances 1024 B (8 k-rows) per k-step.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (TMEM -> registers -> smem staging -> coalesced global), each owning its TMEM lane quarter.
-// Persistent: one CTA per SM loops over 128 x BLOCK_N output tiles; two TMEM accumulators let the epilogue of
-// one tile overlap the TMA/MMA main loop of the next.
+// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global), each owning its TMEM lane quarter.
+// One 128 x BLOCK_N output tile per CTA; two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <cstdlib>
 
@@ -31,7 +30,7 @@ struct TcArgs {
   const float* bias; const float* residual; const float* aux_in; float* aux_out;
   int M, N, K;
   int64_t ldc, ldr, ldaux;
-  int batch_inner, nbatch;
+  int batch_inner;
   int64_t sCo, sCi;
   float alpha; int act; int accumulate; int split_k; int k_per_split;
   float drop_scale; uint32_t drop_thresh; uint64_t drop_seed; uint32_t drop_stream;
@@ -46,9 +45,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -123,42 +119,36 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn, bool b_
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
 }
 
-// Persistent, warp-specialised kernel.  Every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... in
-// (batch, m, n) order (n fastest) so that concurrently running CTAs share A rows / B panels in L2.
-//   warp 0      TMA producer   : smem ring of STAGES {A,B} k-blocks, continues across tiles
-//   warp 1      MMA issuer     : tcgen05.mma into one of TWO TMEM accumulators (ping-pong)
-//   warps 2..5  epilogue       : TMEM -> registers -> private smem staging -> coalesced float4 global I/O
-// The epilogue of tile i overlaps the TMA/MMA main loop of tile i+1 (tmem_full / tmem_empty mbarriers).
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
   constexpr uint32_t A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 4;
   constexpr uint32_t B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
-  constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
-  constexpr int LDS = BLOCK_N + 4;                        // padded staging row (floats)
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  float* sStage = reinterpret_cast<float*>(sB + STAGES * B_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + 4 * 32 * LDS);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;           // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (g.N + BLOCK_N - 1) / BLOCK_N, tiles_m = (g.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
-  const int tiles_mn = tiles_n * tiles_m;
-  const int total_tiles = tiles_mn * g.nbatch * g.split_k;
+  const int m0 = blockIdx.y * TC_BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  int z = blockIdx.z, ks = 0;
+  if (g.split_k > 1) { ks = z % g.split_k; z /= g.split_k; }
+  const int zo = z / g.batch_inner, zi = z % g.batch_inner;
+  const int kbeg = ks * g.k_per_split;
+  const int kend = min(g.K, kbeg + g.k_per_split);
+  const int nkb = (kend - kbeg + TC_BLOCK_K - 1) / TC_BLOCK_K;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar + a, 1); mbar_init(tmem_empty_bar + a, 4); }
+    mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -167,180 +157,158 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile index -> coordinates
-  auto decode = [&](int t, int& m0, int& n0, int& zi, int& zo, int& ks, int& kbeg, int& nkb) {
-    int zs = t / tiles_mn, r = t - zs * tiles_mn;
-    int mi = r / tiles_n, ni = r - mi * tiles_n;
-    m0 = mi * TC_BLOCK_M; n0 = ni * BLOCK_N;
-    ks = zs % g.split_k; int z = zs / g.split_k;
-    zo = z / g.batch_inner; zi = z - zo * g.batch_inner;
-    kbeg = ks * g.k_per_split;
-    int kend = min(g.K, kbeg + g.k_per_split);
-    nkb = (kend - kbeg + TC_BLOCK_K - 1) / TC_BLOCK_K;
-  };
-
   if (warp == 0) {
     // ===================================================== TMA producer
     if (elect_one()) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int m0, n0, zi, zo, ks, kbeg, nkb; decode(t, m0, n0, zi, zo, ks, kbeg, nkb);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar + s, ph ^ 1);
-          mbar_expect_tx(full_bar + s, A_BYTES + B_BYTES);
-          const int k0 = kbeg + kb * TC_BLOCK_K;
-          uint8_t* a_dst = sA + s * A_BYTES;
-          uint8_t* b_dst = sB + s * B_BYTES;
-          if (!A_MN) tma_load_4d(a_dst, &tmA, full_bar + s, k0, m0, zi, zo);
-          else {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        mbar_expect_tx(full_bar + s, A_BYTES + B_BYTES);
+        const int k0 = kbeg + kb * TC_BLOCK_K;
+        uint8_t* a_dst = sA + s * A_BYTES;
+        uint8_t* b_dst = sB + s * B_BYTES;
+        if (!A_MN) tma_load_4d(a_dst, &tmA, full_bar + s, k0, m0, zi, zo);
+        else {
 #pragma unroll
-            for (int sl = 0; sl < TC_BLOCK_M / 32; ++sl) tma_load_4d(a_dst + sl * 4096, &tmA, full_bar + s, m0 + sl * 32, k0, zi, zo);
-          }
-          if (!B_MN) tma_load_4d(b_dst, &tmB, full_bar + s, k0, n0, zi, zo);
-          else {
+          for (int sl = 0; sl < TC_BLOCK_M / 32; ++sl) tma_load_4d(a_dst + sl * 4096, &tmA, full_bar + s, m0 + sl * 32, k0, zi, zo);
+        }
+        if (!B_MN) tma_load_4d(b_dst, &tmB, full_bar + s, k0, n0, zi, zo);
+        else {
 #pragma unroll
-            for (int sl = 0; sl < BLOCK_N / 32; ++sl) tma_load_4d(b_dst + sl * 4096, &tmB, full_bar + s, n0 + sl * 32, k0, zi, zo);
-          }
+          for (int sl = 0; sl < BLOCK_N / 32; ++sl) tma_load_4d(b_dst + sl * 4096, &tmB, full_bar + s, n0 + sl * 32, k0, zi, zo);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     constexpr uint32_t idesc = make_idesc_tf32(BLOCK_N, A_MN, B_MN);
-    uint32_t it = 0, lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      int m0, n0, zi, zo, ks, kbeg, nkb; decode(t, m0, n0, zi, zo, ks, kbeg, nkb);
-      const uint32_t acc = lt & 1;
-      mbar_wait(tmem_empty_bar + acc, ((lt >> 1) & 1) ^ 1);        // epilogue drained this accumulator
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(full_bar + s, ph);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar + s, ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+      if (elect_one()) {
+        const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < TC_BLOCK_K / TC_UMMA_K; ++kk) {
-            const uint64_t ad = A_MN ? make_smem_desc(a_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(a_base + kk * 32, 16, 1024, 2);
-            const uint64_t bd = B_MN ? make_smem_desc(b_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(b_base + kk * 32, 16, 1024, 2);
-            umma_tf32(tmem_d, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty_bar + s);                         // frees the smem slot once these MMAs retire
-          if (kb == nkb - 1) umma_commit(tmem_full_bar + acc);  // accumulator complete -> epilogue
+        for (int kk = 0; kk < TC_BLOCK_K / TC_UMMA_K; ++kk) {
+          const uint64_t ad = A_MN ? make_smem_desc(a_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(a_base + kk * 32, 16, 1024, 2);
+          const uint64_t bd = B_MN ? make_smem_desc(b_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(b_base + kk * 32, 16, 1024, 2);
+          umma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
         }
-        __syncwarp();
+        umma_commit(empty_bar + s);                       // frees the smem slot once these MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full_bar);    // accumulator complete -> epilogue
       }
+      __syncwarp();
     }
   } else {
     // ===================================================== epilogue (warps 2..5)
+    // TMEM -> registers (one accumulator row per lane) -> shared-memory staging (the pipeline buffers are idle
+    // once the accumulator is complete) -> row-contiguous float4 global accesses: every load of residual / aux
+    // and every store of C is a fully coalesced 16 B-per-lane transaction.
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
-    float* stage = sStage + (size_t)q * 32 * LDS;
+    const int64_t coff = zo * g.sCo + zi * g.sCi;
+    float* C = g.C + coff;
+    constexpr int LDS = BLOCK_N + 4;                      // padded staging row (floats)
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)q * 32 * LDS;
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+      uint32_t r[16];
+      if (nkb > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4)
+        *reinterpret_cast<float4*>(stage + lane * LDS + c0 + j4) =
+            make_float4(__uint_as_float(r[j4]) * g.alpha, __uint_as_float(r[j4 + 1]) * g.alpha,
+                        __uint_as_float(r[j4 + 2]) * g.alpha, __uint_as_float(r[j4 + 3]) * g.alpha);
+    }
+    __syncwarp();
     constexpr int LPR = BLOCK_N / 4;                      // lanes covering one output row
     constexpr int RPI = 32 / LPR;                         // rows handled per iteration
     const int cl = (lane % LPR) * 4;                      // this lane's 4 columns inside the tile
-    uint32_t lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      int m0, n0, zi, zo, ks, kbeg, nkb; decode(t, m0, n0, zi, zo, ks, kbeg, nkb);
-      const int z = zo * g.batch_inner + zi;
-      const uint32_t acc = lt & 1;
-      const int64_t coff = zo * g.sCo + zi * g.sCi;
-      float* C = g.C + coff;
-      mbar_wait(tmem_full_bar + acc, (lt >> 1) & 1);
-      tc_fence_after();
+    const int n = n0 + cl;
+    const int nv = min(4, g.N - n);                       // <= 0: nothing to do for this lane
+    const bool vec_c = ((uintptr_t)C % 16 == 0) && (g.ldc % 4 == 0) && nv == 4;
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g.bias && (g.split_k <= 1 || ks == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < nv) bias4[j] = g.bias[n + j];
+    }
+    const bool vec_r = g.residual && ((uintptr_t)(g.residual + coff) % 16 == 0) && (g.ldr % 4 == 0) && nv == 4;
+    const float* axp = g.aux_in ? g.aux_in : g.aux_out;
+    const bool vec_x = axp && ((uintptr_t)(axp + coff) % 16 == 0) && (g.ldaux % 4 == 0) && nv == 4;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
+    for (int r0 = 0; r0 < 32; r0 += RPI) {
+      const int row = r0 + lane / LPR;
+      const int m = m0 + q * 32 + row;
+      if (m >= g.M || nv <= 0) continue;
+      const float4 t4 = *reinterpret_cast<const float4*>(stage + row * LDS + cl);
+      float v[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
+      float* dst = C + (int64_t)m * g.ldc + n;
+      if (g.split_k > 1) {
+        if (g.residual && ks == 0) {
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4)
-          *reinterpret_cast<float4*>(stage + lane * LDS + c0 + j4) =
-              make_float4(__uint_as_float(r[j4]) * g.alpha, __uint_as_float(r[j4 + 1]) * g.alpha,
-                          __uint_as_float(r[j4 + 2]) * g.alpha, __uint_as_float(r[j4 + 3]) * g.alpha);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar + acc);     // accumulator may be overwritten by tile lt+2
-      const int n = n0 + cl;
-      const int nv = min(4, g.N - n);                       // <= 0: nothing to do for this lane
-      const bool vec_c = ((uintptr_t)C % 16 == 0) && (g.ldc % 4 == 0) && nv == 4;
-      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (g.bias && (g.split_k <= 1 || ks == 0)) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (j < nv) bias4[j] = g.bias[n + j];
-      }
-      const bool vec_r = g.residual && ((uintptr_t)(g.residual + coff) % 16 == 0) && (g.ldr % 4 == 0) && nv == 4;
-      const float* axp = g.aux_in ? g.aux_in : g.aux_out;
-      const bool vec_x = axp && ((uintptr_t)(axp + coff) % 16 == 0) && (g.ldaux % 4 == 0) && nv == 4;
-#pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += RPI) {
-        const int row = r0 + lane / LPR;
-        const int m = m0 + q * 32 + row;
-        if (m >= g.M || nv <= 0) continue;
-        const float4 t4 = *reinterpret_cast<const float4*>(stage + row * LDS + cl);
-        float v[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
-        float* dst = C + (int64_t)m * g.ldc + n;
-        if (g.split_k > 1) {
-          if (g.residual && ks == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < nv) v[j] += g.residual[coff + (int64_t)m * g.ldr + n + j];
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
-          continue;
+          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += g.residual[coff + (int64_t)m * g.ldr + n + j];
         }
-        if (g.act == VU_ACT_GELU) {
-          if (g.aux_out) {
-            float* ax = g.aux_out + coff + (int64_t)m * g.ldaux + n;
-            if (vec_x) *reinterpret_cast<float4*>(ax) = make_float4(v[0], v[1], v[2], v[3]);
-            else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = v[j];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = gelu_exact(v[j]);
-        } else if (g.act == VU_ACT_GELU_BWD) {
-          const float* ax = g.aux_in + coff + (int64_t)m * g.ldaux + n;
-          float a[4] = {0.f, 0.f, 0.f, 0.f};
-          if (vec_x) { float4 tt = *reinterpret_cast<const float4*>(ax); a[0] = tt.x; a[1] = tt.y; a[2] = tt.z; a[3] = tt.w; }
+        for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
+        continue;
+      }
+      if (g.act == VU_ACT_GELU) {
+        if (g.aux_out) {
+          float* ax = g.aux_out + coff + (int64_t)m * g.ldaux + n;
+          if (vec_x) *reinterpret_cast<float4*>(ax) = make_float4(v[0], v[1], v[2], v[3]);
           else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < nv) a[j] = ax[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] *= gelu_exact_grad(a[j]);
-        }
-        if (g.drop_thresh) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint64_t idx = (uint64_t)z * g.M * g.N + (uint64_t)m * g.N + (n + j);
-            v[j] = Philox::keep(g.drop_seed, g.drop_stream, idx, g.drop_thresh) ? v[j] * g.drop_scale : 0.f;
+            for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = v[j];
           }
         }
-        if (g.residual) {
-          const float* rp = g.residual + coff + (int64_t)m * g.ldr + n;
-          if (vec_r) { float4 tt = *reinterpret_cast<const float4*>(rp); v[0] += tt.x; v[1] += tt.y; v[2] += tt.z; v[3] += tt.w; }
-          else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rp[j];
-          }
+        for (int j = 0; j < 4; ++j) v[j] = gelu_exact(v[j]);
+      } else if (g.act == VU_ACT_GELU_BWD) {
+        const float* ax = g.aux_in + coff + (int64_t)m * g.ldaux + n;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec_x) { float4 t = *reinterpret_cast<const float4*>(ax); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) a[j] = ax[j];
         }
-        if (vec_c) {
-          float4 o = make_float4(v[0], v[1], v[2], v[3]);
-          if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-          *reinterpret_cast<float4*>(dst) = o;
-        } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nv) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
+        for (int j = 0; j < 4; ++j) v[j] *= gelu_exact_grad(a[j]);
+      }
+      if (g.drop_thresh) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint64_t idx = (uint64_t)z * g.M * g.N + (uint64_t)m * g.N + (n + j);
+          v[j] = Philox::keep(g.drop_seed, g.drop_stream, idx, g.drop_thresh) ? v[j] * g.drop_scale : 0.f;
         }
       }
-      __syncwarp();                                          // staging rows are rewritten by the next tile
+      if (g.residual) {
+        const float* rp = g.residual + coff + (int64_t)m * g.ldr + n;
+        if (vec_r) { float4 t = *reinterpret_cast<const float4*>(rp); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rp[j];
+        }
+      }
+      if (vec_c) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+        *reinterpret_cast<float4*>(dst) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nv) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
+      }
     }
   }
   tc_fence_before();
@@ -394,12 +362,12 @@ static bool encode_operand(CUtensorMap* tm, const float* base, int64_t contig, i
 }
 
 template <int BLOCK_N, int STAGES>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& g, bool a_mn, bool b_mn,
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& g, bool a_mn, bool b_mn, int nbatch,
                      cudaStream_t s) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BLOCK_M * TC_BLOCK_K * 4 + BLOCK_N * TC_BLOCK_K * 4) +
-                          (size_t)4 * 32 * (BLOCK_N + 4) * 4 + 1024 + 256;
-  const int64_t tiles = cdiv(g.N, BLOCK_N) * cdiv(g.M, TC_BLOCK_M) * g.nbatch * g.split_k;
-  dim3 grid((unsigned)std::min<int64_t>(tiles, sm_count()));       // persistent: one CTA per SM
+  constexpr size_t ring = (size_t)STAGES * (TC_BLOCK_M * TC_BLOCK_K * 4 + BLOCK_N * TC_BLOCK_K * 4);
+  constexpr size_t staging = (size_t)4 * 32 * (BLOCK_N + 4) * 4;     // epilogue staging reuses the ring
+  constexpr size_t smem = (ring > staging ? ring : staging) + 1024 + 256;
+  dim3 grid((unsigned)cdiv(g.N, BLOCK_N), (unsigned)cdiv(g.M, TC_BLOCK_M), (unsigned)(nbatch * g.split_k));
   dim3 block(192);
 #define VU_TC_LAUNCH(AMN, BMN)                                                                                   \
   do {                                                                                                            \
@@ -450,11 +418,12 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   g.mn_lbo = 4096; g.mn_sbo = 512;
   if (const char* e = getenv("VU_TC_MN_LBO")) g.mn_lbo = (uint32_t)atoi(e);
   if (const char* e = getenv("VU_TC_MN_SBO")) g.mn_sbo = (uint32_t)atoi(e);
-  g.nbatch = bi * bo;
+  const int nbatch = bi * bo;
   int rc;
-  if (block_n == 32) rc = launch_tc<32, 6>(tmA, tmB, g, a_mn, b_mn, s);
-  else if (block_n == 64) rc = launch_tc<64, 5>(tmA, tmB, g, a_mn, b_mn, s);
-  else rc = launch_tc<128, 4>(tmA, tmB, g, a_mn, b_mn, s);
+  if (block_n == 32) rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  else if (block_n == 64) rc = launch_tc<64, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  else if (g.k_per_split <= TC_BLOCK_K) rc = launch_tc<128, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);   // one k-block: 3 CTAs/SM
+  else rc = launch_tc<128, 3>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
   *handled = true;
   return rc;
 }

@@ -4,41 +4,64 @@
 
 namespace vu {
 
-// one CTA per image; two passes (mean, then centred variance) like ATen's CPU kernel -> fp32-exact statistics
-__global__ void __launch_bounds__(1024)
-ln_stats_kernel(const float* __restrict__ x, int64_t n, float eps, float* __restrict__ stats) {
+// grid (VU_LN_SPLIT, B): every CTA reduces one slice of an image with two passes (mean, then centred sum of
+// squares -- the slice is L1/L2 resident for the second pass); slices are merged exactly (Chan et al.) by a tiny
+// finalize kernel.  fp32-exact statistics like ATen's, but B*VU_LN_SPLIT CTAs instead of B.
+__global__ void __launch_bounds__(512)
+ln_stats_partial_kernel(const float* __restrict__ x, int64_t n, int64_t len, float* __restrict__ part) {
   __shared__ double red[32];
   __shared__ float s_mean;
-  const float* xb = x + (int64_t)blockIdx.x * n;
-  const bool vec = (n % 4 == 0) && ((uintptr_t)xb % 16 == 0);
+  const int64_t beg = (int64_t)blockIdx.x * len, end = min(n, beg + len);
+  const float* xb = x + (int64_t)blockIdx.y * n;
+  const int64_t cnt = max((int64_t)0, end - beg);
+  const bool vec = (beg % 4 == 0) && (cnt % 4 == 0) && ((uintptr_t)xb % 16 == 0);
   double v[1]; float acc = 0.f;
   if (vec) {
-    const float4* x4 = reinterpret_cast<const float4*>(xb);
-    for (int64_t i = threadIdx.x; i < n / 4; i += blockDim.x) { float4 t = x4[i]; acc += (t.x + t.y) + (t.z + t.w); }
+    const float4* x4 = reinterpret_cast<const float4*>(xb + beg);
+    for (int64_t i = threadIdx.x; i < cnt / 4; i += blockDim.x) { float4 t = x4[i]; acc += (t.x + t.y) + (t.z + t.w); }
   } else {
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += xb[i];
+    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) acc += xb[i];
   }
   v[0] = acc; block_sum<1>(v, red);
-  if (threadIdx.x == 0) s_mean = (float)(v[0] / (double)n);
+  if (threadIdx.x == 0) s_mean = cnt > 0 ? (float)(v[0] / (double)cnt) : 0.f;
   __syncthreads();
   const float mean = s_mean;
   acc = 0.f;
   if (vec) {
-    const float4* x4 = reinterpret_cast<const float4*>(xb);
-    for (int64_t i = threadIdx.x; i < n / 4; i += blockDim.x) {
+    const float4* x4 = reinterpret_cast<const float4*>(xb + beg);
+    for (int64_t i = threadIdx.x; i < cnt / 4; i += blockDim.x) {
       float4 t = x4[i];
       float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
       acc += (a * a + b * b) + (c * c + d * d);
     }
   } else {
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { float a = xb[i] - mean; acc = fmaf(a, a, acc); }
+    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) { float a = xb[i] - mean; acc = fmaf(a, a, acc); }
   }
   v[0] = acc; block_sum<1>(v, red);
   if (threadIdx.x == 0) {
-    float var = (float)(v[0] / (double)n);
-    stats[2 * blockIdx.x] = mean;
-    stats[2 * blockIdx.x + 1] = 1.0f / sqrtf(var + eps);
+    float* o = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+    o[0] = mean; o[1] = (float)v[0];
   }
+}
+
+__global__ void ln_stats_finalize_kernel(const float* __restrict__ part, int B, int S, int64_t n, int64_t len, float eps,
+                                         float* __restrict__ stats) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double tot = 0, mean = 0;
+  for (int s = 0; s < S; ++s) {
+    double c = (double)max((int64_t)0, min(n, (int64_t)(s + 1) * len) - (int64_t)s * len);
+    mean += c * (double)part[((int64_t)b * S + s) * 2]; tot += c;
+  }
+  mean /= tot;
+  double m2 = 0;
+  for (int s = 0; s < S; ++s) {
+    double c = (double)max((int64_t)0, min(n, (int64_t)(s + 1) * len) - (int64_t)s * len);
+    double d = (double)part[((int64_t)b * S + s) * 2] - mean;
+    m2 += (double)part[((int64_t)b * S + s) * 2 + 1] + c * d * d;
+  }
+  stats[2 * b] = (float)mean;
+  stats[2 * b + 1] = 1.0f / sqrtf((float)(m2 / tot) + eps);
 }
 
 template <int V>
@@ -62,22 +85,34 @@ ln_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, co
   }
 }
 
-// scratch[2b] = sum g*w ; scratch[2b+1] = sum g*w*xhat   (one CTA per image)
-__global__ void __launch_bounds__(1024)
+// part[(b*S+s)*2 + {0,1}] = slice sums of g*w and g*w*xhat   (grid (S, B)); merged by ln_bwd_finalize_kernel
+__global__ void __launch_bounds__(512)
 ln_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
-                    const float* __restrict__ w, int64_t n, float* __restrict__ scratch) {
+                    const float* __restrict__ w, int64_t n, int64_t len, float* __restrict__ part) {
   __shared__ double red[64];
-  const int64_t b = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * len, end = min(n, beg + len);
   const float mean = stats[2 * b], rstd = stats[2 * b + 1];
   const float* gb = g + b * n; const float* xb = x + b * n;
   float a1 = 0.f, a2 = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
     float gw = gb[i] * w[i];
     a1 += gw; a2 = fmaf(gw, (xb[i] - mean) * rstd, a2);
   }
   double v[2] = {a1, a2};
   block_sum<2>(v, red);
-  if (threadIdx.x == 0) { scratch[2 * b] = (float)v[0]; scratch[2 * b + 1] = (float)v[1]; }
+  if (threadIdx.x == 0) {
+    float* o = part + (b * gridDim.x + blockIdx.x) * 2;
+    o[0] = (float)v[0]; o[1] = (float)v[1];
+  }
+}
+
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ part, int B, int S, float* __restrict__ out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double a1 = 0, a2 = 0;
+  for (int s = 0; s < S; ++s) { a1 += (double)part[((int64_t)b * S + s) * 2]; a2 += (double)part[((int64_t)b * S + s) * 2 + 1]; }
+  out[2 * b] = (float)a1; out[2 * b + 1] = (float)a2;
 }
 
 // dx = rstd * (g*w - a1/n - xhat * a2/n);  dw += sum_b g*xhat;  db += sum_b g
@@ -118,11 +153,15 @@ ln_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, co
 
 }  // namespace vu
 
-extern "C" int vu_ln_stats(const float* x, int B, int64_t n, float eps, float* stats, void* stream) {
+extern "C" int vu_ln_stats(const float* x, int B, int64_t n, float eps, float* stats, float* scratch, void* stream) {
   using namespace vu;
   const char* fn = "vu_ln_stats";
-  VU_REQUIRE(x && stats && B > 0 && n > 0, fn, "bad arguments");
-  ln_stats_kernel<<<B, 1024, 0, as_stream(stream)>>>(x, n, eps, stats);
+  VU_REQUIRE(x && stats && scratch && B > 0 && n > 0, fn, "bad arguments");
+  const int S = VU_LN_SPLIT;
+  const int64_t len = cdiv(cdiv(n, S), 4) * 4;
+  cudaStream_t s = as_stream(stream);
+  ln_stats_partial_kernel<<<dim3(S, B), 512, 0, s>>>(x, n, len, scratch);
+  ln_stats_finalize_kernel<<<(unsigned)cdiv(B, 128), 128, 0, s>>>(scratch, B, S, n, len, eps, stats);
   return check_launch(fn);
 }
 
@@ -146,7 +185,11 @@ extern "C" int vu_ln_bwd(const float* g, const float* x, const float* stats, con
   const char* fn = "vu_ln_bwd";
   VU_REQUIRE(g && x && stats && w && dx && dw && db && scratch && B > 0 && n > 0, fn, "bad arguments");
   cudaStream_t s = as_stream(stream);
-  ln_bwd_stats_kernel<<<B, 1024, 0, s>>>(g, x, stats, w, n, scratch);
+  const int S = VU_LN_SPLIT;
+  const int64_t len = cdiv(cdiv(n, S), 4) * 4;
+  float* part = scratch + 2 * (int64_t)B;          // scratch: [2B merged | 2*S*B partials]
+  ln_bwd_stats_kernel<<<dim3(S, B), 512, 0, s>>>(g, x, stats, w, n, len, part);
+  ln_bwd_finalize_kernel<<<(unsigned)cdiv(B, 128), 128, 0, s>>>(part, B, S, scratch);
   int rc = check_launch(fn); if (rc) return rc;
   bool vec = (n % 4 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dx % 16 == 0);
   int64_t work = vec ? n / 4 : n;

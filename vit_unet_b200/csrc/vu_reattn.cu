@@ -105,6 +105,72 @@ reattn_stats_kernel(const float* __restrict__ P, int B, int N, int ld, QuadCtx q
   }
 }
 
+// Fused train-mode pass: one warp owns the rows (b, i) of ALL heads: softmax of every head in place, then the
+// centred moments of the freshly written probabilities (re-read from L1/L2) -- one HBM read of S, one write of P.
+template <int H>
+__global__ void __launch_bounds__(256)
+softmax_stats_kernel(float* __restrict__ S, int B, int N, int ld, float scale, QuadCtx q, double* __restrict__ sums) {
+  constexpr int NV = H + H * (H + 1) / 2;
+  __shared__ double red[NV * 32];
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float sl2 = scale * 1.4426950408889634f;
+  const int64_t head_stride = (int64_t)N * ld, img_stride = head_stride * H;
+  const int64_t rows = (int64_t)B * N;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  for (int64_t r = wid; r < rows; r += nw) {
+    const int64_t b = r / N; const int i = (int)(r - b * N);
+    const int64_t row_off = b * img_stride + (int64_t)i * ld;
+#pragma unroll 1
+    for (int g = 0; g < H; ++g) {
+      float* row = S + row_off + g * head_stride;
+      float mx = -INFINITY;
+      for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j] * sl2);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < N; j += 32) { float e = exp2f(fmaf(row[j], sl2, -mx)); row[j] = e; sum += e; }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      for (int j = lane; j < N; j += 32) row[j] *= inv;
+      for (int j = N + lane; j < ld; j += 32) row[j] = 0.f;
+    }
+    __syncwarp();
+    for (int j = lane * 4; j < ld; j += 128) {
+      float4 p[H];
+#pragma unroll
+      for (int g = 0; g < H; ++g) {
+        const int64_t off = row_off + g * head_stride + j;
+        p[g] = load_pd(S + off, (uint64_t)off, q); centre(p[g], j, q);
+      }
+      int k = H;
+#pragma unroll
+      for (int g = 0; g < H; ++g) {
+        acc[g] += sum4(p[g]);
+#pragma unroll
+        for (int g2 = g; g2 < H; ++g2) { acc[k] += dot4(p[g], p[g2]); ++k; }
+      }
+    }
+  }
+  double v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = acc[i];
+  block_sum<NV>(v, red);
+  if (threadIdx.x == 0) {
+    int k = H;
+    for (int g = 0; g < H; ++g) {
+      atomicAdd(sums + g, v[g]);
+      for (int g2 = g; g2 < H; ++g2) {
+        atomicAdd(sums + H + g * H + g2, v[k]);
+        if (g2 != g) atomicAdd(sums + H + g2 * H + g, v[k]);
+        ++k;
+      }
+    }
+  }
+}
+
 // one block: statistics -> folded affine + saved (mean, invstd) + running-stat update
 __global__ void reattn_bn_finalize_kernel(const double* __restrict__ sums, double count, int H, int N,
                                           const float* __restrict__ W, const float* __restrict__ bconv,
@@ -175,6 +241,63 @@ reattn_mix_kernel(const float* __restrict__ P, float* __restrict__ A, const floa
       }
       *reinterpret_cast<float4*>(A + off + h * head_stride) = a;
     }
+  }
+}
+
+// Backward fusion: one read of P and dA gives both the recomputed mixed map A (needed for dV = A^T dO) and the
+// backward reductions red[h] += sum dA_h, red[H + h*H + g] += sum dA_h (Pd_g - c).
+template <int H>
+__global__ void __launch_bounds__(256)
+reattn_mix_reduce_kernel(const float* __restrict__ P, const float* __restrict__ dA, float* __restrict__ A,
+                         const float* __restrict__ fold, int B, int N, int ld, QuadCtx q, double* __restrict__ out) {
+  constexpr int NV = H + H * H;
+  __shared__ double red[NV * 32];
+  __shared__ float sF[H * H + H];
+  for (int i = threadIdx.x; i < H * H + H; i += blockDim.x) sF[i] = fold[i];
+  __syncthreads();
+  const int ld4 = ld >> 2;
+  const int64_t head_stride = (int64_t)N * ld, img_stride = head_stride * H;
+  const int64_t per_img4 = (int64_t)N * ld4, total = per_img4 * B;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t / per_img4; int64_t r = t - b * per_img4;
+    int j = (int)(r % ld4) * 4;
+    int64_t off = b * img_stride + r * 4;
+    float4 p[H];
+#pragma unroll
+    for (int g = 0; g < H; ++g) p[g] = load_pd(P + off + g * head_stride, (uint64_t)(off + g * head_stride), q);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float bb = sF[H * H + h];
+      float4 a = make_float4(bb, bb, bb, bb);
+#pragma unroll
+      for (int g = 0; g < H; ++g) {
+        float w = sF[h * H + g];
+        a.x = fmaf(w, p[g].x, a.x); a.y = fmaf(w, p[g].y, a.y); a.z = fmaf(w, p[g].z, a.z); a.w = fmaf(w, p[g].w, a.w);
+      }
+      if (j + 3 >= N) { if (j + 0 >= N) a.x = 0.f; if (j + 1 >= N) a.y = 0.f; if (j + 2 >= N) a.z = 0.f; if (j + 3 >= N) a.w = 0.f; }
+      *reinterpret_cast<float4*>(A + off + h * head_stride) = a;
+    }
+#pragma unroll
+    for (int g = 0; g < H; ++g) centre(p[g], j, q);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float4 d = *reinterpret_cast<const float4*>(dA + off + h * head_stride);
+      if (j + 3 >= N) { if (j + 0 >= N) d.x = 0.f; if (j + 1 >= N) d.y = 0.f; if (j + 2 >= N) d.z = 0.f; if (j + 3 >= N) d.w = 0.f; }
+      acc[h] += sum4(d);
+#pragma unroll
+      for (int g = 0; g < H; ++g) acc[H + h * H + g] += dot4(d, p[g]);
+    }
+  }
+  double v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = acc[i];
+  block_sum<NV>(v, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) atomicAdd(out + i, v[i]);
   }
 }
 
@@ -463,5 +586,30 @@ extern "C" int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, in
   int blocks = grid_for((int64_t)B * N * 32, 128, 12);
   VU_DISPATCH_H(h, fn, reattn_bwd_rows_kernel<HH><<<blocks, 128, 0, as_stream(stream)>>>(
       P, dA_dS, B, N, ld, W, bconv, gamma, saved, coef, train, scale, q));
+  return check_launch(fn);
+}
+
+extern "C" int vu_softmax_stats(float* S, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
+                                uint32_t stream_id, double* sums, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_softmax_stats";
+  VU_REQUIRE(VU_MAP_ARGS_OK(S) && sums, fn, "bad arguments (maps need ld % 4 == 0 and 16-byte alignment)");
+  VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
+  QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  int blocks = grid_for((int64_t)B * N * 32, 256, 8);
+  VU_DISPATCH_H(h, fn, softmax_stats_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(S, B, N, ld, scale, q, sums));
+  return check_launch(fn);
+}
+
+extern "C" int vu_reattn_mix_reduce(const float* P, const float* dA, float* A, const float* fold, int B, int h, int N,
+                                    int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_reattn_mix_reduce";
+  VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA && A && fold && red && ((uintptr_t)dA % 16 == 0) && ((uintptr_t)A % 16 == 0), fn,
+             "bad arguments");
+  VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
+  QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);
+  VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, dA, A, fold, B, N, ld, q, red));
   return check_launch(fn);
 }

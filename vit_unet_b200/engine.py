@@ -122,14 +122,15 @@ class Engine:
         ops.gemm(q, k, Pm, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
                  sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
         scale = float(hd) ** -0.5
-        ops.softmax_rows(Pm, B * h * N, N, ld, scale)
         Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
         bm = P[pre + "reatten_matrix.bias"]
         adrop = g.attn_drop if train else 0.0
         sums = None
-        if train:
+        if train:     # softmax + centred moments of the dropped maps in one pass
             sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device)
-            ops.reattn_stats(Pm, B, h, N, ld, adrop, seed, sid, sums)
+            ops.softmax_stats(Pm, B, h, N, ld, scale, adrop, seed, sid, sums)
+        else:
+            ops.softmax_rows(Pm, B * h * N, N, ld, scale)
         fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
         ops.reattn_bn_finalize(sums, B * N * N, h, N, Wm, bm, P[pre + "var_norm.weight"], P[pre + "var_norm.bias"],
                                P[pre + "var_norm.running_mean"], P[pre + "var_norm.running_var"],
@@ -172,17 +173,17 @@ class Engine:
         # recompute the mixed map, then dV = A^T dO ; dA = dO V^T
         Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
         bm = P[pre + "reatten_matrix.bias"]
+        # dA = dO V^T first, then ONE pass over (P, dA) recomputes the mixed map A and the backward reductions
+        dA = torch.zeros((B, h, N, ld), dtype=torch.float32, device=dy.device) if ld != N else _empty((B, h, N, ld), dy)
+        ops.gemm(dO, v, dA, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
+                 sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
         A = _empty((B, h, N, ld), dy)
-        ops.reattn_mix(Pm, A, sv["fold"], B, h, N, ld, adrop, seed, sid)
+        red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
+        ops.reattn_mix_reduce(Pm, dA, A, sv["fold"], B, h, N, ld, adrop, seed, sid, red)
         dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
         ops.gemm(A, dO, dv, N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B,
                  batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
-        dA = A   # reuse the buffer: A is dead once dV is formed
-        ops.gemm(dO, v, dA, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
-                 sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
-        del dO
-        red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
-        ops.reattn_bwd_reduce(Pm, dA, B, h, N, ld, adrop, seed, sid, red)
+        del dO, A
         coef = _empty((2 * h,), dy)
         gamma = P[pre + "var_norm.weight"]
         ops.reattn_bwd_params(red, sv["sums"], B, h, N, Wm, bm, gamma, sv["bn"], train, coef,
@@ -265,7 +266,7 @@ class Engine:
         n, M = N * D, B * N
         prec = _PRECISION["value"]
         ln1, ln2 = self._ln_names(pre)
-        scratch = _empty((B, 2), dx2)
+        scratch = _empty((B, ops.LN_SCRATCH), dx2)
         dy2 = torch.empty_like(dx2)
         ops.ln_bwd(dx2, sv["y2"], sv["st2"], P[ln2 + "weight"], dy2, G[ln2 + "weight"], G[ln2 + "bias"], scratch, B, n)
         W1, W2 = P[pre + "FeedForward.net.0.weight"], P[pre + "FeedForward.net.3.weight"]

@@ -163,6 +163,16 @@ def softmax_rows(S, rows, N, ld, scale):
     call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream())
 
 
+def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums):
+    call("vu_softmax_stats", _chk(S, "S"), B, h, N, ld, scale, drop_p, seed, sid, _chk(sums, "sums", torch.float64),
+         _stream())
+
+
+def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red):
+    call("vu_reattn_mix_reduce", _chk(P, "P"), _chk(dA, "dA"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld,
+         drop_p, seed, sid, _chk(red, "red", torch.float64), _stream())
+
+
 def reattn_stats(P, B, h, N, ld, drop_p, seed, sid, sums):
     call("vu_reattn_stats", _chk(P, "P"), B, h, N, ld, drop_p, seed, sid, _chk(sums, "sums", torch.float64), _stream())
 
@@ -198,8 +208,13 @@ def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, sca
 
 
 # ----------------------------------------------------------------------------------------- layer norm
-def ln_stats(x, B, n, eps, stats):
-    call("vu_ln_stats", _chk(x, "x"), B, n, eps, _chk(stats, "stats"), _stream())
+LN_SCRATCH = 2 + 2 * _lib.LN_SPLIT      # floats of scratch per image for ln_stats / ln_bwd
+
+
+def ln_stats(x, B, n, eps, stats, scratch=None):
+    if scratch is None:
+        scratch = torch.empty(B * LN_SCRATCH, dtype=torch.float32, device=x.device)
+    call("vu_ln_stats", _chk(x, "x"), B, n, eps, _chk(stats, "stats"), _chk(scratch, "scratch"), _stream())
 
 
 def ln_apply(x, stats, w, b, out, B, n):
