@@ -41,6 +41,16 @@ def _peaks():
     return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+def _ncu_traffic(kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this round (profiles/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    return d.get(kernel_class)
+
+
 def _synthetic(B, gen_seed=0):
     """clean=rand, x=clamp(clean+0.1*randn,0,1) normalised like run_denoising.py:54."""
     g = torch.Generator().manual_seed(gen_seed)
@@ -235,13 +245,26 @@ def run_cuda(args):
     roof = {"bound": "tensor", "achieved": None, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": None,
             "traffic": None, "peak_source": peaks["src"]}
     if prof is not None:
-        k = prof.summary()
-        top = k["top"]
-        roof.update({"kernel": top["name"], "achieved": top["tflops"], "frac": top["tflops"] / peaks["tflops"],
+        k = prof.summary(peaks["tflops"], peaks["hbm"])
+        by = k["by_kernel"]
+        # the dominant kernel = the class with the largest device time inside the timed region; its bound is the
+        # roofline it sits closest to (algorithmic flops vs algorithmic HBM bytes of the op)
+        top_name = max(by, key=lambda n: by[n]["ms"])
+        top = by[top_name]
+        tensor_bound = top["tensor_frac"] >= top["hbm_frac"]
+        roof.update({"kernel": top_name, "bound": "tensor" if tensor_bound else "hbm",
+                     "achieved": top["tflops"] if tensor_bound else top["gbs"],
+                     "peak": peaks["tflops"] if tensor_bound else peaks["hbm"],
+                     "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                     "frac": top["tensor_frac"] if tensor_bound else top["hbm_frac"],
                      "kernel_ms_per_step": top["ms"] / args.steps, "kernel_share_of_step": top["ms"] / ms,
-                     "launches_timed": top["launches"], "by_kernel": k["by_kernel"]})
+                     "launches_timed": top["launches"], "all_kernels_ms_per_step": k["total_kernel_ms"] / args.steps,
+                     "by_kernel": by})
+        tr = _ncu_traffic(top_name)
+        if tr is not None:
+            roof["traffic"] = tr
     roof["step_tflops"] = value / world * FLOPS_PER_IMAGE_FWD_BWD / 1e12
-    roof["step_frac"] = roof["step_tflops"] / peaks["tflops"]
+    roof["step_tensor_frac"] = roof["step_tflops"] / peaks["tflops"]
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -274,7 +297,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
-    ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "tf32"), choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 tensor-core contractions (default, the performance mode); fp32: CUDA-core exact mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--min-warmup", type=int, default=3, help="lower only for profiler runs (numbers under ncu are never bench values)")
     ap.add_argument("--kernel-timing", type=int, default=1, help="CUDA-event timing of every GEMM launch (roofline)")

@@ -314,3 +314,30 @@ def test_inference_batch_slicing_is_exact():
         assert net._eval_chunk(7) == 3
         sliced = net(x.cuda())
     assert torch.equal(full, sliced)
+
+
+def test_fused_adamw_matches_torch_adamw():
+    """N1: three training steps with FusedAdamW (per-tensor path, then flat single-launch path) vs torch.optim.AdamW
+    driven by the SAME gradients (copied from the CUDA model), parameters compared after every step."""
+    import vit_unet_b200 as vu
+    _, kw, _ = CONFIGS["tiny_head"]
+    for flat in (False, True):
+        net = _quiet(vu.HViT_UNet, **kw)
+        net.load_state_dict(fill_state_dict(net.state_dict()))
+        net.to("cuda").train()
+        twin = {n: p.detach().clone().requires_grad_(True) for n, p in net.named_parameters()}
+        ref_opt = torch.optim.AdamW(list(twin.values()), lr=1e-3, weight_decay=0.05)
+        opt = vu.FusedAdamW(net.parameters(), lr=1e-3, weight_decay=0.05)
+        if flat:
+            opt.flatten(net)
+        x, y = make_input(2, 3, 32)
+        for step in range(3):
+            opt.zero_grad(set_to_none=True)
+            vu.mse_loss(net(x.cuda()), y.cuda()).backward()
+            for n, p in net.named_parameters():
+                twin[n].grad = p.grad.detach().clone()
+            if flat:
+                assert opt._flat_grads_alias()          # the single-launch path is the one exercised
+            opt.step(); ref_opt.step()
+            for n, p in net.named_parameters():
+                assert _rel(p, twin[n]) <= 2e-6, (flat, step, n, _rel(p, twin[n]))

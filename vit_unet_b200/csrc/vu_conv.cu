@@ -3,8 +3,6 @@
 //   * PatchEncoder conv (README variant) and the reconstruction conv: whole-image 'same' conv (model.py:428)
 // One thread per pixel, all C output channels of all fused convs in registers; the 9*C input taps come from
 // L1 (each input float is reused 9*C*nconv times), so HBM sees one read of x and one write per output.
-#include <initializer_list>
-
 #include "vu_common.cuh"
 
 namespace vu {
@@ -191,217 +189,6 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
-// =====================================================================================================
-// Quad variants: one thread owns 4 horizontally adjacent pixels (x0 % 4 == 0).  With every patch size a
-// multiple of 4 the quad is contiguous and 16 B aligned in every layout, so the centre taps are float4 loads,
-// outputs are float4 stores, and each loaded value feeds up to 12 FMAs per output channel instead of 3.
-// A 3 x 6 neighbourhood per channel is gathered once (zeros outside the border patch), then pure FMAs.
-struct QuadGeom {
-  ConvGeom g;
-  uint32_t quads_per_image, total_quads;
-};
-
-// neighbourhood of channel plane `plane` (pointer to channel-0 data of this image + c*cs) around (y, x0..x0+3):
-// nb[ky][0..5] = value at (y+ky-1, x0-1 .. x0+4), zero outside the border patch / image.
-__device__ __forceinline__ void load_nb(const float* __restrict__ img, const Layout& L, int64_t cs, int c, int y, int x0,
-                                        int iy, int ix0, int limy, int limx, float (&nb)[3][6]) {
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const bool rok = (unsigned)(iy + ky - 1) < (unsigned)limy;
-    if (rok) {
-      const int yy = y + ky - 1;
-      const float4 m = *reinterpret_cast<const float4*>(img + L.at(0, yy, x0) + c * cs);
-      nb[ky][1] = m.x; nb[ky][2] = m.y; nb[ky][3] = m.z; nb[ky][4] = m.w;
-      nb[ky][0] = ix0 > 0 ? __ldg(img + L.at(0, yy, x0 - 1) + c * cs) : 0.f;
-      nb[ky][5] = ix0 + 4 < limx ? __ldg(img + L.at(0, yy, x0 + 4) + c * cs) : 0.f;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 6; ++e) nb[ky][e] = 0.f;
-    }
-  }
-}
-
-__device__ __forceinline__ void quad_coords(const ConvGeom& g, const Layout& order, uint32_t qi, uint32_t qpi,
-                                            uint32_t& b, int& y, int& x0, int& iy, int& ix0, int& limy, int& limx) {
-  b = qi / qpi;
-  const uint32_t pix = (qi - b * qpi) * 4;
-  order.pixel(pix, y, x0);
-  tap_setup(g, y, x0, iy, ix0, limy, limx);
-}
-
-template <int C, int NCONV>
-__global__ void __launch_bounds__(256)
-conv3x3_fwd_quad_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                        float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2, QuadGeom qg) {
-  const ConvGeom& g = qg.g;
-  __shared__ float sw[NCONV * C * C * 9];
-  __shared__ float sb[NCONV * C];
-  for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < NCONV * C; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int64_t cs = g.lin.cstride(), ocs = g.lout.cstride();
-  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < qg.total_quads; qi += gridDim.x * blockDim.x) {
-    uint32_t b; int y, x0, iy, ix0, limy, limx;
-    quad_coords(g, g.lout, qi, qg.quads_per_image, b, y, x0, iy, ix0, limy, limx);
-    const float* xb = x + (int64_t)b * g.per_image;
-    float acc[NCONV][C][4];
-#pragma unroll
-    for (int k = 0; k < NCONV; ++k)
-#pragma unroll
-      for (int co = 0; co < C; ++co)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[k][co][e] = sb[k * C + co];
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci) {
-      float nb[3][6];
-      load_nb(xb, g.lin, cs, ci, y, x0, iy, ix0, limy, limx, nb);
-#pragma unroll
-      for (int k = 0; k < NCONV; ++k)
-#pragma unroll
-        for (int co = 0; co < C; ++co)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const float wv = sw[((k * C + co) * C + ci) * 9 + ky * 3 + kx];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[k][co][e] = fmaf(nb[ky][e + kx], wv, acc[k][co][e]);
-            }
-    }
-    const int64_t obase = (int64_t)b * g.per_image + g.lout.at(0, y, x0);
-#pragma unroll
-    for (int k = 0; k < NCONV; ++k) {
-      float* op = k == 0 ? o0 : (k == 1 ? o1 : o2);
-#pragma unroll
-      for (int co = 0; co < C; ++co)
-        *reinterpret_cast<float4*>(op + obase + co * ocs) = make_float4(acc[k][co][0], acc[k][co][1], acc[k][co][2], acc[k][co][3]);
-    }
-  }
-}
-
-// dx[ci](y, x0+e) = sum_k sum_co sum_{ky,kx} dy_k[co](y-ky+1, x0+e-kx+1) * w_k[co][ci][ky][kx]
-template <int C, int NCONV>
-__global__ void __launch_bounds__(256)
-conv3x3_bwd_data_quad_kernel(const float* __restrict__ d0, const float* __restrict__ d1, const float* __restrict__ d2,
-                             const float* __restrict__ w, float* __restrict__ dx, QuadGeom qg, int accumulate) {
-  const ConvGeom& g = qg.g;
-  __shared__ float sw[NCONV * C * C * 9];
-  for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int64_t cs = g.lin.cstride(), ocs = g.lout.cstride();
-  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < qg.total_quads; qi += gridDim.x * blockDim.x) {
-    uint32_t b; int y, x0, iy, ix0, limy, limx;
-    quad_coords(g, g.lout, qi, qg.quads_per_image, b, y, x0, iy, ix0, limy, limx);
-    float acc[C][4];
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[ci][e] = 0.f;
-#pragma unroll
-    for (int k = 0; k < NCONV; ++k) {
-      const float* db = (k == 0 ? d0 : (k == 1 ? d1 : d2)) + (int64_t)b * g.per_image;
-#pragma unroll
-      for (int co = 0; co < C; ++co) {
-        float nb[3][6];
-        load_nb(db, g.lin, cs, co, y, x0, iy, ix0, limy, limx, nb);
-        // source pixel (y - ky + 1, x - kx + 1): neighbourhood row index 2-ky, column e + 2 - kx
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const float wv = sw[((k * C + co) * C + ci) * 9 + ky * 3 + kx];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[ci][e] = fmaf(nb[2 - ky][e + 2 - kx], wv, acc[ci][e]);
-            }
-      }
-    }
-    const int64_t obase = (int64_t)b * g.per_image + g.lout.at(0, y, x0);
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci) {
-      float4* p = reinterpret_cast<float4*>(dx + obase + ci * ocs);
-      float4 o = make_float4(acc[ci][0], acc[ci][1], acc[ci][2], acc[ci][3]);
-      if (accumulate) { float4 c = *p; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-      *p = o;
-    }
-  }
-}
-
-// dw[k][co][ci][ky][kx] += sum dy_k[co](y, x) * x[ci](y+ky-1, x+kx-1); grid.y = conv k; quads in x's layout order.
-template <int C>
-__global__ void __launch_bounds__(256)
-conv3x3_bwd_weight_quad_kernel(const float* __restrict__ x, const float* __restrict__ d0, const float* __restrict__ d1,
-                               const float* __restrict__ d2, float* __restrict__ dw, float* __restrict__ dbias,
-                               QuadGeom qg) {
-  const ConvGeom& g = qg.g;
-  constexpr int NACC = C * (C * 9 + 1);
-  const int k = blockIdx.y;
-  const float* dy = k == 0 ? d0 : (k == 1 ? d1 : d2);
-  float acc[NACC];
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-  const int64_t cs = g.lin.cstride(), dcs = g.lout.cstride();
-  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < qg.total_quads; qi += gridDim.x * blockDim.x) {
-    uint32_t b; int y, x0, iy, ix0, limy, limx;
-    quad_coords(g, g.lin, qi, qg.quads_per_image, b, y, x0, iy, ix0, limy, limx);
-    const float* xb = x + (int64_t)b * g.per_image;
-    const float* db = dy + (int64_t)b * g.per_image + g.lout.at(0, y, x0);
-    float dv[C][4];
-#pragma unroll
-    for (int co = 0; co < C; ++co) {
-      const float4 t = *reinterpret_cast<const float4*>(db + co * dcs);
-      dv[co][0] = t.x; dv[co][1] = t.y; dv[co][2] = t.z; dv[co][3] = t.w;
-      acc[co * (C * 9 + 1) + C * 9] += (t.x + t.y) + (t.z + t.w);
-    }
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci) {
-      float nb[3][6];
-      load_nb(xb, g.lin, cs, ci, y, x0, iy, ix0, limy, limx, nb);
-#pragma unroll
-      for (int co = 0; co < C; ++co)
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            float a = acc[co * (C * 9 + 1) + ci * 9 + ky * 3 + kx];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) a = fmaf(dv[co][e], nb[ky][e + kx], a);
-            acc[co * (C * 9 + 1) + ci * 9 + ky * 3 + kx] = a;
-          }
-    }
-  }
-  __shared__ float red[NACC][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) {
-    float v = warp_sum(acc[i]);
-    if (lane == 0) red[i][warp] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < NACC) {
-    float sres = 0.f;
-    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) sres += red[threadIdx.x][wv];
-    const int co = threadIdx.x / (C * 9 + 1), e = threadIdx.x % (C * 9 + 1);
-    if (e < C * 9) atomicAdd(dw + ((int64_t)(k * C + co) * C) * 9 + e, sres);
-    else if (dbias) atomicAdd(dbias + k * C + co, sres);
-  }
-}
-
-static bool quad_ok(const ConvGeom& g, int W, std::initializer_list<const void*> ptrs) {
-  auto ok = [&](int p) { return p == 0 ? (W % 4 == 0) : (p % 4 == 0); };
-  if (!(ok(g.lin.p) && ok(g.lout.p) && ok(g.bp))) return false;
-  if (g.lin.C > 3) return false;
-  for (const void* p : ptrs) if (p && ((uintptr_t)p % 16 != 0)) return false;
-  return true;
-}
-static QuadGeom make_quad(const ConvGeom& g) {
-  QuadGeom q; q.g = g;
-  q.quads_per_image = (uint32_t)(g.lin.H * g.lin.W / 4);
-  q.total_quads = (uint32_t)(g.npix_total / 4);
-  return q;
-}
-
 static int make_geom(const char* fn, ConvGeom& g, int p_in, int p_out, int border_p, int B, int C, int H, int W) {
   VU_REQUIRE(B > 0 && H > 0 && W > 0, fn, "empty shape");
   VU_REQUIRE((int64_t)B * H * W < (int64_t)1 << 31, fn, "B*H*W must be below 2^31 pixels per call");
@@ -435,22 +222,6 @@ extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const flo
   int threads = 256;
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
-  if (quad_ok(g, W, {x, out0, out1, out2})) {
-    QuadGeom qg = make_quad(g);
-    int qb = (int)std::min<int64_t>(cdiv(qg.total_quads, threads), (int64_t)sm_count() * 16);
-    switch (C) {
-      case 1: if (nconv == 1) conv3x3_fwd_quad_kernel<1, 1><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg);
-              else if (nconv == 2) conv3x3_fwd_quad_kernel<1, 2><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg);
-              else conv3x3_fwd_quad_kernel<1, 3><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg); break;
-      case 2: if (nconv == 1) conv3x3_fwd_quad_kernel<2, 1><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg);
-              else if (nconv == 2) conv3x3_fwd_quad_kernel<2, 2><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg);
-              else conv3x3_fwd_quad_kernel<2, 3><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg); break;
-      default: if (nconv == 1) conv3x3_fwd_quad_kernel<3, 1><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg);
-              else if (nconv == 2) conv3x3_fwd_quad_kernel<3, 2><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg);
-              else conv3x3_fwd_quad_kernel<3, 3><<<qb, threads, 0, s>>>(x, w, bias, out0, out1, out2, qg); break;
-    }
-    return check_launch(fn);
-  }
   VU_DISPATCH_C(C,
     if (nconv == 1) conv3x3_fwd_kernel<CC, 1><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
     else if (nconv == 2) conv3x3_fwd_kernel<CC, 2><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
@@ -469,22 +240,6 @@ extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const flo
   int threads = 256;
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
-  if (quad_ok(g, W, {dy0, dy1, dy2, dx})) {
-    QuadGeom qg = make_quad(g);
-    int qb = (int)std::min<int64_t>(cdiv(qg.total_quads, threads), (int64_t)sm_count() * 16);
-    switch (C) {
-      case 1: if (nconv == 1) conv3x3_bwd_data_quad_kernel<1, 1><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate);
-              else if (nconv == 2) conv3x3_bwd_data_quad_kernel<1, 2><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate);
-              else conv3x3_bwd_data_quad_kernel<1, 3><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate); break;
-      case 2: if (nconv == 1) conv3x3_bwd_data_quad_kernel<2, 1><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate);
-              else if (nconv == 2) conv3x3_bwd_data_quad_kernel<2, 2><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate);
-              else conv3x3_bwd_data_quad_kernel<2, 3><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate); break;
-      default: if (nconv == 1) conv3x3_bwd_data_quad_kernel<3, 1><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate);
-              else if (nconv == 2) conv3x3_bwd_data_quad_kernel<3, 2><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate);
-              else conv3x3_bwd_data_quad_kernel<3, 3><<<qb, threads, 0, s>>>(dy0, dy1, dy2, w, dx, qg, accumulate); break;
-    }
-    return check_launch(fn);
-  }
   VU_DISPATCH_C(C,
     if (nconv == 1) conv3x3_bwd_data_kernel<CC, 1><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);
     else if (nconv == 2) conv3x3_bwd_data_kernel<CC, 2><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);
@@ -504,15 +259,6 @@ extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, 
   int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 4), (int64_t)sm_count() * 4);
   if (bx < 1) bx = 1;
   cudaStream_t s = as_stream(stream);
-  if (quad_ok(g, W, {x, dy0, dy1, dy2})) {
-    QuadGeom qg = make_quad(g);
-    int qb = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(qg.total_quads, threads * 2), (int64_t)sm_count() * 4));
-    dim3 grid(qb, nconv);
-    if (C == 1) conv3x3_bwd_weight_quad_kernel<1><<<grid, threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, qg);
-    else if (C == 2) conv3x3_bwd_weight_quad_kernel<2><<<grid, threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, qg);
-    else conv3x3_bwd_weight_quad_kernel<3><<<grid, threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, qg);
-    return check_launch(fn);
-  }
   VU_DISPATCH_C(C,
     if (CC <= 3) conv3x3_bwd_weight_kernel<CC, (CC <= 3)><<<dim3(bx, nconv), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g);
     else conv3x3_bwd_weight_kernel<CC, false><<<dim3(bx, nconv * C), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g));

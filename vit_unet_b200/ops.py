@@ -40,79 +40,29 @@ def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
-# ----------------------------------------------------------------------------------------- layout
-def repatch(x, out, B, Cc, H, W, p_in, p_out):
-    call("vu_repatch", _chk(x, "in"), _chk(out, "out"), B, Cc, H, W, p_in, p_out, _stream())
-    return out
-
-
-def pe_fwd(x, p_in, table, p_table, out, p_out, B, Cc, H, W):
-    call("vu_pe_fwd", _chk(x, "in"), p_in, _chk(table, "table"), p_table, _chk(out, "out"), p_out,
-         B, Cc, H, W, _stream())
-    return out
-
-
-def pe_bwd_table(dout, p_out, dtable, p_table, B, Cc, H, W, accumulate=False):
-    call("vu_pe_bwd_table", _chk(dout, "dout"), p_out, _chk(dtable, "dtable"), p_table, B, Cc, H, W,
-         int(accumulate), _stream())
-    return dtable
-
-
-# ----------------------------------------------------------------------------------------- convs
-def conv3x3_fwd(x, p_x, w, bias, outs, p_out, border_p, B, Cc, H, W):
-    n = len(outs)
-    ptrs = [_chk(o, f"out{i}") for i, o in enumerate(outs)] + [None] * (3 - n)
-    call("vu_conv3x3_fwd", _chk(x, "x"), p_x, _chk(w, "w"), _opt(bias, "bias"), n, ptrs[0], ptrs[1], ptrs[2],
-         p_out, border_p, B, Cc, H, W, _stream())
-    return outs
-
-
-def conv3x3_bwd_data(dys, p_dy, w, dx, p_dx, border_p, B, Cc, H, W, accumulate=False):
-    n = len(dys)
-    ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
-    call("vu_conv3x3_bwd_data", ptrs[0], ptrs[1], ptrs[2], p_dy, _chk(w, "w"), n, _chk(dx, "dx"), p_dx,
-         border_p, B, Cc, H, W, int(accumulate), _stream())
-    return dx
-
-
-def conv3x3_bwd_weight(x, p_x, dys, p_dy, dw, dbias, border_p, B, Cc, H, W):
-    n = len(dys)
-    ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
-    call("vu_conv3x3_bwd_weight", _chk(x, "x"), p_x, ptrs[0], ptrs[1], ptrs[2], p_dy, n, _chk(dw, "dw"),
-         _opt(dbias, "dbias"), border_p, B, Cc, H, W, _stream())
-
-
 # ----------------------------------------------------------------------------------------- kernel timing
 class KernelTimer:
-    """CUDA-event timing of individual launches on the launching stream (bench.py roofline)."""
+    """CUDA-event timing of every launch on the launching stream, with the ALGORITHMIC flops / HBM bytes of the op
+    (what the math needs, not what the kernel happens to move) -> live roofline table in bench.py."""
 
     def __init__(self):
-        self.records = []          # (name, flops, start_event, end_event)
+        self.records = []          # (class name, flops, bytes, start_event, end_event)
 
-    def time(self, name, flops):
-        timer = self
-
-        class _Ctx:
-            def __enter__(self_inner):
-                self_inner.e0 = torch.cuda.Event(enable_timing=True)
-                self_inner.e1 = torch.cuda.Event(enable_timing=True)
-                self_inner.e0.record()
-
-            def __exit__(self_inner, *a):
-                self_inner.e1.record()
-                timer.records.append((name, flops, self_inner.e0, self_inner.e1))
-        return _Ctx()
-
-    def summary(self):
+    def summary(self, peak_tflops, peak_gbs):
         torch.cuda.synchronize()
         agg = {}
-        for name, flops, e0, e1 in self.records:
-            a = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
-            a["ms"] += e0.elapsed_time(e1); a["flops"] += flops; a["launches"] += 1
-        by = {k: {"ms": v["ms"], "launches": v["launches"],
-                  "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0} for k, v in agg.items()}
-        top_name = max(by, key=lambda k: by[k]["ms"])
-        return {"by_kernel": by, "top": dict(by[top_name], name=top_name)}
+        for name, flops, nbytes, e0, e1 in self.records:
+            a = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            a["ms"] += e0.elapsed_time(e1); a["flops"] += flops; a["bytes"] += nbytes; a["launches"] += 1
+        total = sum(a["ms"] for a in agg.values()) or 1.0
+        by = {}
+        for k, v in agg.items():
+            sec = max(v["ms"], 1e-9) * 1e-3
+            tf, gbs = v["flops"] / sec / 1e12, v["bytes"] / sec / 1e9
+            by[k] = {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 4), "launches": v["launches"],
+                     "tflops": round(tf, 2), "gbs": round(gbs, 1), "tensor_frac": round(tf / peak_tflops, 4),
+                     "hbm_frac": round(gbs / peak_gbs, 4)}
+        return {"by_kernel": by, "total_kernel_ms": total}
 
 
 _TIMER = {"t": None}
@@ -120,6 +70,62 @@ _TIMER = {"t": None}
 
 def set_kernel_timer(t):
     _TIMER["t"] = t
+
+
+def _call(name, *args, flops=0.0, nbytes=0.0, cls=None):
+    t = _TIMER["t"]
+    if t is None:
+        call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    t.records.append((cls or name, float(flops), float(nbytes), e0, e1))
+
+
+# ----------------------------------------------------------------------------------------- layout
+def repatch(x, out, B, Cc, H, W, p_in, p_out):
+    _call("vu_repatch", _chk(x, "in"), _chk(out, "out"), B, Cc, H, W, p_in, p_out, _stream(), nbytes=2 * 4.0 * B * Cc * H * W)
+    return out
+
+
+def pe_fwd(x, p_in, table, p_table, out, p_out, B, Cc, H, W):
+    _call("vu_pe_fwd", _chk(x, "in"), p_in, _chk(table, "table"), p_table, _chk(out, "out"), p_out,
+          B, Cc, H, W, _stream(), nbytes=2 * 4.0 * B * Cc * H * W)
+    return out
+
+
+def pe_bwd_table(dout, p_out, dtable, p_table, B, Cc, H, W, accumulate=False):
+    _call("vu_pe_bwd_table", _chk(dout, "dout"), p_out, _chk(dtable, "dtable"), p_table, B, Cc, H, W,
+          int(accumulate), _stream(), nbytes=4.0 * B * Cc * H * W)
+    return dtable
+
+
+# ----------------------------------------------------------------------------------------- convs
+def conv3x3_fwd(x, p_x, w, bias, outs, p_out, border_p, B, Cc, H, W):
+    n = len(outs)
+    ptrs = [_chk(o, f"out{i}") for i, o in enumerate(outs)] + [None] * (3 - n)
+    _call("vu_conv3x3_fwd", _chk(x, "x"), p_x, _chk(w, "w"), _opt(bias, "bias"), n, ptrs[0], ptrs[1], ptrs[2],
+          p_out, border_p, B, Cc, H, W, _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W, flops=18.0 * n * Cc * Cc * B * H * W)
+    return outs
+
+
+def conv3x3_bwd_data(dys, p_dy, w, dx, p_dx, border_p, B, Cc, H, W, accumulate=False):
+    n = len(dys)
+    ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
+    _call("vu_conv3x3_bwd_data", ptrs[0], ptrs[1], ptrs[2], p_dy, _chk(w, "w"), n, _chk(dx, "dx"), p_dx,
+          border_p, B, Cc, H, W, int(accumulate), _stream(), nbytes=(1 + n + int(accumulate)) * 4.0 * B * Cc * H * W,
+          flops=18.0 * n * Cc * Cc * B * H * W)
+    return dx
+
+
+def conv3x3_bwd_weight(x, p_x, dys, p_dy, dw, dbias, border_p, B, Cc, H, W):
+    n = len(dys)
+    ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
+    _call("vu_conv3x3_bwd_weight", _chk(x, "x"), p_x, ptrs[0], ptrs[1], ptrs[2], p_dy, n, _chk(dw, "dw"),
+          _opt(dbias, "dbias"), border_p, B, Cc, H, W, _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W,
+          flops=18.0 * n * Cc * Cc * B * H * W)
 
 
 # ----------------------------------------------------------------------------------------- GEMM
@@ -143,38 +149,42 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
     d.alpha, d.act, d.accumulate, d.split_k = alpha, act, int(accumulate), split_k
     d.drop_p, d.drop_seed, d.drop_stream = drop_p, drop_seed, drop_stream
     d.precision = precision
-    t = _TIMER["t"]
-    if t is not None:
-        kind = "gemm_tcgen05_tf32" if precision == PREC_TF32 else "gemm_simt_fp32"
-        with t.time(kind, 2.0 * M * N * K * batch_outer * batch_inner):
-            call("vu_gemm", C.byref(d), _stream())
+    nb = batch_outer * batch_inner
+    kind = "gemm_tcgen05_tf32" if precision == PREC_TF32 else "gemm_simt_fp32"
+    # classes: contractions over the head dim that WRITE an NxN map / contractions that READ a map / token GEMMs
+    if nb > 1:
+        cls = kind + (":map_out(QK^T,dA)" if N == M and K < N else ":map_in(PV,dV,dQ,dK)")
     else:
-        call("vu_gemm", C.byref(d), _stream())
+        cls = kind + ":tokens(proj,FF,dgrad,wgrad)"
+    extra = (residual is not None) + int(accumulate) + (aux_in is not None) + (aux_out is not None)
+    _call("vu_gemm", C.byref(d), _stream(), flops=2.0 * M * N * K * nb,
+          nbytes=4.0 * nb * (M * K + K * N + M * N * (1 + extra)), cls=cls)
     return Cm
 
 
 def colsum(X, M, N, ld, out, accumulate=False):
-    call("vu_colsum", _chk(X, "X"), M, N, ld, _chk(out, "out"), int(accumulate), _stream())
+    _call("vu_colsum", _chk(X, "X"), M, N, ld, _chk(out, "out"), int(accumulate), _stream(), nbytes=4.0 * M * N)
     return out
 
 
 # ----------------------------------------------------------------------------------------- re-attention
 def softmax_rows(S, rows, N, ld, scale):
-    call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream())
+    _call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream(), nbytes=8.0 * rows * N)
 
 
 def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums):
-    call("vu_softmax_stats", _chk(S, "S"), B, h, N, ld, scale, drop_p, seed, sid, _chk(sums, "sums", torch.float64),
-         _stream())
+    _call("vu_softmax_stats", _chk(S, "S"), B, h, N, ld, scale, drop_p, seed, sid, _chk(sums, "sums", torch.float64),
+          _stream(), nbytes=2 * 4.0 * B * h * N * N)
 
 
 def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red):
-    call("vu_reattn_mix_reduce", _chk(P, "P"), _chk(dA, "dA"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld,
-         drop_p, seed, sid, _chk(red, "red", torch.float64), _stream())
+    _call("vu_reattn_mix_reduce", _chk(P, "P"), _chk(dA, "dA"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld,
+          drop_p, seed, sid, _chk(red, "red", torch.float64), _stream(), nbytes=3 * 4.0 * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
 def reattn_stats(P, B, h, N, ld, drop_p, seed, sid, sums):
-    call("vu_reattn_stats", _chk(P, "P"), B, h, N, ld, drop_p, seed, sid, _chk(sums, "sums", torch.float64), _stream())
+    _call("vu_reattn_stats", _chk(P, "P"), B, h, N, ld, drop_p, seed, sid, _chk(sums, "sums", torch.float64), _stream(),
+          nbytes=4.0 * B * h * N * N)
 
 
 def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nbt, eps, momentum, train,
@@ -186,12 +196,13 @@ def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nb
 
 
 def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid):
-    call("vu_reattn_mix", _chk(P, "P"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream())
+    _call("vu_reattn_mix", _chk(P, "P"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream(),
+          nbytes=2 * 4.0 * B * h * N * N, flops=2.0 * h * B * h * N * N)
 
 
 def reattn_bwd_reduce(P, dA, B, h, N, ld, drop_p, seed, sid, red):
-    call("vu_reattn_bwd_reduce", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, drop_p, seed, sid,
-         _chk(red, "red", torch.float64), _stream())
+    _call("vu_reattn_bwd_reduce", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, drop_p, seed, sid,
+          _chk(red, "red", torch.float64), _stream(), nbytes=2 * 4.0 * B * h * N * N)
 
 
 def reattn_bwd_params(red, sums, B, h, N, W, bconv, gamma, saved, train, coef, dW, dbconv, dgamma, dbeta):
@@ -202,9 +213,9 @@ def reattn_bwd_params(red, sums, B, h, N, W, bconv, gamma, saved, train, coef, d
 
 
 def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid):
-    call("vu_reattn_bwd_rows", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
-         _chk(gamma, "gamma"), _chk(saved, "saved"), _chk(coef, "coef"), int(train), scale, drop_p, seed, sid,
-         _stream())
+    _call("vu_reattn_bwd_rows", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
+          _chk(gamma, "gamma"), _chk(saved, "saved"), _chk(coef, "coef"), int(train), scale, drop_p, seed, sid,
+          _stream(), nbytes=3 * 4.0 * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
 # ----------------------------------------------------------------------------------------- layer norm
@@ -214,37 +225,39 @@ LN_SCRATCH = 2 + 2 * _lib.LN_SPLIT      # floats of scratch per image for ln_sta
 def ln_stats(x, B, n, eps, stats, scratch=None):
     if scratch is None:
         scratch = torch.empty(B * LN_SCRATCH, dtype=torch.float32, device=x.device)
-    call("vu_ln_stats", _chk(x, "x"), B, n, eps, _chk(stats, "stats"), _chk(scratch, "scratch"), _stream())
+    _call("vu_ln_stats", _chk(x, "x"), B, n, eps, _chk(stats, "stats"), _chk(scratch, "scratch"), _stream(),
+          nbytes=4.0 * B * n)
 
 
 def ln_apply(x, stats, w, b, out, B, n):
-    call("vu_ln_apply", _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(b, "b"), _chk(out, "out"), B, n,
-         _stream())
+    _call("vu_ln_apply", _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(b, "b"), _chk(out, "out"), B, n,
+          _stream(), nbytes=8.0 * B * n + 8.0 * n)
 
 
 def ln_bwd(g, x, stats, w, dx, dw, db, scratch, B, n):
-    call("vu_ln_bwd", _chk(g, "g"), _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(dx, "dx"),
-         _chk(dw, "dw"), _chk(db, "db"), _chk(scratch, "scratch"), B, n, _stream())
+    _call("vu_ln_bwd", _chk(g, "g"), _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(dx, "dx"),
+          _chk(dw, "dw"), _chk(db, "db"), _chk(scratch, "scratch"), B, n, _stream(), nbytes=12.0 * B * n + 12.0 * n)
 
 
 # ----------------------------------------------------------------------------------------- losses / misc
 def loss_fwd(kind, pred, target, sums, loss):
-    call("vu_loss_fwd", LOSS_KINDS[kind], _chk(pred, "pred"), _chk(target, "target"), pred.numel(),
-         _chk(sums, "sums", torch.float64), _chk(loss, "loss"), _stream())
+    _call("vu_loss_fwd", LOSS_KINDS[kind], _chk(pred, "pred"), _chk(target, "target"), pred.numel(),
+          _chk(sums, "sums", torch.float64), _chk(loss, "loss"), _stream(), nbytes=8.0 * pred.numel())
 
 
 def loss_bwd(kind, pred, target, sums, gscale, dpred):
-    call("vu_loss_bwd", LOSS_KINDS[kind], _chk(pred, "pred"), _chk(target, "target"), pred.numel(),
-         _chk(sums, "sums", torch.float64), _chk(gscale, "gscale"), _chk(dpred, "dpred"), _stream())
+    _call("vu_loss_bwd", LOSS_KINDS[kind], _chk(pred, "pred"), _chk(target, "target"), pred.numel(),
+          _chk(sums, "sums", torch.float64), _chk(gscale, "gscale"), _chk(dpred, "dpred"), _stream(),
+          nbytes=12.0 * pred.numel())
 
 
 def dropout(x, out, p, seed, sid):
-    call("vu_dropout", _chk(x, "in"), _chk(out, "out"), x.numel(), p, seed, sid, _stream())
+    _call("vu_dropout", _chk(x, "in"), _chk(out, "out"), x.numel(), p, seed, sid, _stream(), nbytes=8.0 * x.numel())
     return out
 
 
 def axpby(x, y, a, b):
-    call("vu_axpby", _chk(x, "x"), _chk(y, "y"), x.numel(), a, b, _stream())
+    _call("vu_axpby", _chk(x, "x"), _chk(y, "y"), x.numel(), a, b, _stream(), nbytes=12.0 * x.numel())
     return y
 
 
