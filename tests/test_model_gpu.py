@@ -248,7 +248,7 @@ def test_dropout_gradients_match_finite_differences():
     CUDA forward itself (same seed => same masks)."""
     import vit_unet_b200 as vu
     kw = dict(depth=1, depth_te=1, size_bottleneck=1, preprocessing="conv", im_size=16, patch_size=8,
-              num_channels=3, hidden_dim=16, num_heads=2, attn_drop=0.25, proj_drop=0.25, linear_drop=0)
+              num_channels=3, hidden_dim=16, num_heads=2, attn_drop=0.25, proj_drop=0.25, linear_drop=0.25)
     net = _quiet(vu.HViT_UNet, **kw)
     net.load_state_dict(fill_state_dict(net.state_dict()))
     net.to("cuda").train()
@@ -261,7 +261,8 @@ def test_dropout_gradients_match_finite_differences():
     net.zero_grad(); loss().backward()
     p = dict(net.named_parameters())["Encoders.0.FeedForward.net.3.bias"]
     q = dict(net.named_parameters())["Encoders.0.ReAttn.proj.bias"]
-    for prm, idx in ((p, 5), (q, 17)):
+    r = dict(net.named_parameters())["Encoders.0.FeedForward.net.0.bias"]
+    for prm, idx in ((p, 5), (q, 17), (r, 3)):
         g = prm.grad.view(-1)[idx].item()
         with torch.no_grad():
             eps = 1e-2

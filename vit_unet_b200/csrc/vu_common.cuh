@@ -24,12 +24,19 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // reference: patch()/unflatten()/unpatch(), model.py:8-35.
 struct Layout {
   int C, H, W, p, gw, pp;   // gw = W/p, pp = p*p
+  int ps;                   // log2(p) when p is a power of two (shift/mask index math), else -1
   __host__ __device__ Layout() {}
   __host__ __device__ Layout(int C_, int H_, int W_, int p_) : C(C_), H(H_), W(W_), p(p_) {
     gw = p ? W / p : 1; pp = p * p;
+    ps = -1;
+    if (p > 0 && (p & (p - 1)) == 0) { ps = 0; while ((1 << ps) < p) ++ps; }
   }
   __device__ __forceinline__ int64_t at(int c, int y, int x) const {
     if (p == 0) return ((int64_t)c * H + y) * W + x;
+    if (ps >= 0) {
+      const int r = y >> ps, q = x >> ps, i = y & (p - 1), j = x & (p - 1);
+      return (((int64_t)(r * gw + q) * C + c) << (2 * ps)) + (i << ps) + j;
+    }
     int r = y / p, q = x / p;
     int i = y - r * p, j = x - q * p;
     return ((int64_t)(r * gw + q) * C + c) * pp + i * p + j;
@@ -38,14 +45,21 @@ struct Layout {
   // pix enumerates (token, i, j) for p>0 and (y, x) for p==0.  (pix < H*W always fits 32 bits.)
   __device__ __forceinline__ void pixel(uint32_t pix, int& y, int& x) const {
     if (p == 0) { y = (int)(pix / (uint32_t)W); x = (int)(pix - (uint32_t)y * W); return; }
-    int n = (int)(pix / (uint32_t)pp); int rem = (int)(pix - (uint32_t)n * pp);
-    int i = rem / p, j = rem - i * p;
+    int n, i, j;
+    if (ps >= 0) {
+      n = (int)(pix >> (2 * ps)); const int rem = (int)(pix & (uint32_t)(pp - 1));
+      i = rem >> ps; j = rem & (p - 1);
+    } else {
+      n = (int)(pix / (uint32_t)pp); const int rem = (int)(pix - (uint32_t)n * pp);
+      i = rem / p; j = rem - i * p;
+    }
     int r = n / gw, q = n - r * gw;
     y = r * p + i; x = q * p + j;
   }
   // offset of channel-0 value for linear pixel index pix, and stride between channels
   __device__ __forceinline__ int64_t base_of(uint32_t pix) const {
     if (p == 0) return pix;
+    if (ps >= 0) { const uint32_t n = pix >> (2 * ps); return ((int64_t)n * C << (2 * ps)) + (pix & (uint32_t)(pp - 1)); }
     uint32_t n = pix / (uint32_t)pp; uint32_t rem = pix - n * pp;
     return (int64_t)n * C * pp + rem;
   }

@@ -15,7 +15,11 @@ struct ConvGeom {
 };
 
 __device__ __forceinline__ void tap_setup(const ConvGeom& g, int y, int x, int& iy, int& ix, int& limy, int& limx) {
-  if (g.bp) { iy = y % g.bp; ix = x % g.bp; limy = g.bp; limx = g.bp; }
+  if (g.bp) {
+    if ((g.bp & (g.bp - 1)) == 0) { iy = y & (g.bp - 1); ix = x & (g.bp - 1); }
+    else { iy = y % g.bp; ix = x % g.bp; }
+    limy = g.bp; limx = g.bp;
+  }
   else { iy = y; ix = x; limy = g.lin.H; limx = g.lin.W; }
 }
 

@@ -244,20 +244,22 @@ class Engine:
         ops.ln_stats(y1, B, n, 1e-5, st1)
         x1 = _empty((B, N, D), x)
         ops.ln_apply(y1, st1, P[ln1 + "weight"], P[ln1 + "bias"], x1, B, n)
-        if train and g.linear_drop > 0:
-            raise NotImplementedError("linear_drop > 0 is not implemented on the CUDA path (all presets use 0)")
+        ldrop = g.linear_drop if train else 0.0        # Dropout after GELU and after the second Linear (model.py:105,107)
         pre_act, act = _empty((M, Hd), x), _empty((M, Hd), x)
         self._gemm_tokens(x1, P[pre + "FeedForward.net.0.weight"], act, M, Hd, D,
-                          bias=P[pre + "FeedForward.net.0.bias"], act=ops.ACT_GELU, aux_out=pre_act, ldaux=Hd)
+                          bias=P[pre + "FeedForward.net.0.bias"], act=ops.ACT_GELU, aux_out=pre_act, ldaux=Hd,
+                          drop_p=ldrop, drop_seed=seed, drop_stream=sid + 2)
         y2 = _empty((B, N, D), x)
         self._gemm_tokens(act, P[pre + "FeedForward.net.3.weight"], y2, M, D, Hd,
-                          bias=P[pre + "FeedForward.net.3.bias"], residual=x1)
+                          bias=P[pre + "FeedForward.net.3.bias"], residual=x1,
+                          drop_p=ldrop, drop_seed=seed, drop_stream=sid + 3)
         st2 = _empty((B, 2), x)
         ops.ln_stats(y2, B, n, 1e-5, st2)
         x2 = _empty((B, N, D), x)
         ops.ln_apply(y2, st2, P[ln2 + "weight"], P[ln2 + "bias"], x2, B, n)
         if saved is not None:
-            saved.update(attn=sv_attn, y1=y1, st1=st1, x1=x1, pre_act=pre_act, act=act, y2=y2, st2=st2)
+            saved.update(attn=sv_attn, y1=y1, st1=st1, x1=x1, pre_act=pre_act, act=act, y2=y2, st2=st2, ldrop=ldrop,
+                         seed=seed, sid=sid)
         return x2
 
     def _block_bwd(self, P, G, pre, dx2, l, B, sv):
@@ -270,12 +272,15 @@ class Engine:
         dy2 = torch.empty_like(dx2)
         ops.ln_bwd(dx2, sv["y2"], sv["st2"], P[ln2 + "weight"], dy2, G[ln2 + "weight"], G[ln2 + "bias"], scratch, B, n)
         W1, W2 = P[pre + "FeedForward.net.0.weight"], P[pre + "FeedForward.net.3.weight"]
-        # FF2: dpre = (dy2 @ W2) * gelu'(pre) ; dW2 = dy2^T act ; db2 = colsum(dy2)
+        # FF2: dpre = drop(dy2d @ W2) * gelu'(pre) ; dW2 = dy2d^T act ; db2 = colsum(dy2d), dy2d = drop-mask(dy2)
+        ldrop, seed, sid = sv["ldrop"], sv["seed"], sv["sid"]
+        dy2d = ops.dropout(dy2, torch.empty_like(dy2), ldrop, seed, sid + 3) if ldrop > 0 else dy2
         dpre = _empty((M, Hd), dx2)
-        ops.gemm(dy2, W2, dpre, M, Hd, D, trans_b=False, lda=D, ldb=Hd, ldc=Hd, act=ops.ACT_GELU_BWD,
-                 aux_in=sv["pre_act"], ldaux=Hd, precision=prec)
-        self._wgrad(dy2, sv["act"], G[pre + "FeedForward.net.3.weight"], M, D, Hd)
-        ops.colsum(dy2, M, D, D, G[pre + "FeedForward.net.3.bias"], accumulate=True)
+        ops.gemm(dy2d, W2, dpre, M, Hd, D, trans_b=False, lda=D, ldb=Hd, ldc=Hd, act=ops.ACT_GELU_BWD,
+                 aux_in=sv["pre_act"], ldaux=Hd, drop_p=ldrop, drop_seed=seed, drop_stream=sid + 2, precision=prec)
+        self._wgrad(dy2d, sv["act"], G[pre + "FeedForward.net.3.weight"], M, D, Hd)
+        ops.colsum(dy2d, M, D, D, G[pre + "FeedForward.net.3.bias"], accumulate=True)
+        del dy2d
         # FF1: dx1 = dpre @ W1 + dy2 ; dW1 = dpre^T x1 ; db1 = colsum(dpre)
         dx1 = torch.empty_like(dx2)
         ops.gemm(dpre, W1, dx1, M, D, Hd, trans_b=False, lda=Hd, ldb=D, ldc=D, residual=dy2, precision=prec)
@@ -311,7 +316,7 @@ class Engine:
             if kind == "block":
                 _, pre, l = st
                 x = self._block_fwd(P, pre, x, l, B, train, seed, sid, sv)
-                sid += 2
+                sid += 4
             elif kind == "down":
                 l = st[1]
                 skips[l] = x
