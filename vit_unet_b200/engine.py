@@ -10,6 +10,7 @@ level, so "downsampling"/"upsampling" are permutations (vu_repatc
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -18,6 +19,14 @@ import torch
 from . import ops
 
 _PRECISION = {"value": ops.PREC_FP32}
+_CHUNK_STREAM = 4096          # Philox stream offset per image slice (layer stream ids stay far below this)
+# bytes of attention maps a slice may keep live between consecutive launches (two maps: S/P and A, or P-slice and
+# dA/dS); sized against the 126 MB L2 of B200.  0 disables slicing.
+_MAP_L2_BYTES = {"value": int(float(os.environ.get("VU_MAP_L2_MB", "80")) * (1 << 20))}
+
+
+def set_map_l2_budget(megabytes: float) -> None:
+    _MAP_L2_BYTES["value"] = int(megabytes * (1 << 20))
 
 
 def set_precision(mode: str) -> None:
@@ -103,6 +112,14 @@ class Engine:
         """out[M,N] = A[M,K] @ W[N,K]^T (+epilogue): the nn.Linear shape."""
         return ops.gemm(A, W, out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, precision=_PRECISION["value"], **kw)
 
+    @staticmethod
+    def _map_chunk(B, h, N, ld):
+        """Images per slice so that two (c,h,N,ld) fp32 maps fit the L2 budget."""
+        budget = _MAP_L2_BYTES["value"]
+        if budget <= 0:
+            return B
+        return max(1, min(B, budget // (2 * h * N * ld * 4)))
+
     # ------------------------------------------------------------------------------------------- attention
     def _attn_fwd(self, P, pre, xq, xkv, l, B, train, seed, sid, residual, saved):
         g = self.g
@@ -118,36 +135,64 @@ class Engine:
             ops.conv3x3_fwd(xq, p, wq.contiguous(), None, [q], p, p, B, g.C, g.S, g.S)
             wcat = torch.cat([wk.reshape(-1), wv.reshape(-1)])
             ops.conv3x3_fwd(xkv, p, wcat, None, [k, v], p, p, B, g.C, g.S, g.S)
-        Pm = _empty((B, h, N, ld), xq)
-        ops.gemm(q, k, Pm, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
-                 sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
+        # The (B,h,N,N) maps are processed in slices of `c` images sized so that the maps a kernel chain hands from
+        # one launch to the next (S -> P -> A, ~2 live maps) stay resident in the 126 MB L2: HBM then sees P once on
+        # the way out (it is saved for backward) and once on the way back in, instead of ~6 full passes.
         scale = float(hd) ** -0.5
         Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
         bm = P[pre + "reatten_matrix.bias"]
         adrop = g.attn_drop if train else 0.0
-        sums = None
-        if train:     # softmax + centred moments of the dropped maps in one pass
-            sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device)
-            ops.softmax_stats(Pm, B, h, N, ld, scale, adrop, seed, sid, sums)
-        else:
-            ops.softmax_rows(Pm, B * h * N, N, ld, scale)
-        fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
-        ops.reattn_bn_finalize(sums, B * N * N, h, N, Wm, bm, P[pre + "var_norm.weight"], P[pre + "var_norm.bias"],
-                               P[pre + "var_norm.running_mean"], P[pre + "var_norm.running_var"],
-                               P.get(pre + "var_norm.num_batches_tracked"), 1e-5, 0.1, train, fold, bn_saved)
-        A = _empty((B, h, N, ld), xq)
-        ops.reattn_mix(Pm, A, fold, B, h, N, ld, adrop, seed, sid)
+        c = self._map_chunk(B, h, N, ld)
+        keep_P = saved is not None
+        Pm = _empty((B if (keep_P or train) else c, h, N, ld), xq)
+        A = _empty((c, h, N, ld), xq)
         O = _empty((B, N, D), xq)
-        ops.gemm(A, v, O, N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B, batch_inner=h,
-                 sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
+        fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
+        sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device) if train else None
+
+        def scores(b0, bc, dst):
+            ops.gemm(q[b0:b0 + bc], k[b0:b0 + bc], dst, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=bc,
+                     batch_inner=h, sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
+
+        def mix_pv(b0, bc, src, ci):
+            ops.reattn_mix(src, A[:bc], fold, bc, h, N, ld, adrop, seed, sid + _CHUNK_STREAM * ci)
+            ops.gemm(A[:bc], v[b0:b0 + bc], O[b0:b0 + bc], N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=bc,
+                     batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
+
+        def finalize():
+            ops.reattn_bn_finalize(sums, B * N * N, h, N, Wm, bm, P[pre + "var_norm.weight"], P[pre + "var_norm.bias"],
+                                   P[pre + "var_norm.running_mean"], P[pre + "var_norm.running_var"],
+                                   P.get(pre + "var_norm.num_batches_tracked"), 1e-5, 0.1, train, fold, bn_saved)
+
+        if train:
+            # batch statistics couple all images: phase 1 (scores, softmax, moments) per slice, then phase 2
+            for ci, b0 in enumerate(range(0, B, c)):
+                bc = min(c, B - b0)
+                scores(b0, bc, Pm[b0:b0 + bc])
+                ops.softmax_stats(Pm[b0:b0 + bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums)
+            finalize()
+            for ci, b0 in enumerate(range(0, B, c)):
+                bc = min(c, B - b0)
+                mix_pv(b0, bc, Pm[b0:b0 + bc], ci)
+        else:
+            finalize()                                   # running statistics: the whole chain runs per slice
+            for ci, b0 in enumerate(range(0, B, c)):
+                bc = min(c, B - b0)
+                dst = Pm[b0:b0 + bc] if keep_P else Pm[:bc]
+                scores(b0, bc, dst)
+                ops.softmax_rows(dst, bc * h * N, N, ld, scale)
+                mix_pv(b0, bc, dst, ci)
         del A
+        if not keep_P:
+            del Pm
+            Pm = None
         y = _empty((B, N, D), xq)
         pdrop = g.proj_drop if train else 0.0
         self._gemm_tokens(O, P[pre + "proj.weight"], y, B * N, D, D, bias=P[pre + "proj.bias"],
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums, seed=seed, sid=sid,
-                         adrop=adrop, pdrop=pdrop, train=train)
+                         adrop=adrop, pdrop=pdrop, train=train, chunk=c)
         return y
 
     def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):
@@ -173,31 +218,50 @@ class Engine:
         # recompute the mixed map, then dV = A^T dO ; dA = dO V^T
         Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
         bm = P[pre + "reatten_matrix.bias"]
-        # dA = dO V^T first, then ONE pass over (P, dA) recomputes the mixed map A and the backward reductions
-        dA = torch.zeros((B, h, N, ld), dtype=torch.float32, device=dy.device) if ld != N else _empty((B, h, N, ld), dy)
-        ops.gemm(dO, v, dA, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
-                 sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
-        A = _empty((B, h, N, ld), dy)
-        red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
-        ops.reattn_mix_reduce(Pm, dA, A, sv["fold"], B, h, N, ld, adrop, seed, sid, red)
-        dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
-        ops.gemm(A, dO, dv, N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B,
-                 batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
-        del dO, A
-        coef = _empty((2 * h,), dy)
+        # Same image slices as forward (identical Philox streams).  Phase A per slice: dA = dO V^T, one pass over
+        # (P, dA) -> recomputed mixed map A + backward reductions, dV = A^T dO.  Then the closed-form parameter
+        # gradients / BatchNorm-backward means.  Phase B per slice: dA again (a K = head_dim GEMM, cheaper than an HBM
+        # round trip), dA -> dS in place, dQ = dS K, dK = dS^T Q.  Only P crosses HBM (twice).
+        c = sv["chunk"]
+        scale = float(hd) ** -0.5
         gamma = P[pre + "var_norm.weight"]
+        dA = torch.zeros((c, h, N, ld), dtype=torch.float32, device=dy.device) if ld != N else _empty((c, h, N, ld), dy)
+        A = _empty((c, h, N, ld), dy)
+        dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
+        red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
+
+        def grad_map(b0, bc):
+            ops.gemm(dO[b0:b0 + bc], v[b0:b0 + bc], dA[:bc], N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld,
+                     batch_outer=bc, batch_inner=h, sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld),
+                     precision=prec)
+
+        for ci, b0 in enumerate(range(0, B, c)):
+            bc = min(c, B - b0)
+            grad_map(b0, bc)
+            ops.reattn_mix_reduce(Pm[b0:b0 + bc], dA[:bc], A[:bc], sv["fold"], bc, h, N, ld, adrop, seed,
+                                  sid + _CHUNK_STREAM * ci, red)
+            ops.gemm(A[:bc], dO[b0:b0 + bc], dv[b0:b0 + bc], N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D, ldc=D,
+                     batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd),
+                     precision=prec)
+        del A
+        coef = _empty((2 * h,), dy)
         ops.reattn_bwd_params(red, sv["sums"], B, h, N, Wm, bm, gamma, sv["bn"], train, coef,
                               G[pre + "reatten_matrix.weight"], G[pre + "reatten_matrix.bias"],
                               G[pre + "var_norm.weight"], G[pre + "var_norm.bias"])
-        scale = float(hd) ** -0.5
-        ops.reattn_bwd_rows(Pm, dA, B, h, N, ld, Wm, bm, gamma, sv["bn"], coef, train, scale, adrop, seed, sid)
-        dS = dA
-        # dQ = dS K ; dK = dS^T Q
-        ops.gemm(dS, k, dq, N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B, batch_inner=h,
-                 sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
-        ops.gemm(dS, q, dk, N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=B,
-                 batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
-        del dS, dA
+        single = c >= B           # one slice: dA from phase A is still intact
+        for ci, b0 in enumerate(range(0, B, c)):
+            bc = min(c, B - b0)
+            if not single:
+                grad_map(b0, bc)
+            ops.reattn_bwd_rows(Pm[b0:b0 + bc], dA[:bc], bc, h, N, ld, Wm, bm, gamma, sv["bn"], coef, train, scale,
+                                adrop, seed, sid + _CHUNK_STREAM * ci)
+            ops.gemm(dA[:bc], k[b0:b0 + bc], dq[b0:b0 + bc], N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D,
+                     batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd),
+                     precision=prec)
+            ops.gemm(dA[:bc], q[b0:b0 + bc], dk[b0:b0 + bc], N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D,
+                     ldc=D, batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd),
+                     precision=prec)
+        del dO, dA
         wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
         xq, xkv = sv["xq"], sv["xkv"]
         C, S = g.C, g.S
