@@ -256,7 +256,7 @@ def one_image_slices():
     import vit_unet_b200 as vu
     vu.set_map_l2_budget(1e-4)
     yield
-    vu.set_map_l2_budget(80)
+    vu.set_map_l2_budget(0)
 
 
 def test_sliced_attention_matches_oracle(one_image_slices):

@@ -1,0 +1,11 @@
+#!/bin/sh
+# Run on the GPU box: full ncu capture of one L2-shaped block (fwd+bwd), export compact CSVs, drop the big report.
+set -e
+B=${1:-32}
+ncu --set full --clock-control none --import-source on --profile-from-start off -f -o /tmp/prof_block \
+    python tools/profile_block.py $B tf32 > gpurun_out/ncu_block.log 2>&1
+ncu -i /tmp/prof_block.ncu-rep --page raw --csv > gpurun_out/ncu_block_raw.csv 2>/dev/null
+for k in conv3x3_bwd_weight reattn_bwd_rows softmax_stats reattn_mix_reduce; do
+  ncu -i /tmp/prof_block.ncu-rep --page source --csv -k regex:$k -c 1 > gpurun_out/ncu_src_$k.csv 2>/dev/null || true
+done
+ls -la gpurun_out/

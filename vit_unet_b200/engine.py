@@ -21,8 +21,10 @@ from . import ops
 _PRECISION = {"value": ops.PREC_FP32}
 _CHUNK_STREAM = 4096          # Philox stream offset per image slice (layer stream ids stay far below this)
 # bytes of attention maps a slice may keep live between consecutive launches (two maps: S/P and A, or P-slice and
-# dA/dS); sized against the 126 MB L2 of B200.  0 disables slicing.
-_MAP_L2_BYTES = {"value": int(float(os.environ.get("VU_MAP_L2_MB", "80")) * (1 << 20))}
+# dA/dS) when the batch is processed in image slices meant to stay L2-resident.  0 disables slicing (default):
+# measured on B200 (Base, 64 images) slicing LOSES -- 80 MB: 822 img/s, 160 MB: 985 img/s, off: 1283 img/s -- the
+# per-slice launches are too small to fill 148 SMs and the launch count grows 4x.  Kept for memory-bound inference.
+_MAP_L2_BYTES = {"value": int(float(os.environ.get("VU_MAP_L2_MB", "0")) * (1 << 20))}
 
 
 def set_map_l2_budget(megabytes: float) -> None:
