@@ -171,8 +171,11 @@ def run_cuda(args):
     vu.set_precision(args.precision)
     B = args.batch
     torch.manual_seed(0)
+    kw = dict(BASE_KW)
+    if args.dropout is not None:           # experiments only; the headline run keeps the preset's 0.2/0.2/0
+        kw.update(attn_drop=args.dropout, proj_drop=args.dropout)
     with contextlib.redirect_stdout(io.StringIO()):
-        net = vu.HViT_UNet(**BASE_KW)
+        net = vu.HViT_UNet(**kw)
     net.to(dev).train()
     model = DataParallel(net) if world > 1 else net
     x_h, y_h = _synthetic(B, gen_seed=rank)
@@ -272,7 +275,7 @@ def run_cuda(args):
             "config": {"workload": "ViT_UNet Base denoising training step, L1 loss, 3x224x224 (BASELINE configs[2])",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "step": "zero_grad + forward + L1 loss + backward" + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
-                       "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)", "precision": args.precision,
+                       "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)" if args.dropout is None else f"OVERRIDDEN to {args.dropout}", "precision": args.precision,
                        "l2": "per-step working set (saved activations + attention maps, GBs) >> 126 MB L2"},
             "clocks": clocks.summary(), "roofline": roof,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.nbytes + y_pin.nbytes),
@@ -300,6 +303,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "tf32"), choices=["fp32", "tf32"],
                     help="tf32: tcgen05 tensor-core contractions (default, the performance mode); fp32: CUDA-core exact mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=None, help="override attn/proj dropout (experiments; default = preset 0.2)")
     ap.add_argument("--min-warmup", type=int, default=3, help="lower only for profiler runs (numbers under ncu are never bench values)")
     ap.add_argument("--kernel-timing", type=int, default=1, help="CUDA-event timing of every GEMM launch (roofline)")
     args = ap.parse_args()

@@ -120,7 +120,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn, bool b_
 }
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, 3)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
   constexpr uint32_t A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 4;
   constexpr uint32_t B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
@@ -394,6 +394,9 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   const bool b_mn = d.trans_b == 0;        // B(k,n) = B[k*ldb + n]  -> n contiguous
   const int bi = d.batch_inner > 0 ? d.batch_inner : 1, bo = d.batch_outer > 0 ? d.batch_outer : 1;
   int block_n = d.N <= 32 ? 32 : (d.N <= 64 ? 64 : 128);
+  const int kps0 = (int)cdiv(cdiv(d.K, d.split_k > 1 ? d.split_k : 1), TC_BLOCK_K) * TC_BLOCK_K;
+  const bool one_kb_narrow = block_n == 128 && kps0 <= TC_BLOCK_K && getenv("VU_TC_QK128") == nullptr;
+  if (one_kb_narrow) block_n = 64;      // box width of the B operand must match the kernel's BLOCK_N
   CUtensorMap tmA, tmB;
   bool ok;
   if (!a_mn) ok = encode_operand(&tmA, d.A, d.K, d.M, d.lda, bi, d.sAi, bo, d.sAo, TC_BLOCK_K, TC_BLOCK_M, false);
@@ -421,8 +424,9 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   const int nbatch = bi * bo;
   int rc;
   if (block_n == 32) rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  else if (one_kb_narrow) rc = launch_tc<64, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);   // one k-block, output-bound: 6 CTAs/SM
   else if (block_n == 64) rc = launch_tc<64, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
-  else if (g.k_per_split <= TC_BLOCK_K) rc = launch_tc<128, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);   // one k-block: 3 CTAs/SM
+  else if (g.k_per_split <= TC_BLOCK_K) rc = launch_tc<128, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
   else rc = launch_tc<128, 3>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
   *handled = true;
   return rc;
