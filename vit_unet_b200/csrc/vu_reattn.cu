@@ -107,7 +107,7 @@ reattn_stats_kernel(const float* __restrict__ P, int B, int N, int ld, QuadCtx q
 
 // Fused train-mode pass: one warp owns the rows (b, i) of ALL heads: softmax of every head in place, then the
 // centred moments of the freshly written probabilities (re-read from L1/L2) -- one HBM read of S, one write of P.
-template <int H, int RC>
+template <int H>
 __global__ void __launch_bounds__(256)
 softmax_stats_kernel(float* __restrict__ S, int B, int N, int ld, float scale, QuadCtx q, double* __restrict__ sums) {
   constexpr int NV = H + H * (H + 1) / 2;
@@ -127,38 +127,15 @@ softmax_stats_kernel(float* __restrict__ S, int B, int N, int ld, float scale, Q
 #pragma unroll 1
     for (int g = 0; g < H; ++g) {
       float* row = S + row_off + g * head_stride;
-      if (N <= 32 * RC) {
-        // the whole row lives in registers: one global read, one global write per element
-        float e[RC];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int t = 0; t < RC; ++t) {
-          const int j = lane + 32 * t;
-          e[t] = (t * 32 < N && j < N) ? row[j] * sl2 : -INFINITY;
-          mx = fmaxf(mx, e[t]);
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
-#pragma unroll
-        for (int t = 0; t < RC; ++t) { e[t] = exp2f(e[t] - mx); sum += e[t]; }     // exp2(-inf) = 0 for the tail
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-#pragma unroll
-        for (int t = 0; t < RC; ++t) {
-          const int j = lane + 32 * t;
-          if (t * 32 < ld && j < ld) row[j] = j < N ? e[t] * inv : 0.f;
-        }
-      } else {
-        float mx = -INFINITY;
-        for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j] * sl2);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < N; j += 32) { float e = exp2f(fmaf(row[j], sl2, -mx)); row[j] = e; sum += e; }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        for (int j = lane; j < N; j += 32) row[j] *= inv;
-        for (int j = N + lane; j < ld; j += 32) row[j] = 0.f;
-      }
+      float mx = -INFINITY;
+      for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j] * sl2);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < N; j += 32) { float e = exp2f(fmaf(row[j], sl2, -mx)); row[j] = e; sum += e; }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      for (int j = lane; j < N; j += 32) row[j] *= inv;
+      for (int j = N + lane; j < ld; j += 32) row[j] = 0.f;
     }
     __syncwarp();
     for (int j = lane * 4; j < ld; j += 128) {
@@ -270,32 +247,21 @@ reattn_mix_kernel(const float* __restrict__ P, float* __restrict__ A, const floa
 // Backward fusion: one read of P and dA gives both the recomputed mixed map A (needed for dV = A^T dO) and the
 // backward reductions red[h] += sum dA_h, red[H + h*H + g] += sum dA_h (Pd_g - c).
 template <int H>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(256)
 reattn_mix_reduce_kernel(const float* __restrict__ P, const float* __restrict__ dA, float* __restrict__ A,
                          const float* __restrict__ fold, int B, int N, int ld, QuadCtx q, double* __restrict__ out) {
-  // Two adjacent threads share one quad: both read the H probability quads (identical addresses -> one
-  // transaction), each owns half of the OUTPUT heads (its rows of A, s1 and X').  Halves the accumulators per
-  // thread so that two 256-thread CTAs fit per SM.
-  constexpr int HH = H >= 2 ? H / 2 : 1;             // output heads per thread
-  constexpr int SPLIT = H >= 2 ? 2 : 1;
-  constexpr int NV = HH + HH * H;
+  constexpr int NV = H + H * H;
   __shared__ double red[NV * 32];
-  __shared__ double tot[H + H * H];
   __shared__ float sF[H * H + H];
   for (int i = threadIdx.x; i < H * H + H; i += blockDim.x) sF[i] = fold[i];
-  for (int i = threadIdx.x; i < H + H * H; i += blockDim.x) tot[i] = 0.0;
   __syncthreads();
-  const int half = threadIdx.x % SPLIT;              // which half of the output heads
-  const int h0 = half * HH;
   const int ld4 = ld >> 2;
   const int64_t head_stride = (int64_t)N * ld, img_stride = head_stride * H;
   const int64_t per_img4 = (int64_t)N * ld4, total = per_img4 * B;
   float acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-  const int64_t tid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SPLIT;
-  const int64_t nthr = ((int64_t)gridDim.x * blockDim.x) / SPLIT;
-  for (int64_t t = tid; t < total; t += nthr) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = t / per_img4; int64_t r = t - b * per_img4;
     int j = (int)(r % ld4) * 4;
     int64_t off = b * img_stride + r * 4;
@@ -303,8 +269,7 @@ reattn_mix_reduce_kernel(const float* __restrict__ P, const float* __restrict__ 
 #pragma unroll
     for (int g = 0; g < H; ++g) p[g] = load_pd(P + off + g * head_stride, (uint64_t)(off + g * head_stride), q);
 #pragma unroll
-    for (int hh = 0; hh < HH; ++hh) {
-      const int h = h0 + hh;
+    for (int h = 0; h < H; ++h) {
       float bb = sF[H * H + h];
       float4 a = make_float4(bb, bb, bb, bb);
 #pragma unroll
@@ -318,31 +283,22 @@ reattn_mix_reduce_kernel(const float* __restrict__ P, const float* __restrict__ 
 #pragma unroll
     for (int g = 0; g < H; ++g) centre(p[g], j, q);
 #pragma unroll
-    for (int hh = 0; hh < HH; ++hh) {
-      const int h = h0 + hh;
+    for (int h = 0; h < H; ++h) {
       float4 d = *reinterpret_cast<const float4*>(dA + off + h * head_stride);
       if (j + 3 >= N) { if (j + 0 >= N) d.x = 0.f; if (j + 1 >= N) d.y = 0.f; if (j + 2 >= N) d.z = 0.f; if (j + 3 >= N) d.w = 0.f; }
-      acc[hh] += sum4(d);
+      acc[h] += sum4(d);
 #pragma unroll
-      for (int g = 0; g < H; ++g) acc[HH + hh * H + g] += dot4(d, p[g]);
+      for (int g = 0; g < H; ++g) acc[H + h * H + g] += dot4(d, p[g]);
     }
   }
-  // block reduction per half (threads of the other half contribute zeros), then one atomic per value
-#pragma unroll 1
-  for (int hf = 0; hf < SPLIT; ++hf) {
-    double v[NV];
+  double v[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = (half == hf) ? (double)acc[i] : 0.0;
-    block_sum<NV>(v, red);
-    if (threadIdx.x == 0) {
-      for (int hh = 0; hh < HH; ++hh) {
-        tot[hf * HH + hh] = v[hh];
-        for (int g = 0; g < H; ++g) tot[H + (hf * HH + hh) * H + g] = v[HH + hh * H + g];
-      }
-    }
-    __syncthreads();
+  for (int i = 0; i < NV; ++i) v[i] = acc[i];
+  block_sum<NV>(v, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) atomicAdd(out + i, v[i]);
   }
-  for (int i = threadIdx.x; i < H + H * H; i += blockDim.x) atomicAdd(out + i, tot[i]);
 }
 
 // ------------------------------------------------------------------ backward reductions
@@ -436,18 +392,18 @@ __global__ void reattn_bwd_params_kernel(const double* __restrict__ red, const d
 //   dPd_g = sum_h W[h][g] dM_h ;  dP_g = keep_g dPd_g / (1-p)
 //   r_g   = sum_j dP_g P_g ;       dS_g = scale * P_g (dP_g - r_g)           (written over dA)
 template <int H>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128)
 reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int B, int N, int ld,
                        const float* __restrict__ W, const float* __restrict__ bconv, const float* __restrict__ gamma,
                        const float* __restrict__ saved, const float* __restrict__ coef, int train, float scale,
                        QuadCtx q) {
   __shared__ float sW[H * H];
-  __shared__ float sOff[H], sA2[H], sK[H], sM1[H];
+  __shared__ float sOff[H], sInv[H], sK[H], sM1[H], sM2[H];
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = W[i];
   if (threadIdx.x < H) {
     int h = threadIdx.x;
-    sOff[h] = bconv[h] - saved[h]; sK[h] = gamma[h] * saved[H + h];
-    sM1[h] = train ? coef[h] : 0.f; sA2[h] = train ? saved[H + h] * coef[H + h] : 0.f;   // invstd_h * m2_h
+    sOff[h] = bconv[h] - saved[h]; sInv[h] = saved[H + h]; sK[h] = gamma[h] * saved[H + h];
+    sM1[h] = train ? coef[h] : 0.f; sM2[h] = train ? coef[H + h] : 0.f;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -462,32 +418,32 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int 
 #pragma unroll
     for (int g = 0; g < H; ++g) rg[g] = 0.f;
     for (int j = lane * 4; j < ld; j += 128) {
-      float4 p[H], dm[H];
-      uint32_t keep[H];                      // 4 mask bits per head
-      const uint32_t valid = (j + 0 < N ? 1u : 0u) | (j + 1 < N ? 2u : 0u) | (j + 2 < N ? 4u : 0u) | (j + 3 < N ? 8u : 0u);
+      float4 p[H], pd[H], dm[H];
+      uint4 keep[H];
 #pragma unroll
       for (int g = 0; g < H; ++g) {
         p[g] = *reinterpret_cast<const float4*>(P + row_off + g * head_stride + j);
-        keep[g] = valid;
+        pd[g] = p[g];
+        keep[g] = make_uint4(1, 1, 1, 1);
         if (q.thresh) {
           uint4 rr = Philox::gen(q.seed, q.stream, (uint64_t)(row_off + g * head_stride + j) >> 2);
-          keep[g] &= (rr.x >= q.thresh ? 1u : 0u) | (rr.y >= q.thresh ? 2u : 0u) | (rr.z >= q.thresh ? 4u : 0u) |
-                     (rr.w >= q.thresh ? 8u : 0u);
+          keep[g] = make_uint4(rr.x >= q.thresh, rr.y >= q.thresh, rr.z >= q.thresh, rr.w >= q.thresh);
+          pd[g].x = keep[g].x ? p[g].x * q.dscale : 0.f; pd[g].y = keep[g].y ? p[g].y * q.dscale : 0.f;
+          pd[g].z = keep[g].z ? p[g].z * q.dscale : 0.f; pd[g].w = keep[g].w ? p[g].w * q.dscale : 0.f;
         }
       }
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        const float4 d = *reinterpret_cast<const float4*>(dA + row_off + h * head_stride + j);
+        float4 d = *reinterpret_cast<const float4*>(dA + row_off + h * head_stride + j);
         float4 t = d;
         if (train) {
           float4 m = make_float4(sOff[h], sOff[h], sOff[h], sOff[h]);
 #pragma unroll
           for (int g = 0; g < H; ++g) {
-            const float w = sW[h * H + g] * q.dscale;          // Pd = keep * P * dscale
-            m.x = fmaf(w, (keep[g] & 1u) ? p[g].x : 0.f, m.x); m.y = fmaf(w, (keep[g] & 2u) ? p[g].y : 0.f, m.y);
-            m.z = fmaf(w, (keep[g] & 4u) ? p[g].z : 0.f, m.z); m.w = fmaf(w, (keep[g] & 8u) ? p[g].w : 0.f, m.w);
+            float w = sW[h * H + g];
+            m.x = fmaf(w, pd[g].x, m.x); m.y = fmaf(w, pd[g].y, m.y); m.z = fmaf(w, pd[g].z, m.z); m.w = fmaf(w, pd[g].w, m.w);
           }
-          const float a2 = sA2[h], a1 = sM1[h];
+          const float a2 = sInv[h] * sM2[h], a1 = sM1[h];
           t.x = d.x - a1 - m.x * a2; t.y = d.y - a1 - m.y * a2; t.z = d.z - a1 - m.z * a2; t.w = d.w - a1 - m.w * a2;
         }
         const float kh = sK[h];
@@ -498,11 +454,11 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int 
         float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          const float w = sW[h * H + g];
+          float w = sW[h * H + g];
           dp.x = fmaf(w, dm[h].x, dp.x); dp.y = fmaf(w, dm[h].y, dp.y); dp.z = fmaf(w, dm[h].z, dp.z); dp.w = fmaf(w, dm[h].w, dp.w);
         }
-        dp.x = (keep[g] & 1u) ? dp.x * q.dscale : 0.f; dp.y = (keep[g] & 2u) ? dp.y * q.dscale : 0.f;
-        dp.z = (keep[g] & 4u) ? dp.z * q.dscale : 0.f; dp.w = (keep[g] & 8u) ? dp.w * q.dscale : 0.f;
+        dp.x = (keep[g].x && j + 0 < N) ? dp.x * q.dscale : 0.f; dp.y = (keep[g].y && j + 1 < N) ? dp.y * q.dscale : 0.f;
+        dp.z = (keep[g].z && j + 2 < N) ? dp.z * q.dscale : 0.f; dp.w = (keep[g].w && j + 3 < N) ? dp.w * q.dscale : 0.f;
         rg[g] += dot4(dp, p[g]);
         *reinterpret_cast<float4*>(dA + row_off + g * head_stride + j) = dp;
       }
@@ -641,8 +597,7 @@ extern "C" int vu_softmax_stats(float* S, int B, int h, int N, int ld, float sca
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   int blocks = grid_for((int64_t)B * N * 32, 256, 8);
-  if (ld <= 256) { VU_DISPATCH_H(h, fn, softmax_stats_kernel<HH, 8><<<blocks, 256, 0, as_stream(stream)>>>(S, B, N, ld, scale, q, sums)); }
-  else { VU_DISPATCH_H(h, fn, softmax_stats_kernel<HH, 32><<<blocks, 256, 0, as_stream(stream)>>>(S, B, N, ld, scale, q, sums)); }
+  VU_DISPATCH_H(h, fn, softmax_stats_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(S, B, N, ld, scale, q, sums));
   return check_launch(fn);
 }
 
@@ -654,7 +609,7 @@ extern "C" int vu_reattn_mix_reduce(const float* P, const float* dA, float* A, c
              "bad arguments");
   VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
-  int blocks = grid_for((int64_t)B * N * (ld / 4) * 2, 128 * 2, 12);
-  VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH><<<blocks, 128, 0, as_stream(stream)>>>(P, dA, A, fold, B, N, ld, q, red));
+  int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);
+  VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, dA, A, fold, B, N, ld, q, red));
   return check_launch(fn);
 }
