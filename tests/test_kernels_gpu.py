@@ -164,7 +164,7 @@ def test_gemm_dropout_matches_standalone(ops):
     _close(out, exp, name="dropout epilogue")
     frac = (exp == 0).float().mean().item()
     assert 0.25 < frac < 0.35
-    assert torch.allclose(exp[exp != 0], plain[exp != 0] / 0.7, rtol=1e-6)
+    assert torch.allclose(exp[exp != 0], plain[exp != 0] / 0.7, rtol=1e-4)       # p is quantised to 16 bits
 
 
 def test_colsum(ops):

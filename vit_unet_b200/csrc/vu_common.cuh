@@ -66,34 +66,38 @@ struct Layout {
   __device__ __forceinline__ int64_t cstride() const { return p == 0 ? (int64_t)H * W : pp; }
 };
 
-// ------------------------------------------------------------------ Philox4x32-10 (counter-based RNG)
-// keyed by (seed, stream id); counter = element index / 4.  Same generator in every kernel that
-// needs the mask of a given element, so masks never have to be stored.
+// ------------------------------------------------------------------ counter-based dropout RNG
+// One 64-bit SplitMix-style hash per QUAD of consecutive elements, keyed by (seed, stream id, element index / 4),
+// yields four 16-bit uniforms: element e of the quad is kept iff its 16 bits >= thresh16 (= round(p * 65536)).
+// ~20 integer instructions per quad (Philox4x32-10 needs ~70), which matters because the attention-map kernels
+// regenerate the mask in five passes instead of storing it.  The same function is used by every kernel that needs
+// the mask of a given element, so masks never have to be stored.  (Struct keeps its historical name.)
 struct Philox {
   __device__ __forceinline__ static uint4 gen(uint64_t seed, uint32_t stream, uint64_t ctr) {
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0x5eed5eedu;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
+    uint64_t x = ctr * 0x9E3779B97F4A7C15ull + seed;
+    x ^= (uint64_t)stream * 0xD1B54A32D192ED03ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return make_uint4(lo & 0xFFFFu, lo >> 16, hi & 0xFFFFu, hi >> 16);
   }
-  // keep-probability test for one element index; thresh = p * 2^32 (drop if r < thresh)
+  // keep test for one element index; thresh = p * 2^16 (drop if r < thresh)
   __device__ __forceinline__ static bool keep(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thresh) {
     uint4 r = gen(seed, stream, idx >> 2);
     uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
     return v >= thresh;
   }
 };
+// 16-bit threshold and the matching unbiased keep-scale 1 / (1 - thresh/65536)
 static inline uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  if (t < 0) t = 0; if (t > 4294967295.0) t = 4294967295.0;
+  double t = (double)p * 65536.0 + 0.5;
+  if (t < 0) t = 0; if (t > 65535.0) t = 65535.0;
   return (uint32_t)t;
+}
+static inline float drop_keep_scale(float p) {
+  if (!(p > 0.f)) return 1.0f;
+  return (float)(1.0 / (1.0 - (double)drop_threshold(p) / 65536.0));
 }
 
 // ------------------------------------------------------------------ reductions

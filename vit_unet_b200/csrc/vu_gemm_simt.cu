@@ -245,7 +245,7 @@ int gemm_simt(const vu_gemm_desc& d, cudaStream_t s) {
   g.alpha = d.alpha; g.act = d.act; g.accumulate = d.accumulate;
   g.split_k = d.split_k > 1 ? d.split_k : 1;
   g.drop_thresh = d.drop_p > 0.f ? drop_threshold(d.drop_p) : 0u;
-  g.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
+  g.drop_scale = drop_keep_scale(d.drop_p);
   g.drop_seed = d.drop_seed; g.drop_stream = d.drop_stream;
   const int nbatch = (d.batch_outer > 0 ? d.batch_outer : 1) * g.batch_inner;
   // split boundaries on multiples of 16 so vector loads stay aligned

@@ -416,7 +416,7 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   g.k_per_split = kps;
   g.split_k = (int)cdiv(g.K, kps);
   g.drop_thresh = d.drop_p > 0.f ? drop_threshold(d.drop_p) : 0u;
-  g.drop_scale = d.drop_p > 0.f ? 1.0f / (1.0f - d.drop_p) : 1.0f;
+  g.drop_scale = drop_keep_scale(d.drop_p);
   g.drop_seed = d.drop_seed; g.drop_stream = d.drop_stream;
   g.mn_lbo = 4096; g.mn_sbo = 512;
   if (const char* e = getenv("VU_TC_MN_LBO")) g.mn_lbo = (uint32_t)atoi(e);

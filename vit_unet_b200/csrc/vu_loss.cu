@@ -113,7 +113,7 @@ extern "C" int vu_dropout(const float* in, float* out, int64_t n, float p, uint6
   const char* fn = "vu_dropout";
   VU_REQUIRE(in && out && n > 0 && p >= 0.f && p < 1.f, fn, "bad arguments");
   uint32_t th = p > 0.f ? drop_threshold(p) : 0u;
-  dropout_kernel<<<ew_grid(cdiv(n, 4)), 256, 0, as_stream(stream)>>>(in, out, n, th, 1.f / (1.f - p), seed, stream_id);
+  dropout_kernel<<<ew_grid(cdiv(n, 4)), 256, 0, as_stream(stream)>>>(in, out, n, th, drop_keep_scale(p), seed, stream_id);
   return check_launch(fn);
 }
 

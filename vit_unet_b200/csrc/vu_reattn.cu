@@ -487,7 +487,7 @@ static int grid_for(int64_t work_items, int threads, int per_sm) {
 static QuadCtx make_ctx(float drop_p, uint64_t seed, uint32_t stream_id, int N) {
   QuadCtx q;
   q.thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
-  q.dscale = 1.f / (1.f - drop_p); q.seed = seed; q.stream = stream_id; q.c = 1.0f / (float)N; q.N = N;
+  q.dscale = drop_keep_scale(drop_p); q.seed = seed; q.stream = stream_id; q.c = 1.0f / (float)N; q.N = N;
   return q;
 }
 
