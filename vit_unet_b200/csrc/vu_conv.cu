@@ -134,7 +134,7 @@ conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ 
 // of one conv, so the 9*C taps of x are loaded once per conv) or (k, co) pairs (narrow fallback for C == 4).
 // Pixels are grid-strided in x's own layout order.  Here g.lin describes x, g.lout describes dy.
 template <int C, bool WIDE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 3)
 conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ d0, const float* __restrict__ d1,
                           const float* __restrict__ d2, float* __restrict__ dw, float* __restrict__ dbias,
                           ConvGeom g) {
@@ -149,31 +149,46 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
   const uint32_t hw = (uint32_t)(g.lin.H * g.lin.W), total = (uint32_t)g.npix_total;     // host checks < 2^31
   const int64_t cs = g.lin.cstride(), dcs = g.lout.cstride();
   const int rs = g.bp ? g.bp : g.lin.W;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+  // gather one pixel: dy of the NCO output channels and the 9*C taps of x (zeros outside the border patch)
+  auto gather = [&](uint32_t t, float (&dv)[NCO], float (&xv)[C][9]) {
     const uint32_t b = t / hw, pix = t - b * hw;
     int y, xx; g.lin.pixel(pix, y, xx);
     int iy, ix, limy, limx; tap_setup(g, y, xx, iy, ix, limy, limx);
-    float dv[NCO];
     const int64_t dbase = (int64_t)b * g.per_image + g.lout.at(co0, y, xx);
 #pragma unroll
-    for (int c = 0; c < NCO; ++c) { dv[c] = __ldg(dy + dbase + c * dcs); acc[c * (C * 9 + 1) + C * 9] += dv[c]; }
+    for (int c = 0; c < NCO; ++c) dv[c] = __ldg(dy + dbase + c * dcs);
     const float* xb = x + (int64_t)b * g.per_image;
-    int64_t base = g.lin.base_of(pix);
+    const int64_t base = g.lin.base_of(pix);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        bool ok = (unsigned)(iy + ky - 1) < (unsigned)limy && (unsigned)(ix + kx - 1) < (unsigned)limx;
-        if (!ok) continue;
-        int64_t off = g.fast ? base + (ky - 1) * rs + (kx - 1) : g.lin.at(0, y + ky - 1, xx + kx - 1);
+        const bool ok = (unsigned)(iy + ky - 1) < (unsigned)limy && (unsigned)(ix + kx - 1) < (unsigned)limx;
+        const int64_t off = !ok ? 0 : (g.fast ? base + (ky - 1) * rs + (kx - 1) : g.lin.at(0, y + ky - 1, xx + kx - 1));
 #pragma unroll
-        for (int ci = 0; ci < C; ++ci) {
-          float xv = __ldg(xb + off + ci * cs);
-#pragma unroll
-          for (int c = 0; c < NCO; ++c)
-            acc[c * (C * 9 + 1) + ci * 9 + ky * 3 + kx] = fmaf(dv[c], xv, acc[c * (C * 9 + 1) + ci * 9 + ky * 3 + kx]);
-        }
+        for (int ci = 0; ci < C; ++ci) xv[ci][ky * 3 + kx] = ok ? __ldg(xb + off + ci * cs) : 0.f;
       }
+  };
+  auto accumulate = [&](const float (&dv)[NCO], const float (&xv)[C][9]) {
+#pragma unroll
+    for (int c = 0; c < NCO; ++c) {
+      acc[c * (C * 9 + 1) + C * 9] += dv[c];
+#pragma unroll
+      for (int ci = 0; ci < C; ++ci)
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+          acc[c * (C * 9 + 1) + ci * 9 + tp] = fmaf(dv[c], xv[ci][tp], acc[c * (C * 9 + 1) + ci * 9 + tp]);
+    }
+  };
+  // two pixels per iteration: both gathers are issued before either accumulation (more loads in flight per warp)
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += 2 * stride) {
+    float dv0[NCO], xv0[C][9], dv1[NCO], xv1[C][9];
+    gather(t, dv0, xv0);
+    const bool second = t + stride < total;
+    if (second) gather(t + stride, dv1, xv1);
+    accumulate(dv0, xv0);
+    if (second) accumulate(dv1, xv1);
   }
   __shared__ float red[NACC][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,8 +274,8 @@ extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, 
   VU_REQUIRE(x && dy0 && dw && nconv >= 1 && nconv <= 3, fn, "null pointer or nconv outside 1..3");
   VU_REQUIRE((nconv < 2 || dy1) && (nconv < 3 || dy2), fn, "missing gradient pointer");
   ConvGeom g; int rc = make_geom(fn, g, p_x, p_dy, border_p, B, C, H, W); if (rc) return rc;
-  int threads = 256;
-  int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 4), (int64_t)sm_count() * 4);
+  int threads = 128;
+  int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 8), (int64_t)sm_count() * 6);
   if (bx < 1) bx = 1;
   cudaStream_t s = as_stream(stream);
   VU_DISPATCH_C(C,

@@ -130,7 +130,11 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  // barriers live past BOTH the pipeline ring and the epilogue staging area that later reuses the ring's space
+  constexpr uint32_t RING_BYTES = STAGES * (A_BYTES + B_BYTES);
+  constexpr uint32_t STAGING_BYTES = 4u * 32u * (BLOCK_N + 4) * 4u;
+  constexpr uint32_t BAR_OFFSET = ((RING_BYTES > STAGING_BYTES ? RING_BYTES : STAGING_BYTES) + 15u) & ~15u;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);

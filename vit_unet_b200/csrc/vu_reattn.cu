@@ -26,13 +26,10 @@ softmax_rows_kernel(float* __restrict__ S, int64_t rows, int N, int ld, float sc
     for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j] * sl2);
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      float e = exp2f(fmaf(row[j], sl2, -mx));
-      row[j] = e; sum += e;
-    }
+    for (int j = lane; j < N; j += 32) sum += exp2f(fmaf(row[j], sl2, -mx));
     sum = warp_sum(sum);
     float inv = 1.0f / sum;
-    for (int j = lane; j < N; j += 32) row[j] *= inv;
+    for (int j = lane; j < N; j += 32) row[j] = exp2f(fmaf(row[j], sl2, -mx)) * inv;
     for (int j = N + lane; j < ld; j += 32) row[j] = 0.f;
   }
 }
@@ -127,15 +124,30 @@ softmax_stats_kernel(float* __restrict__ S, int B, int N, int ld, float scale, Q
 #pragma unroll 1
     for (int g = 0; g < H; ++g) {
       float* row = S + row_off + g * head_stride;
+      // sweep 1 (float4): row maximum;  sweep 2: sum of exp2;  sweep 3: write exp2 * 1/sum (pads -> 0).
+      // sweeps 2 and 3 recompute exp2 instead of storing the un-normalised value: 3 reads (L1 after the first) + 1 write
       float mx = -INFINITY;
-      for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j] * sl2);
+      for (int j = lane * 4; j < ld; j += 128) {
+        const float4 t = *reinterpret_cast<const float4*>(row + j);
+        if (j + 0 < N) mx = fmaxf(mx, t.x * sl2); if (j + 1 < N) mx = fmaxf(mx, t.y * sl2);
+        if (j + 2 < N) mx = fmaxf(mx, t.z * sl2); if (j + 3 < N) mx = fmaxf(mx, t.w * sl2);
+      }
       mx = warp_max(mx);
       float sum = 0.f;
-      for (int j = lane; j < N; j += 32) { float e = exp2f(fmaf(row[j], sl2, -mx)); row[j] = e; sum += e; }
+      for (int j = lane * 4; j < ld; j += 128) {
+        const float4 t = *reinterpret_cast<const float4*>(row + j);
+        if (j + 0 < N) sum += exp2f(fmaf(t.x, sl2, -mx)); if (j + 1 < N) sum += exp2f(fmaf(t.y, sl2, -mx));
+        if (j + 2 < N) sum += exp2f(fmaf(t.z, sl2, -mx)); if (j + 3 < N) sum += exp2f(fmaf(t.w, sl2, -mx));
+      }
       sum = warp_sum(sum);
       const float inv = 1.0f / sum;
-      for (int j = lane; j < N; j += 32) row[j] *= inv;
-      for (int j = N + lane; j < ld; j += 32) row[j] = 0.f;
+      for (int j = lane * 4; j < ld; j += 128) {
+        const float4 t = *reinterpret_cast<const float4*>(row + j);
+        float4 o;
+        o.x = j + 0 < N ? exp2f(fmaf(t.x, sl2, -mx)) * inv : 0.f; o.y = j + 1 < N ? exp2f(fmaf(t.y, sl2, -mx)) * inv : 0.f;
+        o.z = j + 2 < N ? exp2f(fmaf(t.z, sl2, -mx)) * inv : 0.f; o.w = j + 3 < N ? exp2f(fmaf(t.w, sl2, -mx)) * inv : 0.f;
+        *reinterpret_cast<float4*>(row + j) = o;
+      }
     }
     __syncwarp();
     for (int j = lane * 4; j < ld; j += 128) {
