@@ -41,14 +41,19 @@ def _peaks():
     return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
-def _ncu_traffic(kernel_class):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this round (profiles/ncu_traffic.json), or None."""
+def _ncu_traffic(kernel_class, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch (the Base L2-level
+    attention block, where 92 % of the map bytes live), from this round's committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, captured at 32 images), scaled linearly to `batch` images.  None if absent."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
-        return None
+        return None, None
     d = json.load(open(path))
-    return d.get(kernel_class)
+    key = "vu_gemm_tf32_tc" if kernel_class.startswith("gemm_tcgen05") else kernel_class
+    e = d.get(key)
+    if not e:
+        return None, None
+    return e["bytes_per_image"] * batch, f"largest launch ({e['shape']}), ncu capture at {e['captured_batch']} images scaled to {batch}"
 
 
 def _synthetic(B, gen_seed=0):
@@ -263,9 +268,10 @@ def run_cuda(args):
                      "kernel_ms_per_step": top["ms"] / args.steps, "kernel_share_of_step": top["ms"] / ms,
                      "launches_timed": top["launches"], "all_kernels_ms_per_step": k["total_kernel_ms"] / args.steps,
                      "by_kernel": by})
-        tr = _ncu_traffic(top_name)
+        tr, note = _ncu_traffic(top_name, B)
         if tr is not None:
             roof["traffic"] = tr
+            roof["traffic_note"] = note
     roof["step_tflops"] = value / world * FLOPS_PER_IMAGE_FWD_BWD / 1e12
     roof["step_tensor_frac"] = roof["step_tflops"] / peaks["tflops"]
 
