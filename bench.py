@@ -259,7 +259,7 @@ def run_cuda(args):
         # roofline it sits closest to (algorithmic flops vs algorithmic HBM bytes of the op)
         top_name = max(by, key=lambda n: by[n]["ms"])
         top = by[top_name]
-        tensor_bound = top["tensor_frac"] >= top["hbm_frac"]
+        tensor_bound = top["tensor_frac"] >= top["hbm_frac"] or top_name.startswith("gemm_simt")
         roof.update({"kernel": top_name, "bound": "tensor" if tensor_bound else "hbm",
                      "achieved": top["tflops"] if tensor_bound else top["gbs"],
                      "peak": peaks["tflops"] if tensor_bound else peaks["hbm"],

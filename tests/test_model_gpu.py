@@ -370,3 +370,62 @@ def test_fused_adamw_matches_torch_adamw():
             opt.step(); ref_opt.step()
             for n, p in net.named_parameters():
                 assert _rel(p, twin[n]) <= 2e-6, (flat, step, n, _rel(p, twin[n]))
+
+
+def test_large_preset_eval_parity():
+    """BASELINE configs[3] architecture (Large: depth_te=4, size_bottleneck=4): eval forward within 1e-5."""
+    import vit_unet_b200 as vu
+    ref = _quiet(O.get_vit_unet, "large", variant="head")
+    net = _quiet(vu.get_vit_unet, "large")
+    sd = fill_state_dict(ref.state_dict())
+    ref.load_state_dict(sd); net.load_state_dict(sd)
+    net.to("cuda")
+    assert sum(p.numel() for p in net.parameters()) == 69_064_902
+    x, _ = make_input(1, 3, 224)
+    ref.eval(); net.eval()
+    with torch.no_grad():
+        assert _rel(net(x.cuda()), ref(x)) <= 1e-5
+
+
+def test_base_1ch_dice_segmentation_step():
+    """BASELINE configs[4]: Base, 1 channel, soft-Dice loss (README.md:91-101) on CT-shaped synthetic slices with disc
+    masks.  Eval-mode forward + backward (well conditioned) against the oracle; train mode must run and be finite."""
+    import vit_unet_b200 as vu
+    ref = _quiet(O.get_vit_unet, "base", variant="head", num_channels=1, attn_drop=0.0, proj_drop=0.0)
+    net = _quiet(vu.HViT_UNet, depth=2, depth_te=2, size_bottleneck=2, preprocessing="conv", im_size=224,
+                 patch_size=32, num_channels=1, hidden_dim=128, num_heads=8, attn_drop=0.0, proj_drop=0.0, linear_drop=0)
+    assert sum(p.numel() for p in net.parameters()) == 6_228_718
+    sd = fill_state_dict(ref.state_dict())
+    ref.load_state_dict(sd); net.load_state_dict(sd)
+    net.to("cuda")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, 224, 224, generator=g) * 0.25 + 0.5
+    yy, xx = torch.meshgrid(torch.arange(224), torch.arange(224), indexing="ij")
+    y = torch.zeros(2, 1, 224, 224)
+    for b, (cy, cx, r) in enumerate([(80, 100, 30), (150, 60, 22)]):
+        y[b, 0] = ((yy - cy) ** 2 + (xx - cx) ** 2 <= r * r).float()
+    ref.eval(); net.eval()
+    ref.zero_grad(); net.zero_grad()
+    lr = O.dice_loss(ref(x), y); lr.backward()
+    ln = vu.dice_loss(net(x.cuda()), y.cuda()); ln.backward()
+    assert abs(lr.item() - ln.item()) <= 1e-5 * abs(lr.item()) + 1e-7
+    gr = dict(ref.named_parameters())
+    cond = conditioning(copy.deepcopy(ref), x, y)        # L1-based yardstick is a fair proxy for conditioning here
+    for n, p in net.named_parameters():
+        if cond[f"evg_cond:{n}"] > CHAOS:
+            continue
+        assert _rel(p.grad, gr[n].grad) <= 1e-4 + YARD * cond[f"evg_cond:{n}"], n
+    net.train()
+    net.zero_grad()
+    vu.dice_loss(net(x.cuda()), y.cuda()).backward()
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("B", [1, 3, 5])
+def test_odd_batch_sizes(B):
+    variant, kw, _ = CONFIGS["tiny_head"]
+    ref, net = _pair(variant, kw)
+    x, y = make_input(B, 3, 32, seed=B)
+    ref.eval(); net.eval()
+    with torch.no_grad():
+        assert _rel(net(x.cuda()), ref(x)) <= 1e-5
