@@ -32,6 +32,19 @@ BASE_KW = dict(depth=2, depth_te=2, size_bottleneck=2, preprocessing="conv", im_
                num_channels=3, hidden_dim=128, num_heads=8, attn_drop=0.2, proj_drop=0.2, linear_drop=0)
 
 
+# BASELINE.json configs; "base_train" (configs[2]) is the headline metric, the others are extra bench modes
+WORKLOADS = {
+    "base_train": dict(kw={}, train=True, loss="l1", flops=23.26e9,
+                       name="ViT_UNet Base denoising training step, L1 loss, 3x224x224 (BASELINE configs[2])"),
+    "lite_infer": dict(kw=dict(depth_te=1, patch_size=16, hidden_dim=64, num_heads=4), train=False, loss="l1", flops=9.311e9,
+                       name="ViT_UNet Lite inference (eval forward), 3x224x224 (BASELINE configs[1])"),
+    "large_train": dict(kw=dict(depth_te=4, size_bottleneck=4), train=True, loss="l1", flops=42.4e9,
+                        name="ViT_UNet Large denoising training step, L1 loss (BASELINE configs[3] architecture, TF32 not bf16)"),
+    "base1ch_dice": dict(kw=dict(num_channels=1), train=True, loss="dice", flops=5.46e9,
+                         name="ViT_UNet Base 1-channel segmentation step, soft-Dice loss (BASELINE configs[4])"),
+}
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -176,22 +189,30 @@ def run_cuda(args):
     vu.set_precision(args.precision)
     B = args.batch
     torch.manual_seed(0)
-    kw = dict(BASE_KW)
+    wl = WORKLOADS[args.workload]
+    kw = dict(BASE_KW, **wl["kw"])
     if args.dropout is not None:           # experiments only; the headline run keeps the preset's 0.2/0.2/0
         kw.update(attn_drop=args.dropout, proj_drop=args.dropout)
     with contextlib.redirect_stdout(io.StringIO()):
         net = vu.HViT_UNet(**kw)
-    net.to(dev).train()
-    model = DataParallel(net) if world > 1 else net
+    net.to(dev).train(wl["train"])
+    model = DataParallel(net) if (world > 1 and wl["train"]) else net
     x_h, y_h = _synthetic(B, gen_seed=rank)
+    if kw["num_channels"] == 1:            # CT-like slices, binary disc masks
+        x_h = (x_h[:, :1] * 0.224 + 0.456).contiguous()
+        y_h = (y_h[:, :1] > 0.5).float().contiguous()
     x_pin, y_pin = x_h.pin_memory(), y_h.pin_memory()
     x_d, y_d = x_h.to(dev), y_h.to(dev)
     params = [p for p in net.parameters()]
+    loss_fn = {"l1": vu.l1_loss, "dice": vu.dice_loss}[wl["loss"]]
 
     def step(x, y):
+        if not wl["train"]:                # inference: batch-sharded forward, no collective
+            with torch.no_grad():
+                return (model(x) - y).abs().mean()
         for p in params:
             p.grad = None
-        loss = vu.l1_loss(model(x), y)
+        loss = loss_fn(model(x), y)
         loss.backward()
         return loss
 
@@ -272,22 +293,23 @@ def run_cuda(args):
         if tr is not None:
             roof["traffic"] = tr
             roof["traffic_note"] = note
-    roof["step_tflops"] = value / world * FLOPS_PER_IMAGE_FWD_BWD / 1e12
+    roof["step_tflops"] = value / world * wl["flops"] / 1e12
     roof["step_tensor_frac"] = roof["step_tflops"] / peaks["tflops"]
 
-    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": METRIC if args.workload == "base_train" else wl["name"] + " images/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-            "config": {"workload": "ViT_UNet Base denoising training step, L1 loss, 3x224x224 (BASELINE configs[2])",
+            "config": {"workload": wl["name"],
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "step": "zero_grad + forward + L1 loss + backward" + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
+                       "step": ("zero_grad + forward + loss + backward" + (" + bucketed NCCL grad all-reduce" if world > 1 else ""))
+                               if wl["train"] else "eval forward under no_grad (batch-sharded, no collective)",
                        "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)" if args.dropout is None else f"OVERRIDDEN to {args.dropout}", "precision": args.precision,
                        "l2": "per-step working set (saved activations + attention maps, GBs) >> 126 MB L2"},
             "clocks": clocks.summary(), "roofline": roof,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.nbytes + y_pin.nbytes),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": loss_host},
             "gpu_launches": launches}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "base_train":
         cores = os.cpu_count() or 1
         sec, _ = cpu_reference_step_time(args.cpu_batch, 2, 1, cores)
         line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": cores, "kind": "port",
@@ -304,6 +326,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="base_train", choices=["base_train", "lite_infer", "large_train", "base1ch_dice"],
+                    help="base_train is the headline (BASELINE.json metric); the others are extra modes")
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
     ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "tf32"), choices=["fp32", "tf32"],
