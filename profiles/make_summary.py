@@ -94,6 +94,32 @@ def launches():
     open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write("\n".join(out) + "\n")
 
 
+def gemm_summary():
+    raw = os.path.join(ROOT, "gpurun_out", "ncu_gemm_raw.csv")
+    shapes = os.path.join(ROOT, "gpurun_out", "gemm_shapes.txt")
+    if not (os.path.exists(raw) and os.path.exists(shapes)):
+        return
+    rows = list(csv.reader(open(raw)))
+    hdr, units = rows[0], rows[1]
+    keys = ["Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread"]
+    out = [f"# {tag}: tcgen05 TF32 GEMM (`gemm_tf32_tc_kernel`) on the token-GEMM shapes of a Base step, 64 images\n",
+           "## CUDA-event timings (`python tools/gemm_bench.py 64`, 10 launches each after 3 warm-ups)\n", "```",
+           open(shapes).read().rstrip(), "```\n",
+           "## `ncu --set full --clock-control none -k regex:gemm_tf32_tc -c 2` on the first shape "
+           "(L0 proj forward, M=3136 N=3072 K=3072)\n", "| metric | launch 1 | launch 2 |", "|---|---:|---:|"]
+    for k in keys:
+        if k in hdr:
+            i = hdr.index(k)
+            out.append(f"| `{k}` ({units[i]}) | " + " | ".join(r[i] for r in rows[2:4]) + " |")
+    out.append("\nSASS check (`cuobjdump -sass vit_unet_b200/libvitunet_b200.so | grep -c ...`): `UTCHMMA` (tcgen05.mma), "
+               "`UTMALDG.4D` (TMA), `LDTM` (tcgen05.ld), `SYNCS.*TRYWAIT` (mbarrier) are all present; no `HMMA`.")
+    open(os.path.join(ROOT, "profiles", f"{tag}_gemm_tcgen05.md"), "w").write("\n".join(out) + "\n")
+
+
 block_table()
 launches()
+gemm_summary()
 print("written:", sorted(os.listdir(os.path.join(ROOT, "profiles"))))
