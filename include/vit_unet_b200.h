@@ -144,6 +144,17 @@ int vu_loss_fwd(int kind, const float* pred, const float* target, int64_t n, dou
 int vu_loss_bwd(int kind, const float* pred, const float* target, int64_t n, const double* sums,
                 const float* gscale, float* dpred, void* stream);
 
+/* ---------------------------------------------------------------- callers either side of the path */
+/* N2: per-image PSNR on the device (functions.py:7-19 + skimage.metrics.peak_signal_noise_ratio):
+ * psnr[b] = 10 log10(range^2 / mean((pred_b - target_b)^2)), range = data_range if > 0 else 1 (min(target_b) >= 0) or 2.
+ * scratch: B doubles + B floats. */
+int vu_psnr(const float* pred, const float* target, int B, int64_t n, float data_range, double* scratch, float* psnr,
+            void* stream);
+/* N4: input pipeline step of DenoisingDataset (dataset.py:65-68) + Normalize (run_denoising.py:54) on the device:
+ * uint8 HWC -> float32 CHW, dst = (src * scale - mean) / std */
+int vu_u8hwc_to_chw(const uint8_t* src, float* dst, int B, int C, int H, int W, float scale, float mean, float std,
+                    void* stream);
+
 /* ---------------------------------------------------------------- misc */
 /* out = in * keep / (1-p), keep from the same Philox stream the GEMM epilogue uses (index = flat element) */
 int vu_dropout(const float* in, float* out, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream);

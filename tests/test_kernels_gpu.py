@@ -352,3 +352,19 @@ def test_reattn_fused_passes_match_separate_kernels(ops, h, N, p):
     ops.reattn_mix_reduce(P1, dA, A2, fold, B, h, N, ld, p, 5, 2, r2)
     assert torch.equal(A1, A2)
     _close(r2, r1, rtol=1e-6, name="fused reductions")
+
+
+def test_psnr_and_input_pipeline(ops):
+    """N2 / N4: device PSNR vs the skimage formula; uint8 HWC -> normalised float CHW vs numpy."""
+    g = torch.Generator().manual_seed(0)
+    y = torch.rand(5, 3, 40, 40, generator=g)
+    y[1] -= 0.5                                       # negative values -> skimage data_range 2 for that image
+    out = y + 0.05 * torch.randn(5, 3, 40, 40, generator=g)
+    got = ops.psnr(out.cuda(), y.cuda()).cpu()
+    mse = ((out - y) ** 2).flatten(1).mean(1).double()
+    dr = torch.tensor([1.0, 2.0, 1.0, 1.0, 1.0], dtype=torch.float64)
+    _close(got, 10 * torch.log10(dr * dr / mse), rtol=1e-5, name="psnr")
+    _close(ops.psnr(out.cuda(), y.cuda(), 4.0), 10 * torch.log10(16.0 / mse), rtol=1e-5, name="psnr fixed range")
+    img = torch.randint(0, 256, (3, 20, 24, 3), dtype=torch.uint8, generator=g)
+    exp = ((img.float() / 255.0 - 0.456) / 0.224).permute(0, 3, 1, 2)
+    _close(ops.u8hwc_to_chw(img.cuda(), 1 / 255.0, 0.456, 0.224), exp, rtol=1e-5, name="u8hwc->chw")

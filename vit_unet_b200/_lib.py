@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitunet_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class VuError(RuntimeError):
@@ -59,6 +59,8 @@ SIGNATURES = {
     "vu_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p],
     "vu_loss_fwd": [_i, _p, _p, _l, _p, _p, _p],
     "vu_loss_bwd": [_i, _p, _p, _l, _p, _p, _p, _p],
+    "vu_psnr": [_p, _p, _i, _l, _f, _p, _p, _p],
+    "vu_u8hwc_to_chw": [_p, _p, _i, _i, _i, _i, _f, _f, _f, _p],
     "vu_dropout": [_p, _p, _l, _f, _u64, _u32, _p],
     "vu_axpby": [_p, _p, _l, _f, _f, _p],
     "vu_adamw": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _f, _p],
@@ -72,7 +74,7 @@ _SPECIAL = {
 _lib = None
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
-_KERNELS_PER_CALL = {"vu_ln_bwd": 3, "vu_ln_stats": 2, "vu_loss_fwd": 2}
+_KERNELS_PER_CALL = {"vu_ln_bwd": 3, "vu_ln_stats": 2, "vu_loss_fwd": 2, "vu_psnr": 3}
 LN_SPLIT = 8
 _launches = 0
 

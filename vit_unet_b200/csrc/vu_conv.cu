@@ -7,6 +7,12 @@
 
 namespace vu {
 
+// Filter weights / biases of the launch in flight live in __constant__ memory: after full unrolling every weight is
+// an immediate constant-bank operand of its FFMA (no LDS / register per weight).  They are refreshed with a
+// stream-ordered device-to-device cudaMemcpyToSymbolAsync before each launch (972 B at most).
+__constant__ float c_w[3 * 4 * 4 * 9];
+__constant__ float c_b[3 * 4];
+
 struct ConvGeom {
   Layout lin, lout;      // storage layouts of the tensor(s) read / written
   int bp;                // border patch (0: image)
@@ -28,11 +34,6 @@ template <int C, int NCONV>
 __global__ void __launch_bounds__(256)
 conv3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2, ConvGeom g) {
-  __shared__ float sw[NCONV * C * C * 9];
-  __shared__ float sb[NCONV * C];
-  for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < NCONV * C; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
   const uint32_t hw = (uint32_t)(g.lin.H * g.lin.W), total = (uint32_t)g.npix_total;     // host checks < 2^31
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const uint32_t b = t / hw, pix = t - b * hw;
@@ -71,11 +72,11 @@ conv3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
       float* op = k == 0 ? o0 : (k == 1 ? o1 : o2);
 #pragma unroll
       for (int co = 0; co < C; ++co) {
-        float acc = sb[k * C + co];
+        float acc = c_b[k * C + co];
 #pragma unroll
         for (int ci = 0; ci < C; ++ci)
 #pragma unroll
-          for (int tp = 0; tp < 9; ++tp) acc = fmaf(v[ci][tp], sw[((k * C + co) * C + ci) * 9 + tp], acc);
+          for (int tp = 0; tp < 9; ++tp) acc = fmaf(v[ci][tp], c_w[((k * C + co) * C + ci) * 9 + tp], acc);
         op[obase + co * ocs] = acc;
       }
     }
@@ -87,9 +88,6 @@ template <int C, int NCONV>
 __global__ void __launch_bounds__(256)
 conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ d1, const float* __restrict__ d2,
                         const float* __restrict__ w, float* __restrict__ dx, ConvGeom g, int accumulate) {
-  __shared__ float sw[NCONV * C * C * 9];
-  for (int i = threadIdx.x; i < NCONV * C * C * 9; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
   const uint32_t hw = (uint32_t)(g.lin.H * g.lin.W), total = (uint32_t)g.npix_total;     // host checks < 2^31
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const uint32_t b = t / hw, pix = t - b * hw;
@@ -116,7 +114,7 @@ conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ 
           for (int co = 0; co < C; ++co) {
             float dv = __ldg(dp + co * cs);
 #pragma unroll
-            for (int ci = 0; ci < C; ++ci) acc[ci] = fmaf(dv, sw[((k * C + co) * C + ci) * 9 + ky * 3 + kx], acc[ci]);
+            for (int ci = 0; ci < C; ++ci) acc[ci] = fmaf(dv, c_w[((k * C + co) * C + ci) * 9 + ky * 3 + kx], acc[ci]);
           }
         }
       }
@@ -208,6 +206,20 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
+static int upload_filters(const char* fn, const float* w, const float* bias, int nconv, int C, cudaStream_t s) {
+  if (cudaMemcpyToSymbolAsync(c_w, w, sizeof(float) * nconv * C * C * 9, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return check_launch(fn);
+  if (bias) {
+    if (cudaMemcpyToSymbolAsync(c_b, bias, sizeof(float) * nconv * C, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return check_launch(fn);
+  } else {
+    static const float zeros[12] = {0};
+    if (cudaMemcpyToSymbolAsync(c_b, zeros, sizeof(float) * nconv * C, 0, cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return check_launch(fn);
+  }
+  return VU_OK;
+}
+
 static int make_geom(const char* fn, ConvGeom& g, int p_in, int p_out, int border_p, int B, int C, int H, int W) {
   VU_REQUIRE(B > 0 && H > 0 && W > 0, fn, "empty shape");
   VU_REQUIRE((int64_t)B * H * W < (int64_t)1 << 31, fn, "B*H*W must be below 2^31 pixels per call");
@@ -241,6 +253,7 @@ extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const flo
   int threads = 256;
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
+  rc = upload_filters(fn, w, bias, nconv, C, s); if (rc) return rc;
   VU_DISPATCH_C(C,
     if (nconv == 1) conv3x3_fwd_kernel<CC, 1><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
     else if (nconv == 2) conv3x3_fwd_kernel<CC, 2><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
@@ -259,6 +272,7 @@ extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const flo
   int threads = 256;
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
+  rc = upload_filters(fn, w, nullptr, nconv, C, s); if (rc) return rc;
   VU_DISPATCH_C(C,
     if (nconv == 1) conv3x3_bwd_data_kernel<CC, 1><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);
     else if (nconv == 2) conv3x3_bwd_data_kernel<CC, 2><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);

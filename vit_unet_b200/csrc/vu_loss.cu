@@ -80,6 +80,55 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// per-image sum of squared error: grid (VU_LN_SPLIT, B) partial sums merged with atomics (out zeroed by the caller)
+__global__ void __launch_bounds__(512)
+image_sse_kernel(const float* __restrict__ p, const float* __restrict__ t, int64_t n, int64_t len, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int64_t beg = (int64_t)blockIdx.x * len, end = min(n, beg + len);
+  const float* pb = p + (int64_t)blockIdx.y * n; const float* tb = t + (int64_t)blockIdx.y * n;
+  float acc = 0.f;
+  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) { float d = pb[i] - tb[i]; acc = fmaf(d, d, acc); }
+  double v[1] = {acc};
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, v[0]);
+}
+// psnr[b] = 10 log10(range_b^2 / mse_b); range_b = data_range if > 0 else (min(target_b) >= 0 ? 1 : 2)  (skimage rule)
+__global__ void psnr_finalize_kernel(const double* __restrict__ sse, const float* __restrict__ tmin, int B, int64_t n,
+                                     float data_range, float* __restrict__ out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float dr = data_range > 0.f ? data_range : (tmin[b] >= 0.f ? 1.f : 2.f);
+  double mse = sse[b] / (double)n;
+  out[b] = (float)(10.0 * log10((double)dr * dr / mse));
+}
+__global__ void __launch_bounds__(512)
+image_min_kernel(const float* __restrict__ t, int64_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  const float* tb = t + (int64_t)blockIdx.x * n;
+  float m = INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fminf(m, tb[i]);
+  m = -warp_max(-m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : INFINITY;
+    v = -warp_max(-v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+  }
+}
+
+// uint8 HWC (cv2.imread layout, any channel count C <= 4) -> float32 CHW, (v * scale - mean) / std per element:
+// DenoisingDataset.__getitem__ (dataset.py:65-68: /255, transpose(2,0,1)) + albumentations.Normalize (run_denoising.py:54)
+__global__ void __launch_bounds__(256)
+u8hwc_to_chw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t total, int C, int HW, float scale,
+                    float mean, float inv_std) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = e / ((int64_t)C * HW); int r = (int)(e - b * C * HW);
+    int c = r / HW, pix = r - c * HW;                      // enumerate in OUTPUT (CHW) order: coalesced stores
+    dst[e] = ((float)src[(b * HW + pix) * C + c] * scale - mean) * inv_std;
+  }
+}
+
 static int ew_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)sm_count() * 16)); }
 
 }  // namespace vu
@@ -133,5 +182,32 @@ extern "C" int vu_adamw(float* p, const float* g, float* m, float* v, int64_t n,
   float bc1 = 1.0f - powf(beta1, (float)step);
   float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
   adamw_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale);
+  return check_launch(fn);
+}
+
+extern "C" int vu_psnr(const float* pred, const float* target, int B, int64_t n, float data_range, double* scratch,
+                       float* psnr, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_psnr";
+  VU_REQUIRE(pred && target && scratch && psnr && B > 0 && n > 0, fn, "bad arguments");
+  cudaStream_t s = as_stream(stream);
+  // scratch: B doubles (sse) followed by B floats (per-image min of target)
+  if (cudaMemsetAsync(scratch, 0, sizeof(double) * B, s) != cudaSuccess) return check_launch(fn);
+  float* tmin = reinterpret_cast<float*>(scratch + B);
+  const int S = VU_LN_SPLIT;
+  const int64_t len = cdiv(n, S);
+  image_sse_kernel<<<dim3(S, B), 512, 0, s>>>(pred, target, n, len, scratch);
+  image_min_kernel<<<B, 512, 0, s>>>(target, n, tmin);
+  psnr_finalize_kernel<<<(unsigned)cdiv(B, 128), 128, 0, s>>>(scratch, tmin, B, n, data_range, psnr);
+  return check_launch(fn);
+}
+
+extern "C" int vu_u8hwc_to_chw(const uint8_t* src, float* dst, int B, int C, int H, int W, float scale, float mean,
+                               float std, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_u8hwc_to_chw";
+  VU_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0 && std != 0.f, fn, "bad arguments");
+  int64_t total = (int64_t)B * C * H * W;
+  u8hwc_to_chw_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(src, dst, total, C, H * W, scale, mean, 1.0f / std);
   return check_launch(fn);
 }

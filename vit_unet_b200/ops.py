@@ -251,6 +251,26 @@ def loss_bwd(kind, pred, target, sums, gscale, dpred):
           nbytes=12.0 * pred.numel())
 
 
+def psnr(pred, target, data_range=0.0):
+    """Per-image PSNR (B,) on the device; data_range <= 0 selects skimage's float rule (1 if min(target) >= 0 else 2)."""
+    B = pred.shape[0]
+    n = pred.numel() // B
+    scratch = torch.empty(2 * B, dtype=torch.float64, device=pred.device)
+    out = torch.empty(B, dtype=torch.float32, device=pred.device)
+    _call("vu_psnr", _chk(pred, "pred"), _chk(target, "target"), B, n, float(data_range),
+          _chk(scratch, "scratch", torch.float64), _chk(out, "psnr"), _stream(), nbytes=12.0 * pred.numel())
+    return out
+
+
+def u8hwc_to_chw(src, scale=1.0 / 255.0, mean=0.0, std=1.0):
+    """uint8 (B,H,W,C) -> float32 (B,C,H,W), (src*scale - mean)/std."""
+    B, H, W, Cc = src.shape
+    dst = torch.empty((B, Cc, H, W), dtype=torch.float32, device=src.device)
+    _call("vu_u8hwc_to_chw", _chk(src, "src", torch.uint8), _chk(dst, "dst"), B, Cc, H, W, scale, mean, std, _stream(),
+          nbytes=5.0 * src.numel())
+    return dst
+
+
 def dropout(x, out, p, seed, sid):
     _call("vu_dropout", _chk(x, "in"), _chk(out, "out"), x.numel(), p, seed, sid, _stream(), nbytes=8.0 * x.numel())
     return out
