@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="base_train", choices=["base_train", "lite_infer", "large_train", "base1ch_dice"],
                     help="base_train is the headline (BASELINE.json metric); the others are extra modes")
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (SURVEY 8(d) C3: 64..256; ~40 GB of the 180 GB at 256)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
     ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "tf32"), choices=["fp32", "tf32"],
                     help="tf32: tcgen05 tensor-core contractions (default, the performance mode); fp32: CUDA-core exact mode")
