@@ -430,3 +430,12 @@ def test_odd_batch_sizes(B):
     ref.eval(); net.eval()
     with torch.no_grad():
         assert _rel(net(x.cuda()), ref(x)) <= 1e-5
+
+
+def test_three_heads_and_unaligned_head_dim():
+    """num_heads = 3 (any count in 1..8 is supported) with head dims 64 / 16; exercises the generic head dispatch."""
+    kw = dict(depth=1, depth_te=1, size_bottleneck=1, preprocessing="conv", im_size=32, patch_size=8,
+              num_channels=3, hidden_dim=16, num_heads=3, attn_drop=0.0, proj_drop=0.0, linear_drop=0)
+    ref, net = _pair("head", kw)
+    x, y = make_input(2, 3, 32)
+    _compare(ref, net, x, y)

@@ -509,9 +509,13 @@ static QuadCtx make_ctx(float drop_p, uint64_t seed, uint32_t stream_id, int N) 
   switch (h) {                                                      \
     case 1: { constexpr int HH = 1; __VA_ARGS__; } break;           \
     case 2: { constexpr int HH = 2; __VA_ARGS__; } break;           \
+    case 3: { constexpr int HH = 3; __VA_ARGS__; } break;           \
     case 4: { constexpr int HH = 4; __VA_ARGS__; } break;           \
+    case 5: { constexpr int HH = 5; __VA_ARGS__; } break;           \
+    case 6: { constexpr int HH = 6; __VA_ARGS__; } break;           \
+    case 7: { constexpr int HH = 7; __VA_ARGS__; } break;           \
     case 8: { constexpr int HH = 8; __VA_ARGS__; } break;           \
-    default: return vu::fail_arg(fn, "num_heads must be 1, 2, 4 or 8"); \
+    default: return vu::fail_arg(fn, "num_heads must be in 1..8");  \
   }
 #define VU_MAP_ARGS_OK(P) ((P) && B > 0 && N > 0 && ld >= N && ld % 4 == 0 && ((uintptr_t)(P) % 16 == 0))
 
