@@ -41,6 +41,10 @@ int vu_pe_fwd(const float* in, int p_in, const float* table, int p_table, float*
 int vu_pe_bwd_table(const float* dout, int p_out, float* dtable, int p_table,
                     int B, int C, int H, int W, int accumulate, void* stream);
 
+/* dst[b][h][e][n] (bfloat16, row pitch ldn >= N, ldn % 8 == 0) = src[b][n][h*(D/h) + e]: per-head transposed bf16
+ * copy of a (B,N,D) token tensor = K-major B operand of the bf16 attention GEMMs (head split of model.py:152). */
+int vu_heads_transpose_bf16(const float* src, void* dst, int B, int N, int D, int h, int ldn, void* stream);
+
 /* ---------------------------------------------------------------- 3x3 convs (model.py:137-139,152-154,428) */
 /* nconv (1..3) bias-optional 3x3 C->C convs sharing one input.  Zero padding at the borders of
  * `border_p`-sized patches (border_p == 0: image borders).  w: [nconv][C][C][3][3], bias: [nconv][C] or NULL.
@@ -80,6 +84,9 @@ typedef struct vu_gemm_desc {
   float drop_p;           /* >0: inverted dropout on act(...) keyed by (drop_seed, drop_stream, m*N+n) */
   uint64_t drop_seed; uint32_t drop_stream;
   int precision;          /* VU_PREC_* */
+  /* element types (tensor-core path only): 0 = float32, 1 = bfloat16.  A and B must agree; a bf16 B operand must be
+   * K-major (trans_b = 1); a bf16 C supports alpha/bias only.  ld* and batch strides count elements of that type. */
+  int a_bf16, b_bf16, c_bf16;
 } vu_gemm_desc;
 
 int vu_gemm(const vu_gemm_desc* d_host, void* stream);
@@ -105,15 +112,16 @@ int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, int N, const
                           const float* gamma, const float* beta, float* running_mean, float* running_var,
                           int64_t* num_batches_tracked, float eps, float momentum, int train,
                           float* fold, float* saved, void* stream);
-/* A_h = sum_g alpha'[h,g]*drop(P_g) + beta'[h] */
-int vu_reattn_mix(const float* P, float* A, const float* fold, int B, int h, int N, int ld,
+/* A_h = sum_g alpha'[h,g]*drop(P_g) + beta'[h].  map_bf16 != 0: A is stored as bfloat16 (same (B,h,N,ld) indexing,
+ * ld % 8 == 0); the mixed map and the gradient map may be bf16, the probabilities P are always fp32. */
+int vu_reattn_mix(const float* P, void* A, int map_bf16, const float* fold, int B, int h, int N, int ld,
                   float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 /* backward reductions: red[h + h*h] (double, caller zeroes) += { s1_h = sum dA_h,  X'_{hg} = sum dA_h (Pd_g - c) } */
 int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, float drop_p, uint64_t seed,
                          uint32_t stream_id, double* red, void* stream);
 /* fused backward pass: A = mix(P) (as vu_reattn_mix) AND the reductions of vu_reattn_bwd_reduce, one read of P, dA */
-int vu_reattn_mix_reduce(const float* P, const float* dA, float* A, const float* fold, int B, int h, int N, int ld,
-                         float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream);
+int vu_reattn_mix_reduce(const float* P, const void* dA, void* A, int map_bf16, const float* fold, int B, int h, int N,
+                         int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream);
 /* closed-form parameter gradients from (red, sums): dW[h*h], dbconv[h], dgamma[h], dbeta[h] are ACCUMULATED
  * (atomic; caller zeroes); coef[2h] = BatchNorm-backward means {mean dA_h, mean dA_h*Ahat_h} for vu_reattn_bwd_rows.
  * sums may be NULL when train == 0. */
@@ -121,7 +129,7 @@ int vu_reattn_bwd_params(const double* red, const double* sums, int B, int h, in
                          const float* bconv, const float* gamma, const float* saved, int train,
                          float* coef, float* dW, float* dbconv, float* dgamma, float* dbeta, void* stream);
 /* in place dA -> dS (gradient of the pre-softmax scores) */
-int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, int N, int ld, const float* W,
+int vu_reattn_bwd_rows(const float* P, void* dA_dS, int map_bf16, int B, int h, int N, int ld, const float* W,
                        const float* bconv, const float* gamma, const float* saved, const float* coef,
                        int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 

@@ -155,3 +155,88 @@ def test_model_tf32_within_1e2():
     def psnr(o):
         return 10 * torch.log10(4.0 / ((o - clean) ** 2).flatten(1).mean(1))
     assert (psnr(a) - psnr(b)).abs().max().item() < 0.01
+
+
+# ------------------------------------------------------------------------------------------------ bf16 operands
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (784, 24, 784), (300, 72, 200), (256, 128, 512)])
+@pytest.mark.parametrize("ta", [False, True])
+def test_tc_gemm_bf16_operands(ops, M, N, K, ta):
+    """kind::f16 path: bf16 A (K-major or MN-major) x bf16 K-major B -> fp32 C."""
+    def pad8(n): return (n + 7) // 8 * 8
+    A = torch.zeros(K, pad8(M)) if ta else torch.zeros(M, pad8(K))
+    if ta: A[:, :M] = _rand(K, M, seed=1)
+    else: A[:, :K] = _rand(M, K, seed=1)
+    Bm = torch.zeros(N, pad8(K)); Bm[:, :K] = _rand(N, K, seed=2)
+    Ab, Bb = A.bfloat16(), Bm.bfloat16()
+    Al = (Ab[:, :M].t() if ta else Ab[:, :K]).double()
+    exp = Al @ Bb[:, :K].double().t()
+    out = torch.full((M, (N + 3) // 4 * 4), 7.0, device="cuda")
+    ops.gemm(Ab.cuda(), Bb.cuda(), out, M, N, K, trans_a=ta, trans_b=True, lda=A.shape[1], ldb=Bm.shape[1],
+             ldc=out.shape[1], precision=ops.PREC_TF32)
+    _close(out[:, :N], exp, 2e-5 * math.sqrt(K) + 1e-5, name=f"bf16 gemm ta={ta}")     # inputs are exact bf16 values
+    assert torch.all(out[:, N:] == 7.0)
+
+
+def test_tc_gemm_bf16_output_and_transposed_heads(ops):
+    """dA = dO V^T written as bf16; A.V / A^T.dO with the per-head transposed bf16 copies (the engine's bf16-map path)."""
+    B, h, Nt, hd = 2, 8, 784, 24
+    D = h * hd
+    dO, v = _rand(B, Nt, D, seed=7), _rand(B, Nt, D, seed=8)
+    dA = torch.zeros(B, h, Nt, Nt, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(dO.cuda(), v.cuda(), dA, Nt, Nt, hd, trans_b=True, lda=D, ldb=D, ldc=Nt, batch_outer=B, batch_inner=h,
+             sA=(Nt * D, hd), sB=(Nt * D, hd), sC=(h * Nt * Nt, Nt * Nt), precision=ops.PREC_TF32)
+    d4, v4 = dO.reshape(B, Nt, h, hd).double(), v.reshape(B, Nt, h, hd).double()
+    exp = torch.einsum("bihe,bjhe->bhij", d4, v4)
+    _close(dA.float(), exp, 6e-3, "bf16 map output")
+    vt = ops.heads_transpose_bf16(v.cuda(), B, Nt, D, h)
+    assert torch.equal(vt[..., :Nt].float().cpu(), v.reshape(B, Nt, h, hd).permute(0, 2, 3, 1).bfloat16().float())
+    O = torch.zeros(B, Nt, D, device="cuda")
+    ldn = vt.shape[-1]
+    ops.gemm(dA, vt, O, Nt, hd, Nt, trans_b=True, lda=Nt, ldb=ldn, ldc=D, batch_outer=B, batch_inner=h,
+             sA=(h * Nt * Nt, Nt * Nt), sB=(h * hd * ldn, hd * ldn), sC=(Nt * D, hd), precision=ops.PREC_TF32)
+    expO = torch.einsum("bhij,bjhe->bihe", dA.float().cpu().double(), vt[..., :Nt].float().cpu().double().permute(0, 3, 1, 2)
+                        ).reshape(B, Nt, D)
+    _close(O, expO, 1e-4, "bf16 A.V")
+    dV = torch.zeros(B, Nt, D, device="cuda")
+    ops.gemm(dA, vt, dV, Nt, hd, Nt, trans_a=True, trans_b=True, lda=Nt, ldb=ldn, ldc=D, batch_outer=B, batch_inner=h,
+             sA=(h * Nt * Nt, Nt * Nt), sB=(h * hd * ldn, hd * ldn), sC=(Nt * D, hd), precision=ops.PREC_TF32)
+    expdV = torch.einsum("bhij,bihe->bjhe", dA.float().cpu().double(), vt[..., :Nt].float().cpu().double().permute(0, 3, 1, 2)
+                         ).reshape(B, Nt, D)
+    _close(dV, expdV, 1e-4, "bf16 A^T.dO")
+
+
+def test_model_bf16_maps_within_1e2():
+    """TF32 path with bf16 storage of the mixed / gradient maps: eval output within 1e-2 of the oracle, PSNR delta
+    < 0.01 dB, and the training-step gradients stay close to the fp32-map TF32 path."""
+    import contextlib, io
+    import vit_unet_b200 as vu
+    from make_golden import CONFIGS, fill_state_dict, make_input
+    from oracle import vit_unet_oracle as O
+    _, kw, _ = CONFIGS["base_head"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref, net = O.HViT_UNet(**kw), vu.HViT_UNet(**kw)
+    sd = fill_state_dict(ref.state_dict())
+    ref.load_state_dict(sd); net.load_state_dict(sd); net.to("cuda")
+    x, clean = make_input(2, 3, 224)
+    ref.eval(); net.eval()
+    vu.set_precision("tf32")
+    grads = {}
+    try:
+        for mode in (False, True):
+            vu.set_bf16_maps(mode)
+            with torch.no_grad():
+                out = net(x.cuda()).cpu()
+            if mode:
+                a = ref(x).detach()
+                rel = ((a - out).abs().max() / a.abs().max()).item()
+                assert rel <= 1e-2, rel
+                psnr = lambda o: 10 * torch.log10(4.0 / ((o - clean) ** 2).flatten(1).mean(1))
+                assert (psnr(a) - psnr(out)).abs().max().item() < 0.01
+            net.zero_grad()
+            vu.l1_loss(net(x.cuda()), clean.cuda()).backward()       # eval-mode gradients: well conditioned
+            grads[mode] = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+    finally:
+        vu.set_bf16_maps(False); vu.set_precision("fp32")
+    worst = max(((grads[True][n] - grads[False][n]).abs().max() / grads[False][n].abs().max().clamp_min(1e-30)).item()
+                for n in grads[False] if grads[False][n].abs().max() > 1e-8)
+    assert worst <= 5e-2, worst

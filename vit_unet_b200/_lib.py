@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitunet_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class VuError(RuntimeError):
@@ -30,6 +30,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float), ("act", C.c_int), ("accumulate", C.c_int), ("split_k", C.c_int),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint64), ("drop_stream", C.c_uint32),
         ("precision", C.c_int),
+        ("a_bf16", C.c_int), ("b_bf16", C.c_int), ("c_bf16", C.c_int),
     ]
 
 
@@ -38,6 +39,7 @@ _p, _i, _l, _f, _u64, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint
 # name -> argtypes; every function returns int (status) unless listed in _SPECIAL
 SIGNATURES = {
     "vu_repatch": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "vu_heads_transpose_bf16": [_p, _p, _i, _i, _i, _i, _i, _p],
     "vu_pe_fwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     "vu_pe_bwd_table": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "vu_conv3x3_fwd": [_p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
@@ -47,13 +49,13 @@ SIGNATURES = {
     "vu_colsum": [_p, _l, _i, _l, _p, _i, _p],
     "vu_softmax_rows": [_p, _l, _i, _i, _f, _p],
     "vu_softmax_stats": [_p, _i, _i, _i, _i, _f, _f, _u64, _u32, _p, _p],
-    "vu_reattn_mix_reduce": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
+    "vu_reattn_mix_reduce": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_stats": [_p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bn_finalize": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p],
-    "vu_reattn_mix": [_p, _p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p],
+    "vu_reattn_mix": [_p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p],
     "vu_reattn_bwd_reduce": [_p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bwd_params": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
-    "vu_reattn_bwd_rows": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _f, _u64, _u32, _p],
+    "vu_reattn_bwd_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _f, _u64, _u32, _p],
     "vu_ln_stats": [_p, _i, _l, _f, _p, _p, _p],
     "vu_ln_apply": [_p, _p, _p, _p, _p, _i, _l, _p],
     "vu_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p],

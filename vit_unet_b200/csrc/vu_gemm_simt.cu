@@ -298,10 +298,13 @@ extern "C" int vu_gemm(const vu_gemm_desc* d, void* stream) {
     VU_REQUIRE(d->act == VU_ACT_NONE && d->drop_p == 0.f, fn, "split_k cannot be combined with activation/dropout");
   VU_REQUIRE(d->drop_p == 0.f || d->ldc == d->N, fn, "dropout epilogue needs a dense C (ldc == N)");
   cudaStream_t s = as_stream(stream);
+  const bool any_bf16 = d->a_bf16 || d->b_bf16 || d->c_bf16;
+  VU_REQUIRE(!any_bf16 || d->precision == VU_PREC_TF32, fn, "bfloat16 operands need the tensor-core path (precision = VU_PREC_TF32)");
   if (d->precision == VU_PREC_TF32) {
     bool handled = false;
     int rc = gemm_tc(*d, s, &handled);
     if (rc != VU_OK || handled) return rc;
+    VU_REQUIRE(!any_bf16, fn, "bfloat16 GEMM could not be mapped onto the tensor-core kernel");
     // shapes the tensor-core kernel does not cover fall through to the CUDA-core kernel (same numerics class
     // or better); this is a kernel choice inside the CUDA path, not a CPU fallback.
   } else {

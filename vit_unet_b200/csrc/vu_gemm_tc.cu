@@ -15,6 +15,7 @@
 // warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global), each owning its TMEM lane quarter.
 // One 128 x BLOCK_N output tile per CTA; two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 #include "vu_common.cuh"
@@ -35,6 +36,7 @@ struct TcArgs {
   float alpha; int act; int accumulate; int split_k; int k_per_split;
   float drop_scale; uint32_t drop_thresh; uint64_t drop_seed; uint32_t drop_stream;
   uint32_t mn_lbo, mn_sbo;      // MN-major descriptor strides (bytes)
+  int c_bf16;                   // C is __nv_bfloat16 (plain store / accumulate only)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -90,6 +92,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -114,14 +124,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 // cute::UMMA::InstrDescriptor: F32 accumulate, TF32 x TF32, M=128
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn, bool b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, bool bf16) {
+  const uint32_t fmt = bf16 ? 1u : 2u;        // F16F32Format: 1 = BF16, 2 = TF32
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+// BF16 = true: both operands are __nv_bfloat16 (kind::f16, 64 elements per 128-byte k-block, UMMA_K = 16); the B
+// operand must then be K-major (the engine keeps transposed bf16 copies of q/k/v/dO for that), A may be MN-major
+// with the ordinary SWIZZLE_128B atoms (64 elements x 8 k-rows; two 8 KB slabs per stage).
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool BF16>
 __global__ void __launch_bounds__(192, 3)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
+  static_assert(!(BF16 && B_MN), "bf16 B operands are K-major");
+  constexpr int KB = BF16 ? 64 : 32;                    // elements per 128-byte k-block
   constexpr uint32_t A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 4;
   constexpr uint32_t B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
@@ -146,7 +162,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int zo = z / g.batch_inner, zi = z % g.batch_inner;
   const int kbeg = ks * g.k_per_split;
   const int kend = min(g.K, kbeg + g.k_per_split);
-  const int nkb = (kend - kbeg + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  const int nkb = (kend - kbeg + KB - 1) / KB;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -169,11 +185,14 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
         mbar_expect_tx(full_bar + s, A_BYTES + B_BYTES);
-        const int k0 = kbeg + kb * TC_BLOCK_K;
+        const int k0 = kbeg + kb * KB;
         uint8_t* a_dst = sA + s * A_BYTES;
         uint8_t* b_dst = sB + s * B_BYTES;
         if (!A_MN) tma_load_4d(a_dst, &tmA, full_bar + s, k0, m0, zi, zo);
-        else {
+        else if (BF16) {
+#pragma unroll
+          for (int sl = 0; sl < TC_BLOCK_M / 64; ++sl) tma_load_4d(a_dst + sl * 8192, &tmA, full_bar + s, m0 + sl * 64, k0, zi, zo);
+        } else {
 #pragma unroll
           for (int sl = 0; sl < TC_BLOCK_M / 32; ++sl) tma_load_4d(a_dst + sl * 4096, &tmA, full_bar + s, m0 + sl * 32, k0, zi, zo);
         }
@@ -186,7 +205,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_N, A_MN, B_MN);
+    constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN, BF16);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
@@ -196,9 +215,12 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
         for (int kk = 0; kk < TC_BLOCK_K / TC_UMMA_K; ++kk) {
-          const uint64_t ad = A_MN ? make_smem_desc(a_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(a_base + kk * 32, 16, 1024, 2);
+          const uint64_t ad = !A_MN ? make_smem_desc(a_base + kk * 32, 16, 1024, 2)
+                              : (BF16 ? make_smem_desc(a_base + kk * 2048, 8192, 1024, 2)
+                                      : make_smem_desc(a_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1));
           const uint64_t bd = B_MN ? make_smem_desc(b_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(b_base + kk * 32, 16, 1024, 2);
-          umma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+          if (BF16) umma_bf16(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+          else umma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar + s);                       // frees the smem slot once these MMAs retire
         if (kb == nkb - 1) umma_commit(tmem_full_bar);    // accumulator complete -> epilogue
@@ -257,6 +279,18 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (m >= g.M || nv <= 0) continue;
       const float4 t4 = *reinterpret_cast<const float4*>(stage + row * LDS + cl);
       float v[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
+      if (g.c_bf16) {          // bf16 map output: plain store (host side rejects epilogues other than alpha/bias)
+        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + coff + (int64_t)m * g.ldc + n;
+        if (nv == 4 && ((uintptr_t)cb % 8 == 0)) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(cb) = pk;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) cb[j] = __float2bfloat16_rn(v[j]);
+        }
+        continue;
+      }
       float* dst = C + (int64_t)m * g.ldc + n;
       if (g.split_k > 1) {
         if (g.residual && ks == 0) {
@@ -342,30 +376,31 @@ static EncodeTiledFn get_encode() {
 }
 
 // 4-D view of one operand: (contiguous extent, rows extent [stride ld], inner batch [stride sI], outer batch [stride sO])
-static bool encode_operand(CUtensorMap* tm, const float* base, int64_t contig, int64_t rows, int64_t ld, int bi,
-                           int64_t sI, int bo, int64_t sO, int box_contig, int box_rows, bool mn_major) {
+static bool encode_operand(CUtensorMap* tm, const void* base, int64_t contig, int64_t rows, int64_t ld, int bi,
+                           int64_t sI, int bo, int64_t sO, int box_contig, int box_rows, bool mn_major, bool bf16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
-  if ((uintptr_t)base % 16 != 0 || ld % 4 != 0) return false;
-  if (bi > 1 && sI % 4 != 0) return false;
-  if (bo > 1 && sO % 4 != 0) return false;
+  const int esz = bf16 ? 2 : 4, al = 16 / esz;          // strides must be multiples of 16 bytes
+  if ((uintptr_t)base % 16 != 0 || ld % al != 0) return false;
+  if (bi > 1 && sI % al != 0) return false;
+  if (bo > 1 && sO % al != 0) return false;
   cuuint64_t dims[4] = {(cuuint64_t)contig, (cuuint64_t)rows, (cuuint64_t)(bi > 0 ? bi : 1), (cuuint64_t)(bo > 0 ? bo : 1)};
   // unused batch dims still need a legal (multiple of 16 B, non-zero) stride
-  cuuint64_t st_i = (bi > 1 ? (cuuint64_t)sI : (cuuint64_t)ld * (cuuint64_t)rows) * 4;
-  cuuint64_t st_o = (bo > 1 ? (cuuint64_t)sO : (cuuint64_t)ld * (cuuint64_t)rows) * 4;
+  cuuint64_t st_i = (bi > 1 ? (cuuint64_t)sI : (cuuint64_t)ld * (cuuint64_t)rows) * esz;
+  cuuint64_t st_o = (bo > 1 ? (cuuint64_t)sO : (cuuint64_t)ld * (cuuint64_t)rows) * esz;
   if (st_i == 0) st_i = 16; if (st_o == 0) st_o = 16;
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, st_i, st_o};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * esz, st_i, st_o};
   cuuint32_t box[4] = {(cuuint32_t)box_contig, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool BF16 = false>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& g, bool a_mn, bool b_mn, int nbatch,
                      cudaStream_t s) {
   constexpr size_t ring = (size_t)STAGES * (TC_BLOCK_M * TC_BLOCK_K * 4 + BLOCK_N * TC_BLOCK_K * 4);
@@ -375,7 +410,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
   dim3 block(192);
 #define VU_TC_LAUNCH(AMN, BMN)                                                                                   \
   do {                                                                                                            \
-    auto kfn = gemm_tf32_tc_kernel<BLOCK_N, STAGES, AMN, BMN>;                                                    \
+    auto kfn = gemm_tf32_tc_kernel<BLOCK_N, STAGES, AMN, BMN, BF16>;                                                    \
     static bool attr_set = false;                                                                                 \
     if (!attr_set) {                                                                                              \
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)       \
@@ -384,31 +419,42 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
     }                                                                                                             \
     kfn<<<grid, block, smem, s>>>(tmA, tmB, g);                                                                   \
   } while (0)
-  if (!a_mn && !b_mn) VU_TC_LAUNCH(false, false);
-  else if (!a_mn && b_mn) VU_TC_LAUNCH(false, true);
-  else if (a_mn && b_mn) VU_TC_LAUNCH(true, true);
-  else VU_TC_LAUNCH(true, false);
+  if constexpr (BF16) {
+    if (!a_mn) VU_TC_LAUNCH(false, false);
+    else VU_TC_LAUNCH(true, false);
+  } else {
+    if (!a_mn && !b_mn) VU_TC_LAUNCH(false, false);
+    else if (!a_mn && b_mn) VU_TC_LAUNCH(false, true);
+    else if (a_mn && b_mn) VU_TC_LAUNCH(true, true);
+    else VU_TC_LAUNCH(true, false);
+  }
 #undef VU_TC_LAUNCH
   return check_launch("vu_gemm(tc)");
 }
 
 int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   *handled = false;
+  const bool bf16 = d.a_bf16 != 0;
+  if ((d.a_bf16 != 0) != (d.b_bf16 != 0)) return fail_arg("vu_gemm", "A and B must have the same element type");
   const bool a_mn = d.trans_a != 0;        // A(m,k) = A[k*lda + m]  -> m contiguous
   const bool b_mn = d.trans_b == 0;        // B(k,n) = B[k*ldb + n]  -> n contiguous
+  if (bf16 && b_mn) return fail_arg("vu_gemm", "bf16 B operand must be K-major (trans_b = 1)");
+  if (d.c_bf16 && (d.residual || d.aux_in || d.aux_out || d.act != VU_ACT_NONE || d.drop_p > 0.f || d.split_k > 1 || d.accumulate))
+    return fail_arg("vu_gemm", "bf16 output supports only alpha/bias epilogues");
   const int bi = d.batch_inner > 0 ? d.batch_inner : 1, bo = d.batch_outer > 0 ? d.batch_outer : 1;
+  const int kb_elems = bf16 ? 64 : TC_BLOCK_K;
   int block_n = d.N <= 32 ? 32 : (d.N <= 64 ? 64 : 128);
-  const int kps0 = (int)cdiv(cdiv(d.K, d.split_k > 1 ? d.split_k : 1), TC_BLOCK_K) * TC_BLOCK_K;
-  const bool one_kb_narrow = block_n == 128 && kps0 <= TC_BLOCK_K && getenv("VU_TC_QK128") == nullptr;
+  const int kps0 = (int)cdiv(cdiv(d.K, d.split_k > 1 ? d.split_k : 1), kb_elems) * kb_elems;
+  const bool one_kb_narrow = !bf16 && block_n == 128 && kps0 <= kb_elems && getenv("VU_TC_QK128") == nullptr;
   if (one_kb_narrow) block_n = 64;      // box width of the B operand must match the kernel's BLOCK_N
   CUtensorMap tmA, tmB;
   bool ok;
-  if (!a_mn) ok = encode_operand(&tmA, d.A, d.K, d.M, d.lda, bi, d.sAi, bo, d.sAo, TC_BLOCK_K, TC_BLOCK_M, false);
-  else ok = encode_operand(&tmA, d.A, d.M, d.K, d.lda, bi, d.sAi, bo, d.sAo, 32, TC_BLOCK_K, true);
-  if (!ok) return VU_OK;
-  if (!b_mn) ok = encode_operand(&tmB, d.B, d.K, d.N, d.ldb, bi, d.sBi, bo, d.sBo, TC_BLOCK_K, block_n, false);
-  else ok = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, 32, TC_BLOCK_K, true);
-  if (!ok) return VU_OK;
+  if (!a_mn) ok = encode_operand(&tmA, d.A, d.K, d.M, d.lda, bi, d.sAi, bo, d.sAo, kb_elems, TC_BLOCK_M, false, bf16);
+  else ok = encode_operand(&tmA, d.A, d.M, d.K, d.lda, bi, d.sAi, bo, d.sAo, bf16 ? 64 : 32, kb_elems, true, bf16);
+  if (!ok) return bf16 ? fail_arg("vu_gemm", "bf16 operand A is not TMA-addressable (16-byte alignment of base/strides)") : VU_OK;
+  if (!b_mn) ok = encode_operand(&tmB, d.B, d.K, d.N, d.ldb, bi, d.sBi, bo, d.sBo, kb_elems, block_n, false, bf16);
+  else ok = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, 32, kb_elems, true, bf16);
+  if (!ok) return bf16 ? fail_arg("vu_gemm", "bf16 operand B is not TMA-addressable (16-byte alignment of base/strides)") : VU_OK;
 
   TcArgs g;
   g.C = d.C; g.bias = d.bias; g.residual = d.residual; g.aux_in = d.aux_in; g.aux_out = d.aux_out;
@@ -416,18 +462,21 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   g.batch_inner = bi; g.sCo = d.sCo; g.sCi = d.sCi;
   g.alpha = d.alpha; g.act = d.act; g.accumulate = d.accumulate;
   g.split_k = d.split_k > 1 ? d.split_k : 1;
-  int kps = (int)cdiv(cdiv(g.K, g.split_k), TC_BLOCK_K) * TC_BLOCK_K;
+  int kps = (int)cdiv(cdiv(g.K, g.split_k), kb_elems) * kb_elems;
   g.k_per_split = kps;
   g.split_k = (int)cdiv(g.K, kps);
   g.drop_thresh = d.drop_p > 0.f ? drop_threshold(d.drop_p) : 0u;
   g.drop_scale = drop_keep_scale(d.drop_p);
   g.drop_seed = d.drop_seed; g.drop_stream = d.drop_stream;
   g.mn_lbo = 4096; g.mn_sbo = 512;
-  if (const char* e = getenv("VU_TC_MN_LBO")) g.mn_lbo = (uint32_t)atoi(e);
-  if (const char* e = getenv("VU_TC_MN_SBO")) g.mn_sbo = (uint32_t)atoi(e);
+  g.c_bf16 = d.c_bf16 != 0;
   const int nbatch = bi * bo;
   int rc;
-  if (block_n == 32) rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  if (bf16) {
+    if (block_n == 32) rc = launch_tc<32, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    else if (block_n == 64) rc = launch_tc<64, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    else rc = launch_tc<128, 3, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  } else if (block_n == 32) rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
   else if (one_kb_narrow) rc = launch_tc<64, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);   // one k-block, output-bound: 6 CTAs/SM
   else if (block_n == 64) rc = launch_tc<64, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
   else if (g.k_per_split <= TC_BLOCK_K) rc = launch_tc<128, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);

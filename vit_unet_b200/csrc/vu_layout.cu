@@ -2,6 +2,8 @@
 // PatchEncoder add (model.py:84-91; ViT_UNet.ipynb c16).  Pure HBM-bound gathers: one read, one write.
 // A run of 4 pixels along x that starts at x % 4 == 0 is contiguous in every layout whose patch size is a
 // multiple of 4, so the common case moves float4s; otherwise a scalar path is used.
+#include <cuda_bf16.h>
+
 #include "vu_common.cuh"
 
 namespace vu {
@@ -81,6 +83,29 @@ pe_bwd_table_kernel(const float* __restrict__ dout, float* __restrict__ dtable, 
   }
 }
 
+// dst[b][h][e][n] (bf16, row pitch ldn) = src[b][n][h*hd + e] (fp32): per-head TRANSPOSED bf16 copy of a token tensor,
+// so that it can be the K-major B operand (k = token index contiguous) of the bf16 tensor-core GEMMs
+// A.V, dS.K, dS^T.Q and A^T.dO.  32x32 smem tile transpose: coalesced reads along e, coalesced writes along n.
+__global__ void __launch_bounds__(256)
+heads_transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int D, int hd, int h,
+                            int ldn) {
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z, b = z / h, hh = z - b * h;
+  const int n0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int n = n0 + ty + r, e = e0 + tx;
+    tile[ty + r][tx] = (n < N && e < hd) ? src[((int64_t)b * N + n) * D + hh * hd + e] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int e = e0 + ty + r, n = n0 + tx;
+    if (e < hd && n < N) dst[(((int64_t)b * h + hh) * hd + e) * ldn + n] = __float2bfloat16_rn(tile[tx][ty + r]);
+  }
+}
+
 static bool layout_ok(int H, int W, int p) { return p == 0 || (p > 0 && H % p == 0 && W % p == 0); }
 static bool vec_ok(int W, int p) { return p == 0 ? (W % 4 == 0) : (p % 4 == 0); }
 
@@ -133,5 +158,15 @@ extern "C" int vu_pe_bwd_table(const float* dout, int p_out, float* dtable, int 
   cudaStream_t s = as_stream(stream);
   if (vec) pe_bwd_table_kernel<4><<<(int)cdiv(per / 4, threads), threads, 0, s>>>(dout, dtable, lo, lt, per, B, accumulate);
   else pe_bwd_table_kernel<1><<<(int)cdiv(per, threads), threads, 0, s>>>(dout, dtable, lo, lt, per, B, accumulate);
+  return check_launch(fn);
+}
+
+extern "C" int vu_heads_transpose_bf16(const float* src, void* dst, int B, int N, int D, int h, int ldn, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_heads_transpose_bf16";
+  VU_REQUIRE(src && dst && B > 0 && N > 0 && D > 0 && h > 0 && D % h == 0 && ldn >= N, fn, "bad arguments");
+  const int hd = D / h;
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(hd, 32), (unsigned)(B * h));
+  heads_transpose_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, N, D, hd, h, ldn);
   return check_launch(fn);
 }

@@ -9,9 +9,27 @@
 // matrix, conv bias, BN gamma/beta) follow in closed form (reattn_bwd_params_kernel) -- the big kernels only stream.
 // Every streaming kernel handles 4 consecutive keys per thread (float4) so that one Philox4x32 call yields the
 // dropout mask of the whole quad; masks are regenerated, never stored.
+#include <cuda_bf16.h>
+
 #include "vu_common.cuh"
 
 namespace vu {
+
+// The mixed map A and the gradient map dA/dS may be stored as bfloat16 (half the HBM bytes; consumed by the bf16
+// tensor-core GEMMs); the probabilities P always stay fp32.
+__device__ __forceinline__ float4 map_ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 map_ld(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void map_st(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void map_st(__nv_bfloat16* p, const float4& v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
 
 // ------------------------------------------------------------------ row softmax (one warp per row)
 __global__ void __launch_bounds__(256)
@@ -222,9 +240,9 @@ __global__ void reattn_bn_finalize_kernel(const double* __restrict__ sums, doubl
 }
 
 // A_h = sum_g fold[h][g] * Pd_g + fold[H*H + h]; 4 positions per thread along j (float4)
-template <int H>
+template <int H, typename MT>
 __global__ void __launch_bounds__(256, 3)
-reattn_mix_kernel(const float* __restrict__ P, float* __restrict__ A, const float* __restrict__ fold,
+reattn_mix_kernel(const float* __restrict__ P, MT* __restrict__ A, const float* __restrict__ fold,
                   int B, int N, int ld, QuadCtx q) {
   __shared__ float sF[H * H + H];
   for (int i = threadIdx.x; i < H * H + H; i += blockDim.x) sF[i] = fold[i];
@@ -251,16 +269,16 @@ reattn_mix_kernel(const float* __restrict__ P, float* __restrict__ A, const floa
       if (j + 3 >= N) {      // keep the pad columns at zero
         if (j + 0 >= N) a.x = 0.f; if (j + 1 >= N) a.y = 0.f; if (j + 2 >= N) a.z = 0.f; if (j + 3 >= N) a.w = 0.f;
       }
-      *reinterpret_cast<float4*>(A + off + h * head_stride) = a;
+      map_st(A + off + h * head_stride, a);
     }
   }
 }
 
 // Backward fusion: one read of P and dA gives both the recomputed mixed map A (needed for dV = A^T dO) and the
 // backward reductions red[h] += sum dA_h, red[H + h*H + g] += sum dA_h (Pd_g - c).
-template <int H>
+template <int H, typename MT>
 __global__ void __launch_bounds__(256)
-reattn_mix_reduce_kernel(const float* __restrict__ P, const float* __restrict__ dA, float* __restrict__ A,
+reattn_mix_reduce_kernel(const float* __restrict__ P, const MT* __restrict__ dA, MT* __restrict__ A,
                          const float* __restrict__ fold, int B, int N, int ld, QuadCtx q, double* __restrict__ out) {
   constexpr int NV = H + H * H;
   __shared__ double red[NV * 32];
@@ -290,13 +308,13 @@ reattn_mix_reduce_kernel(const float* __restrict__ P, const float* __restrict__ 
         a.x = fmaf(w, p[g].x, a.x); a.y = fmaf(w, p[g].y, a.y); a.z = fmaf(w, p[g].z, a.z); a.w = fmaf(w, p[g].w, a.w);
       }
       if (j + 3 >= N) { if (j + 0 >= N) a.x = 0.f; if (j + 1 >= N) a.y = 0.f; if (j + 2 >= N) a.z = 0.f; if (j + 3 >= N) a.w = 0.f; }
-      *reinterpret_cast<float4*>(A + off + h * head_stride) = a;
+      map_st(A + off + h * head_stride, a);
     }
 #pragma unroll
     for (int g = 0; g < H; ++g) centre(p[g], j, q);
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      float4 d = *reinterpret_cast<const float4*>(dA + off + h * head_stride);
+      float4 d = map_ld(dA + off + h * head_stride);
       if (j + 3 >= N) { if (j + 0 >= N) d.x = 0.f; if (j + 1 >= N) d.y = 0.f; if (j + 2 >= N) d.z = 0.f; if (j + 3 >= N) d.w = 0.f; }
       acc[h] += sum4(d);
 #pragma unroll
@@ -403,9 +421,9 @@ __global__ void reattn_bwd_params_kernel(const double* __restrict__ red, const d
 //   dM_h  = k_h (dA_h - m1_h - Ahat_h m2_h)   (train)   |   k_h dA_h   (eval)
 //   dPd_g = sum_h W[h][g] dM_h ;  dP_g = keep_g dPd_g / (1-p)
 //   r_g   = sum_j dP_g P_g ;       dS_g = scale * P_g (dP_g - r_g)           (written over dA)
-template <int H>
+template <int H, typename MT>
 __global__ void __launch_bounds__(128)
-reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int B, int N, int ld,
+reattn_bwd_rows_kernel(const float* __restrict__ P, MT* __restrict__ dA, int B, int N, int ld,
                        const float* __restrict__ W, const float* __restrict__ bconv, const float* __restrict__ gamma,
                        const float* __restrict__ saved, const float* __restrict__ coef, int train, float scale,
                        QuadCtx q) {
@@ -446,7 +464,7 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int 
       }
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        float4 d = *reinterpret_cast<const float4*>(dA + row_off + h * head_stride + j);
+        float4 d = map_ld(dA + row_off + h * head_stride + j);
         float4 t = d;
         if (train) {
           float4 m = make_float4(sOff[h], sOff[h], sOff[h], sOff[h]);
@@ -472,7 +490,7 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int 
         dp.x = (keep[g].x && j + 0 < N) ? dp.x * q.dscale : 0.f; dp.y = (keep[g].y && j + 1 < N) ? dp.y * q.dscale : 0.f;
         dp.z = (keep[g].z && j + 2 < N) ? dp.z * q.dscale : 0.f; dp.w = (keep[g].w && j + 3 < N) ? dp.w * q.dscale : 0.f;
         rg[g] += dot4(dp, p[g]);
-        *reinterpret_cast<float4*>(dA + row_off + g * head_stride + j) = dp;
+        map_st(dA + row_off + g * head_stride + j, dp);
       }
     }
 #pragma unroll
@@ -481,11 +499,11 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dA, int 
 #pragma unroll
       for (int g = 0; g < H; ++g) {
         float4 pv = *reinterpret_cast<const float4*>(P + row_off + g * head_stride + j);
-        float4 dp = *reinterpret_cast<const float4*>(dA + row_off + g * head_stride + j);
+        float4 dp = map_ld(dA + row_off + g * head_stride + j);
         float4 o;
         o.x = scale * pv.x * (dp.x - rg[g]); o.y = scale * pv.y * (dp.y - rg[g]);
         o.z = scale * pv.z * (dp.z - rg[g]); o.w = scale * pv.w * (dp.w - rg[g]);   // pad columns: P == 0 -> 0
-        *reinterpret_cast<float4*>(dA + row_off + g * head_stride + j) = o;
+        map_st(dA + row_off + g * head_stride + j, o);
       }
     }
   }
@@ -555,15 +573,17 @@ extern "C" int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, i
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_mix(const float* P, float* A, const float* fold, int B, int h, int N, int ld,
+extern "C" int vu_reattn_mix(const float* P, void* A, int map_bf16, const float* fold, int B, int h, int N, int ld,
                              float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_mix";
   VU_REQUIRE(VU_MAP_ARGS_OK(P) && A && fold && ((uintptr_t)A % 16 == 0), fn, "bad arguments");
+  VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256, 16);
-  VU_DISPATCH_H(h, fn, reattn_mix_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, A, fold, B, N, ld, q));
+  if (map_bf16) { VU_DISPATCH_H(h, fn, reattn_mix_kernel<HH, __nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)A, fold, B, N, ld, q)); }
+  else { VU_DISPATCH_H(h, fn, reattn_mix_kernel<HH, float><<<blocks, 256, 0, as_stream(stream)>>>(P, (float*)A, fold, B, N, ld, q)); }
   return check_launch(fn);
 }
 
@@ -591,7 +611,7 @@ extern "C" int vu_reattn_bwd_params(const double* red, const double* sums, int B
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, int N, int ld, const float* W,
+extern "C" int vu_reattn_bwd_rows(const float* P, void* dA_dS, int map_bf16, int B, int h, int N, int ld, const float* W,
                                   const float* bconv, const float* gamma, const float* saved, const float* coef,
                                   int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
@@ -600,8 +620,11 @@ extern "C" int vu_reattn_bwd_rows(const float* P, float* dA_dS, int B, int h, in
   VU_REQUIRE(!train || coef, fn, "train mode needs the BN-backward coefficients");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   int blocks = grid_for((int64_t)B * N * 32, 128, 12);
-  VU_DISPATCH_H(h, fn, reattn_bwd_rows_kernel<HH><<<blocks, 128, 0, as_stream(stream)>>>(
-      P, dA_dS, B, N, ld, W, bconv, gamma, saved, coef, train, scale, q));
+  VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
+  if (map_bf16) { VU_DISPATCH_H(h, fn, reattn_bwd_rows_kernel<HH, __nv_bfloat16><<<blocks, 128, 0, as_stream(stream)>>>(
+      P, (__nv_bfloat16*)dA_dS, B, N, ld, W, bconv, gamma, saved, coef, train, scale, q)); }
+  else { VU_DISPATCH_H(h, fn, reattn_bwd_rows_kernel<HH, float><<<blocks, 128, 0, as_stream(stream)>>>(
+      P, (float*)dA_dS, B, N, ld, W, bconv, gamma, saved, coef, train, scale, q)); }
   return check_launch(fn);
 }
 
@@ -617,15 +640,18 @@ extern "C" int vu_softmax_stats(float* S, int B, int h, int N, int ld, float sca
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_mix_reduce(const float* P, const float* dA, float* A, const float* fold, int B, int h, int N,
-                                    int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream) {
+extern "C" int vu_reattn_mix_reduce(const float* P, const void* dA, void* A, int map_bf16, const float* fold, int B, int h,
+                                    int N, int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red,
+                                    void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_mix_reduce";
   VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA && A && fold && red && ((uintptr_t)dA % 16 == 0) && ((uintptr_t)A % 16 == 0), fn,
              "bad arguments");
+  VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);
-  VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(P, dA, A, fold, B, N, ld, q, red));
+  if (map_bf16) { VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH, __nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, B, N, ld, q, red)); }
+  else { VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH, float><<<blocks, 256, 0, as_stream(stream)>>>(P, (const float*)dA, (float*)A, fold, B, N, ld, q, red)); }
   return check_launch(fn);
 }

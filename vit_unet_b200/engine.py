@@ -27,6 +27,15 @@ _CHUNK_STREAM = 4096          # Philox stream offset per image slice (layer stre
 _MAP_L2_BYTES = {"value": int(float(os.environ.get("VU_MAP_L2_MB", "0")) * (1 << 20))}
 
 
+# bf16 storage of the mixed map A and the gradient map dA/dS (probabilities P stay fp32) on the tensor-core path:
+# halves the HBM bytes of the five map-consuming GEMMs and of the map kernels' A / dA traffic.
+_BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "0") == "1"}
+
+
+def set_bf16_maps(on: bool) -> None:
+    _BF16_MAPS["value"] = bool(on)
+
+
 def set_map_l2_budget(megabytes: float) -> None:
     _MAP_L2_BYTES["value"] = int(megabytes * (1 << 20))
 
@@ -146,9 +155,12 @@ class Engine:
         adrop = g.attn_drop if train else 0.0
         c = self._map_chunk(B, h, N, ld)
         keep_P = saved is not None
+        bf16 = prec == ops.PREC_TF32 and _BF16_MAPS["value"] and N % 8 == 0
         Pm = _empty((B if (keep_P or train) else c, h, N, ld), xq)
-        A = _empty((c, h, N, ld), xq)
+        A = torch.empty((c, h, N, ld), dtype=torch.bfloat16 if bf16 else torch.float32, device=xq.device)
         O = _empty((B, N, D), xq)
+        vt = ops.heads_transpose_bf16(v, B, N, D, h) if bf16 else None        # (B,h,hd,ldn): K-major B operand of A.V
+        ldn = vt.shape[-1] if bf16 else 0
         fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
         sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device) if train else None
 
@@ -158,8 +170,14 @@ class Engine:
 
         def mix_pv(b0, bc, src, ci):
             ops.reattn_mix(src, A[:bc], fold, bc, h, N, ld, adrop, seed, sid + _CHUNK_STREAM * ci)
-            ops.gemm(A[:bc], v[b0:b0 + bc], O[b0:b0 + bc], N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D, batch_outer=bc,
-                     batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd), precision=prec)
+            if bf16:
+                ops.gemm(A[:bc], vt[b0:b0 + bc], O[b0:b0 + bc], N, hd, N, trans_b=True, lda=ld, ldb=ldn, ldc=D,
+                         batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(h * hd * ldn, hd * ldn),
+                         sC=(N * D, hd), precision=prec)
+            else:
+                ops.gemm(A[:bc], v[b0:b0 + bc], O[b0:b0 + bc], N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D,
+                         batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd),
+                         precision=prec)
 
         def finalize():
             ops.reattn_bn_finalize(sums, B * N * N, h, N, Wm, bm, P[pre + "var_norm.weight"], P[pre + "var_norm.bias"],
@@ -194,7 +212,7 @@ class Engine:
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums, seed=seed, sid=sid,
-                         adrop=adrop, pdrop=pdrop, train=train, chunk=c)
+                         adrop=adrop, pdrop=pdrop, train=train, chunk=c, bf16=bf16)
         return y
 
     def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):
@@ -227,8 +245,24 @@ class Engine:
         c = sv["chunk"]
         scale = float(hd) ** -0.5
         gamma = P[pre + "var_norm.weight"]
-        dA = torch.zeros((c, h, N, ld), dtype=torch.float32, device=dy.device) if ld != N else _empty((c, h, N, ld), dy)
-        A = _empty((c, h, N, ld), dy)
+        bf16 = sv["bf16"]
+        mdt = torch.bfloat16 if bf16 else torch.float32
+        dA = torch.zeros((c, h, N, ld), dtype=mdt, device=dy.device) if ld != N else torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
+        A = torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
+        if bf16:     # per-head transposed bf16 copies: the K-major B operands of dV = A^T dO, dQ = dS K, dK = dS^T Q
+            dOt, kt, qt = (ops.heads_transpose_bf16(t, B, N, D, h) for t in (dO, k, q))
+            ldn = dOt.shape[-1]
+
+        def map_gemm(Amap, trans_a, Bt, Bf, Cout, b0, bc):
+            """Cout[b0:b0+bc] (B,N,D head-sliced) = op(Amap[:bc]) @ (tokens of head): bf16 maps use the transposed copy Bt"""
+            if bf16:
+                ops.gemm(Amap[:bc], Bt[b0:b0 + bc], Cout[b0:b0 + bc], N, hd, N, trans_a=trans_a, trans_b=True, lda=ld,
+                         ldb=ldn, ldc=D, batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld),
+                         sB=(h * hd * ldn, hd * ldn), sC=(N * D, hd), precision=prec)
+            else:
+                ops.gemm(Amap[:bc], Bf[b0:b0 + bc], Cout[b0:b0 + bc], N, hd, N, trans_a=trans_a, trans_b=False, lda=ld,
+                         ldb=D, ldc=D, batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd),
+                         sC=(N * D, hd), precision=prec)
         dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
         red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
 
@@ -242,9 +276,7 @@ class Engine:
             grad_map(b0, bc)
             ops.reattn_mix_reduce(Pm[b0:b0 + bc], dA[:bc], A[:bc], sv["fold"], bc, h, N, ld, adrop, seed,
                                   sid + _CHUNK_STREAM * ci, red)
-            ops.gemm(A[:bc], dO[b0:b0 + bc], dv[b0:b0 + bc], N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D, ldc=D,
-                     batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd),
-                     precision=prec)
+            map_gemm(A, True, dOt if bf16 else None, dO, dv, b0, bc)
         del A
         coef = _empty((2 * h,), dy)
         ops.reattn_bwd_params(red, sv["sums"], B, h, N, Wm, bm, gamma, sv["bn"], train, coef,
@@ -257,12 +289,8 @@ class Engine:
                 grad_map(b0, bc)
             ops.reattn_bwd_rows(Pm[b0:b0 + bc], dA[:bc], bc, h, N, ld, Wm, bm, gamma, sv["bn"], coef, train, scale,
                                 adrop, seed, sid + _CHUNK_STREAM * ci)
-            ops.gemm(dA[:bc], k[b0:b0 + bc], dq[b0:b0 + bc], N, hd, N, trans_b=False, lda=ld, ldb=D, ldc=D,
-                     batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd),
-                     precision=prec)
-            ops.gemm(dA[:bc], q[b0:b0 + bc], dk[b0:b0 + bc], N, hd, N, trans_a=True, trans_b=False, lda=ld, ldb=D,
-                     ldc=D, batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd), sC=(N * D, hd),
-                     precision=prec)
+            map_gemm(dA, False, kt if bf16 else None, k, dq, b0, bc)
+            map_gemm(dA, True, qt if bf16 else None, q, dk, b0, bc)
         del dO, dA
         wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
         xq, xkv = sv["xq"], sv["xkv"]

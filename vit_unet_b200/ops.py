@@ -18,6 +18,13 @@ PREC_FP32, PREC_TF32 = 0, 1
 LOSS_KINDS = {"l1": 0, "mse": 1, "dice": 2}
 
 
+def _map(t: torch.Tensor, name: str):
+    """attention map buffer: fp32 or bf16 -> (pointer, is_bf16)"""
+    if t.dtype == torch.bfloat16:
+        return _chk(t, name, torch.bfloat16), 1
+    return _chk(t, name), 0
+
+
 def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> int:
     if not t.is_cuda:
         raise VuError(f"{name}: tensor must live on a CUDA device (vit_unet_b200 has no CPU path)")
@@ -90,6 +97,15 @@ def repatch(x, out, B, Cc, H, W, p_in, p_out):
     return out
 
 
+def heads_transpose_bf16(x, B, N, D, h):
+    """(B,N,D) fp32 -> (B,h,D/h,ceil8(N)) bf16, dst[b,h,e,n] = x[b,n,h*hd+e]"""
+    ldn = (N + 7) // 8 * 8
+    out = torch.empty((B, h, D // h, ldn), dtype=torch.bfloat16, device=x.device)
+    _call("vu_heads_transpose_bf16", _chk(x, "src"), _chk(out, "dst", torch.bfloat16), B, N, D, h, ldn, _stream(),
+          nbytes=6.0 * B * N * D)
+    return out
+
+
 def pe_fwd(x, p_in, table, p_table, out, p_out, B, Cc, H, W):
     _call("vu_pe_fwd", _chk(x, "in"), p_in, _chk(table, "table"), p_table, _chk(out, "out"), p_out,
           B, Cc, H, W, _stream(), nbytes=2 * 4.0 * B * Cc * H * W)
@@ -136,7 +152,9 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
          drop_p=0.0, drop_seed=0, drop_stream=0, precision=PREC_FP32):
     """C = act(alpha * op(A) @ op(B) + bias) [dropout] + residual, batched over (outer, inner)."""
     d = GemmDesc()
-    d.A, d.B, d.C = _chk(A, "A"), _chk(Bm, "B"), _chk(Cm, "C")
+    d.a_bf16, d.b_bf16, d.c_bf16 = int(A.dtype == torch.bfloat16), int(Bm.dtype == torch.bfloat16), int(Cm.dtype == torch.bfloat16)
+    d.A, d.B, d.C = _chk(A, "A", A.dtype if d.a_bf16 else torch.float32), _chk(Bm, "B", Bm.dtype if d.b_bf16 else torch.float32), \
+        _chk(Cm, "C", Cm.dtype if d.c_bf16 else torch.float32)
     d.bias, d.residual = _opt(bias, "bias"), _opt(residual, "residual")
     d.aux_in, d.aux_out = _opt(aux_in, "aux_in"), _opt(aux_out, "aux_out")
     d.M, d.N, d.K = M, N, K
@@ -157,8 +175,9 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
     else:
         cls = kind + ":tokens(proj,FF,dgrad,wgrad)"
     extra = (residual is not None) + int(accumulate) + (aux_in is not None) + (aux_out is not None)
+    ea, eb, ec = (2.0 if d.a_bf16 else 4.0), (2.0 if d.b_bf16 else 4.0), (2.0 if d.c_bf16 else 4.0)
     _call("vu_gemm", C.byref(d), _stream(), flops=2.0 * M * N * K * nb,
-          nbytes=4.0 * nb * (M * K + K * N + M * N * (1 + extra)), cls=cls)
+          nbytes=nb * (ea * M * K + eb * K * N + ec * M * N + 4.0 * M * N * extra), cls=cls)
     return Cm
 
 
@@ -178,8 +197,13 @@ def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums):
 
 
 def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red):
-    _call("vu_reattn_mix_reduce", _chk(P, "P"), _chk(dA, "dA"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld,
-          drop_p, seed, sid, _chk(red, "red", torch.float64), _stream(), nbytes=3 * 4.0 * B * h * N * N, flops=4.0 * h * B * h * N * N)
+    pd, bf = _map(dA, "dA")
+    pa, bf2 = _map(A, "A")
+    if bf != bf2:
+        raise VuError("reattn_mix_reduce: A and dA must have the same dtype")
+    _call("vu_reattn_mix_reduce", _chk(P, "P"), pd, pa, bf, _chk(fold, "fold"), B, h, N, ld,
+          drop_p, seed, sid, _chk(red, "red", torch.float64), _stream(),
+          nbytes=(4.0 + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
 def reattn_stats(P, B, h, N, ld, drop_p, seed, sid, sums):
@@ -196,8 +220,9 @@ def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nb
 
 
 def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid):
-    _call("vu_reattn_mix", _chk(P, "P"), _chk(A, "A"), _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream(),
-          nbytes=2 * 4.0 * B * h * N * N, flops=2.0 * h * B * h * N * N)
+    pa, bf = _map(A, "A")
+    _call("vu_reattn_mix", _chk(P, "P"), pa, bf, _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream(),
+          nbytes=(4.0 + (2.0 if bf else 4.0)) * B * h * N * N, flops=2.0 * h * B * h * N * N)
 
 
 def reattn_bwd_reduce(P, dA, B, h, N, ld, drop_p, seed, sid, red):
@@ -213,9 +238,10 @@ def reattn_bwd_params(red, sums, B, h, N, W, bconv, gamma, saved, train, coef, d
 
 
 def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid):
-    _call("vu_reattn_bwd_rows", _chk(P, "P"), _chk(dA, "dA"), B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
+    pd, bf = _map(dA, "dA")
+    _call("vu_reattn_bwd_rows", _chk(P, "P"), pd, bf, B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
           _chk(gamma, "gamma"), _chk(saved, "saved"), _chk(coef, "coef"), int(train), scale, drop_p, seed, sid,
-          _stream(), nbytes=3 * 4.0 * B * h * N * N, flops=4.0 * h * B * h * N * N)
+          _stream(), nbytes=(4.0 + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
 # ----------------------------------------------------------------------------------------- layer norm
