@@ -248,6 +248,7 @@ def run_cuda(args):
     value = B * world * args.steps / (ms / 1e3)
 
     # ---- timed region 2: end to end through the public API with pinned HOST buffers (e2e) -----------------
+    step(x_pin.to(dev, non_blocking=True), y_pin.to(dev, non_blocking=True)).item()      # one untimed e2e warm-up
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -304,6 +305,7 @@ def run_cuda(args):
                        "step": ("zero_grad + forward + loss + backward" + (" + bucketed NCCL grad all-reduce" if world > 1 else ""))
                                if wl["train"] else "eval forward under no_grad (batch-sharded, no collective)",
                        "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)" if args.dropout is None else f"OVERRIDDEN to {args.dropout}", "precision": args.precision,
+                       "maps": ("P fp32; mixed map A and gradient map dA/dS bf16 where N % 8 == 0" if (args.precision == "tf32" and os.environ.get("VU_BF16_MAPS", "1") == "1") else "fp32"),
                        "l2": "per-step working set (saved activations + attention maps, GBs) >> 126 MB L2"},
             "clocks": clocks.summary(), "roofline": roof,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.nbytes + y_pin.nbytes),

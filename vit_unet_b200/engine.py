@@ -29,7 +29,7 @@ _MAP_L2_BYTES = {"value": int(float(os.environ.get("VU_MAP_L2_MB", "0")) * (1 <<
 
 # bf16 storage of the mixed map A and the gradient map dA/dS (probabilities P stay fp32) on the tensor-core path:
 # halves the HBM bytes of the five map-consuming GEMMs and of the map kernels' A / dA traffic.
-_BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "0") == "1"}
+_BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "1") == "1"}      # on by default in the tf32 mode (1e-2 class)
 
 
 def set_bf16_maps(on: bool) -> None:
