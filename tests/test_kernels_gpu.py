@@ -58,10 +58,10 @@ def test_pe_fwd_and_table_grad(ops):
 
 
 # ------------------------------------------------------------------------------------------------ convs
-@pytest.mark.parametrize("C,S,p", [(3, 32, 16), (3, 32, 4), (1, 32, 8), (3, 28, 7)])
+@pytest.mark.parametrize("C,S,p,B", [(3, 32, 16, 2), (3, 32, 4, 2), (1, 32, 8, 2), (3, 28, 7, 2),
+                                       (3, 64, 32, 3), (3, 24, 8, 3), (1, 20, 4, 2), (3, 48, 16, 3), (2, 32, 8, 1)])
 @pytest.mark.parametrize("nconv", [1, 2, 3])
-def test_patch_conv_fwd_bwd(ops, C, S, p, nconv):
-    B = 2
+def test_patch_conv_fwd_bwd(ops, C, S, p, B, nconv):
     img = _rand(B, C, S, S)
     x = O.patchify(img, p).contiguous()
     N, D = x.shape[1], x.shape[2]
@@ -80,8 +80,10 @@ def test_patch_conv_fwd_bwd(ops, C, S, p, nconv):
     ops.conv3x3_bwd_data([d.cuda() for d in dys], p, wcat, dx, p, p, B, C, S, S)
     _close(dx, xr.grad, name="conv dx")
     dw = torch.zeros(nconv * C * C * 9, device="cuda")
-    ops.conv3x3_bwd_weight(x.cuda(), p, [d.cuda() for d in dys], p, dw, None, p, B, C, S, S)
+    db = torch.zeros(nconv * C, device="cuda")
+    ops.conv3x3_bwd_weight(x.cuda(), p, [d.cuda() for d in dys], p, dw, db, p, B, C, S, S)
     _close(dw, torch.cat([w.grad.reshape(-1) for w in wr]), rtol=1e-4, name="conv dw")
+    _close(db, torch.cat([d.reshape(B * N, C, p * p).sum((0, 2)) for d in dys]), rtol=1e-4, name="conv db")
 
 
 @pytest.mark.parametrize("C,S,p", [(3, 32, 16), (1, 64, 32)])

@@ -4,6 +4,8 @@
 // One thread per pixel, all C output channels of all fused convs in registers; the 9*C input taps come from
 // L1 (each input float is reused 9*C*nconv times), so HBM sees one read of x and one write per output.
 #include "vu_common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace vu {
 
@@ -206,6 +208,149 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ backward weights, patch-tiled fast path
+// q/k/v convs with x and dy both in patch layout P == border patch (model.py:152-154 backward).  A CTA walks items of
+// 512 pixels (K whole patches, or half a 32x32 patch); the x tile of an item is staged once in shared memory with a
+// zero halo, so the 9 taps are fixed-offset LDS with no border predicates, and each thread owns a run of 4
+// consecutive pixels of one row: per channel and tap row one LDS.128 + LDS.64 feed 36 FFMAs.  The next item's x and dy
+// are prefetched into registers while the current one is accumulated.  grid.y = fused conv k (C*C*9 + C partial
+// sums per thread); the three CTAs of an item run side by side on one SM and share its x tile through L1/L2.
+template <int C, int P>
+struct WgTile {
+  static constexpr int PS = P == 4 ? 2 : (P == 8 ? 3 : (P == 16 ? 4 : 5));
+  static constexpr int PP = P * P;
+  static constexpr int ITEM = 512;                                  // pixels per item = 4 * blockDim
+  static constexpr int R = (PP >= ITEM) ? ITEM / P : P;             // rows per unit (power of two)
+  static constexpr int RS = R == 4 ? 2 : (R == 8 ? 3 : 4);
+  static constexpr int UPP = P / R;                                 // units per patch
+  static constexpr int K = ITEM / (R * P);                          // units per item
+  static constexpr int ROWS = R + 2;
+  static constexpr int PITCH = P == 4 ? 12 : (P < 32 ? P + 32 : 36);  // % 4 == 0; spreads a phase's rows over banks
+  static constexpr int F4R = P / 4;
+  static constexpr int N4 = K * C * ROWS * F4R;                     // float4 loads per item
+  static constexpr int NF = (N4 + 127) / 128;
+  static constexpr int SMEM = K * C * ROWS * PITCH;
+  static_assert(R == 4 || R == 8 || R == 16, "rows per unit");
+};
+
+template <int C, int P>
+__global__ void __launch_bounds__(128, 3)
+conv3x3_wgrad_patch_kernel(const float* __restrict__ x, const float* __restrict__ d0, const float* __restrict__ d1,
+                           const float* __restrict__ d2, float* __restrict__ dw, float* __restrict__ dbias,
+                           int64_t total_units) {
+  using T = WgTile<C, P>;
+  constexpr int NACC = C * (C * 9 + 1);
+  __shared__ __align__(16) float xs[T::SMEM];
+  __shared__ float red[NACC][4];
+  const int k = blockIdx.y, tid = threadIdx.x;
+  const float* __restrict__ dy = k == 0 ? d0 : (k == 1 ? d1 : d2);
+  for (int i = tid; i < T::SMEM; i += 128) xs[i] = 0.f;
+  float acc[C][C][9], accb[C];
+#pragma unroll
+  for (int co = 0; co < C; ++co) {
+    accb[co] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[co][ci][t] = 0.f;
+  }
+  // this thread's run of 4 pixels inside an item: unit slot s, row i of the unit, columns j0..j0+3
+  const int j0 = (tid * 4) & (P - 1), rowlin = (tid * 4) >> T::PS, s = rowlin >> T::RS, i = rowlin & (T::R - 1);
+  const int64_t n_items = (total_units + T::K - 1) / T::K;
+  float4 xpre[T::NF], dpre[C];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int64_t it) {
+#pragma unroll
+    for (int f = 0; f < T::NF; ++f) {
+      const int e = tid + 128 * f;
+      xpre[f] = zero4;
+      if (e < T::N4) {
+        const int c4 = e % T::F4R, rr = (e / T::F4R) % T::ROWS, ci = (e / (T::F4R * T::ROWS)) % C,
+                  ss = e / (T::F4R * T::ROWS * C);
+        const int64_t u = it * T::K + ss;
+        const int gr = (int)(u % T::UPP) * T::R + rr - 1;
+        if (u < total_units && (unsigned)gr < (unsigned)P)
+          xpre[f] = __ldg(reinterpret_cast<const float4*>(x + (u / T::UPP) * (C * T::PP) + ci * T::PP + gr * P + 4 * c4));
+      }
+    }
+    const int64_t u = it * T::K + s;
+    const bool ok = u < total_units;
+    const float* dp = dy + (u / T::UPP) * (C * T::PP) + ((int)(u % T::UPP) * T::R + i) * P + j0;
+#pragma unroll
+    for (int co = 0; co < C; ++co) dpre[co] = ok ? __ldg(reinterpret_cast<const float4*>(dp + co * T::PP)) : zero4;
+  };
+  int64_t it = blockIdx.x;
+  if (it < n_items) prefetch(it);
+  const float* xb = xs + (s * C * T::ROWS + i) * T::PITCH + j0;
+  for (; it < n_items; it += gridDim.x) {
+    __syncthreads();                                   // everyone is done reading the previous tile
+#pragma unroll
+    for (int f = 0; f < T::NF; ++f) {
+      const int e = tid + 128 * f;
+      if (e < T::N4) {
+        const int c4 = e % T::F4R, row = e / T::F4R;    // row = (ss*C + ci)*ROWS + rr
+        float* dst = xs + row * T::PITCH + 1 + 4 * c4;
+        dst[0] = xpre[f].x; dst[1] = xpre[f].y; dst[2] = xpre[f].z; dst[3] = xpre[f].w;
+      }
+    }
+    float4 d[C];
+#pragma unroll
+    for (int co = 0; co < C; ++co) d[co] = dpre[co];
+    __syncthreads();
+    if (it + gridDim.x < n_items) prefetch(it + gridDim.x);
+#pragma unroll
+    for (int co = 0; co < C; ++co) accb[co] += (d[co].x + d[co].y) + (d[co].z + d[co].w);
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float* r = xb + (ci * T::ROWS + ky) * T::PITCH;
+        const float4 a = *reinterpret_cast<const float4*>(r);
+        const float2 b = *reinterpret_cast<const float2*>(r + 4);
+        const float w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int co = 0; co < C; ++co) {
+            float v = acc[co][ci][ky * 3 + kx];
+            v = fmaf(d[co].x, w[kx], v); v = fmaf(d[co].y, w[kx + 1], v);
+            v = fmaf(d[co].z, w[kx + 2], v); v = fmaf(d[co].w, w[kx + 3], v);
+            acc[co][ci][ky * 3 + kx] = v;
+          }
+      }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int co = 0; co < C; ++co) {
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float v = warp_sum(acc[co][ci][t]);
+        if (lane == 0) red[co * (C * 9 + 1) + ci * 9 + t][warp] = v;
+      }
+    const float v = warp_sum(accb[co]);
+    if (lane == 0) red[co * (C * 9 + 1) + C * 9][warp] = v;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    const float sum = (red[tid][0] + red[tid][1]) + (red[tid][2] + red[tid][3]);
+    const int co = tid / (C * 9 + 1), e = tid % (C * 9 + 1);
+    if (e < C * 9) atomicAdd(dw + ((int64_t)(k * C + co) * C) * 9 + e, sum);
+    else if (dbias) atomicAdd(dbias + k * C + co, sum);
+  }
+}
+
+template <int C, int P>
+static void launch_wgrad_patch(const float* x, const float* d0, const float* d1, const float* d2, int nconv,
+                               float* dw, float* dbias, int64_t patches, cudaStream_t s) {
+  using T = WgTile<C, P>;
+  const int64_t units = patches * T::UPP, items = (units + T::K - 1) / T::K;
+  const int per_sm = nconv == 3 ? 1 : (nconv == 2 ? 2 : 3);        // 3 resident CTAs per SM over (x, y)
+  const int bx = (int)std::min<int64_t>(items, (int64_t)sm_count() * per_sm);
+  conv3x3_wgrad_patch_kernel<C, P><<<dim3(bx, nconv), 128, 0, s>>>(x, d0, d1, d2, dw, dbias, units);
+}
+
 static int upload_filters(const char* fn, const float* w, const float* bias, int nconv, int C, cudaStream_t s) {
   if (cudaMemcpyToSymbolAsync(c_w, w, sizeof(float) * nconv * C * C * 9, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
     return check_launch(fn);
@@ -288,10 +433,19 @@ extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, 
   VU_REQUIRE(x && dy0 && dw && nconv >= 1 && nconv <= 3, fn, "null pointer or nconv outside 1..3");
   VU_REQUIRE((nconv < 2 || dy1) && (nconv < 3 || dy2), fn, "missing gradient pointer");
   ConvGeom g; int rc = make_geom(fn, g, p_x, p_dy, border_p, B, C, H, W); if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (g.fast && p_x == p_dy && C <= 3 && (p_x == 4 || p_x == 8 || p_x == 16 || p_x == 32) && !getenv("VU_CONV_WGRAD_GENERIC")) {
+    const int64_t patches = (int64_t)B * (H / p_x) * (W / p_x);
+#define VU_WG(CC, PPX) launch_wgrad_patch<CC, PPX>(x, dy0, dy1, dy2, nconv, dw, dbias, patches, s)
+#define VU_WG_P(CC) (p_x == 4 ? VU_WG(CC, 4) : p_x == 8 ? VU_WG(CC, 8) : p_x == 16 ? VU_WG(CC, 16) : VU_WG(CC, 32))
+    if (C == 1) VU_WG_P(1); else if (C == 2) VU_WG_P(2); else VU_WG_P(3);
+#undef VU_WG_P
+#undef VU_WG
+    return check_launch(fn);
+  }
   int threads = 128;
   int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 8), (int64_t)sm_count() * 6);
   if (bx < 1) bx = 1;
-  cudaStream_t s = as_stream(stream);
   VU_DISPATCH_C(C,
     if (CC <= 3) conv3x3_bwd_weight_kernel<CC, (CC <= 3)><<<dim3(bx, nconv), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g);
     else conv3x3_bwd_weight_kernel<CC, false><<<dim3(bx, nconv * C), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g));
