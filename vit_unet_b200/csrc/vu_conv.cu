@@ -6,6 +6,7 @@
 #include "vu_common.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace vu {
 
@@ -351,6 +352,131 @@ static void launch_wgrad_patch(const float* x, const float* d0, const float* d1,
   conv3x3_wgrad_patch_kernel<C, P><<<dim3(bx, nconv), 128, 0, s>>>(x, d0, d1, d2, dw, dbias, units);
 }
 
+// ------------------------------------------------------------------ forward / backward-data, patch-tiled fast paths
+// Same tiling as the weight-gradient kernel above: items of 512 pixels, source planes staged in shared memory with a
+// zero halo (x: C planes; dy: NCONV*C planes), one run of 4 consecutive pixels per thread, filters as constant-bank
+// FFMA operands, float4 stores.  Used when source, destination and border patch agree (the q/k/v convs).
+template <int P, int NPL>
+struct PatchTile {
+  static constexpr int PS = P == 4 ? 2 : (P == 8 ? 3 : (P == 16 ? 4 : 5));
+  static constexpr int PP = P * P;
+  static constexpr int ITEM = 512;
+  static constexpr int R = (PP >= ITEM) ? ITEM / P : P;
+  static constexpr int RS = R == 4 ? 2 : (R == 8 ? 3 : 4);
+  static constexpr int UPP = P / R;
+  static constexpr int K = ITEM / (R * P);
+  static constexpr int ROWS = R + 2;
+  static constexpr int PITCH = P + 4;
+  static constexpr int F4R = P / 4;
+  static constexpr int N4 = K * NPL * ROWS * F4R;
+  static constexpr int NF = (N4 + 127) / 128;
+  static constexpr int SMEM = K * NPL * ROWS * PITCH;
+};
+
+// stage helpers shared by both kernels: plane pl of unit u lives at src(pl) + patch*CPP + (pl % C)*PP
+template <int C, int NCONV, int P, bool DGRAD>
+__global__ void __launch_bounds__(128, DGRAD ? 3 : 4)
+conv3x3_patch_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
+                     float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
+                     int64_t total_units, int accumulate) {
+  constexpr int NPL = DGRAD ? NCONV * C : C;
+  using T = PatchTile<P, NPL>;
+  __shared__ __align__(16) float xs[T::SMEM];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < T::SMEM; i += 128) xs[i] = 0.f;
+  const int j0 = (tid * 4) & (P - 1), rowlin = (tid * 4) >> T::PS, s = rowlin >> T::RS, i = rowlin & (T::R - 1);
+  const int64_t n_items = (total_units + T::K - 1) / T::K;
+  float4 pre[T::NF];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int64_t it) {
+#pragma unroll
+    for (int f = 0; f < T::NF; ++f) {
+      const int e = tid + 128 * f;
+      pre[f] = zero4;
+      if (e < T::N4) {
+        const int c4 = e % T::F4R, rr = (e / T::F4R) % T::ROWS, pl = (e / (T::F4R * T::ROWS)) % NPL,
+                  ss = e / (T::F4R * T::ROWS * NPL);
+        const int64_t u = it * T::K + ss;
+        const int gr = (int)(u % T::UPP) * T::R + rr - 1;
+        const float* src = DGRAD ? (pl / C == 0 ? s0 : (pl / C == 1 ? s1 : s2)) : s0;
+        if (u < total_units && (unsigned)gr < (unsigned)P)
+          pre[f] = __ldg(reinterpret_cast<const float4*>(src + (u / T::UPP) * (C * T::PP) + (pl % C) * T::PP + gr * P + 4 * c4));
+      }
+    }
+  };
+  int64_t it = blockIdx.x;
+  if (it < n_items) prefetch(it);
+  const float* xb = xs + (s * NPL * T::ROWS + i) * T::PITCH + j0;
+  for (; it < n_items; it += gridDim.x) {
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < T::NF; ++f) {
+      const int e = tid + 128 * f;
+      if (e < T::N4) {
+        float* dst = xs + (e / T::F4R) * T::PITCH + 1 + 4 * (e % T::F4R);
+        dst[0] = pre[f].x; dst[1] = pre[f].y; dst[2] = pre[f].z; dst[3] = pre[f].w;
+      }
+    }
+    __syncthreads();
+    const int64_t u = it * T::K + s;
+    if (it + gridDim.x < n_items) prefetch(it + gridDim.x);
+    constexpr int NOUT = DGRAD ? C : NCONV * C;
+    float4 acc[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) { const float b = DGRAD ? 0.f : c_b[o]; acc[o] = make_float4(b, b, b, b); }
+#pragma unroll
+    for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+      for (int wy = 0; wy < 3; ++wy) {
+        const float* r = xb + (pl * T::ROWS + wy) * T::PITCH;
+        const float4 a = *reinterpret_cast<const float4*>(r);
+        const float2 b = *reinterpret_cast<const float2*>(r + 4);
+        const float w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+#pragma unroll
+        for (int wx = 0; wx < 3; ++wx)
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o) {
+            // forward: plane = ci, o = (k, co), tap (wy, wx).  dgrad: plane = (k, co), o = ci, tap (2-wy, 2-wx).
+            const float wt = DGRAD ? c_w[(pl * C + o) * 9 + (2 - wy) * 3 + (2 - wx)]
+                                   : c_w[(o * C + pl) * 9 + wy * 3 + wx];
+            acc[o].x = fmaf(w[wx], wt, acc[o].x); acc[o].y = fmaf(w[wx + 1], wt, acc[o].y);
+            acc[o].z = fmaf(w[wx + 2], wt, acc[o].z); acc[o].w = fmaf(w[wx + 3], wt, acc[o].w);
+          }
+      }
+    if (u < total_units) {
+      const int64_t off = (u / T::UPP) * (C * T::PP) + ((int)(u % T::UPP) * T::R + i) * P + j0;
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) {
+        float* op = DGRAD ? o0 : (o / C == 0 ? o0 : (o / C == 1 ? o1 : o2));
+        float4* dst = reinterpret_cast<float4*>(op + off + (o % C) * T::PP);
+        float4 v = acc[o];
+        if (DGRAD && accumulate) { const float4 t = *dst; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        *dst = v;
+      }
+    }
+  }
+}
+
+template <int C, int NCONV, bool DGRAD>
+static bool launch_patch_conv(int p, const float* s0, const float* s1, const float* s2, float* o0, float* o1, float* o2,
+                              int64_t patches, int accumulate, cudaStream_t st) {
+  auto go = [&](auto tag) {
+    constexpr int P = decltype(tag)::value;
+    using T = PatchTile<P, DGRAD ? NCONV * C : C>;
+    const int64_t units = patches * T::UPP, items = (units + T::K - 1) / T::K;
+    const int bx = (int)std::min<int64_t>(items, (int64_t)sm_count() * (DGRAD ? 3 : 4));
+    conv3x3_patch_kernel<C, NCONV, P, DGRAD><<<bx, 128, 0, st>>>(s0, s1, s2, o0, o1, o2, units, accumulate);
+  };
+  constexpr int NPL = DGRAD ? NCONV * C : C;
+  if constexpr (PatchTile<4, NPL>::SMEM * 4 <= 48 * 1024) {        // static shared memory limit
+    if (p == 4) { go(std::integral_constant<int, 4>()); return true; }
+  }
+  if (p == 8) { go(std::integral_constant<int, 8>()); return true; }
+  if (p == 16) { go(std::integral_constant<int, 16>()); return true; }
+  if (p == 32) { go(std::integral_constant<int, 32>()); return true; }
+  return false;
+}
+
 static int upload_filters(const char* fn, const float* w, const float* bias, int nconv, int C, cudaStream_t s) {
   if (cudaMemcpyToSymbolAsync(c_w, w, sizeof(float) * nconv * C * C * 9, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
     return check_launch(fn);
@@ -399,6 +525,16 @@ extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const flo
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
   rc = upload_filters(fn, w, bias, nconv, C, s); if (rc) return rc;
+  if (g.fast && p_x == p_out && C <= 3 && p_x >= 4 && !getenv("VU_CONV_GENERIC")) {
+    const int64_t patches = (int64_t)B * (H / p_x) * (W / p_x);
+    bool done = false;
+#define VU_PC(CC, NC) done = launch_patch_conv<CC, NC, false>(p_x, x, nullptr, nullptr, out0, out1, out2, patches, 0, s)
+#define VU_PC_N(CC) do { if (nconv == 1) VU_PC(CC, 1); else if (nconv == 2) VU_PC(CC, 2); else VU_PC(CC, 3); } while (0)
+    if (C == 1) VU_PC_N(1); else if (C == 2) VU_PC_N(2); else VU_PC_N(3);
+#undef VU_PC_N
+#undef VU_PC
+    if (done) return check_launch(fn);
+  }
   VU_DISPATCH_C(C,
     if (nconv == 1) conv3x3_fwd_kernel<CC, 1><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
     else if (nconv == 2) conv3x3_fwd_kernel<CC, 2><<<blocks, threads, 0, s>>>(x, w, bias, out0, out1, out2, g);
@@ -418,6 +554,16 @@ extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const flo
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
   rc = upload_filters(fn, w, nullptr, nconv, C, s); if (rc) return rc;
+  if (g.fast && p_dy == p_dx && C <= 3 && p_dy >= 4 && !getenv("VU_CONV_GENERIC")) {
+    const int64_t patches = (int64_t)B * (H / p_dy) * (W / p_dy);
+    bool done = false;
+#define VU_PC(CC, NC) done = launch_patch_conv<CC, NC, true>(p_dy, dy0, dy1, dy2, dx, nullptr, nullptr, patches, accumulate, s)
+#define VU_PC_N(CC) do { if (nconv == 1) VU_PC(CC, 1); else if (nconv == 2) VU_PC(CC, 2); else VU_PC(CC, 3); } while (0)
+    if (C == 1) VU_PC_N(1); else if (C == 2) VU_PC_N(2); else VU_PC_N(3);
+#undef VU_PC_N
+#undef VU_PC
+    if (done) return check_launch(fn);
+  }
   VU_DISPATCH_C(C,
     if (nconv == 1) conv3x3_bwd_data_kernel<CC, 1><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);
     else if (nconv == 2) conv3x3_bwd_data_kernel<CC, 2><<<blocks, threads, 0, s>>>(dy0, dy1, dy2, w, dx, g, accumulate);
