@@ -102,9 +102,11 @@ int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scale, void* st
  * The BatchNorm batch statistics of M_h = sum_g W[h,g] Pd_g + b[h] follow in closed form (vu_reattn_bn_finalize). */
 int vu_reattn_stats(const float* P, int B, int h, int N, int ld, float drop_p, uint64_t seed, uint32_t stream_id,
                     double* sums, void* stream);
-/* fused train-mode pass: in-place softmax of every head + the moments above in ONE read of S / write of P */
+/* fused train-mode pass: in-place softmax of every head + the moments above in ONE read of S / write of P.
+ * precision = VU_PREC_TF32 lets the moments of 8-head maps without pad columns be accumulated by TF32 warp MMAs
+ * (centred inputs, fp32 accumulation); VU_PREC_FP32 keeps the exact CUDA-core sums. */
 int vu_softmax_stats(float* S, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
-                     uint32_t stream_id, double* sums, void* stream);
+                     uint32_t stream_id, double* sums, int precision, void* stream);
 /* fold conv1x1 + BatchNorm into one affine:  fold[h*h + h] = {alpha'[h][g], beta'[h]};
  * saved[2h] = {mean_h, invstd_h}.  train=1: batch statistics from `sums` (+ running-stat update,
  * momentum, unbiased variance, num_batches_tracked += 1); train=0: running statistics. model.py:136,159 */

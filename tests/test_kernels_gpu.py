@@ -356,6 +356,50 @@ def test_reattn_fused_passes_match_separate_kernels(ops, h, N, p):
     _close(r2, r1, rtol=1e-6, name="fused reductions")
 
 
+@pytest.mark.parametrize("N", [40, 64, 200, 328, 784])      # > 256: CTA-per-row variants
+@pytest.mark.parametrize("p", [0.0, 0.2])
+@pytest.mark.parametrize("train", [False, True])
+def test_reattn_tensor_core_path(ops, N, p, train):
+    """8 heads, no pad columns, bf16 maps: the warp-MMA formulation (vu_reattn_mma.cuh) against the CUDA-core fp32
+    kernels on the same inputs.  Tolerances: TF32 rounding of centred inputs for the sums, bf16 storage for the maps."""
+    B, h, ld, scale = (3 if N < 300 else 2), 8, N, 0.41
+    bf = lambda t: t.to(torch.bfloat16)
+    S = (_rand(B, h, N, N, seed=1, scale=3.0)).cuda()
+    P1, P2 = S.clone(), S.clone()
+    s1 = torch.zeros(h + h * h, dtype=torch.float64, device="cuda"); s2 = torch.zeros_like(s1)
+    ops.softmax_rows(P1, B * h * N, N, ld, scale)
+    ops.reattn_stats(P1, B, h, N, ld, p, 5, 2, s1)
+    ops.softmax_stats(P2, B, h, N, ld, scale, p, 5, 2, s2, precision=ops.PREC_TF32)
+    _close(P2, P1, rtol=1e-5, name="softmax (online, mma path)")
+    _close(s2, s1, rtol=3e-4, name="moments (tf32 mma)")
+    W = _rand(h, h, seed=2, scale=0.6).cuda()
+    bc, gm, bt = _rand(h, seed=3, scale=0.01).cuda(), (1 + _rand(h, seed=4, scale=0.3)).cuda(), _rand(h, seed=5, scale=0.01).cuda()
+    rm, rv = _rand(h, seed=6, scale=0.01).cuda(), ((1 + _rand(h, seed=7, scale=0.3)) * 1e-3).cuda()
+    fold, saved = torch.empty(h * h + h, device="cuda"), torch.empty(2 * h, device="cuda")
+    ops.reattn_bn_finalize(s1 if train else None, B * N * N, h, N, W, bc, gm, bt, rm, rv, None, 1e-5, 0.1, train, fold, saved)
+    A1 = torch.empty_like(P1); A2 = torch.empty(B, h, N, ld, dtype=torch.bfloat16, device="cuda")
+    ops.reattn_mix(P1, A1, fold, B, h, N, ld, p, 5, 2)
+    ops.reattn_mix(P1, A2, fold, B, h, N, ld, p, 5, 2)
+    _close(A2.float(), A1, rtol=6e-3, name="mixed map (mma, bf16)")
+    dA = bf(_rand(B, h, N, N, seed=3).cuda())
+    dA32 = dA.float()
+    r1 = torch.zeros(h + h * h, dtype=torch.float64, device="cuda"); r2 = torch.zeros_like(r1)
+    A3 = torch.empty_like(A2)
+    ops.reattn_bwd_reduce(P1, dA32, B, h, N, ld, p, 5, 2, r1)
+    ops.reattn_mix_reduce(P1, dA, A3, fold, B, h, N, ld, p, 5, 2, r2)
+    assert torch.equal(A3, A2)
+    _close(r2[:h], r1[:h], rtol=1e-5, name="s1 (mma)")
+    _close(r2[h:], r1[h:], rtol=2e-3, name="X' (tf32 mma)")
+    dW, dbc, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"),
+                        torch.zeros(h, device="cuda"), torch.zeros(h, device="cuda"))
+    coef = torch.empty(2 * h, device="cuda")
+    ops.reattn_bwd_params(r1, s1 if train else None, B, h, N, W, bc, gm, saved, train, coef, dW, dbc, dg, dbt)
+    d1, d2 = dA32.clone(), dA.clone()
+    ops.reattn_bwd_rows(P1, d1, B, h, N, ld, W, bc, gm, saved, coef, train, scale, p, 5, 2)
+    ops.reattn_bwd_rows(P1, d2, B, h, N, ld, W, bc, gm, saved, coef, train, scale, p, 5, 2)
+    _close(d2.float(), d1, rtol=1.5e-2, name="dS (mma, bf16)")
+
+
 def test_psnr_and_input_pipeline(ops):
     """N2 / N4: device PSNR vs the skimage formula; uint8 HWC -> normalised float CHW vs numpy."""
     g = torch.Generator().manual_seed(0)

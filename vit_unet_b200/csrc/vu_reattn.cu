@@ -10,6 +10,8 @@
 // Every streaming kernel handles 4 consecutive keys per thread (float4) so that one Philox4x32 call yields the
 // dropout mask of the whole quad; masks are regenerated, never stored.
 #include <cuda_bf16.h>
+#include <algorithm>
+#include <cstdlib>
 
 #include "vu_common.cuh"
 
@@ -509,6 +511,25 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, MT* __restrict__ dA, int B, 
   }
 }
 
+}  // namespace vu
+#include "vu_reattn_mma.cuh"
+namespace vu {
+
+// 8-head tensor-core formulation (vu_reattn_mma.cuh): TF32 path, no pad columns.  VU_MAP_MMA=0 disables it.
+static bool mma_path(int h, int N, int ld) {
+  static const bool on = []() { const char* e = getenv("VU_MAP_MMA"); return !(e && e[0] == '0'); }();
+  return on && h == 8 && ld == N && N % 8 == 0;
+}
+// persistent grid: as many CTAs as are resident (occupancy query, cached per kernel), capped by the work
+template <typename K>
+static int resident_grid(K kernel, int threads, int64_t warps_of_work) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const int64_t need = cdiv(warps_of_work, threads / 32);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * per_sm));
+}
+
 static int grid_for(int64_t work_items, int threads, int per_sm) {
   int64_t b = cdiv(work_items, threads);
   int64_t cap = (int64_t)sm_count() * per_sm;
@@ -581,6 +602,12 @@ extern "C" int vu_reattn_mix(const float* P, void* A, int map_bf16, const float*
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  if (map_bf16 && mma_path(h, N, ld)) {
+    const int64_t tiles = cdiv((int64_t)N * N / 4, 8) * B;
+    const int grid = resident_grid(mma::reattn_mix_mma_kernel, 256, cdiv(tiles, 2));
+    mma::reattn_mix_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)A, fold, B, N, q);
+    return check_launch(fn);
+  }
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256, 16);
   if (map_bf16) { VU_DISPATCH_H(h, fn, reattn_mix_kernel<HH, __nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)A, fold, B, N, ld, q)); }
   else { VU_DISPATCH_H(h, fn, reattn_mix_kernel<HH, float><<<blocks, 256, 0, as_stream(stream)>>>(P, (float*)A, fold, B, N, ld, q)); }
@@ -619,8 +646,20 @@ extern "C" int vu_reattn_bwd_rows(const float* P, void* dA_dS, int map_bf16, int
   VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA_dS && W && bconv && gamma && saved && ((uintptr_t)dA_dS % 16 == 0), fn, "bad arguments");
   VU_REQUIRE(!train || coef, fn, "train mode needs the BN-backward coefficients");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
-  int blocks = grid_for((int64_t)B * N * 32, 128, 12);
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
+  if (map_bf16 && mma_path(h, N, ld)) {
+    if (N > 256 && N <= 1024) {         // long rows: one CTA per row, row kept in registers between the sweeps
+      const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<4>, 256, (int64_t)B * N * 8);
+      mma::reattn_bwd_rows_mma_cta_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)dA_dS, B, N, W, bconv,
+                                                                                 gamma, saved, coef, train, scale, q);
+      return check_launch(fn);
+    }
+    const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel, 256, (int64_t)B * N);
+    mma::reattn_bwd_rows_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)dA_dS, B, N, W, bconv, gamma,
+                                                                        saved, coef, train, scale, q);
+    return check_launch(fn);
+  }
+  int blocks = grid_for((int64_t)B * N * 32, 128, 12);
   if (map_bf16) { VU_DISPATCH_H(h, fn, reattn_bwd_rows_kernel<HH, __nv_bfloat16><<<blocks, 128, 0, as_stream(stream)>>>(
       P, (__nv_bfloat16*)dA_dS, B, N, ld, W, bconv, gamma, saved, coef, train, scale, q)); }
   else { VU_DISPATCH_H(h, fn, reattn_bwd_rows_kernel<HH, float><<<blocks, 128, 0, as_stream(stream)>>>(
@@ -629,12 +668,23 @@ extern "C" int vu_reattn_bwd_rows(const float* P, void* dA_dS, int map_bf16, int
 }
 
 extern "C" int vu_softmax_stats(float* S, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
-                                uint32_t stream_id, double* sums, void* stream) {
+                                uint32_t stream_id, double* sums, int precision, void* stream) {
   using namespace vu;
   const char* fn = "vu_softmax_stats";
   VU_REQUIRE(VU_MAP_ARGS_OK(S) && sums, fn, "bad arguments (maps need ld % 4 == 0 and 16-byte alignment)");
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  VU_REQUIRE(precision == VU_PREC_FP32 || precision == VU_PREC_TF32, fn, "precision must be VU_PREC_FP32 or VU_PREC_TF32");
+  if (precision == VU_PREC_TF32 && mma_path(h, N, ld)) {
+    if (N > 256 && N <= 1024) {
+      const int grid = resident_grid(mma::softmax_stats_mma_cta_kernel<4>, 256, (int64_t)B * N * 8);
+      mma::softmax_stats_mma_cta_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(S, B, N, scale, q, sums);
+      return check_launch(fn);
+    }
+    const int grid = resident_grid(mma::softmax_stats_mma_kernel, 256, (int64_t)B * N);
+    mma::softmax_stats_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(S, B, N, scale, q, sums);
+    return check_launch(fn);
+  }
   int blocks = grid_for((int64_t)B * N * 32, 256, 8);
   VU_DISPATCH_H(h, fn, softmax_stats_kernel<HH><<<blocks, 256, 0, as_stream(stream)>>>(S, B, N, ld, scale, q, sums));
   return check_launch(fn);
@@ -650,6 +700,13 @@ extern "C" int vu_reattn_mix_reduce(const float* P, const void* dA, void* A, int
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
+  if (map_bf16 && mma_path(h, N, ld)) {
+    const int64_t tiles = cdiv((int64_t)N * N / 4, 8) * B;
+    const int grid = resident_grid(mma::reattn_mix_reduce_mma_kernel, 256, tiles);
+    mma::reattn_mix_reduce_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A,
+                                                                          fold, B, N, q, red);
+    return check_launch(fn);
+  }
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);
   if (map_bf16) { VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH, __nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, B, N, ld, q, red)); }
   else { VU_DISPATCH_H(h, fn, reattn_mix_reduce_kernel<HH, float><<<blocks, 256, 0, as_stream(stream)>>>(P, (const float*)dA, (float*)A, fold, B, N, ld, q, red)); }

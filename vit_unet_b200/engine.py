@@ -189,7 +189,8 @@ class Engine:
             for ci, b0 in enumerate(range(0, B, c)):
                 bc = min(c, B - b0)
                 scores(b0, bc, Pm[b0:b0 + bc])
-                ops.softmax_stats(Pm[b0:b0 + bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums)
+                ops.softmax_stats(Pm[b0:b0 + bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums,
+                                  precision=prec)
             finalize()
             for ci, b0 in enumerate(range(0, B, c)):
                 bc = min(c, B - b0)

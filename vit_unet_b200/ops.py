@@ -191,9 +191,9 @@ def softmax_rows(S, rows, N, ld, scale):
     _call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream(), nbytes=8.0 * rows * N)
 
 
-def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums):
+def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums, precision=PREC_FP32):
     _call("vu_softmax_stats", _chk(S, "S"), B, h, N, ld, scale, drop_p, seed, sid, _chk(sums, "sums", torch.float64),
-          _stream(), nbytes=2 * 4.0 * B * h * N * N)
+          int(precision), _stream(), nbytes=2 * 4.0 * B * h * N * N)
 
 
 def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red):
