@@ -102,10 +102,20 @@ int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scale, void* st
  * The BatchNorm batch statistics of M_h = sum_g W[h,g] Pd_g + b[h] follow in closed form (vu_reattn_bn_finalize). */
 int vu_reattn_stats(const float* P, int B, int h, int N, int ld, float drop_p, uint64_t seed, uint32_t stream_id,
                     double* sums, void* stream);
-/* fused train-mode pass: in-place softmax of every head + the moments above in ONE read of S / write of P.
+/* Storage format flags of the attention maps (`map_fmt` below).  VU_MAP_BF16: the mixed map A and the gradient
+ * map dA/dS are bfloat16 (ld % 8 == 0).  VU_MAP_P_CENTRED_BF16: the probabilities are stored as bfloat16 CENTRED
+ * at the uniform row, Pc = P - 1/N (so the rounding is relative to what head mixing + BatchNorm actually see);
+ * only together with VU_MAP_BF16 and where vu_reattn_tensor_core_path() != 0. */
+enum { VU_MAP_BF16 = 1, VU_MAP_P_CENTRED_BF16 = 2 };
+/* 1 when the 8-head warp-MMA formulation of the map kernels applies (h == 8, ld == N, N % 8 == 0; VU_MAP_MMA=0 in
+ * the environment switches it off): vu_softmax_stats(TF32), vu_reattn_mix / _mix_reduce / _bwd_rows with bf16 maps. */
+int vu_reattn_tensor_core_path(int h, int N, int ld);
+/* fused train-mode pass: softmax of every head + the moments above in ONE read of S / write of P.
+ * Pc == NULL: P overwrites S in place (fp32).  Pc != NULL: centred bf16 probabilities are written to Pc (same
+ * (B,h,N,ld) indexing), S is left untouched and the moments are those of the ROUNDED map.
  * precision = VU_PREC_TF32 lets the moments of 8-head maps without pad columns be accumulated by TF32 warp MMAs
  * (centred inputs, fp32 accumulation); VU_PREC_FP32 keeps the exact CUDA-core sums. */
-int vu_softmax_stats(float* S, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
+int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
                      uint32_t stream_id, double* sums, int precision, void* stream);
 /* fold conv1x1 + BatchNorm into one affine:  fold[h*h + h] = {alpha'[h][g], beta'[h]};
  * saved[2h] = {mean_h, invstd_h}.  train=1: batch statistics from `sums` (+ running-stat update,
@@ -114,15 +124,14 @@ int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, int N, const
                           const float* gamma, const float* beta, float* running_mean, float* running_var,
                           int64_t* num_batches_tracked, float eps, float momentum, int train,
                           float* fold, float* saved, void* stream);
-/* A_h = sum_g alpha'[h,g]*drop(P_g) + beta'[h].  map_bf16 != 0: A is stored as bfloat16 (same (B,h,N,ld) indexing,
- * ld % 8 == 0); the mixed map and the gradient map may be bf16, the probabilities P are always fp32. */
-int vu_reattn_mix(const float* P, void* A, int map_bf16, const float* fold, int B, int h, int N, int ld,
+/* A_h = sum_g alpha'[h,g]*drop(P_g) + beta'[h].  map_fmt: see VU_MAP_* (P fp32 or centred bf16; A fp32 or bf16). */
+int vu_reattn_mix(const void* P, void* A, int map_fmt, const float* fold, int B, int h, int N, int ld,
                   float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 /* backward reductions: red[h + h*h] (double, caller zeroes) += { s1_h = sum dA_h,  X'_{hg} = sum dA_h (Pd_g - c) } */
 int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, float drop_p, uint64_t seed,
                          uint32_t stream_id, double* red, void* stream);
 /* fused backward pass: A = mix(P) (as vu_reattn_mix) AND the reductions of vu_reattn_bwd_reduce, one read of P, dA */
-int vu_reattn_mix_reduce(const float* P, const void* dA, void* A, int map_bf16, const float* fold, int B, int h, int N,
+int vu_reattn_mix_reduce(const void* P, const void* dA, void* A, int map_fmt, const float* fold, int B, int h, int N,
                          int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream);
 /* closed-form parameter gradients from (red, sums): dW[h*h], dbconv[h], dgamma[h], dbeta[h] are ACCUMULATED
  * (atomic; caller zeroes); coef[2h] = BatchNorm-backward means {mean dA_h, mean dA_h*Ahat_h} for vu_reattn_bwd_rows.
@@ -131,7 +140,7 @@ int vu_reattn_bwd_params(const double* red, const double* sums, int B, int h, in
                          const float* bconv, const float* gamma, const float* saved, int train,
                          float* coef, float* dW, float* dbconv, float* dgamma, float* dbeta, void* stream);
 /* in place dA -> dS (gradient of the pre-softmax scores) */
-int vu_reattn_bwd_rows(const float* P, void* dA_dS, int map_bf16, int B, int h, int N, int ld, const float* W,
+int vu_reattn_bwd_rows(const void* P, void* dA_dS, int map_fmt, int B, int h, int N, int ld, const float* W,
                        const float* bconv, const float* gamma, const float* saved, const float* coef,
                        int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 

@@ -398,6 +398,24 @@ def test_reattn_tensor_core_path(ops, N, p, train):
     ops.reattn_bwd_rows(P1, d1, B, h, N, ld, W, bc, gm, saved, coef, train, scale, p, 5, 2)
     ops.reattn_bwd_rows(P1, d2, B, h, N, ld, W, bc, gm, saved, coef, train, scale, p, 5, 2)
     _close(d2.float(), d1, rtol=1.5e-2, name="dS (mma, bf16)")
+    # probabilities stored as centred bf16 (Pc = P - 1/N): same kernels, half the bytes for P
+    Pc = torch.empty(B, h, N, ld, dtype=torch.bfloat16, device="cuda")
+    s3 = torch.zeros_like(s1)
+    S3 = S.clone()
+    ops.softmax_stats(S3, B, h, N, ld, scale, p, 5, 2, s3, precision=ops.PREC_TF32, Pc=Pc)
+    assert torch.equal(S3, S)                                   # scores untouched
+    _close(Pc.float(), P1 - 1.0 / N, rtol=4e-3, name="centred bf16 probabilities")
+    _close(s3, s1, rtol=8e-3, name="moments of the rounded map")
+    A4 = torch.empty_like(A2)
+    ops.reattn_mix(Pc, A4, fold, B, h, N, ld, p, 5, 2)
+    _close(A4.float(), A1, rtol=1.2e-2, name="mixed map (centred bf16 P)")
+    r3 = torch.zeros_like(r1); A5 = torch.empty_like(A2)
+    ops.reattn_mix_reduce(Pc, dA, A5, fold, B, h, N, ld, p, 5, 2, r3)
+    assert torch.equal(A5, A4)
+    _close(r3[h:], r1[h:], rtol=4e-3, name="X' (centred bf16 P)")
+    d3 = dA.clone()
+    ops.reattn_bwd_rows(Pc, d3, B, h, N, ld, W, bc, gm, saved, coef, train, scale, p, 5, 2)
+    _close(d3.float(), d1, rtol=2.5e-2, name="dS (centred bf16 P)")
 
 
 def test_psnr_and_input_pipeline(ops):

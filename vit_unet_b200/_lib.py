@@ -48,7 +48,7 @@ SIGNATURES = {
     "vu_gemm": [C.POINTER(GemmDesc), _p],
     "vu_colsum": [_p, _l, _i, _l, _p, _i, _p],
     "vu_softmax_rows": [_p, _l, _i, _i, _f, _p],
-    "vu_softmax_stats": [_p, _i, _i, _i, _i, _f, _f, _u64, _u32, _p, _i, _p],
+    "vu_softmax_stats": [_p, _p, _i, _i, _i, _i, _f, _f, _u64, _u32, _p, _i, _p],
     "vu_reattn_mix_reduce": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_stats": [_p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bn_finalize": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p],
@@ -71,6 +71,7 @@ _SPECIAL = {
     "vu_version": ([], C.c_int),
     "vu_last_error": ([], C.c_char_p),
     "vu_device_sm_count": ([_i], C.c_int),
+    "vu_reattn_tensor_core_path": ([_i, _i, _i], C.c_int),
 }
 
 _lib = None

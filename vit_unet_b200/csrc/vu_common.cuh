@@ -67,20 +67,28 @@ struct Layout {
 };
 
 // ------------------------------------------------------------------ counter-based dropout RNG
-// One 64-bit SplitMix-style hash per QUAD of consecutive elements, keyed by (seed, stream id, element index / 4),
-// yields four 16-bit uniforms: element e of the quad is kept iff its 16 bits >= thresh16 (= round(p * 65536)).
-// ~20 integer instructions per quad (Philox4x32-10 needs ~70), which matters because the attention-map kernels
-// regenerate the mask in five passes instead of storing it.  The same function is used by every kernel that needs
-// the mask of a given element, so masks never have to be stored.  (Struct keeps its historical name.)
+// One 32-bit multiply-xorshift chain (murmur3 finaliser) per QUAD of consecutive elements, keyed by (seed, stream id)
+// and counted by the low 32 bits of (element index / 4), yields four 16-bit uniforms: element e of the quad is kept
+// iff its 16 bits >= thresh16 (= round(p * 65536)).  ~15 integer instructions per quad, all 32-bit (the attention-map
+// kernels regenerate the mask in five passes instead of storing it, and were issue-bound on a 64-bit hash).  The same
+// function is used by every kernel that needs the mask of a given element, so masks never have to be stored; the
+// mask pattern repeats every 2^34 elements of one stream.  (Struct keeps its historical name.)
 struct Philox {
+  __host__ __device__ __forceinline__ static uint32_t key(uint64_t seed, uint32_t stream) {
+    uint32_t k = (uint32_t)seed * 0x9E3779B1u ^ (uint32_t)(seed >> 32) * 0x85EBCA77u;
+    k ^= stream * 0xC2B2AE3Du + 0x27D4EB2Fu;
+    k ^= k >> 15; k *= 0x2C1B3C6Du; k ^= k >> 12; k *= 0x297A2D39u; k ^= k >> 15;
+    return k;
+  }
+  __device__ __forceinline__ static uint4 gen_k(uint32_t key, uint32_t ctr) {
+    uint32_t h = ctr * 0x9E3779B1u + key;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    uint32_t g = (h ^ key) * 0x27D4EB2Fu;
+    g ^= g >> 15; g *= 0x165667B1u; g ^= g >> 13;
+    return make_uint4(h & 0xFFFFu, h >> 16, g & 0xFFFFu, g >> 16);
+  }
   __device__ __forceinline__ static uint4 gen(uint64_t seed, uint32_t stream, uint64_t ctr) {
-    uint64_t x = ctr * 0x9E3779B97F4A7C15ull + seed;
-    x ^= (uint64_t)stream * 0xD1B54A32D192ED03ull;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-    return make_uint4(lo & 0xFFFFu, lo >> 16, hi & 0xFFFFu, hi >> 16);
+    return gen_k(key(seed, stream), (uint32_t)ctr);
   }
   // keep test for one element index; thresh = p * 2^16 (drop if r < thresh)
   __device__ __forceinline__ static bool keep(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thresh) {

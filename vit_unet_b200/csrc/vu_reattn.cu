@@ -58,11 +58,12 @@ softmax_rows_kernel(float* __restrict__ S, int64_t rows, int N, int ld, float sc
 // P quad of head g at (b, i, j..j+3) with dropout applied and the centre subtracted; invalid (pad) lanes -> 0.
 struct QuadCtx {
   uint32_t thresh; float dscale; uint64_t seed; uint32_t stream; float c; int N;
+  uint32_t key;          // Philox::key(seed, stream), computed on the host
 };
 __device__ __forceinline__ float4 load_pd(const float* __restrict__ p, uint64_t flat_idx, const QuadCtx& q) {
   float4 v = *reinterpret_cast<const float4*>(p);
   if (q.thresh) {
-    uint4 rr = Philox::gen(q.seed, q.stream, flat_idx >> 2);
+    uint4 rr = Philox::gen_k(q.key, (uint32_t)(flat_idx >> 2));
     v.x = rr.x >= q.thresh ? v.x * q.dscale : 0.f; v.y = rr.y >= q.thresh ? v.y * q.dscale : 0.f;
     v.z = rr.z >= q.thresh ? v.z * q.dscale : 0.f; v.w = rr.w >= q.thresh ? v.w * q.dscale : 0.f;
   }
@@ -458,7 +459,7 @@ reattn_bwd_rows_kernel(const float* __restrict__ P, MT* __restrict__ dA, int B, 
         pd[g] = p[g];
         keep[g] = make_uint4(1, 1, 1, 1);
         if (q.thresh) {
-          uint4 rr = Philox::gen(q.seed, q.stream, (uint64_t)(row_off + g * head_stride + j) >> 2);
+          uint4 rr = Philox::gen_k(q.key, (uint32_t)((uint64_t)(row_off + g * head_stride + j) >> 2));
           keep[g] = make_uint4(rr.x >= q.thresh, rr.y >= q.thresh, rr.z >= q.thresh, rr.w >= q.thresh);
           pd[g].x = keep[g].x ? p[g].x * q.dscale : 0.f; pd[g].y = keep[g].y ? p[g].y * q.dscale : 0.f;
           pd[g].z = keep[g].z ? p[g].z * q.dscale : 0.f; pd[g].w = keep[g].w ? p[g].w * q.dscale : 0.f;
@@ -518,13 +519,13 @@ namespace vu {
 // 8-head tensor-core formulation (vu_reattn_mma.cuh): TF32 path, no pad columns.  VU_MAP_MMA=0 disables it.
 static bool mma_path(int h, int N, int ld) {
   static const bool on = []() { const char* e = getenv("VU_MAP_MMA"); return !(e && e[0] == '0'); }();
-  return on && h == 8 && ld == N && N % 8 == 0;
+  return on && h == 8 && ld == N && N % 8 == 0 && N <= 8192;   // 32-bit offsets inside one image
 }
 // persistent grid: as many CTAs as are resident (occupancy query, cached per kernel), capped by the work
 template <typename K>
-static int resident_grid(K kernel, int threads, int64_t warps_of_work) {
+static int resident_grid(K kernel, int threads, int64_t warps_of_work, size_t dyn_smem = 0) {
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem);
   if (per_sm < 1) per_sm = 1;
   const int64_t need = cdiv(warps_of_work, threads / 32);
   return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * per_sm));
@@ -539,6 +540,7 @@ static QuadCtx make_ctx(float drop_p, uint64_t seed, uint32_t stream_id, int N) 
   QuadCtx q;
   q.thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
   q.dscale = drop_keep_scale(drop_p); q.seed = seed; q.stream = stream_id; q.c = 1.0f / (float)N; q.N = N;
+  q.key = Philox::key(seed, stream_id);
   return q;
 }
 
@@ -557,6 +559,8 @@ static QuadCtx make_ctx(float drop_p, uint64_t seed, uint32_t stream_id, int N) 
     default: return vu::fail_arg(fn, "num_heads must be in 1..8");  \
   }
 #define VU_MAP_ARGS_OK(P) ((P) && B > 0 && N > 0 && ld >= N && ld % 4 == 0 && ((uintptr_t)(P) % 16 == 0))
+
+extern "C" int vu_reattn_tensor_core_path(int h, int N, int ld) { return vu::mma_path(h, N, ld) ? 1 : 0; }
 
 extern "C" int vu_softmax_rows(float* S, int64_t rows, int N, int ld, float scale, void* stream) {
   using namespace vu;
@@ -594,18 +598,27 @@ extern "C" int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, i
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_mix(const float* P, void* A, int map_bf16, const float* fold, int B, int h, int N, int ld,
+extern "C" int vu_reattn_mix(const void* Pv, void* A, int map_fmt, const float* fold, int B, int h, int N, int ld,
                              float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_mix";
+  const int map_bf16 = map_fmt & VU_MAP_BF16, p_bf16 = map_fmt & VU_MAP_P_CENTRED_BF16;
+  const float* P = (const float*)Pv;
   VU_REQUIRE(VU_MAP_ARGS_OK(P) && A && fold && ((uintptr_t)A % 16 == 0), fn, "bad arguments");
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
+  VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   if (map_bf16 && mma_path(h, N, ld)) {
-    const int64_t tiles = cdiv((int64_t)N * N / 4, 8) * B;
-    const int grid = resident_grid(mma::reattn_mix_mma_kernel, 256, cdiv(tiles, 2));
-    mma::reattn_mix_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)A, fold, B, N, q);
+    VU_REQUIRE(B <= 65535, fn, "at most 65535 images per call on the tensor-core map path");
+    const int64_t tiles = cdiv((int64_t)N * N / 4, 8);          // per image; grid = (x, B)
+    if (p_bf16) {
+      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 2 * 8));      // 8 warps x 2 tiles x ~8 iterations per CTA
+      mma::reattn_mix_mma_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)Pv, (__nv_bfloat16*)A, fold, N, q);
+    } else {
+      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 2 * 8));
+      mma::reattn_mix_mma_kernel<float><<<dim3(gx, B), 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)A, fold, N, q);
+    }
     return check_launch(fn);
   }
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256, 16);
@@ -638,25 +651,39 @@ extern "C" int vu_reattn_bwd_params(const double* red, const double* sums, int B
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_bwd_rows(const float* P, void* dA_dS, int map_bf16, int B, int h, int N, int ld, const float* W,
+extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int B, int h, int N, int ld, const float* W,
                                   const float* bconv, const float* gamma, const float* saved, const float* coef,
                                   int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_bwd_rows";
+  const int map_bf16 = map_fmt & VU_MAP_BF16, p_bf16 = map_fmt & VU_MAP_P_CENTRED_BF16;
+  const float* P = (const float*)Pv;
   VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA_dS && W && bconv && gamma && saved && ((uintptr_t)dA_dS % 16 == 0), fn, "bad arguments");
   VU_REQUIRE(!train || coef, fn, "train mode needs the BN-backward coefficients");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
+  VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
   if (map_bf16 && mma_path(h, N, ld)) {
+    cudaStream_t st = as_stream(stream);
+    __nv_bfloat16* d = (__nv_bfloat16*)dA_dS;
+    const __nv_bfloat16* Pb = (const __nv_bfloat16*)Pv;
     if (N > 256 && N <= 1024) {         // long rows: one CTA per row, row kept in registers between the sweeps
-      const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<4>, 256, (int64_t)B * N * 8);
-      mma::reattn_bwd_rows_mma_cta_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)dA_dS, B, N, W, bconv,
-                                                                                 gamma, saved, coef, train, scale, q);
+      if (p_bf16) {
+        const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<4, __nv_bfloat16>, 256, (int64_t)B * N * 8);
+        mma::reattn_bwd_rows_mma_cta_kernel<4, __nv_bfloat16><<<grid, 256, 0, st>>>(Pb, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+      } else {
+        const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<4, float>, 256, (int64_t)B * N * 8);
+        mma::reattn_bwd_rows_mma_cta_kernel<4, float><<<grid, 256, 0, st>>>(P, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+      }
       return check_launch(fn);
     }
-    const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel, 256, (int64_t)B * N);
-    mma::reattn_bwd_rows_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)dA_dS, B, N, W, bconv, gamma,
-                                                                        saved, coef, train, scale, q);
+    if (p_bf16) {
+      const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel<__nv_bfloat16>, 256, (int64_t)B * N);
+      mma::reattn_bwd_rows_mma_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(Pb, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+    } else {
+      const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel<float>, 256, (int64_t)B * N);
+      mma::reattn_bwd_rows_mma_kernel<float><<<grid, 256, 0, st>>>(P, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+    }
     return check_launch(fn);
   }
   int blocks = grid_for((int64_t)B * N * 32, 128, 12);
@@ -667,7 +694,7 @@ extern "C" int vu_reattn_bwd_rows(const float* P, void* dA_dS, int map_bf16, int
   return check_launch(fn);
 }
 
-extern "C" int vu_softmax_stats(float* S, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
+extern "C" int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
                                 uint32_t stream_id, double* sums, int precision, void* stream) {
   using namespace vu;
   const char* fn = "vu_softmax_stats";
@@ -675,14 +702,21 @@ extern "C" int vu_softmax_stats(float* S, int B, int h, int N, int ld, float sca
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   VU_REQUIRE(precision == VU_PREC_FP32 || precision == VU_PREC_TF32, fn, "precision must be VU_PREC_FP32 or VU_PREC_TF32");
-  if (precision == VU_PREC_TF32 && mma_path(h, N, ld)) {
-    if (N > 256 && N <= 1024) {
-      const int grid = resident_grid(mma::softmax_stats_mma_cta_kernel<4>, 256, (int64_t)B * N * 8);
-      mma::softmax_stats_mma_cta_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(S, B, N, scale, q, sums);
+  const bool use_mma = precision == VU_PREC_TF32 && mma_path(h, N, ld);
+  VU_REQUIRE(!Pc || (use_mma && (uintptr_t)Pc % 16 == 0), fn,
+             "centred bf16 output needs VU_PREC_TF32, h == 8, ld == N, N % 8 == 0 and 16-byte alignment");
+  if (use_mma) {
+    if (N > 256 && N <= 1024) {          // asynchronous row pipeline (cp.async.bulk ring in shared memory)
+      constexpr int ST = 2;
+      const size_t smem = mma::bulk_smem_bytes(ST, 8 * N);
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(mma::softmax_stats_mma_bulk_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      const int grid = resident_grid(mma::softmax_stats_mma_bulk_kernel<ST>, mma::kBulkThreads, (int64_t)B * N * 9, smem);
+      mma::softmax_stats_mma_bulk_kernel<ST><<<grid, mma::kBulkThreads, smem, as_stream(stream)>>>(S, (__nv_bfloat16*)Pc, B, N, scale, q, sums);
       return check_launch(fn);
     }
     const int grid = resident_grid(mma::softmax_stats_mma_kernel, 256, (int64_t)B * N);
-    mma::softmax_stats_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(S, B, N, scale, q, sums);
+    mma::softmax_stats_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(S, (__nv_bfloat16*)Pc, B, N, scale, q, sums);
     return check_launch(fn);
   }
   int blocks = grid_for((int64_t)B * N * 32, 256, 8);
@@ -690,21 +724,31 @@ extern "C" int vu_softmax_stats(float* S, int B, int h, int N, int ld, float sca
   return check_launch(fn);
 }
 
-extern "C" int vu_reattn_mix_reduce(const float* P, const void* dA, void* A, int map_bf16, const float* fold, int B, int h,
+extern "C" int vu_reattn_mix_reduce(const void* Pv, const void* dA, void* A, int map_fmt, const float* fold, int B, int h,
                                     int N, int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red,
                                     void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_mix_reduce";
+  const int map_bf16 = map_fmt & VU_MAP_BF16, p_bf16 = map_fmt & VU_MAP_P_CENTRED_BF16;
+  const float* P = (const float*)Pv;
   VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA && A && fold && red && ((uintptr_t)dA % 16 == 0) && ((uintptr_t)A % 16 == 0), fn,
              "bad arguments");
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
+  VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   if (map_bf16 && mma_path(h, N, ld)) {
-    const int64_t tiles = cdiv((int64_t)N * N / 4, 8) * B;
-    const int grid = resident_grid(mma::reattn_mix_reduce_mma_kernel, 256, tiles);
-    mma::reattn_mix_reduce_mma_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A,
-                                                                          fold, B, N, q, red);
+    VU_REQUIRE(B <= 65535, fn, "at most 65535 images per call on the tensor-core map path");
+    const int64_t tiles = cdiv((int64_t)N * N / 4, 8);          // per image; grid = (x, B)
+    if (p_bf16) {
+      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 16));          // 8 warps x ~16 iterations per CTA
+      mma::reattn_mix_reduce_mma_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, as_stream(stream)>>>(
+          (const __nv_bfloat16*)Pv, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
+    } else {
+      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 16));
+      mma::reattn_mix_reduce_mma_kernel<float><<<dim3(gx, B), 256, 0, as_stream(stream)>>>(
+          P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
+    }
     return check_launch(fn);
   }
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);

@@ -25,6 +25,10 @@ __device__ __forceinline__ uint32_t tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ uint32_t bits(float x) { return __float_as_uint(x); }
+// round-to-nearest (half away from zero) on the 13 mantissa bits the tensor core drops: one integer add.  Used for
+// the statistics, where a truncation bias (-0.7 * 2^-10 on every second moment) would shift the BatchNorm variance.
+__device__ __forceinline__ uint32_t rnd(float x) { return __float_as_uint(x) + 0x1000u; }
 __device__ __forceinline__ void mma8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                      uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -38,9 +42,11 @@ __device__ __forceinline__ int sigma(int n) { return (n >> 1) + ((n & 1) << 2); 
 // lane's fragment of the 8x8 weight matrix (see frag_fwd / frag_bwd).
 __device__ __forceinline__ void mix_pair(const float4& x0, const float4& x1, uint32_t b0, uint32_t b1,
                                          float4& y0, float4& y1) {
+  // data operands go in as raw fp32 bits: the tensor core reads the top 19 bits (truncation, 2^-11 mean relative
+  // shrink of CENTRED values -- far below the bf16 rounding of the stored result); only the weights are rounded (rna)
   float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
-  mma8(c, tf32(x0.x), tf32(x0.y), tf32(x1.x), tf32(x1.y), b0, b1);    // rows e / e+8 = components 0 / 1
-  mma8(d, tf32(x0.z), tf32(x0.w), tf32(x1.z), tf32(x1.w), b0, b1);    // rows e / e+8 = components 2 / 3
+  mma8(c, bits(x0.x), bits(x0.y), bits(x1.x), bits(x1.y), b0, b1);    // rows e / e+8 = components 0 / 1
+  mma8(d, bits(x0.z), bits(x0.w), bits(x1.z), bits(x1.w), b0, b1);    // rows e / e+8 = components 2 / 3
   y0 = make_float4(c[0], c[2], d[0], d[2]);
   y1 = make_float4(c[1], c[3], d[1], d[3]);
 }
@@ -53,10 +59,10 @@ __device__ __forceinline__ void frag_bwd(const float* __restrict__ F, int e, int
   b0 = tf32(F[k4 * H + sigma(e)]); b1 = tf32(F[(k4 + 4) * H + sigma(e)]);
 }
 
-// dropout of one quad in place; returns the keep bits (bit t = component t kept)
-__device__ __forceinline__ uint32_t drop_quad(float4& v, uint64_t flat_idx, const QuadCtx& q) {
+// dropout of one quad in place (ctr = low 32 bits of element index / 4); returns the keep bits (bit t = component t)
+__device__ __forceinline__ uint32_t drop_quad(float4& v, uint32_t ctr, const QuadCtx& q) {
   if (!q.thresh) return 0xFu;
-  const uint4 rr = Philox::gen(q.seed, q.stream, flat_idx >> 2);
+  const uint4 rr = Philox::gen_k(q.key, ctr);
   const uint32_t m = (rr.x >= q.thresh ? 1u : 0u) | (rr.y >= q.thresh ? 2u : 0u) | (rr.z >= q.thresh ? 4u : 0u) |
                      (rr.w >= q.thresh ? 8u : 0u);
   v.x = (m & 1u) ? v.x * q.dscale : 0.f; v.y = (m & 2u) ? v.y * q.dscale : 0.f;
@@ -64,20 +70,60 @@ __device__ __forceinline__ uint32_t drop_quad(float4& v, uint64_t flat_idx, cons
   return m;
 }
 __device__ __forceinline__ void sub4(float4& v, float c) { v.x -= c; v.y -= c; v.z -= c; v.w -= c; }
+__device__ __forceinline__ void add4(float4& v, float c) { v.x += c; v.y += c; v.z += c; v.w += c; }
+__device__ __forceinline__ void mul4(float4& v, float c) { v.x *= c; v.y *= c; v.z *= c; v.w *= c; }
+__device__ __forceinline__ float hsum4(const float4& v) { return (v.x + v.y) + (v.z + v.w); }
+__device__ __forceinline__ float hmax4(const float4& v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
 __device__ __forceinline__ float comp(const float4& v, int u) { return u == 0 ? v.x : (u == 1 ? v.y : (u == 2 ? v.z : v.w)); }
 __device__ __forceinline__ float4 ldq(const float* p) { return *reinterpret_cast<const float4*>(p); }
 constexpr float4 kZero4 = {0.f, 0.f, 0.f, 0.f};
+// The probabilities are read either as fp32 P or as CENTRED bf16 (Pc = P - 1/N, see softmax_stats_*): the bf16
+// rounding is then relative to the deviation from the uniform row, which is what the head mixing + BatchNorm see.
+__device__ __forceinline__ float4 ldp(const float* p, float) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldp(const __nv_bfloat16* p, float c) { float4 v = map_ld(p); add4(v, c); return v; }
 
-// block-wide reduction of the 8 + 64 accumulators of a statistics kernel (s[head e] on lanes k4 == 0, M[e][2k4..+1]
-// on every lane) followed by one double atomicAdd per entry.  256 threads.
-__device__ __forceinline__ void reduce_stats(float s, float m0, float m1, double* __restrict__ out) {
-  __shared__ float part[8][H + H * H];
+__device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+  return u;
+}
+__device__ __forceinline__ float4 unpack_bf16x4(const uint2& u) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// write one quad of probabilities: fp32 in place over S, or centred bf16 into Pc (then continue with the ROUNDED
+// value, so the moments describe exactly the map the later kernels read back)
+__device__ __forceinline__ void emit_p(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, int off, float4& p, float c) {
+  if (Pc) {
+    float4 d = p; sub4(d, c);
+    const uint2 u = pack_bf16x4(d);
+    *reinterpret_cast<uint2*>(Pc + off) = u;
+    p = unpack_bf16x4(u); add4(p, c);
+  } else {
+    *reinterpret_cast<float4*>(S + off) = p;
+  }
+}
+// G'/X' style accumulation in the stats layout: C[e][2k4..2k4+1] += sum_keys A_e[key] * B_n[key] over this lane's 8 keys
+__device__ __forceinline__ void mma_keys(float (&c)[4], const float4& a_lo, const float4& a_hi, const float4& b_lo,
+                                         const float4& b_hi) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    mma8(c, rnd(comp(a_lo, u)), 0u, rnd(comp(a_hi, u)), 0u, rnd(comp(b_lo, u)), rnd(comp(b_hi, u)));
+}
+
+// sum over the 8 warps of the 8 + 64 statistics accumulators (s[head e] after the 4-lane reduction, M[e][2k4..+1] on
+// every lane), one double atomicAdd per entry.  `part` is [8][72] shared floats; warps >= 8 only join the barrier.
+__device__ __forceinline__ void reduce_stats(float (*part)[H + H * H], bool consumer, float s, float m0, float m1,
+                                             double* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  if (k4 == 0) part[warp][e] = s;
-  part[warp][H + e * H + 2 * k4] = m0;
-  part[warp][H + e * H + 2 * k4 + 1] = m1;
+  if (consumer) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (k4 == 0) part[warp][e] = s;
+    part[warp][H + e * H + 2 * k4] = m0;
+    part[warp][H + e * H + 2 * k4 + 1] = m1;
+  }
   __syncthreads();
   if (threadIdx.x < H + H * H) {
     double t = 0;
@@ -87,32 +133,35 @@ __device__ __forceinline__ void reduce_stats(float s, float m0, float m1, double
   }
 }
 
-// ------------------------------------------------------------------ forward: softmax + centred moments
+// All index arithmetic below is 32-bit: one image of maps has 8*N*N < 2^31 elements (N <= 8192, checked by the
+// dispatcher); the 64-bit image base is added to the pointers once per row / CTA.
+
+// ------------------------------------------------------------------ forward: softmax + centred moments (short rows)
 // One warp per row (b, i), all 8 heads at once in the stats layout (lane = head e, key quads k4 and k4+4 of each
-// 32-key tile).  Sweep A: online (max, sum) of exp2; sweep B (re-read from L1/L2): write P, accumulate
-// s'_g = sum (Pd_g - c) and G' = sum (Pd - c)(Pd - c)^T (4 MMAs per tile, K = keys).
+// 32-key tile).  Sweep A: online (max, sum) of exp2; sweep B (re-read from L1): write P, accumulate
+// s'_g = sum (Pd_g - c) and G' = sum (Pd - c)(Pd - c)^T (4 MMAs per tile, K = keys).  Used for N <= 256.
 __global__ void __launch_bounds__(256)
-softmax_stats_mma_kernel(float* __restrict__ S, int B, int N, float scale, QuadCtx q, double* __restrict__ sums) {
+softmax_stats_mma_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, int B, int N, float scale, QuadCtx q,
+                         double* __restrict__ sums) {
+  __shared__ float part[8][H + H * H];
   const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const float sl2 = scale * 1.4426950408889634f;
-  const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3;
-  const int64_t head_stride = (int64_t)N * N, img_stride = head_stride * H, rows = (int64_t)B * N;
+  const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3, hs = N * N, rows = B * N;
   float cg[4] = {0.f, 0.f, 0.f, 0.f}, s = 0.f;
-  for (int64_t r = wid; r < rows; r += nw) {
-    const int64_t b = r / N; const int i = (int)(r - b * N);
-    const int64_t row_off = b * img_stride + e * head_stride + (int64_t)i * N;
-    float* row = S + row_off;
+  for (int r = wid; r < rows; r += nw) {
+    const int b = r / N, i = r - b * N;
+    const int64_t base = (int64_t)b * hs * H;
+    const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
+    const int roff = e * hs + i * N;
+    float* Sb = S + base; __nv_bfloat16* Pb = Pc ? Pc + base : nullptr;
     float m = -INFINITY, l = 0.f;
     for (int t = 0; t < ntiles; ++t) {
       const int qa = t * 8 + k4, qb = qa + 4;
-      const bool va = qa < ld4, vb = qb < ld4;
-      float4 xa = va ? ldq(row + 4 * qa) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      float4 xb = vb ? ldq(row + 4 * qb) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      xa.x *= sl2; xa.y *= sl2; xa.z *= sl2; xa.w *= sl2; xb.x *= sl2; xb.y *= sl2; xb.z *= sl2; xb.w *= sl2;
-      const float mq = fmaxf(fmaxf(fmaxf(xa.x, xa.y), fmaxf(xa.z, xa.w)), fmaxf(fmaxf(xb.x, xb.y), fmaxf(xb.z, xb.w)));
-      const float mn = fmaxf(m, mq);
+      float4 xa = qa < ld4 ? ldq(Sb + roff + 4 * qa) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      float4 xb = qb < ld4 ? ldq(Sb + roff + 4 * qb) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      mul4(xa, sl2); mul4(xb, sl2);
+      const float mn = fmaxf(m, fmaxf(hmax4(xa), hmax4(xb)));
       if (mn > -INFINITY) {
         l = l * exp2f(m - mn) + ((exp2f(xa.x - mn) + exp2f(xa.y - mn)) + (exp2f(xa.z - mn) + exp2f(xa.w - mn))) +
             ((exp2f(xb.x - mn) + exp2f(xb.y - mn)) + (exp2f(xb.z - mn) + exp2f(xb.w - mn)));
@@ -129,68 +178,64 @@ softmax_stats_mma_kernel(float* __restrict__ S, int B, int N, float scale, QuadC
     const float inv = 1.0f / l;
     for (int t = 0; t < ntiles; ++t) {
       const int qa = t * 8 + k4, qb = qa + 4;
-      const bool va = qa < ld4, vb = qb < ld4;
       float4 pa = kZero4, pb = kZero4;
-      if (va) {
-        const float4 x = ldq(row + 4 * qa);
+      if (qa < ld4) {
+        const float4 x = ldq(Sb + roff + 4 * qa);
         pa = make_float4(exp2f(fmaf(x.x, sl2, -m)) * inv, exp2f(fmaf(x.y, sl2, -m)) * inv,
                          exp2f(fmaf(x.z, sl2, -m)) * inv, exp2f(fmaf(x.w, sl2, -m)) * inv);
-        *reinterpret_cast<float4*>(row + 4 * qa) = pa;
-        drop_quad(pa, (uint64_t)(row_off + 4 * qa), q); sub4(pa, q.c);
+        emit_p(Sb, Pb, roff + 4 * qa, pa, q.c);
+        drop_quad(pa, ctr0 + ((uint32_t)roff >> 2) + qa, q); sub4(pa, q.c);
       }
-      if (vb) {
-        const float4 x = ldq(row + 4 * qb);
+      if (qb < ld4) {
+        const float4 x = ldq(Sb + roff + 4 * qb);
         pb = make_float4(exp2f(fmaf(x.x, sl2, -m)) * inv, exp2f(fmaf(x.y, sl2, -m)) * inv,
                          exp2f(fmaf(x.z, sl2, -m)) * inv, exp2f(fmaf(x.w, sl2, -m)) * inv);
-        *reinterpret_cast<float4*>(row + 4 * qb) = pb;
-        drop_quad(pb, (uint64_t)(row_off + 4 * qb), q); sub4(pb, q.c);
+        emit_p(Sb, Pb, roff + 4 * qb, pb, q.c);
+        drop_quad(pb, ctr0 + ((uint32_t)roff >> 2) + qb, q); sub4(pb, q.c);
       }
-      s += ((pa.x + pa.y) + (pa.z + pa.w)) + ((pb.x + pb.y) + (pb.z + pb.w));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t ua = tf32(comp(pa, u)), ub = tf32(comp(pb, u));
-        mma8(cg, ua, 0u, ub, 0u, ua, ub);
-      }
+      s += hsum4(pa) + hsum4(pb);
+      mma_keys(cg, pa, pb, pa, pb);
     }
   }
-  reduce_stats(s, cg[0], cg[1], sums);
+  reduce_stats(part, true, s, cg[0], cg[1], sums);
 }
 
 // ------------------------------------------------------------------ forward: A = fold . (Pd - c) + shift'
-// Flat tiles of 32 consecutive positions of one image (rows are contiguous: ld == N), pair layout.
+// grid (x, B): flat tiles of 32 consecutive positions of image blockIdx.y (rows are contiguous: ld == N), pair layout.
+template <typename PT>
 __global__ void __launch_bounds__(256)
-reattn_mix_mma_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ A, const float* __restrict__ fold,
-                      int B, int N, QuadCtx q) {
+reattn_mix_mma_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ A, const float* __restrict__ fold,
+                      int N, QuadCtx q) {
   const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
   uint32_t b0, b1; frag_fwd(fold, e, k4, b0, b1);
   float sh0 = 0.f, sh1 = 0.f;
 #pragma unroll
   for (int g = 0; g < H; ++g) { sh0 += fold[k4 * H + g]; sh1 += fold[(k4 + 4) * H + g]; }
   sh0 = fmaf(sh0, q.c, fold[H * H + k4]); sh1 = fmaf(sh1, q.c, fold[H * H + k4 + 4]);
-  const int64_t head_stride = (int64_t)N * N, img_stride = head_stride * H;
-  const int64_t quads = head_stride >> 2, tiles = (quads + 7) >> 3, total = tiles * B;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t t = wid; t < total; t += 2 * nw) {
-    int64_t off[2]; bool ok[2]; float4 x0[2], x1[2];
+  const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3;
+  const int64_t base = (int64_t)blockIdx.y * hs * H;
+  const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
+  const PT* Pi = P + base; __nv_bfloat16* Ai = A + base;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int t = wid; t < tiles; t += 2 * nw) {
+    int off[2]; bool ok[2]; float4 x0[2], x1[2];
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
-      const int64_t tt = t + v * nw;
-      const int64_t b = tt / tiles, quad = (tt - b * tiles) * 8 + e;
-      ok[v] = tt < total && quad < quads;
-      off[v] = b * img_stride + k4 * head_stride + quad * 4;
-      x0[v] = ok[v] ? ldq(P + off[v]) : kZero4;
-      x1[v] = ok[v] ? ldq(P + off[v] + 4 * head_stride) : kZero4;
+      const int tt = t + v * nw, quad = tt * 8 + e;
+      ok[v] = tt < tiles && quad < quads;
+      off[v] = k4 * hs + quad * 4;
+      x0[v] = ok[v] ? ldp(Pi + off[v], q.c) : kZero4;
+      x1[v] = ok[v] ? ldp(Pi + off[v] + 4 * hs, q.c) : kZero4;
     }
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
-      if (t + v * nw >= total) break;                       // warp-uniform
-      drop_quad(x0[v], (uint64_t)off[v], q); drop_quad(x1[v], (uint64_t)(off[v] + 4 * head_stride), q);
+      if (t + v * nw >= tiles) break;                       // warp-uniform
+      drop_quad(x0[v], ctr0 + ((uint32_t)off[v] >> 2), q); drop_quad(x1[v], ctr0 + ((uint32_t)off[v] >> 2) + hs, q);
       sub4(x0[v], q.c); sub4(x1[v], q.c);
       float4 y0, y1; mix_pair(x0[v], x1[v], b0, b1, y0, y1);
       if (ok[v]) {
-        y0.x += sh0; y0.y += sh0; y0.z += sh0; y0.w += sh0; y1.x += sh1; y1.y += sh1; y1.z += sh1; y1.w += sh1;
-        map_st(A + off[v], y0); map_st(A + off[v] + 4 * head_stride, y1);
+        add4(y0, sh0); add4(y1, sh1);
+        map_st(Ai + off[v], y0); map_st(Ai + off[v] + 4 * hs, y1);
       }
     }
   }
@@ -198,112 +243,132 @@ reattn_mix_mma_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ A
 
 // ------------------------------------------------------------------ backward pass 1: A = mix(P) recomputed + reductions
 // red[h] += sum dA_h ;  red[H + h*H + g] += sum dA_h (Pd_g - c).  The mix runs in the pair layout, the reductions in
-// the stats layout (second read of the same 1 KB P tile hits L1).
+// the stats layout (second read of the same P tile hits L1).  grid (x, B).
+template <typename PT>
 __global__ void __launch_bounds__(256)
-reattn_mix_reduce_mma_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__ dA,
-                             __nv_bfloat16* __restrict__ A, const float* __restrict__ fold, int B, int N, QuadCtx q,
+reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const __nv_bfloat16* __restrict__ dA,
+                             __nv_bfloat16* __restrict__ A, const float* __restrict__ fold, int N, QuadCtx q,
                              double* __restrict__ out) {
+  __shared__ float part[8][H + H * H];
   const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
   uint32_t b0, b1; frag_fwd(fold, e, k4, b0, b1);
   float sh0 = 0.f, sh1 = 0.f;
 #pragma unroll
   for (int g = 0; g < H; ++g) { sh0 += fold[k4 * H + g]; sh1 += fold[(k4 + 4) * H + g]; }
   sh0 = fmaf(sh0, q.c, fold[H * H + k4]); sh1 = fmaf(sh1, q.c, fold[H * H + k4 + 4]);
-  const int64_t head_stride = (int64_t)N * N, img_stride = head_stride * H;
-  const int64_t quads = head_stride >> 2, tiles = (quads + 7) >> 3, total = tiles * B;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3;
+  const int64_t base = (int64_t)blockIdx.y * hs * H;
+  const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
+  const PT* Pi = P + base; const __nv_bfloat16* Di = dA + base; __nv_bfloat16* Ai = A + base;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   float cx[4] = {0.f, 0.f, 0.f, 0.f}, s1 = 0.f;
-  for (int64_t t = wid; t < total; t += nw) {
-    const int64_t b = t / tiles, tile = t - b * tiles, ibase = b * img_stride;
+  for (int t = wid; t < tiles; t += nw) {
     // pair layout: mixed map
-    const int64_t quad = tile * 8 + e;
+    const int quad = t * 8 + e;
     const bool ok = quad < quads;
-    const int64_t off = ibase + k4 * head_stride + quad * 4;
-    float4 x0 = ok ? ldq(P + off) : kZero4, x1 = ok ? ldq(P + off + 4 * head_stride) : kZero4;
+    const int off = k4 * hs + quad * 4;
+    float4 x0 = ok ? ldp(Pi + off, q.c) : kZero4, x1 = ok ? ldp(Pi + off + 4 * hs, q.c) : kZero4;
     // stats layout: head e, quads k4 and k4 + 4 of the tile
-    const int64_t qa = tile * 8 + k4, qb = qa + 4;
+    const int qa = t * 8 + k4, qb = qa + 4;
     const bool va = qa < quads, vb = qb < quads;
-    const int64_t offa = ibase + e * head_stride + qa * 4, offb = offa + 16;
-    float4 pa = va ? ldq(P + offa) : kZero4, pb = vb ? ldq(P + offb) : kZero4;
-    const float4 da = va ? map_ld(dA + offa) : kZero4, db = vb ? map_ld(dA + offb) : kZero4;
-    drop_quad(x0, (uint64_t)off, q); drop_quad(x1, (uint64_t)(off + 4 * head_stride), q);
+    const int offa = e * hs + qa * 4, offb = offa + 16;
+    float4 pa = va ? ldp(Pi + offa, q.c) : kZero4, pb = vb ? ldp(Pi + offb, q.c) : kZero4;
+    const float4 da = va ? map_ld(Di + offa) : kZero4, db = vb ? map_ld(Di + offb) : kZero4;
+    drop_quad(x0, ctr0 + ((uint32_t)off >> 2), q); drop_quad(x1, ctr0 + ((uint32_t)off >> 2) + hs, q);
     sub4(x0, q.c); sub4(x1, q.c);
     float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1);
     if (ok) {
-      y0.x += sh0; y0.y += sh0; y0.z += sh0; y0.w += sh0; y1.x += sh1; y1.y += sh1; y1.z += sh1; y1.w += sh1;
-      map_st(A + off, y0); map_st(A + off + 4 * head_stride, y1);
+      add4(y0, sh0); add4(y1, sh1);
+      map_st(Ai + off, y0); map_st(Ai + off + 4 * hs, y1);
     }
-    if (va) { drop_quad(pa, (uint64_t)offa, q); sub4(pa, q.c); }
-    if (vb) { drop_quad(pb, (uint64_t)offb, q); sub4(pb, q.c); }
-    s1 += ((da.x + da.y) + (da.z + da.w)) + ((db.x + db.y) + (db.z + db.w));
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      mma8(cx, tf32(comp(da, u)), 0u, tf32(comp(db, u)), 0u, tf32(comp(pa, u)), tf32(comp(pb, u)));
+    if (va) { drop_quad(pa, ctr0 + ((uint32_t)offa >> 2), q); sub4(pa, q.c); }
+    if (vb) { drop_quad(pb, ctr0 + ((uint32_t)offb >> 2), q); sub4(pb, q.c); }
+    s1 += hsum4(da) + hsum4(db);
+    mma_keys(cx, da, db, pa, pb);
   }
-  reduce_stats(s1, cx[0], cx[1], out);
+  reduce_stats(part, true, s1, cx[0], cx[1], out);
 }
 
 // ------------------------------------------------------------------ backward pass 2: dA -> dS in place
-// One warp per row (b, i), pair layout:
 //   dM_h  = k_h (dA_h - m1_h - Ahat_h m2_h)   (train)   |   k_h dA_h   (eval),   Ahat_h = (M_h - mean_h) invstd_h
 //   dPd_g = sum_h W[h][g] dM_h ;  dP_g = keep_g dPd_g / (1-p) ;  r_g = sum_j dP_g P_g ;  dS_g = scale P_g (dP_g - r_g)
-__global__ void __launch_bounds__(256)
-reattn_bwd_rows_mma_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ dA, int B, int N,
-                           const float* __restrict__ W, const float* __restrict__ bconv,
-                           const float* __restrict__ gamma, const float* __restrict__ saved,
-                           const float* __restrict__ coef, int train, float scale, QuadCtx q) {
-  const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
+// Per-lane constants of the pair layout (heads k4 and k4 + 4).
+struct RowsConst {
   uint32_t f0, f1, g0, g1;
-  frag_fwd(W, e, k4, f0, f1);           // M_h   = sum_g W[h][g] Pd_g
-  frag_bwd(W, e, k4, g0, g1);           // dPd_g = sum_h W[h][g] dM_h
   float offp[2], a1[2], a2[2], kh[2];
+};
+__device__ __forceinline__ RowsConst rows_const(const float* __restrict__ W, const float* __restrict__ bconv,
+                                                const float* __restrict__ gamma, const float* __restrict__ saved,
+                                                const float* __restrict__ coef, int train, float c, int e, int k4) {
+  RowsConst k;
+  frag_fwd(W, e, k4, k.f0, k.f1);           // M_h   = sum_g W[h][g] Pd_g
+  frag_bwd(W, e, k4, k.g0, k.g1);           // dPd_g = sum_h W[h][g] dM_h
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
     const int h = k4 + 4 * v;
     float rs = 0.f;
 #pragma unroll
     for (int g = 0; g < H; ++g) rs += W[h * H + g];
-    offp[v] = bconv[h] - saved[h] + q.c * rs;             // M_h - mean_h = sum_g W_hg (Pd_g - c) + offp
-    a1[v] = train ? coef[h] : 0.f;
-    a2[v] = train ? saved[H + h] * coef[H + h] : 0.f;
-    kh[v] = gamma[h] * saved[H + h];
+    k.offp[v] = bconv[h] - saved[h] + c * rs;             // M_h - mean_h = sum_g W_hg (Pd_g - c) + offp
+    k.a1[v] = train ? coef[h] : 0.f;
+    k.a2[v] = train ? saved[H + h] * coef[H + h] : 0.f;
+    k.kh[v] = gamma[h] * saved[H + h];
   }
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3;
-  const int64_t head_stride = (int64_t)N * N, img_stride = head_stride * H, rows = (int64_t)B * N;
-  for (int64_t r = wid; r < rows; r += nw) {
-    const int64_t b = r / N; const int i = (int)(r - b * N);
-    const int64_t row_off = b * img_stride + k4 * head_stride + (int64_t)i * N;
+  return k;
+}
+// one tile of pass 1: (p0, p1) probabilities, (t0, t1) = dA in, dP out (before bf16 rounding)
+__device__ __forceinline__ void rows_tile(const RowsConst& k, const QuadCtx& q, int train, uint32_t ctr, int hs,
+                                          const float4& p0, const float4& p1, float4& t0, float4& t1) {
+  float4 x0 = p0, x1 = p1;
+  const uint32_t m0 = drop_quad(x0, ctr, q), m1 = drop_quad(x1, ctr + hs, q);
+  if (train) {
+    sub4(x0, q.c); sub4(x1, q.c);
+    float4 M0, M1; mix_pair(x0, x1, k.f0, k.f1, M0, M1);
+    const float c0 = -k.a1[0] - k.offp[0] * k.a2[0], c1 = -k.a1[1] - k.offp[1] * k.a2[1];
+    t0.x = fmaf(-M0.x, k.a2[0], t0.x + c0); t0.y = fmaf(-M0.y, k.a2[0], t0.y + c0);
+    t0.z = fmaf(-M0.z, k.a2[0], t0.z + c0); t0.w = fmaf(-M0.w, k.a2[0], t0.w + c0);
+    t1.x = fmaf(-M1.x, k.a2[1], t1.x + c1); t1.y = fmaf(-M1.y, k.a2[1], t1.y + c1);
+    t1.z = fmaf(-M1.z, k.a2[1], t1.z + c1); t1.w = fmaf(-M1.w, k.a2[1], t1.w + c1);
+  }
+  mul4(t0, k.kh[0]); mul4(t1, k.kh[1]);
+  float4 dp0, dp1; mix_pair(t0, t1, k.g0, k.g1, dp0, dp1);
+  t0.x = (m0 & 1u) ? dp0.x * q.dscale : 0.f; t0.y = (m0 & 2u) ? dp0.y * q.dscale : 0.f;
+  t0.z = (m0 & 4u) ? dp0.z * q.dscale : 0.f; t0.w = (m0 & 8u) ? dp0.w * q.dscale : 0.f;
+  t1.x = (m1 & 1u) ? dp1.x * q.dscale : 0.f; t1.y = (m1 & 2u) ? dp1.y * q.dscale : 0.f;
+  t1.z = (m1 & 4u) ? dp1.z * q.dscale : 0.f; t1.w = (m1 & 8u) ? dp1.w * q.dscale : 0.f;
+}
+__device__ __forceinline__ float4 ds_quad(const float4& p, const float4& dp, float r, float scale) {
+  return make_float4(scale * p.x * (dp.x - r), scale * p.y * (dp.y - r), scale * p.z * (dp.z - r), scale * p.w * (dp.w - r));
+}
+
+// short rows (N <= 256): one warp per row, pair layout, second sweep re-reads P and dP from L1
+template <typename PT>
+__global__ void __launch_bounds__(256)
+reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ dA, int B, int N,
+                           const float* __restrict__ W, const float* __restrict__ bconv,
+                           const float* __restrict__ gamma, const float* __restrict__ saved,
+                           const float* __restrict__ coef, int train, float scale, QuadCtx q) {
+  const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
+  const RowsConst kc = rows_const(W, bconv, gamma, saved, coef, train, q.c, e, k4);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3, hs = N * N, rows = B * N;
+  for (int r = wid; r < rows; r += nw) {
+    const int b = r / N, i = r - b * N;
+    const int64_t base = (int64_t)b * hs * H;
+    const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
+    const PT* Pi = P + base; __nv_bfloat16* Di = dA + base;
+    const int roff = k4 * hs + i * N;
     float rg0 = 0.f, rg1 = 0.f;
     for (int t = 0; t < ntiles; ++t) {
       const int quad = t * 8 + e;
       const bool ok = quad < ld4;
-      const int64_t off0 = row_off + 4 * quad, off1 = off0 + 4 * head_stride;
-      const float4 p0 = ok ? ldq(P + off0) : kZero4, p1 = ok ? ldq(P + off1) : kZero4;
-      const float4 d0 = ok ? map_ld(dA + off0) : kZero4, d1 = ok ? map_ld(dA + off1) : kZero4;
-      float4 x0 = p0, x1 = p1;
-      const uint32_t m0 = drop_quad(x0, (uint64_t)off0, q), m1 = drop_quad(x1, (uint64_t)off1, q);
-      float4 t0 = d0, t1 = d1;
-      if (train) {
-        sub4(x0, q.c); sub4(x1, q.c);
-        float4 M0, M1; mix_pair(x0, x1, f0, f1, M0, M1);
-        t0.x = d0.x - a1[0] - (M0.x + offp[0]) * a2[0]; t0.y = d0.y - a1[0] - (M0.y + offp[0]) * a2[0];
-        t0.z = d0.z - a1[0] - (M0.z + offp[0]) * a2[0]; t0.w = d0.w - a1[0] - (M0.w + offp[0]) * a2[0];
-        t1.x = d1.x - a1[1] - (M1.x + offp[1]) * a2[1]; t1.y = d1.y - a1[1] - (M1.y + offp[1]) * a2[1];
-        t1.z = d1.z - a1[1] - (M1.z + offp[1]) * a2[1]; t1.w = d1.w - a1[1] - (M1.w + offp[1]) * a2[1];
-      }
-      t0.x *= kh[0]; t0.y *= kh[0]; t0.z *= kh[0]; t0.w *= kh[0];
-      t1.x *= kh[1]; t1.y *= kh[1]; t1.z *= kh[1]; t1.w *= kh[1];
-      float4 dp0, dp1; mix_pair(t0, t1, g0, g1, dp0, dp1);
-      dp0.x = (m0 & 1u) ? dp0.x * q.dscale : 0.f; dp0.y = (m0 & 2u) ? dp0.y * q.dscale : 0.f;
-      dp0.z = (m0 & 4u) ? dp0.z * q.dscale : 0.f; dp0.w = (m0 & 8u) ? dp0.w * q.dscale : 0.f;
-      dp1.x = (m1 & 1u) ? dp1.x * q.dscale : 0.f; dp1.y = (m1 & 2u) ? dp1.y * q.dscale : 0.f;
-      dp1.z = (m1 & 4u) ? dp1.z * q.dscale : 0.f; dp1.w = (m1 & 8u) ? dp1.w * q.dscale : 0.f;
+      const int off = roff + 4 * quad;
+      const float4 p0 = ok ? ldp(Pi + off, q.c) : kZero4, p1 = ok ? ldp(Pi + off + 4 * hs, q.c) : kZero4;
+      float4 t0 = ok ? map_ld(Di + off) : kZero4, t1 = ok ? map_ld(Di + off + 4 * hs) : kZero4;
+      rows_tile(kc, q, train, ctr0 + ((uint32_t)off >> 2), hs, p0, p1, t0, t1);
       if (ok) {
-        rg0 += dot4(dp0, p0); rg1 += dot4(dp1, p1);
-        map_st(dA + off0, dp0); map_st(dA + off1, dp1);
+        rg0 += dot4(t0, p0); rg1 += dot4(t1, p1);
+        map_st(Di + off, t0); map_st(Di + off + 4 * hs, t1);
       }
     }
 #pragma unroll
@@ -313,13 +378,10 @@ reattn_bwd_rows_mma_kernel(const float* __restrict__ P, __nv_bfloat16* __restric
     for (int t = 0; t < ntiles; ++t) {
       const int quad = t * 8 + e;
       if (quad < ld4) {
-        const int64_t off0 = row_off + 4 * quad, off1 = off0 + 4 * head_stride;
-        const float4 p0 = ldq(P + off0), p1 = ldq(P + off1);
-        const float4 dp0 = map_ld(dA + off0), dp1 = map_ld(dA + off1);
-        map_st(dA + off0, make_float4(scale * p0.x * (dp0.x - rg0), scale * p0.y * (dp0.y - rg0),
-                                      scale * p0.z * (dp0.z - rg0), scale * p0.w * (dp0.w - rg0)));
-        map_st(dA + off1, make_float4(scale * p1.x * (dp1.x - rg1), scale * p1.y * (dp1.y - rg1),
-                                      scale * p1.z * (dp1.z - rg1), scale * p1.w * (dp1.w - rg1)));
+        const int off = roff + 4 * quad;
+        const float4 p0 = ldp(Pi + off, q.c), p1 = ldp(Pi + off + 4 * hs, q.c);
+        const float4 dp0 = map_ld(Di + off), dp1 = map_ld(Di + off + 4 * hs);
+        map_st(Di + off, ds_quad(p0, dp0, rg0, scale)); map_st(Di + off + 4 * hs, ds_quad(p1, dp1, rg1, scale));
       }
     }
   }
@@ -327,161 +389,45 @@ reattn_bwd_rows_mma_kernel(const float* __restrict__ P, __nv_bfloat16* __restric
 
 // ------------------------------------------------------------------ long rows: one CTA (8 warps) per row
 // For N > 256 the 8-head row (N * 32 bytes) no longer stays in L1 between the two sweeps of the warp-per-row kernels
-// and, with every warp of the GPU on a different row, not even in L2.  These variants spread the 32-key tiles of a
-// row over the 8 warps of a CTA (TPW tiles per warp) and keep the row in registers between the sweeps: S / P / dA
-// cross HBM exactly once.  Row-wide quantities (max, sum of exp, r_g) are combined through shared memory.
-template <int TPW>
-__global__ void __launch_bounds__(256)
-softmax_stats_mma_cta_kernel(float* __restrict__ S, int B, int N, float scale, QuadCtx q, double* __restrict__ sums) {
-  __shared__ float smax[2][8][H], ssum[2][8][H];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
-  const float sl2 = scale * 1.4426950408889634f;
-  const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3;
-  const int64_t head_stride = (int64_t)N * N, img_stride = head_stride * H, rows = (int64_t)B * N;
-  float cg[4] = {0.f, 0.f, 0.f, 0.f}, s = 0.f;
-  int par = 0;
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x, par ^= 1) {
-    const int64_t b = r / N; const int i = (int)(r - b * N);
-    const int64_t row_off = b * img_stride + e * head_stride + (int64_t)i * N;
-    float* row = S + row_off;
-    float4 xa[TPW], xb[TPW];
-    float m = -INFINITY;
-#pragma unroll
-    for (int tt = 0; tt < TPW; ++tt) {
-      const int qa = (w + 8 * tt) * 8 + k4, qb = qa + 4;
-      xa[tt] = qa < ld4 ? ldq(row + 4 * qa) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      xb[tt] = qb < ld4 ? ldq(row + 4 * qb) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    }
-#pragma unroll
-    for (int tt = 0; tt < TPW; ++tt) {
-      xa[tt].x *= sl2; xa[tt].y *= sl2; xa[tt].z *= sl2; xa[tt].w *= sl2;
-      xb[tt].x *= sl2; xb[tt].y *= sl2; xb[tt].z *= sl2; xb[tt].w *= sl2;
-      m = fmaxf(m, fmaxf(fmaxf(fmaxf(xa[tt].x, xa[tt].y), fmaxf(xa[tt].z, xa[tt].w)),
-                         fmaxf(fmaxf(xb[tt].x, xb[tt].y), fmaxf(xb[tt].z, xb[tt].w))));
-    }
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    if (k4 == 0) smax[par][w][e] = m;
-    __syncthreads();
-#pragma unroll
-    for (int ww = 0; ww < 8; ++ww) m = fmaxf(m, smax[par][ww][e]);
-    float l = 0.f;
-#pragma unroll
-    for (int tt = 0; tt < TPW; ++tt) {
-      xa[tt].x = exp2f(xa[tt].x - m); xa[tt].y = exp2f(xa[tt].y - m); xa[tt].z = exp2f(xa[tt].z - m); xa[tt].w = exp2f(xa[tt].w - m);
-      xb[tt].x = exp2f(xb[tt].x - m); xb[tt].y = exp2f(xb[tt].y - m); xb[tt].z = exp2f(xb[tt].z - m); xb[tt].w = exp2f(xb[tt].w - m);
-      l += ((xa[tt].x + xa[tt].y) + (xa[tt].z + xa[tt].w)) + ((xb[tt].x + xb[tt].y) + (xb[tt].z + xb[tt].w));
-    }
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    if (k4 == 0) ssum[par][w][e] = l;
-    __syncthreads();
-    l = 0.f;
-#pragma unroll
-    for (int ww = 0; ww < 8; ++ww) l += ssum[par][ww][e];
-    const float inv = 1.0f / l;
-#pragma unroll
-    for (int tt = 0; tt < TPW; ++tt) {
-      if (w + 8 * tt >= ntiles) break;                                   // warp-uniform
-      const int qa = (w + 8 * tt) * 8 + k4, qb = qa + 4;
-      float4 pa = kZero4, pb = kZero4;
-      if (qa < ld4) {
-        pa = make_float4(xa[tt].x * inv, xa[tt].y * inv, xa[tt].z * inv, xa[tt].w * inv);
-        *reinterpret_cast<float4*>(row + 4 * qa) = pa;
-        drop_quad(pa, (uint64_t)(row_off + 4 * qa), q); sub4(pa, q.c);
-      }
-      if (qb < ld4) {
-        pb = make_float4(xb[tt].x * inv, xb[tt].y * inv, xb[tt].z * inv, xb[tt].w * inv);
-        *reinterpret_cast<float4*>(row + 4 * qb) = pb;
-        drop_quad(pb, (uint64_t)(row_off + 4 * qb), q); sub4(pb, q.c);
-      }
-      s += ((pa.x + pa.y) + (pa.z + pa.w)) + ((pb.x + pb.y) + (pb.z + pb.w));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t ua = tf32(comp(pa, u)), ub = tf32(comp(pb, u));
-        mma8(cg, ua, 0u, ub, 0u, ua, ub);
-      }
-    }
-  }
-  reduce_stats(s, cg[0], cg[1], sums);
-}
-
-__device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
-  return u;
-}
-__device__ __forceinline__ float4 unpack_bf16x4(const uint2& u) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
-template <int TPW>
+// and, with every warp of the GPU on a different row, not even in L2.  This variant spreads the 32-key tiles of a
+// row over the 8 warps of a CTA (TPW tiles per warp) and keeps the row in registers between the sweeps: P and dA
+// cross HBM exactly once.  The row sums r_g are combined through shared memory.
+template <int TPW, typename PT>
 __global__ void __launch_bounds__(256, 2)
-reattn_bwd_rows_mma_cta_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ dA, int B, int N,
+reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ dA, int B, int N,
                                const float* __restrict__ W, const float* __restrict__ bconv,
                                const float* __restrict__ gamma, const float* __restrict__ saved,
                                const float* __restrict__ coef, int train, float scale, QuadCtx q) {
   __shared__ float srg[2][8][H];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
-  uint32_t f0, f1, g0, g1;
-  frag_fwd(W, e, k4, f0, f1);
-  frag_bwd(W, e, k4, g0, g1);
-  float offp[2], a1[2], a2[2], kh[2];
-#pragma unroll
-  for (int v = 0; v < 2; ++v) {
-    const int h = k4 + 4 * v;
-    float rs = 0.f;
-#pragma unroll
-    for (int g = 0; g < H; ++g) rs += W[h * H + g];
-    offp[v] = bconv[h] - saved[h] + q.c * rs;
-    a1[v] = train ? coef[h] : 0.f;
-    a2[v] = train ? saved[H + h] * coef[H + h] : 0.f;
-    kh[v] = gamma[h] * saved[H + h];
-  }
-  const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3;
-  const int64_t head_stride = (int64_t)N * N, img_stride = head_stride * H, rows = (int64_t)B * N;
+  const RowsConst kc = rows_const(W, bconv, gamma, saved, coef, train, q.c, e, k4);
+  const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3, hs = N * N, rows = B * N;
   int par = 0;
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x, par ^= 1) {
-    const int64_t b = r / N; const int i = (int)(r - b * N);
-    const int64_t row_off = b * img_stride + k4 * head_stride + (int64_t)i * N;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x, par ^= 1) {
+    const int b = r / N, i = r - b * N;
+    const int64_t base = (int64_t)b * hs * H;
+    const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
+    const PT* Pi = P + base; __nv_bfloat16* Di = dA + base;
+    const int roff = k4 * hs + i * N;
     float4 p0[TPW], p1[TPW]; uint2 k0[TPW], k1[TPW];      // k: dA on the way in, dP between the sweeps (bf16 x 4)
 #pragma unroll
     for (int tt = 0; tt < TPW; ++tt) {
       const int quad = (w + 8 * tt) * 8 + e;
       const bool ok = quad < ld4;
-      const int64_t off0 = row_off + 4 * quad, off1 = off0 + 4 * head_stride;
-      p0[tt] = ok ? ldq(P + off0) : kZero4; p1[tt] = ok ? ldq(P + off1) : kZero4;
-      k0[tt] = ok ? *reinterpret_cast<const uint2*>(dA + off0) : make_uint2(0u, 0u);
-      k1[tt] = ok ? *reinterpret_cast<const uint2*>(dA + off1) : make_uint2(0u, 0u);
+      const int off = roff + 4 * quad;
+      p0[tt] = ok ? ldp(Pi + off, q.c) : kZero4; p1[tt] = ok ? ldp(Pi + off + 4 * hs, q.c) : kZero4;
+      k0[tt] = ok ? *reinterpret_cast<const uint2*>(Di + off) : make_uint2(0u, 0u);
+      k1[tt] = ok ? *reinterpret_cast<const uint2*>(Di + off + 4 * hs) : make_uint2(0u, 0u);
     }
     float rg0 = 0.f, rg1 = 0.f;
 #pragma unroll
     for (int tt = 0; tt < TPW; ++tt) {
       if (w + 8 * tt >= ntiles) break;                                   // warp-uniform
-      const int quad = (w + 8 * tt) * 8 + e;
-      const int64_t off0 = row_off + 4 * quad, off1 = off0 + 4 * head_stride;
-      float4 x0 = p0[tt], x1 = p1[tt];
-      const uint32_t m0 = drop_quad(x0, (uint64_t)off0, q), m1 = drop_quad(x1, (uint64_t)off1, q);
+      const int off = roff + 4 * ((w + 8 * tt) * 8 + e);
       float4 t0 = unpack_bf16x4(k0[tt]), t1 = unpack_bf16x4(k1[tt]);
-      if (train) {
-        sub4(x0, q.c); sub4(x1, q.c);
-        float4 M0, M1; mix_pair(x0, x1, f0, f1, M0, M1);
-        t0.x = t0.x - a1[0] - (M0.x + offp[0]) * a2[0]; t0.y = t0.y - a1[0] - (M0.y + offp[0]) * a2[0];
-        t0.z = t0.z - a1[0] - (M0.z + offp[0]) * a2[0]; t0.w = t0.w - a1[0] - (M0.w + offp[0]) * a2[0];
-        t1.x = t1.x - a1[1] - (M1.x + offp[1]) * a2[1]; t1.y = t1.y - a1[1] - (M1.y + offp[1]) * a2[1];
-        t1.z = t1.z - a1[1] - (M1.z + offp[1]) * a2[1]; t1.w = t1.w - a1[1] - (M1.w + offp[1]) * a2[1];
-      }
-      t0.x *= kh[0]; t0.y *= kh[0]; t0.z *= kh[0]; t0.w *= kh[0];
-      t1.x *= kh[1]; t1.y *= kh[1]; t1.z *= kh[1]; t1.w *= kh[1];
-      float4 dp0, dp1; mix_pair(t0, t1, g0, g1, dp0, dp1);
-      dp0.x = (m0 & 1u) ? dp0.x * q.dscale : 0.f; dp0.y = (m0 & 2u) ? dp0.y * q.dscale : 0.f;
-      dp0.z = (m0 & 4u) ? dp0.z * q.dscale : 0.f; dp0.w = (m0 & 8u) ? dp0.w * q.dscale : 0.f;
-      dp1.x = (m1 & 1u) ? dp1.x * q.dscale : 0.f; dp1.y = (m1 & 2u) ? dp1.y * q.dscale : 0.f;
-      dp1.z = (m1 & 4u) ? dp1.z * q.dscale : 0.f; dp1.w = (m1 & 8u) ? dp1.w * q.dscale : 0.f;
-      rg0 += dot4(dp0, p0[tt]); rg1 += dot4(dp1, p1[tt]);                 // invalid quads: P == 0
-      k0[tt] = pack_bf16x4(dp0); k1[tt] = pack_bf16x4(dp1);
+      rows_tile(kc, q, train, ctr0 + ((uint32_t)off >> 2), hs, p0[tt], p1[tt], t0, t1);
+      rg0 += dot4(t0, p0[tt]); rg1 += dot4(t1, p1[tt]);                   // invalid quads: P == 0
+      k0[tt] = pack_bf16x4(t0); k1[tt] = pack_bf16x4(t1);
     }
 #pragma unroll
     for (int o = 4; o <= 16; o <<= 1) {
@@ -496,16 +442,157 @@ reattn_bwd_rows_mma_cta_kernel(const float* __restrict__ P, __nv_bfloat16* __res
     for (int tt = 0; tt < TPW; ++tt) {
       const int quad = (w + 8 * tt) * 8 + e;
       if (quad < ld4) {
-        const int64_t off0 = row_off + 4 * quad, off1 = off0 + 4 * head_stride;
-        const float4 dp0 = unpack_bf16x4(k0[tt]), dp1 = unpack_bf16x4(k1[tt]);
-        const float4 a = p0[tt], c = p1[tt];
-        map_st(dA + off0, make_float4(scale * a.x * (dp0.x - rg0), scale * a.y * (dp0.y - rg0),
-                                      scale * a.z * (dp0.z - rg0), scale * a.w * (dp0.w - rg0)));
-        map_st(dA + off1, make_float4(scale * c.x * (dp1.x - rg1), scale * c.y * (dp1.y - rg1),
-                                      scale * c.z * (dp1.z - rg1), scale * c.w * (dp1.w - rg1)));
+        const int off = roff + 4 * quad;
+        map_st(Di + off, ds_quad(p0[tt], unpack_bf16x4(k0[tt]), rg0, scale));
+        map_st(Di + off + 4 * hs, ds_quad(p1[tt], unpack_bf16x4(k1[tt]), rg1, scale));
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ long rows, asynchronous row pipeline (softmax)
+// A ninth warp streams whole 8-head rows into a shared-memory ring with cp.async.bulk (one bulk copy per head row,
+// completion on an mbarrier), so the next row is in flight while the eight consumer warps make their three sweeps
+// over the current one in shared memory; ~56 registers per thread, 4 CTAs per SM.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int kBulkThreads = 288;          // 8 consumer warps + 1 producer warp
+static inline size_t bulk_smem_bytes(int stages, int floats_per_stage) {
+  return (size_t)stages * floats_per_stage * 4 + 2 * stages * sizeof(uint64_t);
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kBulkThreads)
+softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, int B, int N, float scale, QuadCtx q,
+                              double* __restrict__ sums) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  float* ring = reinterpret_cast<float*>(dsm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + (size_t)STAGES * H * N * 4);
+  uint64_t* empty = full + STAGES;
+  __shared__ float smax[2][8][H], ssum[2][8][H];
+  __shared__ float part[8][H + H * H];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int hs = N * N, rows = B * N;
+  const int nmine = (int)blockIdx.x < rows ? (rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  float cg[4] = {0.f, 0.f, 0.f, 0.f}, s = 0.f;
+  if (w == 8) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int k = 0; k < nmine; ++k) {
+        mbar_wait(empty + st, ph ^ 1u);
+        mbar_expect_tx(full + st, (uint32_t)(H * N * 4));
+        const int r = blockIdx.x + k * gridDim.x, b = r / N, i = r - b * N;
+        const float* src = S + (int64_t)b * hs * H + i * N;
+#pragma unroll
+        for (int h = 0; h < H; ++h) bulk_g2s(ring + (st * H + h) * N, src + h * hs, (uint32_t)(N * 4), full + st);
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    const float sl2 = scale * 1.4426950408889634f;
+    const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3;
+    int st = 0; uint32_t ph = 0;
+    for (int k = 0; k < nmine; ++k) {
+      const int par = k & 1;
+      const int r = blockIdx.x + k * gridDim.x, b = r / N, i = r - b * N;
+      const int64_t base = (int64_t)b * hs * H;
+      const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
+      float* Sb = S + base; __nv_bfloat16* Pb = Pc ? Pc + base : nullptr;
+      const int roff = e * hs + i * N;
+      float* rs = ring + (st * H + e) * N;                          // this lane's head row in shared memory
+      mbar_wait(full + st, ph);
+      float m = -INFINITY;
+      for (int t = w; t < ntiles; t += 8) {
+        const int qa = t * 8 + k4, qb = qa + 4;
+        if (qa < ld4) m = fmaxf(m, hmax4(ldq(rs + 4 * qa)));
+        if (qb < ld4) m = fmaxf(m, hmax4(ldq(rs + 4 * qb)));
+      }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      if (k4 == 0) smax[par][w][e] = m;
+      bar_consumers();
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) m = fmaxf(m, smax[par][ww][e]);
+      m *= sl2;                                                    // scale > 0: max commutes with the scaling
+      float l = 0.f;
+      for (int t = w; t < ntiles; t += 8) {
+        const int qa = t * 8 + k4, qb = qa + 4;
+        if (qa < ld4) {
+          float4 x = ldq(rs + 4 * qa);
+          x.x = exp2f(fmaf(x.x, sl2, -m)); x.y = exp2f(fmaf(x.y, sl2, -m)); x.z = exp2f(fmaf(x.z, sl2, -m)); x.w = exp2f(fmaf(x.w, sl2, -m));
+          *reinterpret_cast<float4*>(rs + 4 * qa) = x;
+          l += hsum4(x);
+        }
+        if (qb < ld4) {
+          float4 x = ldq(rs + 4 * qb);
+          x.x = exp2f(fmaf(x.x, sl2, -m)); x.y = exp2f(fmaf(x.y, sl2, -m)); x.z = exp2f(fmaf(x.z, sl2, -m)); x.w = exp2f(fmaf(x.w, sl2, -m));
+          *reinterpret_cast<float4*>(rs + 4 * qb) = x;
+          l += hsum4(x);
+        }
+      }
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      if (k4 == 0) ssum[par][w][e] = l;
+      bar_consumers();
+      l = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) l += ssum[par][ww][e];
+      const float inv = 1.0f / l;
+      for (int t = w; t < ntiles; t += 8) {
+        const int qa = t * 8 + k4, qb = qa + 4;
+        float4 pa = kZero4, pb = kZero4;
+        if (qa < ld4) {
+          pa = ldq(rs + 4 * qa); mul4(pa, inv);
+          emit_p(Sb, Pb, roff + 4 * qa, pa, q.c);
+          drop_quad(pa, ctr0 + ((uint32_t)roff >> 2) + qa, q); sub4(pa, q.c);
+        }
+        if (qb < ld4) {
+          pb = ldq(rs + 4 * qb); mul4(pb, inv);
+          emit_p(Sb, Pb, roff + 4 * qb, pb, q.c);
+          drop_quad(pb, ctr0 + ((uint32_t)roff >> 2) + qb, q); sub4(pb, q.c);
+        }
+        s += hsum4(pa) + hsum4(pb);
+        mma_keys(cg, pa, pb, pa, pb);
+      }
+      fence_proxy_async();                 // our generic-proxy writes to the stage precede the next bulk copy into it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + st);
+      if (++st == STAGES) { st = 0; ph ^= 1u; }
+    }
+  }
+  reduce_stats(part, w < 8, s, cg[0], cg[1], sums);
 }
 
 }  // namespace mma

@@ -32,8 +32,18 @@ _MAP_L2_BYTES = {"value": int(float(os.environ.get("VU_MAP_L2_MB", "0")) * (1 <<
 _BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "1") == "1"}      # on by default in the tf32 mode (1e-2 class)
 
 
+# centred bf16 probabilities (train, tf32 mode): halves the saved-map memory; off by default (about +1% images/s only,
+# the map kernels are issue-bound rather than HBM-bound once the mixing runs on the tensor cores)
+_BF16_PROBS = {"value": os.environ.get("VU_BF16_PROBS", "0") == "1"}
+
+
 def set_bf16_maps(on: bool) -> None:
     _BF16_MAPS["value"] = bool(on)
+
+
+def set_bf16_probs(on: bool) -> None:
+    """Store the train-mode attention probabilities as centred bf16 (P - 1/N) where the tensor-core map path applies."""
+    _BF16_PROBS["value"] = bool(on)
 
 
 def set_map_l2_budget(megabytes: float) -> None:
@@ -156,7 +166,14 @@ class Engine:
         c = self._map_chunk(B, h, N, ld)
         keep_P = saved is not None
         bf16 = prec == ops.PREC_TF32 and _BF16_MAPS["value"] and N % 8 == 0
-        Pm = _empty((B if (keep_P or train) else c, h, N, ld), xq)
+        # train mode on the tensor-core map path: probabilities are kept as CENTRED bf16 (P - 1/N), scores are a
+        # per-slice fp32 scratch -- the saved map and every later pass over it cost half the bytes
+        pc16 = bf16 and train and _BF16_PROBS["value"] and ops.reattn_tensor_core_path(h, N, ld)
+        if pc16:
+            Pm = torch.empty((B, h, N, ld), dtype=torch.bfloat16, device=xq.device)
+            Sc = _empty((c, h, N, ld), xq)
+        else:
+            Pm = _empty((B if (keep_P or train) else c, h, N, ld), xq)
         A = torch.empty((c, h, N, ld), dtype=torch.bfloat16 if bf16 else torch.float32, device=xq.device)
         O = _empty((B, N, D), xq)
         vt = ops.heads_transpose_bf16(v, B, N, D, h) if bf16 else None        # (B,h,hd,ldn): K-major B operand of A.V
@@ -188,9 +205,14 @@ class Engine:
             # batch statistics couple all images: phase 1 (scores, softmax, moments) per slice, then phase 2
             for ci, b0 in enumerate(range(0, B, c)):
                 bc = min(c, B - b0)
-                scores(b0, bc, Pm[b0:b0 + bc])
-                ops.softmax_stats(Pm[b0:b0 + bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums,
-                                  precision=prec)
+                if pc16:
+                    scores(b0, bc, Sc[:bc])
+                    ops.softmax_stats(Sc[:bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums,
+                                      precision=prec, Pc=Pm[b0:b0 + bc])
+                else:
+                    scores(b0, bc, Pm[b0:b0 + bc])
+                    ops.softmax_stats(Pm[b0:b0 + bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums,
+                                      precision=prec)
             finalize()
             for ci, b0 in enumerate(range(0, B, c)):
                 bc = min(c, B - b0)

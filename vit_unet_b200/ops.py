@@ -18,11 +18,27 @@ PREC_FP32, PREC_TF32 = 0, 1
 LOSS_KINDS = {"l1": 0, "mse": 1, "dice": 2}
 
 
+MAP_BF16, MAP_P_CENTRED_BF16 = 1, 2       # include/vit_unet_b200.h VU_MAP_*
+
+
 def _map(t: torch.Tensor, name: str):
     """attention map buffer: fp32 or bf16 -> (pointer, is_bf16)"""
     if t.dtype == torch.bfloat16:
         return _chk(t, name, torch.bfloat16), 1
     return _chk(t, name), 0
+
+
+def _pmap(P: torch.Tensor, bf_maps: int):
+    """probabilities: fp32, or centred bf16 (only with bf16 maps) -> (pointer, map_fmt flags, bytes per element)"""
+    pp, pbf = _map(P, "P")
+    if pbf and not bf_maps:
+        raise VuError("centred bf16 probabilities need bf16 mixed / gradient maps")
+    return pp, (MAP_BF16 if bf_maps else 0) | (MAP_P_CENTRED_BF16 if pbf else 0), (2.0 if pbf else 4.0)
+
+
+def reattn_tensor_core_path(h: int, N: int, ld: int) -> bool:
+    """True where the C side runs the 8-head warp-MMA map kernels (and accepts centred bf16 probabilities)."""
+    return bool(_lib.load().vu_reattn_tensor_core_path(h, N, ld))
 
 
 def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> int:
@@ -191,9 +207,11 @@ def softmax_rows(S, rows, N, ld, scale):
     _call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream(), nbytes=8.0 * rows * N)
 
 
-def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums, precision=PREC_FP32):
-    _call("vu_softmax_stats", _chk(S, "S"), B, h, N, ld, scale, drop_p, seed, sid, _chk(sums, "sums", torch.float64),
-          int(precision), _stream(), nbytes=2 * 4.0 * B * h * N * N)
+def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums, precision=PREC_FP32, Pc=None):
+    """in place (Pc is None) or S -> centred bf16 Pc"""
+    pc = _chk(Pc, "Pc", torch.bfloat16) if Pc is not None else None
+    _call("vu_softmax_stats", _chk(S, "S"), pc, B, h, N, ld, scale, drop_p, seed, sid, _chk(sums, "sums", torch.float64),
+          int(precision), _stream(), nbytes=(4.0 + (2.0 if Pc is not None else 4.0)) * B * h * N * N)
 
 
 def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red):
@@ -201,9 +219,10 @@ def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red):
     pa, bf2 = _map(A, "A")
     if bf != bf2:
         raise VuError("reattn_mix_reduce: A and dA must have the same dtype")
-    _call("vu_reattn_mix_reduce", _chk(P, "P"), pd, pa, bf, _chk(fold, "fold"), B, h, N, ld,
+    pp, fmt, pb = _pmap(P, bf)
+    _call("vu_reattn_mix_reduce", pp, pd, pa, fmt, _chk(fold, "fold"), B, h, N, ld,
           drop_p, seed, sid, _chk(red, "red", torch.float64), _stream(),
-          nbytes=(4.0 + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
+          nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
 def reattn_stats(P, B, h, N, ld, drop_p, seed, sid, sums):
@@ -221,8 +240,9 @@ def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nb
 
 def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid):
     pa, bf = _map(A, "A")
-    _call("vu_reattn_mix", _chk(P, "P"), pa, bf, _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream(),
-          nbytes=(4.0 + (2.0 if bf else 4.0)) * B * h * N * N, flops=2.0 * h * B * h * N * N)
+    pp, fmt, pb = _pmap(P, bf)
+    _call("vu_reattn_mix", pp, pa, fmt, _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream(),
+          nbytes=(pb + (2.0 if bf else 4.0)) * B * h * N * N, flops=2.0 * h * B * h * N * N)
 
 
 def reattn_bwd_reduce(P, dA, B, h, N, ld, drop_p, seed, sid, red):
@@ -239,9 +259,10 @@ def reattn_bwd_params(red, sums, B, h, N, W, bconv, gamma, saved, train, coef, d
 
 def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid):
     pd, bf = _map(dA, "dA")
-    _call("vu_reattn_bwd_rows", _chk(P, "P"), pd, bf, B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
+    pp, fmt, pb = _pmap(P, bf)
+    _call("vu_reattn_bwd_rows", pp, pd, fmt, B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
           _chk(gamma, "gamma"), _chk(saved, "saved"), _chk(coef, "coef"), int(train), scale, drop_p, seed, sid,
-          _stream(), nbytes=(4.0 + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
+          _stream(), nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
 # ----------------------------------------------------------------------------------------- layer norm
