@@ -177,6 +177,23 @@ def test_tc_gemm_bf16_operands(ops, M, N, K, ta):
     assert torch.all(out[:, N:] == 7.0)
 
 
+@pytest.mark.parametrize("Nt,hd", [(100, 12), (70, 8), (65, 20), (130, 32), (784, 24), (264, 16)])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_scores_gemm_shapes(ops, Nt, hd, out_bf16):
+    """S = alpha Q K^T with head_dim <= 32 runs on the warp-MMA write-stream kernel (vu_gemm_scores.cu): ragged token
+    counts, padded leading dimension (pad columns untouched), fp32 and bf16 maps, head-strided operands."""
+    B, h, alpha = 2, 3, 0.5
+    D, ld = h * hd, (Nt + 7) // 8 * 8
+    q, k = _rand(B, Nt, D, seed=7), _rand(B, Nt, D, seed=8)
+    S = torch.full((B, h, Nt, ld), 7.0, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+    ops.gemm(q.cuda(), k.cuda(), S, Nt, Nt, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=B, batch_inner=h,
+             sA=(Nt * D, hd), sB=(Nt * D, hd), sC=(h * Nt * ld, Nt * ld), alpha=alpha, precision=ops.PREC_TF32)
+    q4, k4 = (t.reshape(B, Nt, h, hd).double() for t in (q, k))
+    exp = alpha * torch.einsum("bihe,bjhe->bhij", q4, k4)
+    _close(S[..., :Nt].float(), exp, 6e-3 if out_bf16 else TOL, "scores")
+    assert torch.all(S[..., Nt:].float() == 7.0)
+
+
 def test_tc_gemm_bf16_output_and_transposed_heads(ops):
     """dA = dO V^T written as bf16; A.V / A^T.dO with the per-head transposed bf16 copies (the engine's bf16-map path)."""
     B, h, Nt, hd = 2, 8, 784, 24

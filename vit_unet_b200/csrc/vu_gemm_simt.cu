@@ -261,6 +261,7 @@ int gemm_simt(const vu_gemm_desc& d, cudaStream_t s) {
 }
 
 int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled);   // vu_gemm_tc.cu
+int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled);   // vu_gemm_scores.cu
 
 // column sums: out[n] (+)= sum_m X[m*ld + n].  grid (N/32, chunks of M); smem transpose-free: each warp
 // owns 32 columns, threads stride over rows, partials combined with atomics.
@@ -302,7 +303,9 @@ extern "C" int vu_gemm(const vu_gemm_desc* d, void* stream) {
   VU_REQUIRE(!any_bf16 || d->precision == VU_PREC_TF32, fn, "bfloat16 operands need the tensor-core path (precision = VU_PREC_TF32)");
   if (d->precision == VU_PREC_TF32) {
     bool handled = false;
-    int rc = gemm_tc(*d, s, &handled);
+    int rc = gemm_scores(*d, s, &handled);        // K <= 32, map-sized output: the HBM write stream kernel
+    if (rc != VU_OK || handled) return rc;
+    rc = gemm_tc(*d, s, &handled);
     if (rc != VU_OK || handled) return rc;
     VU_REQUIRE(!any_bf16, fn, "bfloat16 GEMM could not be mapped onto the tensor-core kernel");
     // shapes the tensor-core kernel does not cover fall through to the CUDA-core kernel (same numerics class
