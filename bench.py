@@ -62,10 +62,14 @@ def _ncu_traffic(kernel_class, batch):
     if not os.path.exists(path):
         return None, None
     d = json.load(open(path))
-    key = "vu_gemm_tf32_tc" if kernel_class.startswith("gemm_tcgen05") else kernel_class
-    e = d.get(key)
-    if not e:
+    # kernel class of the live table -> substring of the ncu kernel name (profiles/make_summary.py keys)
+    sub = {"gemm_tcgen05": "gemm_tf32_tc", "gemm_mma": "scores_mma", "vu_reattn_bwd_rows": "reattn_bwd_rows",
+           "vu_reattn_mix_reduce": "reattn_mix_reduce", "vu_reattn_mix": "reattn_mix_mma", "vu_softmax_stats": "softmax_stats"}
+    want = next((v for k, v in sub.items() if kernel_class.startswith(k)), kernel_class.replace("vu_", ""))
+    cands = [v for k, v in d.items() if want in k]
+    if not cands:
         return None, None
+    e = max(cands, key=lambda v: v["bytes_per_launch"])
     return e["bytes_per_image"] * batch, f"largest launch ({e['shape']}), ncu capture at {e['captured_batch']} images scaled to {batch}"
 
 

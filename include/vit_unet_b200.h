@@ -106,9 +106,12 @@ int vu_reattn_stats(const float* P, int B, int h, int N, int ld, float drop_p, u
  * map dA/dS are bfloat16 (ld % 8 == 0).  VU_MAP_P_CENTRED_BF16: the probabilities are stored as bfloat16 CENTRED
  * at the uniform row, Pc = P - 1/N (so the rounding is relative to what head mixing + BatchNorm actually see);
  * only together with VU_MAP_BF16 and where vu_reattn_tensor_core_path() != 0. */
-enum { VU_MAP_BF16 = 1, VU_MAP_P_CENTRED_BF16 = 2 };
-/* 1 when the 8-head warp-MMA formulation of the map kernels applies (h == 8, ld == N, N % 8 == 0; VU_MAP_MMA=0 in
- * the environment switches it off): vu_softmax_stats(TF32), vu_reattn_mix / _mix_reduce / _bwd_rows with bf16 maps. */
+enum { VU_MAP_BF16 = 1, VU_MAP_P_CENTRED_BF16 = 2, VU_MAP_TF32_MIX = 4 };
+/* VU_MAP_TF32_MIX: fp32 maps, but the 8x8 head mixing may run on TF32 warp MMAs (the tensor-core precision class);
+ * without it (and without VU_MAP_BF16) the map kernels use exact fp32 FMAs. */
+/* 1 when the 8-head warp-MMA formulation of the map kernels applies (h == 8, ld == N, N % 4 == 0; VU_MAP_MMA=0 in
+ * the environment switches it off): vu_softmax_stats(TF32), vu_reattn_mix / _mix_reduce / _bwd_rows with bf16 maps
+ * or VU_MAP_TF32_MIX. */
 int vu_reattn_tensor_core_path(int h, int N, int ld);
 /* fused train-mode pass: softmax of every head + the moments above in ONE read of S / write of P.
  * Pc == NULL: P overwrites S in place (fp32).  Pc != NULL: centred bf16 probabilities are written to Pc (same

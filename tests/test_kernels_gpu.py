@@ -418,6 +418,45 @@ def test_reattn_tensor_core_path(ops, N, p, train):
     _close(d3.float(), d1, rtol=2.5e-2, name="dS (centred bf16 P)")
 
 
+@pytest.mark.parametrize("N,p,train", [(196, 0.2, True), (52, 0.0, True), (196, 0.0, False)])
+def test_reattn_tensor_core_path_fp32_maps(ops, N, p, train):
+    """fp32 maps with tf32=True (VU_MAP_TF32_MIX): N % 4 == 0 but not % 8 (Base level 1, N = 196) still runs the
+    warp-MMA kernels; results against the exact CUDA-core kernels at TF32-class tolerance."""
+    B, h, ld, scale = 3, 8, N, 0.41
+    S = (_rand(B, h, N, N, seed=1, scale=3.0)).cuda()
+    P1, P2 = S.clone(), S.clone()
+    s1 = torch.zeros(h + h * h, dtype=torch.float64, device="cuda"); s2 = torch.zeros_like(s1)
+    ops.softmax_stats(P1, B, h, N, ld, scale, p, 5, 2, s1)
+    ops.softmax_stats(P2, B, h, N, ld, scale, p, 5, 2, s2, precision=ops.PREC_TF32)
+    _close(P2, P1, rtol=1e-5, name="softmax")
+    _close(s2, s1, rtol=3e-4, name="moments")
+    W = _rand(h, h, seed=2, scale=0.6).cuda()
+    bc, gm, bt = _rand(h, seed=3, scale=0.01).cuda(), (1 + _rand(h, seed=4, scale=0.3)).cuda(), _rand(h, seed=5, scale=0.01).cuda()
+    rm, rv = _rand(h, seed=6, scale=0.01).cuda(), ((1 + _rand(h, seed=7, scale=0.3)) * 1e-3).cuda()
+    fold, saved = torch.empty(h * h + h, device="cuda"), torch.empty(2 * h, device="cuda")
+    ops.reattn_bn_finalize(s1 if train else None, B * N * N, h, N, W, bc, gm, bt, rm, rv, None, 1e-5, 0.1, train, fold, saved)
+    A1, A2 = torch.empty_like(P1), torch.empty_like(P1)
+    ops.reattn_mix(P1, A1, fold, B, h, N, ld, p, 5, 2)
+    ops.reattn_mix(P1, A2, fold, B, h, N, ld, p, 5, 2, tf32=True)
+    _close(A2, A1, rtol=2e-3, name="mixed map (tf32 mix)")
+    assert not torch.equal(A1, A2)                       # really the tensor-core kernel
+    dA = _rand(B, h, N, N, seed=3).cuda()
+    r1 = torch.zeros(h + h * h, dtype=torch.float64, device="cuda"); r2 = torch.zeros_like(r1)
+    A3, A4 = torch.empty_like(P1), torch.empty_like(P1)
+    ops.reattn_mix_reduce(P1, dA, A3, fold, B, h, N, ld, p, 5, 2, r1)
+    ops.reattn_mix_reduce(P1, dA, A4, fold, B, h, N, ld, p, 5, 2, r2, tf32=True)
+    assert torch.equal(A4, A2)
+    _close(r2, r1, rtol=2e-3, name="reductions (tf32 mma)")
+    dW, dbc, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"),
+                        torch.zeros(h, device="cuda"), torch.zeros(h, device="cuda"))
+    coef = torch.empty(2 * h, device="cuda")
+    ops.reattn_bwd_params(r1, s1 if train else None, B, h, N, W, bc, gm, saved, train, coef, dW, dbc, dg, dbt)
+    d1, d2 = dA.clone(), dA.clone()
+    ops.reattn_bwd_rows(P1, d1, B, h, N, ld, W, bc, gm, saved, coef, train, scale, p, 5, 2)
+    ops.reattn_bwd_rows(P1, d2, B, h, N, ld, W, bc, gm, saved, coef, train, scale, p, 5, 2, tf32=True)
+    _close(d2, d1, rtol=1.2e-2, name="dS (tf32 mix)")
+
+
 def test_psnr_and_input_pipeline(ops):
     """N2 / N4: device PSNR vs the skimage formula; uint8 HWC -> normalised float CHW vs numpy."""
     g = torch.Generator().manual_seed(0)

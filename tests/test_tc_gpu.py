@@ -90,7 +90,8 @@ def test_tc_gemm_epilogues(ops):
     plain = torch.empty(M, N, device="cuda")
     ops.gemm(A.cuda(), W.cuda(), plain, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, precision=ops.PREC_TF32)
     exp = ops.dropout(plain, torch.empty_like(plain), 0.3, 77, 3)
-    assert torch.equal(out, exp)
+    assert torch.equal(out == 0, exp == 0)                # identical mask (same counter-based stream)
+    _close(out, exp, 1e-3, "dropout epilogue")            # the plain product may come from the warp-MMA kernel
 
 
 def test_tc_gemm_splitk_wgrad(ops):
@@ -177,7 +178,7 @@ def test_tc_gemm_bf16_operands(ops, M, N, K, ta):
     assert torch.all(out[:, N:] == 7.0)
 
 
-@pytest.mark.parametrize("Nt,hd", [(100, 12), (70, 8), (65, 20), (130, 32), (784, 24), (264, 16)])
+@pytest.mark.parametrize("Nt,hd", [(100, 12), (70, 8), (65, 20), (130, 32), (784, 24), (264, 16), (196, 96), (72, 44), (200, 128)])
 @pytest.mark.parametrize("out_bf16", [False, True])
 def test_scores_gemm_shapes(ops, Nt, hd, out_bf16):
     """S = alpha Q K^T with head_dim <= 32 runs on the warp-MMA write-stream kernel (vu_gemm_scores.cu): ragged token
@@ -192,6 +193,15 @@ def test_scores_gemm_shapes(ops, Nt, hd, out_bf16):
     exp = alpha * torch.einsum("bihe,bjhe->bhij", q4, k4)
     _close(S[..., :Nt].float(), exp, 6e-3 if out_bf16 else TOL, "scores")
     assert torch.all(S[..., Nt:].float() == 7.0)
+
+
+def test_scores_gemm_unbatched_tall(ops):
+    """K <= 32 without a batch (a token GEMM shape): the row strips are spread over many CTAs, not one."""
+    M, N, K = 20000, 192, 32
+    A, Bm = _rand(M, K, seed=1), _rand(N, K, seed=2)
+    C = torch.zeros(M, N, device="cuda")
+    ops.gemm(A.cuda(), Bm.cuda(), C, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, precision=ops.PREC_TF32)
+    _close(C, A.double() @ Bm.double().t(), TOL, "tall scores")
 
 
 def test_tc_gemm_bf16_output_and_transposed_heads(ops):

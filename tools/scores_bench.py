@@ -3,7 +3,8 @@
 import sys, torch
 sys.path.insert(0, ".")
 from vit_unet_b200 import ops
-B, h, N = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 8, 784
+B, h = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 8
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 784
 hd = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 D = h * hd
 q = torch.randn(B, N, D, device="cuda"); k = torch.randn(B, N, D, device="cuda")

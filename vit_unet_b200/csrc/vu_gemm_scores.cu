@@ -1,5 +1,5 @@
 // "Scores" GEMM of the attention path on the fine levels:  C[z] (M x N) = alpha * A[z] (M x K) . B[z]^T (N x K),
-// K = head_dim <= 32, M = N = tokens (784 at the Base bottleneck), batched over (image, head):
+// K = head_dim <= 128 (B operand must fit shared memory), M = N = tokens (784 at the Base bottleneck), batched over (image, head):
 //   S = Q K^T (model.py:155)  and  dA = dO V^T (its backward).
 // The contraction is 24 long but the output is the N x N attention map -- 5 GB per launch at 256 images -- so the
 // kernel is an HBM WRITE stream: the general tcgen05 tile kernel (one 128x64 output tile per CTA, TMEM round trip,
@@ -30,6 +30,7 @@ struct ScoresArgs {
   int64_t sAo, sAi, sBo, sBi, sCo, sCi;
   float alpha;
   int vec4;              // B rows can be staged with 16-byte loads
+  int chunks;            // CTAs per batch entry (each takes a contiguous range of 16-row strips)
 };
 
 // shared-memory layout of the B operand: row n at n * PITCH; inside a row the k index is permuted so that the two
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(256)
 scores_mma_kernel(ScoresArgs g) {
   using T = ScoresTile<KS>;
   extern __shared__ __align__(16) uint32_t Bs[];               // N8 * PITCH tf32 words
-  const int z = blockIdx.x, zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
+  const int z = blockIdx.x / g.chunks, chunk = blockIdx.x - z * g.chunks;     // CTA = (batch entry, chunk of row strips)
+  const int zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
   const float* __restrict__ A = g.A + zo * g.sAo + zi * g.sAi;
   const float* __restrict__ B = g.B + zo * g.sBo + zi * g.sBi;
   const int N8 = (g.N + 7) & ~7;
@@ -98,9 +100,11 @@ scores_mma_kernel(ScoresArgs g) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
   const int strips = (g.M + 15) >> 4, ntiles = N8 >> 3, jfull = g.N >> 3;     // tiles < jfull have all 8 columns
   const int halves = ntiles >= 32 ? 2 : 1;                     // work item = (strip, column half)
-  const int items = strips * halves, tph = (ntiles + halves - 1) / halves;
+  const int tph = (ntiles + halves - 1) / halves;
+  const int spc = (strips + g.chunks - 1) / g.chunks;          // strips per chunk
+  const int it0 = chunk * spc * halves, items = min(strips, (chunk + 1) * spc) * halves;
   const int odd = tig & 1;
-  for (int it = w; it < items; it += 8) {
+  for (int it = it0 + w; it < items; it += 8) {
     const int strip = it / halves, half = it - strip * halves;
     const int r0 = strip * 16 + gid, r1 = r0 + 8;
     const bool full_rows = strip * 16 + 16 <= g.M;             // warp-uniform
@@ -207,7 +211,7 @@ static int launch_scores(const ScoresArgs& g, int batch, size_t smem, cudaStream
     cudaFuncSetAttribute(scores_mma_kernel<KS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  scores_mma_kernel<KS, BF16><<<batch, 256, smem, s>>>(g);
+  scores_mma_kernel<KS, BF16><<<(unsigned)(batch * g.chunks), 256, smem, s>>>(g);
   return check_launch("vu_gemm");
 }
 
@@ -216,7 +220,7 @@ int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   *handled = false;
   static const bool on = []() { const char* e = getenv("VU_GEMM_SCORES"); return !(e && e[0] == '0'); }();
   if (!on) return VU_OK;
-  if (d.trans_a || !d.trans_b || d.K > 32 || d.M < 64 || d.N < 64) return VU_OK;
+  if (d.trans_a || !d.trans_b || d.K > 128 || d.M < 64 || d.N < 64) return VU_OK;
   if (d.a_bf16 || d.b_bf16 || d.bias || d.residual || d.aux_in || d.aux_out || d.act != VU_ACT_NONE || d.accumulate ||
       d.split_k > 1 || d.drop_p > 0.f)
     return VU_OK;
@@ -227,7 +231,8 @@ int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   const int need = d.c_bf16 ? 4 : 2;
   if ((uintptr_t)d.C % 8 || d.ldc % need || d.sCo % need || d.sCi % need) return VU_OK;
   (void)esz;
-  const int KS = (d.K + 7) / 8;
+  int KS = (d.K + 7) / 8;                                      // k-steps, rounded up to an instantiated count
+  KS = KS <= 4 ? KS : (KS <= 6 ? 6 : (KS <= 8 ? 8 : (KS <= 12 ? 12 : 16)));
   const int N8 = (d.N + 7) & ~7;
   const int pitch = ((KS * 8) % 16 == 0) ? KS * 8 + 8 : KS * 8;
   const size_t smem = (size_t)N8 * pitch * 4;
@@ -238,13 +243,22 @@ int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   g.sAo = d.sAo; g.sAi = d.sAi; g.sBo = d.sBo; g.sBi = d.sBi; g.sCo = d.sCo; g.sCi = d.sCi;
   g.alpha = d.alpha;
   g.vec4 = (d.K % 4 == 0 && d.ldb % 4 == 0 && d.sBo % 4 == 0 && d.sBi % 4 == 0 && (uintptr_t)d.B % 16 == 0) ? 1 : 0;
+  // enough CTAs to fill the machine, but at least 32 strips (512 rows) per CTA to amortise staging B
+  const int64_t strips = cdiv(d.M, 16);
+  const int64_t want = cdiv((int64_t)sm_count() * 4, batch);
+  g.chunks = (int)std::max<int64_t>(1, std::min<int64_t>(want, strips / 32));
+  if (batch * g.chunks > 0x7fffffff) return VU_OK;
   *handled = true;
 #define VU_SC(KSV) (d.c_bf16 ? launch_scores<KSV, true>(g, (int)batch, smem, s) : launch_scores<KSV, false>(g, (int)batch, smem, s))
   switch (KS) {
     case 1: return VU_SC(1);
     case 2: return VU_SC(2);
     case 3: return VU_SC(3);
-    default: return VU_SC(4);
+    case 4: return VU_SC(4);
+    case 6: return VU_SC(6);
+    case 8: return VU_SC(8);
+    case 12: return VU_SC(12);
+    default: return VU_SC(16);
   }
 #undef VU_SC
 }

@@ -519,7 +519,7 @@ namespace vu {
 // 8-head tensor-core formulation (vu_reattn_mma.cuh): TF32 path, no pad columns.  VU_MAP_MMA=0 disables it.
 static bool mma_path(int h, int N, int ld) {
   static const bool on = []() { const char* e = getenv("VU_MAP_MMA"); return !(e && e[0] == '0'); }();
-  return on && h == 8 && ld == N && N % 8 == 0 && N <= 8192;   // 32-bit offsets inside one image
+  return on && h == 8 && ld == N && N % 4 == 0 && N <= 8192;   // 32-bit offsets inside one image
 }
 // persistent grid: as many CTAs as are resident (occupancy query, cached per kernel), capped by the work
 template <typename K>
@@ -609,16 +609,14 @@ extern "C" int vu_reattn_mix(const void* Pv, void* A, int map_fmt, const float* 
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
   VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
-  if (map_bf16 && mma_path(h, N, ld)) {
+  if ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)) {
     VU_REQUIRE(B <= 65535, fn, "at most 65535 images per call on the tensor-core map path");
     const int64_t tiles = cdiv((int64_t)N * N / 4, 8);          // per image; grid = (x, B)
-    if (p_bf16) {
-      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 2 * 8));      // 8 warps x 2 tiles x ~8 iterations per CTA
-      mma::reattn_mix_mma_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)Pv, (__nv_bfloat16*)A, fold, N, q);
-    } else {
-      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 2 * 8));
-      mma::reattn_mix_mma_kernel<float><<<dim3(gx, B), 256, 0, as_stream(stream)>>>(P, (__nv_bfloat16*)A, fold, N, q);
-    }
+    const dim3 grid((unsigned)std::max<int64_t>(1, cdiv(tiles, 8 * 2 * 8)), B);   // 8 warps x 2 tiles x ~8 iterations per CTA
+    cudaStream_t st = as_stream(stream);
+    if (p_bf16) mma::reattn_mix_mma_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)Pv, (__nv_bfloat16*)A, fold, N, q);
+    else if (map_bf16) mma::reattn_mix_mma_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(P, (__nv_bfloat16*)A, fold, N, q);
+    else mma::reattn_mix_mma_kernel<float, float><<<grid, 256, 0, st>>>(P, (float*)A, fold, N, q);
     return check_launch(fn);
   }
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256, 16);
@@ -663,11 +661,11 @@ extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int 
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
-  if (map_bf16 && mma_path(h, N, ld)) {
+  if ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)) {
     cudaStream_t st = as_stream(stream);
     __nv_bfloat16* d = (__nv_bfloat16*)dA_dS;
     const __nv_bfloat16* Pb = (const __nv_bfloat16*)Pv;
-    if (N > 256 && N <= 1024) {         // long rows: one CTA per row, row kept in registers between the sweeps
+    if (map_bf16 && N > 256 && N <= 1024) {         // long rows: one CTA per row, row kept in registers between the sweeps
       if (p_bf16) {
         const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<4, __nv_bfloat16>, 256, (int64_t)B * N * 8);
         mma::reattn_bwd_rows_mma_cta_kernel<4, __nv_bfloat16><<<grid, 256, 0, st>>>(Pb, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
@@ -678,11 +676,14 @@ extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int 
       return check_launch(fn);
     }
     if (p_bf16) {
-      const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel<__nv_bfloat16>, 256, (int64_t)B * N);
-      mma::reattn_bwd_rows_mma_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(Pb, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+      const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel<__nv_bfloat16, __nv_bfloat16>, 256, (int64_t)B * N);
+      mma::reattn_bwd_rows_mma_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(Pb, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+    } else if (map_bf16) {
+      const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel<float, __nv_bfloat16>, 256, (int64_t)B * N);
+      mma::reattn_bwd_rows_mma_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(P, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
     } else {
-      const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel<float>, 256, (int64_t)B * N);
-      mma::reattn_bwd_rows_mma_kernel<float><<<grid, 256, 0, st>>>(P, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+      const int grid = resident_grid(mma::reattn_bwd_rows_mma_kernel<float, float>, 256, (int64_t)B * N);
+      mma::reattn_bwd_rows_mma_kernel<float, float><<<grid, 256, 0, st>>>(P, (float*)dA_dS, B, N, W, bconv, gamma, saved, coef, train, scale, q);
     }
     return check_launch(fn);
   }
@@ -737,18 +738,16 @@ extern "C" int vu_reattn_mix_reduce(const void* Pv, const void* dA, void* A, int
   VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
   VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
-  if (map_bf16 && mma_path(h, N, ld)) {
+  if ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)) {
     VU_REQUIRE(B <= 65535, fn, "at most 65535 images per call on the tensor-core map path");
     const int64_t tiles = cdiv((int64_t)N * N / 4, 8);          // per image; grid = (x, B)
-    if (p_bf16) {
-      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 16));          // 8 warps x ~16 iterations per CTA
-      mma::reattn_mix_reduce_mma_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, as_stream(stream)>>>(
-          (const __nv_bfloat16*)Pv, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
-    } else {
-      const int gx = (int)std::max<int64_t>(1, cdiv(tiles, 8 * 16));
-      mma::reattn_mix_reduce_mma_kernel<float><<<dim3(gx, B), 256, 0, as_stream(stream)>>>(
-          P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
-    }
+    const dim3 grid((unsigned)std::max<int64_t>(1, cdiv(tiles, 8 * 16)), B);      // 8 warps x ~16 iterations per CTA
+    cudaStream_t st = as_stream(stream);
+    if (p_bf16) mma::reattn_mix_reduce_mma_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
+        (const __nv_bfloat16*)Pv, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
+    else if (map_bf16) mma::reattn_mix_reduce_mma_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(
+        P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
+    else mma::reattn_mix_reduce_mma_kernel<float, float><<<grid, 256, 0, st>>>(P, (const float*)dA, (float*)A, fold, N, q, red);
     return check_launch(fn);
   }
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);

@@ -69,6 +69,8 @@ __device__ __forceinline__ uint32_t drop_quad(float4& v, uint32_t ctr, const Qua
   v.z = (m & 4u) ? v.z * q.dscale : 0.f; v.w = (m & 8u) ? v.w * q.dscale : 0.f;
   return m;
 }
+// 2^x for x <= 0 as one MUFU (ex2() adds a denormal-range rescale around it; a softmax term below 2^-126 may flush)
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void sub4(float4& v, float c) { v.x -= c; v.y -= c; v.z -= c; v.w -= c; }
 __device__ __forceinline__ void add4(float4& v, float c) { v.x += c; v.y += c; v.z += c; v.w += c; }
 __device__ __forceinline__ void mul4(float4& v, float c) { v.x *= c; v.y *= c; v.z *= c; v.w *= c; }
@@ -163,8 +165,8 @@ softmax_stats_mma_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, 
       mul4(xa, sl2); mul4(xb, sl2);
       const float mn = fmaxf(m, fmaxf(hmax4(xa), hmax4(xb)));
       if (mn > -INFINITY) {
-        l = l * exp2f(m - mn) + ((exp2f(xa.x - mn) + exp2f(xa.y - mn)) + (exp2f(xa.z - mn) + exp2f(xa.w - mn))) +
-            ((exp2f(xb.x - mn) + exp2f(xb.y - mn)) + (exp2f(xb.z - mn) + exp2f(xb.w - mn)));
+        l = l * ex2(m - mn) + ((ex2(xa.x - mn) + ex2(xa.y - mn)) + (ex2(xa.z - mn) + ex2(xa.w - mn))) +
+            ((ex2(xb.x - mn) + ex2(xb.y - mn)) + (ex2(xb.z - mn) + ex2(xb.w - mn)));
         m = mn;
       }
     }
@@ -172,7 +174,7 @@ softmax_stats_mma_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, 
     for (int o = 1; o <= 2; o <<= 1) {
       const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
       const float mn = fmaxf(m, mo);
-      l = (m > -INFINITY ? l * exp2f(m - mn) : 0.f) + (mo > -INFINITY ? lo * exp2f(mo - mn) : 0.f);
+      l = (m > -INFINITY ? l * ex2(m - mn) : 0.f) + (mo > -INFINITY ? lo * ex2(mo - mn) : 0.f);
       m = mn;
     }
     const float inv = 1.0f / l;
@@ -181,15 +183,15 @@ softmax_stats_mma_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, 
       float4 pa = kZero4, pb = kZero4;
       if (qa < ld4) {
         const float4 x = ldq(Sb + roff + 4 * qa);
-        pa = make_float4(exp2f(fmaf(x.x, sl2, -m)) * inv, exp2f(fmaf(x.y, sl2, -m)) * inv,
-                         exp2f(fmaf(x.z, sl2, -m)) * inv, exp2f(fmaf(x.w, sl2, -m)) * inv);
+        pa = make_float4(ex2(fmaf(x.x, sl2, -m)) * inv, ex2(fmaf(x.y, sl2, -m)) * inv,
+                         ex2(fmaf(x.z, sl2, -m)) * inv, ex2(fmaf(x.w, sl2, -m)) * inv);
         emit_p(Sb, Pb, roff + 4 * qa, pa, q.c);
         drop_quad(pa, ctr0 + ((uint32_t)roff >> 2) + qa, q); sub4(pa, q.c);
       }
       if (qb < ld4) {
         const float4 x = ldq(Sb + roff + 4 * qb);
-        pb = make_float4(exp2f(fmaf(x.x, sl2, -m)) * inv, exp2f(fmaf(x.y, sl2, -m)) * inv,
-                         exp2f(fmaf(x.z, sl2, -m)) * inv, exp2f(fmaf(x.w, sl2, -m)) * inv);
+        pb = make_float4(ex2(fmaf(x.x, sl2, -m)) * inv, ex2(fmaf(x.y, sl2, -m)) * inv,
+                         ex2(fmaf(x.z, sl2, -m)) * inv, ex2(fmaf(x.w, sl2, -m)) * inv);
         emit_p(Sb, Pb, roff + 4 * qb, pb, q.c);
         drop_quad(pb, ctr0 + ((uint32_t)roff >> 2) + qb, q); sub4(pb, q.c);
       }
@@ -202,9 +204,9 @@ softmax_stats_mma_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, 
 
 // ------------------------------------------------------------------ forward: A = fold . (Pd - c) + shift'
 // grid (x, B): flat tiles of 32 consecutive positions of image blockIdx.y (rows are contiguous: ld == N), pair layout.
-template <typename PT>
+template <typename PT, typename MT>
 __global__ void __launch_bounds__(256)
-reattn_mix_mma_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ A, const float* __restrict__ fold,
+reattn_mix_mma_kernel(const PT* __restrict__ P, MT* __restrict__ A, const float* __restrict__ fold,
                       int N, QuadCtx q) {
   const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
   uint32_t b0, b1; frag_fwd(fold, e, k4, b0, b1);
@@ -215,7 +217,7 @@ reattn_mix_mma_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ A, c
   const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3;
   const int64_t base = (int64_t)blockIdx.y * hs * H;
   const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
-  const PT* Pi = P + base; __nv_bfloat16* Ai = A + base;
+  const PT* Pi = P + base; MT* Ai = A + base;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int t = wid; t < tiles; t += 2 * nw) {
     int off[2]; bool ok[2]; float4 x0[2], x1[2];
@@ -244,10 +246,10 @@ reattn_mix_mma_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ A, c
 // ------------------------------------------------------------------ backward pass 1: A = mix(P) recomputed + reductions
 // red[h] += sum dA_h ;  red[H + h*H + g] += sum dA_h (Pd_g - c).  The mix runs in the pair layout, the reductions in
 // the stats layout (second read of the same P tile hits L1).  grid (x, B).
-template <typename PT>
+template <typename PT, typename MT>
 __global__ void __launch_bounds__(256)
-reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const __nv_bfloat16* __restrict__ dA,
-                             __nv_bfloat16* __restrict__ A, const float* __restrict__ fold, int N, QuadCtx q,
+reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const MT* __restrict__ dA,
+                             MT* __restrict__ A, const float* __restrict__ fold, int N, QuadCtx q,
                              double* __restrict__ out) {
   __shared__ float part[8][H + H * H];
   const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
@@ -259,7 +261,7 @@ reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const __nv_bfloat16* __re
   const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3;
   const int64_t base = (int64_t)blockIdx.y * hs * H;
   const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
-  const PT* Pi = P + base; const __nv_bfloat16* Di = dA + base; __nv_bfloat16* Ai = A + base;
+  const PT* Pi = P + base; const MT* Di = dA + base; MT* Ai = A + base;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   float cx[4] = {0.f, 0.f, 0.f, 0.f}, s1 = 0.f;
   for (int t = wid; t < tiles; t += nw) {
@@ -342,9 +344,9 @@ __device__ __forceinline__ float4 ds_quad(const float4& p, const float4& dp, flo
 }
 
 // short rows (N <= 256): one warp per row, pair layout, second sweep re-reads P and dP from L1
-template <typename PT>
+template <typename PT, typename MT>
 __global__ void __launch_bounds__(256)
-reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ dA, int B, int N,
+reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, MT* __restrict__ dA, int B, int N,
                            const float* __restrict__ W, const float* __restrict__ bconv,
                            const float* __restrict__ gamma, const float* __restrict__ saved,
                            const float* __restrict__ coef, int train, float scale, QuadCtx q) {
@@ -356,7 +358,7 @@ reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__
     const int b = r / N, i = r - b * N;
     const int64_t base = (int64_t)b * hs * H;
     const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
-    const PT* Pi = P + base; __nv_bfloat16* Di = dA + base;
+    const PT* Pi = P + base; MT* Di = dA + base;
     const int roff = k4 * hs + i * N;
     float rg0 = 0.f, rg1 = 0.f;
     for (int t = 0; t < ntiles; ++t) {
@@ -551,13 +553,13 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
         const int qa = t * 8 + k4, qb = qa + 4;
         if (qa < ld4) {
           float4 x = ldq(rs + 4 * qa);
-          x.x = exp2f(fmaf(x.x, sl2, -m)); x.y = exp2f(fmaf(x.y, sl2, -m)); x.z = exp2f(fmaf(x.z, sl2, -m)); x.w = exp2f(fmaf(x.w, sl2, -m));
+          x.x = ex2(fmaf(x.x, sl2, -m)); x.y = ex2(fmaf(x.y, sl2, -m)); x.z = ex2(fmaf(x.z, sl2, -m)); x.w = ex2(fmaf(x.w, sl2, -m));
           *reinterpret_cast<float4*>(rs + 4 * qa) = x;
           l += hsum4(x);
         }
         if (qb < ld4) {
           float4 x = ldq(rs + 4 * qb);
-          x.x = exp2f(fmaf(x.x, sl2, -m)); x.y = exp2f(fmaf(x.y, sl2, -m)); x.z = exp2f(fmaf(x.z, sl2, -m)); x.w = exp2f(fmaf(x.w, sl2, -m));
+          x.x = ex2(fmaf(x.x, sl2, -m)); x.y = ex2(fmaf(x.y, sl2, -m)); x.z = ex2(fmaf(x.z, sl2, -m)); x.w = ex2(fmaf(x.w, sl2, -m));
           *reinterpret_cast<float4*>(rs + 4 * qb) = x;
           l += hsum4(x);
         }

@@ -186,7 +186,8 @@ class Engine:
                      batch_inner=h, sA=(N * D, hd), sB=(N * D, hd), sC=(h * N * ld, N * ld), precision=prec)
 
         def mix_pv(b0, bc, src, ci):
-            ops.reattn_mix(src, A[:bc], fold, bc, h, N, ld, adrop, seed, sid + _CHUNK_STREAM * ci)
+            ops.reattn_mix(src, A[:bc], fold, bc, h, N, ld, adrop, seed, sid + _CHUNK_STREAM * ci,
+                           tf32=prec == ops.PREC_TF32)
             if bf16:
                 ops.gemm(A[:bc], vt[b0:b0 + bc], O[b0:b0 + bc], N, hd, N, trans_b=True, lda=ld, ldb=ldn, ldc=D,
                          batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(h * hd * ldn, hd * ldn),
@@ -298,7 +299,7 @@ class Engine:
             bc = min(c, B - b0)
             grad_map(b0, bc)
             ops.reattn_mix_reduce(Pm[b0:b0 + bc], dA[:bc], A[:bc], sv["fold"], bc, h, N, ld, adrop, seed,
-                                  sid + _CHUNK_STREAM * ci, red)
+                                  sid + _CHUNK_STREAM * ci, red, tf32=prec == ops.PREC_TF32)
             map_gemm(A, True, dOt if bf16 else None, dO, dv, b0, bc)
         del A
         coef = _empty((2 * h,), dy)
@@ -311,7 +312,7 @@ class Engine:
             if not single:
                 grad_map(b0, bc)
             ops.reattn_bwd_rows(Pm[b0:b0 + bc], dA[:bc], bc, h, N, ld, Wm, bm, gamma, sv["bn"], coef, train, scale,
-                                adrop, seed, sid + _CHUNK_STREAM * ci)
+                                adrop, seed, sid + _CHUNK_STREAM * ci, tf32=prec == ops.PREC_TF32)
             map_gemm(dA, False, kt if bf16 else None, k, dq, b0, bc)
             map_gemm(dA, True, qt if bf16 else None, q, dk, b0, bc)
         del dO, dA

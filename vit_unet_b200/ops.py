@@ -18,7 +18,7 @@ PREC_FP32, PREC_TF32 = 0, 1
 LOSS_KINDS = {"l1": 0, "mse": 1, "dice": 2}
 
 
-MAP_BF16, MAP_P_CENTRED_BF16 = 1, 2       # include/vit_unet_b200.h VU_MAP_*
+MAP_BF16, MAP_P_CENTRED_BF16, MAP_TF32_MIX = 1, 2, 4       # include/vit_unet_b200.h VU_MAP_*
 
 
 def _map(t: torch.Tensor, name: str):
@@ -28,12 +28,14 @@ def _map(t: torch.Tensor, name: str):
     return _chk(t, name), 0
 
 
-def _pmap(P: torch.Tensor, bf_maps: int):
-    """probabilities: fp32, or centred bf16 (only with bf16 maps) -> (pointer, map_fmt flags, bytes per element)"""
+def _pmap(P: torch.Tensor, bf_maps: int, tf32: bool = False):
+    """probabilities: fp32, or centred bf16 (only with bf16 maps) -> (pointer, map_fmt flags, bytes per element).
+    tf32: the head mixing may run on TF32 warp MMAs even with fp32 maps (tensor-core precision class)."""
     pp, pbf = _map(P, "P")
     if pbf and not bf_maps:
         raise VuError("centred bf16 probabilities need bf16 mixed / gradient maps")
-    return pp, (MAP_BF16 if bf_maps else 0) | (MAP_P_CENTRED_BF16 if pbf else 0), (2.0 if pbf else 4.0)
+    fmt = (MAP_BF16 if bf_maps else 0) | (MAP_P_CENTRED_BF16 if pbf else 0) | (MAP_TF32_MIX if tf32 else 0)
+    return pp, fmt, (2.0 if pbf else 4.0)
 
 
 def reattn_tensor_core_path(h: int, N: int, ld: int) -> bool:
@@ -185,6 +187,11 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
     d.precision = precision
     nb = batch_outer * batch_inner
     kind = "gemm_tcgen05_tf32" if precision == PREC_TF32 else "gemm_simt_fp32"
+    if (precision == PREC_TF32 and not trans_a and trans_b and K <= 128 and ((N + 7) // 8 * 8) * (K + 8) * 4 <= 200 * 1024
+            and M >= 64 and N >= 64 and not d.a_bf16
+            and bias is None and residual is None and aux_in is None and aux_out is None and act == ACT_NONE
+            and not accumulate and split_k <= 1 and drop_p == 0.0):
+        kind = "gemm_mma_tf32"          # vu_gemm_scores.cu: warp-MMA write-stream kernel (same routing rule as the C side)
     # classes: contractions over the head dim that WRITE an NxN map / contractions that READ a map / token GEMMs
     if nb > 1:
         cls = kind + (":map_out(QK^T,dA)" if N == M and K < N else ":map_in(PV,dV,dQ,dK)")
@@ -214,12 +221,12 @@ def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums, precision=PREC
           int(precision), _stream(), nbytes=(4.0 + (2.0 if Pc is not None else 4.0)) * B * h * N * N)
 
 
-def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red):
+def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red, tf32=False):
     pd, bf = _map(dA, "dA")
     pa, bf2 = _map(A, "A")
     if bf != bf2:
         raise VuError("reattn_mix_reduce: A and dA must have the same dtype")
-    pp, fmt, pb = _pmap(P, bf)
+    pp, fmt, pb = _pmap(P, bf, tf32)
     _call("vu_reattn_mix_reduce", pp, pd, pa, fmt, _chk(fold, "fold"), B, h, N, ld,
           drop_p, seed, sid, _chk(red, "red", torch.float64), _stream(),
           nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
@@ -238,9 +245,9 @@ def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nb
          _chk(fold, "fold"), _chk(saved, "saved"), _stream())
 
 
-def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid):
+def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid, tf32=False):
     pa, bf = _map(A, "A")
-    pp, fmt, pb = _pmap(P, bf)
+    pp, fmt, pb = _pmap(P, bf, tf32)
     _call("vu_reattn_mix", pp, pa, fmt, _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream(),
           nbytes=(pb + (2.0 if bf else 4.0)) * B * h * N * N, flops=2.0 * h * B * h * N * N)
 
@@ -257,9 +264,9 @@ def reattn_bwd_params(red, sums, B, h, N, W, bconv, gamma, saved, train, coef, d
          _stream())
 
 
-def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid):
+def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid, tf32=False):
     pd, bf = _map(dA, "dA")
-    pp, fmt, pb = _pmap(P, bf)
+    pp, fmt, pb = _pmap(P, bf, tf32)
     _call("vu_reattn_bwd_rows", pp, pd, fmt, B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
           _chk(gamma, "gamma"), _chk(saved, "saved"), _chk(coef, "coef"), int(train), scale, drop_p, seed, sid,
           _stream(), nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
