@@ -43,7 +43,7 @@ def block_table():
            "| kernel | grid | " + " | ".join(n for _, n in want) + " |", "|---|---|" + "---:|" * len(want)]
     traffic = {}
     for r in rows[2:]:
-        name = r[col["Kernel Name"]].split("(")[0].replace("void vu::", "").replace("vu::", "")
+        name = r[col["Kernel Name"]].split("(")[0].replace("void vu::", "").replace("vu::", "").replace("void ", "").replace("mma::", "")
         if name.startswith("void at::") or name.startswith("at::"):
             continue
         cells = []
@@ -82,12 +82,12 @@ def launches():
         if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
         ns = float(r["Metric Value"].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6}.get(r.get("Metric Unit", "ns"), 1)
-        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void vu::", "").replace("vu::", "")
+        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void vu::", "").replace("vu::", "").replace("void ", "").replace("mma::", "")
         agg[name][0] += 1; agg[name][1] += ns; n += 1
     tot = sum(v[1] for v in agg.values())
     out = [f"# {tag}: launch list of `bench.py --steps 1 --warmup 1 --min-warmup 1 --batch 32 --precision tf32` under "
            "`ncu --metrics gpu__time_duration.sum --clock-control none`\n",
-           f"{n} launches (3 training steps: warm-up, timed, e2e), {tot / 1e6:.1f} ms of kernel time "
+           f"{n} launches (4 training steps: warm-up, timed, e2e warm-up, e2e), {tot / 1e6:.1f} ms of kernel time "
            "(cold-cache, serialised: compare SHARES).\n", "| kernel | launches | total ms | share |", "|---|---:|---:|---:|"]
     for k, (c, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k}` | {c} | {ns / 1e6:.3f} | {100 * ns / tot:.1f}% |")

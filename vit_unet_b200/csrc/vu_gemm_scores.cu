@@ -31,6 +31,7 @@ struct ScoresArgs {
   float alpha;
   int vec4;              // B rows can be staged with 16-byte loads
   int chunks;            // CTAs per batch entry (each takes a contiguous range of 16-row strips)
+  int staged;            // fp32 output rows are 16-byte aligned: stage 16x32 tiles through shared memory
 };
 
 // shared-memory layout of the B operand: row n at n * PITCH; inside a row the k index is permuted so that the two
@@ -125,6 +126,36 @@ scores_mma_kernel(ScoresArgs g) {
       float* __restrict__ C = reinterpret_cast<float*>(g.C) + zo * g.sCo + zi * g.sCi;
       float* c0p = C + (int64_t)r0 * g.ldc + 2 * tig + 8 * j0;
       float* c1p = c0p + 8 * g.ldc;
+      if (g.staged) {
+        // four n-tiles (32 columns = one 128-byte line per row) at a time through a per-warp staging tile, so every
+        // global store instruction writes 4 full lines (512 contiguous-per-row bytes) instead of 8 x 32-byte sectors
+        float* stg = reinterpret_cast<float*>(Bs + N8 * T::PITCH) + w * (16 * 40);
+        float* crow = C + (int64_t)(strip * 16 + (lane >> 3)) * g.ldc + 4 * (lane & 7);
+        for (; j + 3 < jfast; j += 4, bp += 32 * T::PITCH, c0p += 32, c1p += 32) {
+          float c[4][4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { c[t][0] = 0.f; c[t][1] = 0.f; c[t][2] = 0.f; c[t][3] = 0.f; }
+#pragma unroll
+          for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint2 b = *reinterpret_cast<const uint2*>(bp + 8 * t * T::PITCH + 8 * s);
+              mma_16x8x8(c[t], a[s], b.x, b.y);
+            }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            *reinterpret_cast<float2*>(stg + gid * 40 + 8 * t + 2 * tig) = make_float2(c[t][0], c[t][1]);
+            *reinterpret_cast<float2*>(stg + (gid + 8) * 40 + 8 * t + 2 * tig) = make_float2(c[t][2], c[t][3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + (lane >> 3)) * 40 + 4 * (lane & 7));
+            *reinterpret_cast<float4*>(crow + (int64_t)(4 * i) * g.ldc + 8 * j) = v;
+          }
+          __syncwarp();
+        }
+      }
       for (; j + 1 < jfast; j += 2, bp += 16 * T::PITCH, c0p += 16, c1p += 16) {        // two independent n-tiles
         float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -235,13 +266,16 @@ int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   KS = KS <= 4 ? KS : (KS <= 6 ? 6 : (KS <= 8 ? 8 : (KS <= 12 ? 12 : 16)));
   const int N8 = (d.N + 7) & ~7;
   const int pitch = ((KS * 8) % 16 == 0) ? KS * 8 + 8 : KS * 8;
-  const size_t smem = (size_t)N8 * pitch * 4;
+  static const bool staged_on = []() { const char* e = getenv("VU_SCORES_STAGED"); return !(e && e[0] == '0'); }();
+  const bool staged = staged_on && !d.c_bf16 && d.ldc % 4 == 0 && d.sCo % 4 == 0 && d.sCi % 4 == 0 && (uintptr_t)d.C % 16 == 0;
+  const size_t smem = (size_t)N8 * pitch * 4 + (staged ? 8 * 16 * 40 * 4 : 0);
   if (smem > 200 * 1024) return VU_OK;
   ScoresArgs g;
   g.A = d.A; g.B = d.B; g.C = d.C; g.M = d.M; g.N = d.N; g.K = d.K;
   g.lda = d.lda; g.ldb = d.ldb; g.ldc = d.ldc; g.batch_inner = std::max(1, d.batch_inner);
   g.sAo = d.sAo; g.sAi = d.sAi; g.sBo = d.sBo; g.sBi = d.sBi; g.sCo = d.sCo; g.sCi = d.sCi;
   g.alpha = d.alpha;
+  g.staged = staged ? 1 : 0;
   g.vec4 = (d.K % 4 == 0 && d.ldb % 4 == 0 && d.sBo % 4 == 0 && d.sBi % 4 == 0 && (uintptr_t)d.B % 16 == 0) ? 1 : 0;
   // enough CTAs to fill the machine, but at least 32 strips (512 rows) per CTA to amortise staging B
   const int64_t strips = cdiv(d.M, 16);
