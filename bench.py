@@ -175,7 +175,7 @@ def run_reference(args):
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print_line(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------- CUDA arm
@@ -323,9 +323,12 @@ def run_cuda(args):
         line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": f"oracle port of the reference, Base train step, batch {args.cpu_batch}, "
                                           f"fp32, 2 timed + 1 warm-up steps, {cores} threads"}
-    print(json.dumps(line))
+    print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+print_line = print
 
 
 def main():
@@ -345,6 +348,14 @@ def main():
     ap.add_argument("--min-warmup", type=int, default=3, help="lower only for profiler runs (numbers under ncu are never bench values)")
     ap.add_argument("--kernel-timing", type=int, default=1, help="CUDA-event timing of every GEMM launch (roofline)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 on their own (NCCL prints its version banner
+    # there) are diverted to stderr for the duration of the run; the JSON line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    global print_line
+    print_line = lambda text: (out.write(text + "\n"), out.flush())
     if args.impl == "reference":
         run_reference(args)
     else:
