@@ -133,7 +133,8 @@ int vu_reattn_mix(const void* P, void* A, int map_fmt, const float* fold, int B,
 /* backward reductions: red[h + h*h] (double, caller zeroes) += { s1_h = sum dA_h,  X'_{hg} = sum dA_h (Pd_g - c) } */
 int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, float drop_p, uint64_t seed,
                          uint32_t stream_id, double* red, void* stream);
-/* fused backward pass: A = mix(P) (as vu_reattn_mix) AND the reductions of vu_reattn_bwd_reduce, one read of P, dA */
+/* fused backward pass: A = mix(P) (as vu_reattn_mix) AND the reductions of vu_reattn_bwd_reduce, one read of P, dA.
+ * A == NULL (tensor-core map path only): the caller kept the forward map, only the reductions are computed. */
 int vu_reattn_mix_reduce(const void* P, const void* dA, void* A, int map_fmt, const float* fold, int B, int h, int N,
                          int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream);
 /* closed-form parameter gradients from (red, sums): dW[h*h], dbconv[h], dgamma[h], dbeta[h] are ACCUMULATED

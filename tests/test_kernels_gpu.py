@@ -388,6 +388,9 @@ def test_reattn_tensor_core_path(ops, N, p, train):
     ops.reattn_bwd_reduce(P1, dA32, B, h, N, ld, p, 5, 2, r1)
     ops.reattn_mix_reduce(P1, dA, A3, fold, B, h, N, ld, p, 5, 2, r2)
     assert torch.equal(A3, A2)
+    r2b = torch.zeros_like(r2)                                   # A = None: reductions only (forward map kept)
+    ops.reattn_mix_reduce(P1, dA, None, fold, B, h, N, ld, p, 5, 2, r2b)
+    _close(r2b, r2, rtol=1e-6, name="reductions-only mode")
     _close(r2[:h], r1[:h], rtol=1e-5, name="s1 (mma)")
     _close(r2[h:], r1[h:], rtol=2e-3, name="X' (tf32 mma)")
     dW, dbc, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"),

@@ -732,8 +732,10 @@ extern "C" int vu_reattn_mix_reduce(const void* Pv, const void* dA, void* A, int
   const char* fn = "vu_reattn_mix_reduce";
   const int map_bf16 = map_fmt & VU_MAP_BF16, p_bf16 = map_fmt & VU_MAP_P_CENTRED_BF16;
   const float* P = (const float*)Pv;
-  VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA && A && fold && red && ((uintptr_t)dA % 16 == 0) && ((uintptr_t)A % 16 == 0), fn,
+  VU_REQUIRE(VU_MAP_ARGS_OK(P) && dA && fold && red && ((uintptr_t)dA % 16 == 0) && ((uintptr_t)A % 16 == 0), fn,
              "bad arguments");
+  VU_REQUIRE(A || ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)), fn,
+             "A == NULL (reductions only) is available on the tensor-core map path only");
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
   VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");

@@ -261,13 +261,14 @@ reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const MT* __restrict__ dA
   const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3;
   const int64_t base = (int64_t)blockIdx.y * hs * H;
   const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
-  const PT* Pi = P + base; const MT* Di = dA + base; MT* Ai = A + base;
+  const PT* Pi = P + base; const MT* Di = dA + base; MT* Ai = A ? A + base : nullptr;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   float cx[4] = {0.f, 0.f, 0.f, 0.f}, s1 = 0.f;
+  const bool mix = A != nullptr;                 // A == NULL: the forward map was kept, only the reductions are needed
   for (int t = wid; t < tiles; t += nw) {
     // pair layout: mixed map
     const int quad = t * 8 + e;
-    const bool ok = quad < quads;
+    const bool ok = mix && quad < quads;
     const int off = k4 * hs + quad * 4;
     float4 x0 = ok ? ldp(Pi + off, q.c) : kZero4, x1 = ok ? ldp(Pi + off + 4 * hs, q.c) : kZero4;
     // stats layout: head e, quads k4 and k4 + 4 of the tile
@@ -276,12 +277,14 @@ reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const MT* __restrict__ dA
     const int offa = e * hs + qa * 4, offb = offa + 16;
     float4 pa = va ? ldp(Pi + offa, q.c) : kZero4, pb = vb ? ldp(Pi + offb, q.c) : kZero4;
     const float4 da = va ? map_ld(Di + offa) : kZero4, db = vb ? map_ld(Di + offb) : kZero4;
-    drop_quad(x0, ctr0 + ((uint32_t)off >> 2), q); drop_quad(x1, ctr0 + ((uint32_t)off >> 2) + hs, q);
-    sub4(x0, q.c); sub4(x1, q.c);
-    float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1);
-    if (ok) {
-      add4(y0, sh0); add4(y1, sh1);
-      map_st(Ai + off, y0); map_st(Ai + off + 4 * hs, y1);
+    if (mix) {                                   // warp-uniform
+      drop_quad(x0, ctr0 + ((uint32_t)off >> 2), q); drop_quad(x1, ctr0 + ((uint32_t)off >> 2) + hs, q);
+      sub4(x0, q.c); sub4(x1, q.c);
+      float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1);
+      if (ok) {
+        add4(y0, sh0); add4(y1, sh1);
+        map_st(Ai + off, y0); map_st(Ai + off + 4 * hs, y1);
+      }
     }
     if (va) { drop_quad(pa, ctr0 + ((uint32_t)offa >> 2), q); sub4(pa, q.c); }
     if (vb) { drop_quad(pb, ctr0 + ((uint32_t)offb >> 2), q); sub4(pb, q.c); }

@@ -35,6 +35,7 @@ _BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "1") == "1"}      # on by 
 # centred bf16 probabilities (train, tf32 mode): halves the saved-map memory; off by default (about +1% images/s only,
 # the map kernels are issue-bound rather than HBM-bound once the mixing runs on the tensor cores)
 _BF16_PROBS = {"value": os.environ.get("VU_BF16_PROBS", "0") == "1"}
+_KEEP_MIXED_MAP = {"value": os.environ.get("VU_KEEP_MIXED_MAP", "1") == "1"}
 
 
 def set_bf16_maps(on: bool) -> None:
@@ -226,7 +227,12 @@ class Engine:
                 scores(b0, bc, dst)
                 ops.softmax_rows(dst, bc * h * N, N, ld, scale)
                 mix_pv(b0, bc, dst, ci)
-        del A
+        # one slice on the tensor-core map path: keep the mixed map for backward (dV = A^T dO) instead of recomputing
+        # and re-writing it there -- 2 bytes per map element of extra memory for one pass less over the maps
+        keep_A = (saved is not None and c >= B and _KEEP_MIXED_MAP["value"] and (bf16 or prec == ops.PREC_TF32)
+                  and ops.reattn_tensor_core_path(h, N, ld))
+        if not keep_A:
+            A = None
         if not keep_P:
             del Pm
             Pm = None
@@ -236,7 +242,7 @@ class Engine:
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums, seed=seed, sid=sid,
-                         adrop=adrop, pdrop=pdrop, train=train, chunk=c, bf16=bf16)
+                         adrop=adrop, pdrop=pdrop, train=train, chunk=c, bf16=bf16, A=A)
         return y
 
     def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):
@@ -272,7 +278,8 @@ class Engine:
         bf16 = sv["bf16"]
         mdt = torch.bfloat16 if bf16 else torch.float32
         dA = torch.zeros((c, h, N, ld), dtype=mdt, device=dy.device) if ld != N else torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
-        A = torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
+        A_kept = sv.get("A")
+        A = A_kept if A_kept is not None else torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
         if bf16:     # per-head transposed bf16 copies: the K-major B operands of dV = A^T dO, dQ = dS K, dK = dS^T Q
             dOt, kt, qt = (ops.heads_transpose_bf16(t, B, N, D, h) for t in (dO, k, q))
             ldn = dOt.shape[-1]
@@ -298,10 +305,11 @@ class Engine:
         for ci, b0 in enumerate(range(0, B, c)):
             bc = min(c, B - b0)
             grad_map(b0, bc)
-            ops.reattn_mix_reduce(Pm[b0:b0 + bc], dA[:bc], A[:bc], sv["fold"], bc, h, N, ld, adrop, seed,
-                                  sid + _CHUNK_STREAM * ci, red, tf32=prec == ops.PREC_TF32)
+            ops.reattn_mix_reduce(Pm[b0:b0 + bc], dA[:bc], None if A_kept is not None else A[:bc], sv["fold"], bc, h, N, ld,
+                                  adrop, seed, sid + _CHUNK_STREAM * ci, red, tf32=prec == ops.PREC_TF32)
             map_gemm(A, True, dOt if bf16 else None, dO, dv, b0, bc)
-        del A
+        sv["A"] = None
+        del A, A_kept
         coef = _empty((2 * h,), dy)
         ops.reattn_bwd_params(red, sv["sums"], B, h, N, Wm, bm, gamma, sv["bn"], train, coef,
                               G[pre + "reatten_matrix.weight"], G[pre + "reatten_matrix.bias"],

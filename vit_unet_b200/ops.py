@@ -223,13 +223,15 @@ def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums, precision=PREC
 
 def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red, tf32=False):
     pd, bf = _map(dA, "dA")
-    pa, bf2 = _map(A, "A")
+    pa, bf2 = _map(A, "A") if A is not None else (None, bf)       # A None: reductions only (tensor-core path)
     if bf != bf2:
         raise VuError("reattn_mix_reduce: A and dA must have the same dtype")
     pp, fmt, pb = _pmap(P, bf, tf32)
+    eb = 2.0 if bf else 4.0
     _call("vu_reattn_mix_reduce", pp, pd, pa, fmt, _chk(fold, "fold"), B, h, N, ld,
           drop_p, seed, sid, _chk(red, "red", torch.float64), _stream(),
-          nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
+          nbytes=(pb + eb * (2 if A is not None else 1)) * B * h * N * N,
+          flops=(4.0 if A is not None else 2.0) * h * B * h * N * N)
 
 
 def reattn_stats(P, B, h, N, ld, drop_p, seed, sid, sums):
