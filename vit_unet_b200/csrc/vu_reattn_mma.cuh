@@ -302,22 +302,27 @@ struct RowsConst {
   uint32_t f0, f1, g0, g1;
   float offp[2], a1[2], a2[2], kh[2];
 };
+// The per-head factor k_h = gamma_h invstd_h of dM, the keep scale 1/(1-p) of dP and the softmax scale of dS are all
+// folded into the backward weight fragment: the second MMA directly yields  scale * dPd_g / (1-p).
 __device__ __forceinline__ RowsConst rows_const(const float* __restrict__ W, const float* __restrict__ bconv,
                                                 const float* __restrict__ gamma, const float* __restrict__ saved,
-                                                const float* __restrict__ coef, int train, float c, int e, int k4) {
+                                                const float* __restrict__ coef, int train, const QuadCtx& q, float scale,
+                                                int e, int k4) {
   RowsConst k;
   frag_fwd(W, e, k4, k.f0, k.f1);           // M_h   = sum_g W[h][g] Pd_g
-  frag_bwd(W, e, k4, k.g0, k.g1);           // dPd_g = sum_h W[h][g] dM_h
+  const float s0 = gamma[k4] * saved[H + k4] * q.dscale * scale, s1 = gamma[k4 + 4] * saved[H + k4 + 4] * q.dscale * scale;
+  k.g0 = tf32(W[k4 * H + sigma(e)] * s0);   // scale dPd_g/(1-p) = sum_h (k_h scale/(1-p) W[h][g]) (dA_h - m1_h - Ahat_h m2_h)
+  k.g1 = tf32(W[(k4 + 4) * H + sigma(e)] * s1);
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
     const int h = k4 + 4 * v;
     float rs = 0.f;
 #pragma unroll
     for (int g = 0; g < H; ++g) rs += W[h * H + g];
-    k.offp[v] = bconv[h] - saved[h] + c * rs;             // M_h - mean_h = sum_g W_hg (Pd_g - c) + offp
+    k.offp[v] = bconv[h] - saved[h] + q.c * rs;           // M_h - mean_h = sum_g W_hg (Pd_g - c) + offp
     k.a1[v] = train ? coef[h] : 0.f;
     k.a2[v] = train ? saved[H + h] * coef[H + h] : 0.f;
-    k.kh[v] = gamma[h] * saved[H + h];
+    k.kh[v] = 1.0f;
   }
   return k;
 }
@@ -335,15 +340,13 @@ __device__ __forceinline__ void rows_tile(const RowsConst& k, const QuadCtx& q, 
     t1.x = fmaf(-M1.x, k.a2[1], t1.x + c1); t1.y = fmaf(-M1.y, k.a2[1], t1.y + c1);
     t1.z = fmaf(-M1.z, k.a2[1], t1.z + c1); t1.w = fmaf(-M1.w, k.a2[1], t1.w + c1);
   }
-  mul4(t0, k.kh[0]); mul4(t1, k.kh[1]);
-  float4 dp0, dp1; mix_pair(t0, t1, k.g0, k.g1, dp0, dp1);
-  t0.x = (m0 & 1u) ? dp0.x * q.dscale : 0.f; t0.y = (m0 & 2u) ? dp0.y * q.dscale : 0.f;
-  t0.z = (m0 & 4u) ? dp0.z * q.dscale : 0.f; t0.w = (m0 & 8u) ? dp0.w * q.dscale : 0.f;
-  t1.x = (m1 & 1u) ? dp1.x * q.dscale : 0.f; t1.y = (m1 & 2u) ? dp1.y * q.dscale : 0.f;
-  t1.z = (m1 & 4u) ? dp1.z * q.dscale : 0.f; t1.w = (m1 & 8u) ? dp1.w * q.dscale : 0.f;
+  float4 dp0, dp1; mix_pair(t0, t1, k.g0, k.g1, dp0, dp1);       // = scale * dPd / (1-p), see rows_const
+  t0.x = (m0 & 1u) ? dp0.x : 0.f; t0.y = (m0 & 2u) ? dp0.y : 0.f; t0.z = (m0 & 4u) ? dp0.z : 0.f; t0.w = (m0 & 8u) ? dp0.w : 0.f;
+  t1.x = (m1 & 1u) ? dp1.x : 0.f; t1.y = (m1 & 2u) ? dp1.y : 0.f; t1.z = (m1 & 4u) ? dp1.z : 0.f; t1.w = (m1 & 8u) ? dp1.w : 0.f;
 }
-__device__ __forceinline__ float4 ds_quad(const float4& p, const float4& dp, float r, float scale) {
-  return make_float4(scale * p.x * (dp.x - r), scale * p.y * (dp.y - r), scale * p.z * (dp.z - r), scale * p.w * (dp.w - r));
+// dS = P (scale dP - scale r): dp and r already carry the softmax scale
+__device__ __forceinline__ float4 ds_quad(const float4& p, const float4& dp, float r) {
+  return make_float4(p.x * (dp.x - r), p.y * (dp.y - r), p.z * (dp.z - r), p.w * (dp.w - r));
 }
 
 // short rows (N <= 256): one warp per row, pair layout, second sweep re-reads P and dP from L1
@@ -354,7 +357,7 @@ reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, MT* __restrict__ dA, int B,
                            const float* __restrict__ gamma, const float* __restrict__ saved,
                            const float* __restrict__ coef, int train, float scale, QuadCtx q) {
   const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
-  const RowsConst kc = rows_const(W, bconv, gamma, saved, coef, train, q.c, e, k4);
+  const RowsConst kc = rows_const(W, bconv, gamma, saved, coef, train, q, scale, e, k4);
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3, hs = N * N, rows = B * N;
   for (int r = wid; r < rows; r += nw) {
@@ -386,7 +389,7 @@ reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, MT* __restrict__ dA, int B,
         const int off = roff + 4 * quad;
         const float4 p0 = ldp(Pi + off, q.c), p1 = ldp(Pi + off + 4 * hs, q.c);
         const float4 dp0 = map_ld(Di + off), dp1 = map_ld(Di + off + 4 * hs);
-        map_st(Di + off, ds_quad(p0, dp0, rg0, scale)); map_st(Di + off + 4 * hs, ds_quad(p1, dp1, rg1, scale));
+        map_st(Di + off, ds_quad(p0, dp0, rg0)); map_st(Di + off + 4 * hs, ds_quad(p1, dp1, rg1));
       }
     }
   }
@@ -405,7 +408,7 @@ reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restri
                                const float* __restrict__ coef, int train, float scale, QuadCtx q) {
   __shared__ float srg[2][8][H];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
-  const RowsConst kc = rows_const(W, bconv, gamma, saved, coef, train, q.c, e, k4);
+  const RowsConst kc = rows_const(W, bconv, gamma, saved, coef, train, q, scale, e, k4);
   const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3, hs = N * N, rows = B * N;
   int par = 0;
   for (int r = blockIdx.x; r < rows; r += gridDim.x, par ^= 1) {
@@ -448,8 +451,8 @@ reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restri
       const int quad = (w + 8 * tt) * 8 + e;
       if (quad < ld4) {
         const int off = roff + 4 * quad;
-        map_st(Di + off, ds_quad(p0[tt], unpack_bf16x4(k0[tt]), rg0, scale));
-        map_st(Di + off + 4 * hs, ds_quad(p1[tt], unpack_bf16x4(k1[tt]), rg1, scale));
+        map_st(Di + off, ds_quad(p0[tt], unpack_bf16x4(k0[tt]), rg0));
+        map_st(Di + off + 4 * hs, ds_quad(p1[tt], unpack_bf16x4(k1[tt]), rg1));
       }
     }
   }
