@@ -482,11 +482,26 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
     else if (block_n == 32) rc = launch_tc<32, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     else if (block_n == 64) rc = launch_tc<64, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     else rc = launch_tc<128, 3, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
-  } else if (block_n == 32) rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  } else if (block_n == 32) {
+    if (g.k_per_split <= 1024) rc = launch_tc<32, 2>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    else rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  }
   else if (one_kb_narrow) rc = launch_tc<64, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);   // one k-block, output-bound: 6 CTAs/SM
-  else if (block_n == 64) rc = launch_tc<64, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  else if (block_n == 64) {
+    static const int st64 = []() { const char* e = getenv("VU_TC_STAGES64"); return e ? atoi(e) : 0; }();
+    const bool two = st64 ? st64 == 2 : g.k_per_split <= 1024;
+    if (two) rc = launch_tc<64, 2>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    else rc = launch_tc<64, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  }
   else if (g.k_per_split <= TC_BLOCK_K) rc = launch_tc<128, 1>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
-  else rc = launch_tc<128, 3>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  else {
+    // short contractions are output / HBM bound: two stages (3 CTAs per SM overlap each other's epilogue) beat three
+    // (measured per shape with tools/gemm_bench.py: K <= 768 gains 6-21 %, K >= 3072 loses 3-25 %)
+    static const int st128 = []() { const char* e = getenv("VU_TC_STAGES128"); return e ? atoi(e) : 0; }();
+    const bool two = st128 ? st128 == 2 : g.k_per_split <= 1024;
+    if (two) rc = launch_tc<128, 2>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    else rc = launch_tc<128, 3>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+  }
   *handled = true;
   return rc;
 }
