@@ -666,13 +666,22 @@ extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int 
     __nv_bfloat16* d = (__nv_bfloat16*)dA_dS;
     const __nv_bfloat16* Pb = (const __nv_bfloat16*)Pv;
     if (map_bf16 && N > 256 && N <= 1024) {         // long rows: one CTA per row, row kept in registers between the sweeps
-      if (p_bf16) {
-        const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<4, __nv_bfloat16>, 256, (int64_t)B * N * 8);
-        mma::reattn_bwd_rows_mma_cta_kernel<4, __nv_bfloat16><<<grid, 256, 0, st>>>(Pb, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
-      } else {
-        const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<4, float>, 256, (int64_t)B * N * 8);
-        mma::reattn_bwd_rows_mma_cta_kernel<4, float><<<grid, 256, 0, st>>>(P, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
-      }
+      // (warps, tiles per warp): 5 x 5 when the 32-key tiles divide by five (N = 784: 25 tiles; 10.1 vs 11.5 ms per step
+      // against 8 x 4, where one warp does four rounds and seven do three), else 8 x 4
+      static const int nw_env = []() { const char* e = getenv("VU_ROWS_NW"); return e ? atoi(e) : 0; }();
+      const int ntiles = (N / 4 + 7) / 8;
+      int nw = (ntiles <= 25 && ntiles % 5 == 0) ? 5 : 8;
+      if (ntiles <= 28 && (nw_env == 7)) nw = 7;
+      if (nw_env == 8) nw = 8;
+      if (nw_env == 5 && ntiles <= 25) nw = 5;
+#define VU_ROWS(TPWV, NWV, PTV, PPTR)                                                                               \
+      do {                                                                                                          \
+        const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<TPWV, NWV, PTV>, NWV * 32, (int64_t)B * N * NWV); \
+        mma::reattn_bwd_rows_mma_cta_kernel<TPWV, NWV, PTV><<<grid, NWV * 32, 0, st>>>(PPTR, d, B, N, W, bconv, gamma, saved, coef, train, scale, q); \
+      } while (0)
+      if (p_bf16) { if (nw == 5) VU_ROWS(5, 5, __nv_bfloat16, Pb); else if (nw == 7) VU_ROWS(4, 7, __nv_bfloat16, Pb); else VU_ROWS(4, 8, __nv_bfloat16, Pb); }
+      else { if (nw == 5) VU_ROWS(5, 5, float, P); else if (nw == 7) VU_ROWS(4, 7, float, P); else VU_ROWS(4, 8, float, P); }
+#undef VU_ROWS
       return check_launch(fn);
     }
     if (p_bf16) {
@@ -710,10 +719,21 @@ extern "C" int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld,
     if (N > 256 && N <= 1024) {          // asynchronous row pipeline (cp.async.bulk ring in shared memory)
       constexpr int ST = 2;
       const size_t smem = mma::bulk_smem_bytes(ST, 8 * N);
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(mma::softmax_stats_mma_bulk_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-      const int grid = resident_grid(mma::softmax_stats_mma_bulk_kernel<ST>, mma::kBulkThreads, (int64_t)B * N * 9, smem);
-      mma::softmax_stats_mma_bulk_kernel<ST><<<grid, mma::kBulkThreads, smem, as_stream(stream)>>>(S, (__nv_bfloat16*)Pc, B, N, scale, q, sums);
+      // consumer warps: 8 (measured at N = 784: 8.9 ms per step with 8 warps, 9.0 with 7, 9.7 with the evenly
+      // dividing 5 -- the shared-memory sweeps want the extra warps more than the balance); VU_SOFTMAX_NW overrides
+      static const int nw_env = []() { const char* e = getenv("VU_SOFTMAX_NW"); return e ? atoi(e) : 0; }();
+      int nw = 8;
+      if (nw_env >= 5 && nw_env <= 8) nw = nw_env;
+      cudaStream_t st = as_stream(stream);
+#define VU_SMB(NWV)                                                                                                       \
+      do {                                                                                                                \
+        static bool attr = false;                                                                                         \
+        if (!attr) { cudaFuncSetAttribute(mma::softmax_stats_mma_bulk_kernel<ST, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
+        const int grid = resident_grid(mma::softmax_stats_mma_bulk_kernel<ST, NWV>, (NWV + 1) * 32, (int64_t)B * N * (NWV + 1), smem); \
+        mma::softmax_stats_mma_bulk_kernel<ST, NWV><<<grid, (NWV + 1) * 32, smem, st>>>(S, (__nv_bfloat16*)Pc, B, N, scale, q, sums); \
+      } while (0)
+      if (nw == 5) VU_SMB(5); else if (nw == 6) VU_SMB(6); else if (nw == 7) VU_SMB(7); else VU_SMB(8);
+#undef VU_SMB
       return check_launch(fn);
     }
     const int grid = resident_grid(mma::softmax_stats_mma_kernel, 256, (int64_t)B * N);

@@ -117,7 +117,7 @@ __device__ __forceinline__ void mma_keys(float (&c)[4], const float4& a_lo, cons
 // sum over the 8 warps of the 8 + 64 statistics accumulators (s[head e] after the 4-lane reduction, M[e][2k4..+1] on
 // every lane), one double atomicAdd per entry.  `part` is [8][72] shared floats; warps >= 8 only join the barrier.
 __device__ __forceinline__ void reduce_stats(float (*part)[H + H * H], bool consumer, float s, float m0, float m1,
-                                             double* __restrict__ out) {
+                                             double* __restrict__ out, int nwarps = 8) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
   if (consumer) {
     s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void reduce_stats(float (*part)[H + H * H], bool cons
   if (threadIdx.x < H + H * H) {
     double t = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += (double)part[w][threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) t += (double)part[w][threadIdx.x];
     atomicAdd(out + threadIdx.x, t);
   }
 }
@@ -398,10 +398,11 @@ reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, MT* __restrict__ dA, int B,
 // ------------------------------------------------------------------ long rows: one CTA (8 warps) per row
 // For N > 256 the 8-head row (N * 32 bytes) no longer stays in L1 between the two sweeps of the warp-per-row kernels
 // and, with every warp of the GPU on a different row, not even in L2.  This variant spreads the 32-key tiles of a
-// row over the 8 warps of a CTA (TPW tiles per warp) and keeps the row in registers between the sweeps: P and dA
+// row over the NW warps of a CTA (TPW tiles per warp, NW * TPW >= tiles with as little slack as possible) and keeps
+// the row in registers between the sweeps: P and dA
 // cross HBM exactly once.  The row sums r_g are combined through shared memory.
-template <int TPW, typename PT>
-__global__ void __launch_bounds__(256, 2)
+template <int TPW, int NW, typename PT>
+__global__ void __launch_bounds__(NW * 32, NW >= 7 ? 2 : 3)
 reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ dA, int B, int N,
                                const float* __restrict__ W, const float* __restrict__ bconv,
                                const float* __restrict__ gamma, const float* __restrict__ saved,
@@ -420,7 +421,7 @@ reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restri
     float4 p0[TPW], p1[TPW]; uint2 k0[TPW], k1[TPW];      // k: dA on the way in, dP between the sweeps (bf16 x 4)
 #pragma unroll
     for (int tt = 0; tt < TPW; ++tt) {
-      const int quad = (w + 8 * tt) * 8 + e;
+      const int quad = (w + NW * tt) * 8 + e;
       const bool ok = quad < ld4;
       const int off = roff + 4 * quad;
       p0[tt] = ok ? ldp(Pi + off, q.c) : kZero4; p1[tt] = ok ? ldp(Pi + off + 4 * hs, q.c) : kZero4;
@@ -430,8 +431,8 @@ reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restri
     float rg0 = 0.f, rg1 = 0.f;
 #pragma unroll
     for (int tt = 0; tt < TPW; ++tt) {
-      if (w + 8 * tt >= ntiles) break;                                   // warp-uniform
-      const int off = roff + 4 * ((w + 8 * tt) * 8 + e);
+      if (w + NW * tt >= ntiles) break;                                   // warp-uniform
+      const int off = roff + 4 * ((w + NW * tt) * 8 + e);
       float4 t0 = unpack_bf16x4(k0[tt]), t1 = unpack_bf16x4(k1[tt]);
       rows_tile(kc, q, train, ctr0 + ((uint32_t)off >> 2), hs, p0[tt], p1[tt], t0, t1);
       rg0 += dot4(t0, p0[tt]); rg1 += dot4(t1, p1[tt]);                   // invalid quads: P == 0
@@ -445,10 +446,10 @@ reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restri
     __syncthreads();
     rg0 = 0.f; rg1 = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) { rg0 += srg[par][ww][k4]; rg1 += srg[par][ww][k4 + 4]; }
+    for (int ww = 0; ww < NW; ++ww) { rg0 += srg[par][ww][k4]; rg1 += srg[par][ww][k4 + 4]; }
 #pragma unroll
     for (int tt = 0; tt < TPW; ++tt) {
-      const int quad = (w + 8 * tt) * 8 + e;
+      const int quad = (w + NW * tt) * 8 + e;
       if (quad < ld4) {
         const int off = roff + 4 * quad;
         map_st(Di + off, ds_quad(p0[tt], unpack_bf16x4(k0[tt]), rg0));
@@ -488,15 +489,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_consumers(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-constexpr int kBulkThreads = 288;          // 8 consumer warps + 1 producer warp
 static inline size_t bulk_smem_bytes(int stages, int floats_per_stage) {
   return (size_t)stages * floats_per_stage * 4 + 2 * stages * sizeof(uint64_t);
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(kBulkThreads)
+// NW consumer warps + 1 producer warp (8 by default, see the dispatcher).
+template <int STAGES, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32)
 softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, int B, int N, float scale, QuadCtx q,
                               double* __restrict__ sums) {
   extern __shared__ __align__(128) unsigned char dsm[];
@@ -508,14 +509,14 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int st = 0; st < STAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, 8); }
+    for (int st = 0; st < STAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int hs = N * N, rows = B * N;
   const int nmine = (int)blockIdx.x < rows ? (rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   float cg[4] = {0.f, 0.f, 0.f, 0.f}, s = 0.f;
-  if (w == 8) {
+  if (w == NW) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
       for (int k = 0; k < nmine; ++k) {
@@ -542,7 +543,7 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
       float* rs = ring + (st * H + e) * N;                          // this lane's head row in shared memory
       mbar_wait(full + st, ph);
       float m = -INFINITY;
-      for (int t = w; t < ntiles; t += 8) {
+      for (int t = w; t < ntiles; t += NW) {
         const int qa = t * 8 + k4, qb = qa + 4;
         if (qa < ld4) m = fmaxf(m, hmax4(ldq(rs + 4 * qa)));
         if (qb < ld4) m = fmaxf(m, hmax4(ldq(rs + 4 * qb)));
@@ -550,12 +551,12 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
       if (k4 == 0) smax[par][w][e] = m;
-      bar_consumers();
+      bar_consumers(NW * 32);
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) m = fmaxf(m, smax[par][ww][e]);
+      for (int ww = 0; ww < NW; ++ww) m = fmaxf(m, smax[par][ww][e]);
       m *= sl2;                                                    // scale > 0: max commutes with the scaling
       float l = 0.f;
-      for (int t = w; t < ntiles; t += 8) {
+      for (int t = w; t < ntiles; t += NW) {
         const int qa = t * 8 + k4, qb = qa + 4;
         if (qa < ld4) {
           float4 x = ldq(rs + 4 * qa);
@@ -573,12 +574,12 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
       l += __shfl_xor_sync(0xffffffffu, l, 1);
       l += __shfl_xor_sync(0xffffffffu, l, 2);
       if (k4 == 0) ssum[par][w][e] = l;
-      bar_consumers();
+      bar_consumers(NW * 32);
       l = 0.f;
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) l += ssum[par][ww][e];
+      for (int ww = 0; ww < NW; ++ww) l += ssum[par][ww][e];
       const float inv = 1.0f / l;
-      for (int t = w; t < ntiles; t += 8) {
+      for (int t = w; t < ntiles; t += NW) {
         const int qa = t * 8 + k4, qb = qa + 4;
         float4 pa = kZero4, pb = kZero4;
         if (qa < ld4) {
@@ -600,7 +601,7 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
       if (++st == STAGES) { st = 0; ph ^= 1u; }
     }
   }
-  reduce_stats(part, w < 8, s, cg[0], cg[1], sums);
+  reduce_stats(part, w < NW, s, cg[0], cg[1], sums, NW);
 }
 
 }  // namespace mma
