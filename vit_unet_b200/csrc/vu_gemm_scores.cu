@@ -31,7 +31,7 @@ struct ScoresArgs {
   float alpha;
   int vec4;              // B rows can be staged with 16-byte loads
   int chunks;            // CTAs per batch entry (each takes a contiguous range of 16-row strips)
-  int staged;            // fp32 output rows are 16-byte aligned: stage 16x32 tiles through shared memory
+  int staged;            // output rows are 16-byte aligned: stage 16x32 (fp32) / 16x64 (bf16) tiles through shared memory
 };
 
 // shared-memory layout of the B operand: row n at n * PITCH; inside a row the k index is permuted so that the two
@@ -192,6 +192,38 @@ scores_mma_kernel(ScoresArgs g) {
       __nv_bfloat16* __restrict__ C = reinterpret_cast<__nv_bfloat16*>(g.C) + zo * g.sCo + zi * g.sCi;
       __nv_bfloat16* c0p = C + (int64_t)r0 * g.ldc + 8 * (j0 + odd) + 2 * (tig - odd);
       __nv_bfloat16* c1p = c0p + 8 * g.ldc;
+      if (g.staged) {
+        // eight n-tiles (64 columns = one 128-byte line of bf16 per row) at a time through the per-warp staging tile:
+        // packed bf16 pairs go to shared memory (conflict-free: row pitch 36 words), come back as 16-byte chunks and
+        // leave as full-line stores -- no lane exchange, 4 store instructions per 1024 outputs instead of 16
+        uint32_t* stg = Bs + N8 * T::PITCH + w * (16 * 40);
+        __nv_bfloat16* crow = C + (int64_t)(strip * 16 + (lane >> 3)) * g.ldc + 8 * (lane & 7);
+        for (; j + 7 < jfast; j += 8, bp += 64 * T::PITCH, c0p += 64, c1p += 64) {
+          float c[8][4];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { c[t][0] = 0.f; c[t][1] = 0.f; c[t][2] = 0.f; c[t][3] = 0.f; }
+#pragma unroll
+          for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const uint2 b = *reinterpret_cast<const uint2*>(bp + 8 * t * T::PITCH + 8 * s);
+              mma_16x8x8(c[t], a[s], b.x, b.y);
+            }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(c[t][0], c[t][1]), hi = __floats2bfloat162_rn(c[t][2], c[t][3]);
+            stg[gid * 36 + 4 * t + tig] = *reinterpret_cast<uint32_t*>(&lo);
+            stg[(gid + 8) * 36 + 4 * t + tig] = *reinterpret_cast<uint32_t*>(&hi);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + (4 * i + (lane >> 3)) * 36 + 4 * (lane & 7));
+            *reinterpret_cast<uint4*>(crow + (int64_t)(4 * i) * g.ldc + 8 * j) = v;
+          }
+          __syncwarp();
+        }
+      }
       for (; j < j1; j += 2, bp += 16 * T::PITCH, c0p += 16, c1p += 16) {
         float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
         const bool second = j + 1 < j1;                        // warp-uniform
@@ -267,7 +299,8 @@ int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   const int N8 = (d.N + 7) & ~7;
   const int pitch = ((KS * 8) % 16 == 0) ? KS * 8 + 8 : KS * 8;
   static const bool staged_on = []() { const char* e = getenv("VU_SCORES_STAGED"); return !(e && e[0] == '0'); }();
-  const bool staged = staged_on && !d.c_bf16 && d.ldc % 4 == 0 && d.sCo % 4 == 0 && d.sCi % 4 == 0 && (uintptr_t)d.C % 16 == 0;
+  const int va = d.c_bf16 ? 8 : 4;                             // elements per 16-byte store
+  const bool staged = staged_on && d.ldc % va == 0 && d.sCo % va == 0 && d.sCi % va == 0 && (uintptr_t)d.C % 16 == 0;
   const size_t smem = (size_t)N8 * pitch * 4 + (staged ? 8 * 16 * 40 * 4 : 0);
   if (smem > 200 * 1024) return VU_OK;
   ScoresArgs g;
