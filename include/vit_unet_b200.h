@@ -179,7 +179,7 @@ int vu_u8hwc_to_chw(const uint8_t* src, float* dst, int B, int C, int H, int W, 
                     void* stream);
 
 /* ---------------------------------------------------------------- misc */
-/* out = in * keep / (1-p), keep from the same Philox stream the GEMM epilogue uses (index = flat element) */
+/* out = in * keep / (1-p), keep from the same counter-based stream the GEMM epilogue uses (index = flat element) */
 int vu_dropout(const float* in, float* out, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream);
 /* y = a*x + b*y elementwise */
 int vu_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);

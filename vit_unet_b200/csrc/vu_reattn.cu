@@ -7,7 +7,7 @@
 //     backward        :  s1_h = sum dA_h                  X'_{hg}  = sum dA_h (Pd_g - c)
 // from which the BatchNorm batch statistics, the BatchNorm backward means and ALL parameter gradients (mixing
 // matrix, conv bias, BN gamma/beta) follow in closed form (reattn_bwd_params_kernel) -- the big kernels only stream.
-// Every streaming kernel handles 4 consecutive keys per thread (float4) so that one Philox4x32 call yields the
+// Every streaming kernel handles 4 consecutive keys per thread (float4) so that one counter-hash call yields the
 // dropout mask of the whole quad; masks are regenerated, never stored.
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -18,7 +18,8 @@
 namespace vu {
 
 // The mixed map A and the gradient map dA/dS may be stored as bfloat16 (half the HBM bytes; consumed by the bf16
-// tensor-core GEMMs); the probabilities P always stay fp32.
+// tensor-core GEMMs); the probabilities P are fp32 (or, optionally, centred bf16 on the tensor-core map path, see
+// vu_reattn_mma.cuh).  The kernels in THIS file are the exact fp32 FMA versions for any head count 1..8.
 __device__ __forceinline__ float4 map_ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 map_ld(const __nv_bfloat16* p) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);

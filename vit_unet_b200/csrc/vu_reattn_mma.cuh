@@ -300,7 +300,7 @@ reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const MT* __restrict__ dA
 // Per-lane constants of the pair layout (heads k4 and k4 + 4).
 struct RowsConst {
   uint32_t f0, f1, g0, g1;
-  float offp[2], a1[2], a2[2], kh[2];
+  float offp[2], a1[2], a2[2];
 };
 // The per-head factor k_h = gamma_h invstd_h of dM, the keep scale 1/(1-p) of dP and the softmax scale of dS are all
 // folded into the backward weight fragment: the second MMA directly yields  scale * dPd_g / (1-p).
@@ -322,7 +322,6 @@ __device__ __forceinline__ RowsConst rows_const(const float* __restrict__ W, con
     k.offp[v] = bconv[h] - saved[h] + q.c * rs;           // M_h - mean_h = sum_g W_hg (Pd_g - c) + offp
     k.a1[v] = train ? coef[h] : 0.f;
     k.a2[v] = train ? saved[H + h] * coef[H + h] : 0.f;
-    k.kh[v] = 1.0f;
   }
   return k;
 }

@@ -19,7 +19,7 @@ import torch
 from . import ops
 
 _PRECISION = {"value": ops.PREC_FP32}
-_CHUNK_STREAM = 4096          # Philox stream offset per image slice (layer stream ids stay far below this)
+_CHUNK_STREAM = 4096          # dropout RNG stream offset per image slice (layer stream ids stay far below this)
 # bytes of attention maps a slice may keep live between consecutive launches (two maps: S/P and A, or P-slice and
 # dA/dS) when the batch is processed in image slices meant to stay L2-resident.  0 disables slicing (default):
 # measured on B200 (Base, 64 images) slicing LOSES -- 80 MB: 822 img/s, 160 MB: 985 img/s, off: 1283 img/s -- the
@@ -268,7 +268,7 @@ class Engine:
         # recompute the mixed map, then dV = A^T dO ; dA = dO V^T
         Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
         bm = P[pre + "reatten_matrix.bias"]
-        # Same image slices as forward (identical Philox streams).  Phase A per slice: dA = dO V^T, one pass over
+        # Same image slices as forward (identical dropout RNG streams).  Phase A per slice: dA = dO V^T, one pass over
         # (P, dA) -> recomputed mixed map A + backward reductions, dV = A^T dO.  Then the closed-form parameter
         # gradients / BatchNorm-backward means.  Phase B per slice: dA again (a K = head_dim GEMM, cheaper than an HBM
         # round trip), dA -> dS in place, dQ = dS K, dK = dS^T Q.  Only P crosses HBM (twice).
