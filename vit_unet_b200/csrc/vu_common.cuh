@@ -17,6 +17,16 @@ int sm_count();
 #define VU_REQUIRE(cond, fn, msg) do { if (!(cond)) return vu::fail_arg(fn, msg); } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// Per-kernel function attributes (opt-in dynamic shared memory) are per DEVICE: `seen` is a bit mask of the devices a
+// call site has already configured.  True the first time the current device shows up (benign if two threads race).
+static inline bool first_use_on_device(uint64_t& seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  const uint64_t bit = 1ull << dev;
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------ patch-layout addressing

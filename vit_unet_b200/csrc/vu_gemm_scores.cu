@@ -269,11 +269,9 @@ scores_mma_kernel(ScoresArgs g) {
 
 template <int KS, bool BF16>
 static int launch_scores(const ScoresArgs& g, int batch, size_t smem, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static uint64_t seen = 0;
+  if (first_use_on_device(seen))
     cudaFuncSetAttribute(scores_mma_kernel<KS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
   scores_mma_kernel<KS, BF16><<<(unsigned)(batch * g.chunks), 256, smem, s>>>(g);
   return check_launch("vu_gemm");
 }

@@ -411,11 +411,10 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
 #define VU_TC_LAUNCH(AMN, BMN)                                                                                   \
   do {                                                                                                            \
     auto kfn = gemm_tf32_tc_kernel<BLOCK_N, STAGES, AMN, BMN, BF16>;                                                    \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
+    static uint64_t seen = 0;                                                                                     \
+    if (first_use_on_device(seen)) {                                                                              \
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)       \
         return check_launch("vu_gemm(tc attr)");                                                                  \
-      attr_set = true;                                                                                            \
     }                                                                                                             \
     kfn<<<grid, block, smem, s>>>(tmA, tmB, g);                                                                   \
   } while (0)

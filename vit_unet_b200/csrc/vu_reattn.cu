@@ -728,8 +728,8 @@ extern "C" int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld,
       cudaStream_t st = as_stream(stream);
 #define VU_SMB(NWV)                                                                                                       \
       do {                                                                                                                \
-        static bool attr = false;                                                                                         \
-        if (!attr) { cudaFuncSetAttribute(mma::softmax_stats_mma_bulk_kernel<ST, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
+        static uint64_t seen = 0;                                                                                         \
+        if (first_use_on_device(seen)) cudaFuncSetAttribute(mma::softmax_stats_mma_bulk_kernel<ST, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
         const int grid = resident_grid(mma::softmax_stats_mma_bulk_kernel<ST, NWV>, (NWV + 1) * 32, (int64_t)B * N * (NWV + 1), smem); \
         mma::softmax_stats_mma_bulk_kernel<ST, NWV><<<grid, (NWV + 1) * 32, smem, st>>>(S, (__nv_bfloat16*)Pc, B, N, scale, q, sums); \
       } while (0)
