@@ -58,6 +58,13 @@ def _worker(rank, world, port, q):
         assert len(spans) > 1 and spans[0][1] == net._flat_numel and spans[-1][0] == 0
         assert all(spans[i][0] == spans[i + 1][1] for i in range(len(spans) - 1))
         assert order[0] == "PE." and order[-1] == "conv2d."
+        # BatchNorm running statistics drift apart per rank during training; checkpointing broadcasts rank 0's
+        bufs = dict(net.named_buffers())
+        name = next(n for n in bufs if n.endswith("var_norm.running_mean"))
+        bufs[name].fill_(float(rank + 7))
+        sd = dpm.state_dict()                            # sync_buffers(0) + the reference's key layout
+        assert name in sd and not any(k.startswith("module.") for k in sd)
+        assert torch.all(sd[name] == 7.0), sd[name]
         q.put((rank, "ok"))
     except Exception as e:       # noqa: BLE001
         q.put((rank, f"fail: {e!r}"))

@@ -92,6 +92,24 @@ class DataParallel(torch.nn.Module):
     def forward(self, *a, **k):
         return self.module(*a, **k)
 
+    def sync_buffers(self, src: int = 0) -> None:
+        """Broadcast rank `src`'s buffers (Re-Attention BatchNorm running_mean / running_var / num_batches_tracked) to
+        every rank.  BatchNorm statistics are per-rank during training (standard non-sync-BN data parallelism,
+        SURVEY 8(e)); call this before evaluating or checkpointing so all ranks agree on one set of running stats."""
+        if not (dist.is_initialized() and dist.get_world_size(self.bucketer.pg) > 1):
+            return
+        for _, b in self.module.named_buffers():
+            dist.broadcast(b.data, src=src, group=self.bucketer.pg)
+
+    def state_dict(self, *a, sync_from: Optional[int] = 0, **k):
+        """The wrapped model's state_dict (the reference's key layout, no 'module.' prefix), after sync_buffers()."""
+        if sync_from is not None:
+            self.sync_buffers(sync_from)
+        return self.module.state_dict(*a, **k)
+
+    def load_state_dict(self, sd, *a, **k):
+        return self.module.load_state_dict(sd, *a, **k)
+
 
 def _group_of(name: str) -> str:
     """'Encoders.3.ReAttn.proj.weight' -> 'Encoders.3.' ; 'conv2d.weight' -> 'conv2d.' ; 'PE.x' -> 'PE.'"""
