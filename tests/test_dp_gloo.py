@@ -62,9 +62,32 @@ def _worker(rank, world, port, q):
         bufs = dict(net.named_buffers())
         name = next(n for n in bufs if n.endswith("var_norm.running_mean"))
         bufs[name].fill_(float(rank + 7))
-        sd = dpm.state_dict()                            # sync_buffers(0) + the reference's key layout
+        if rank == 0:                                    # the usual rank-0-only checkpoint: no collective, no hang
+            sd0 = dpm.state_dict()
+            assert torch.all(sd0[name] == 7.0)
+        dpm.sync_buffers(0)                              # explicit collective on every rank
+        sd = dpm.state_dict()                            # the reference's key layout
         assert name in sd and not any(k.startswith("module.") for k in sd)
         assert torch.all(sd[name] == 7.0), sd[name]
+        # src selects the broadcasting rank (a rank inside the process group; the default group here)
+        bufs[name].fill_(float(rank + 20))
+        dpm.sync_buffers(1)
+        assert torch.all(bufs[name] == 21.0)
+        # a model without an output conv has no 'conv2d.' group: Engine.backward still notifies it
+        with contextlib.redirect_stdout(io.StringIO()):
+            net2 = vu.ViT_UNet(depth=1, depth_te=1, size_bottleneck=1, preprocessing="none", num_patches=4, patch_size=8,
+                               num_channels=3, hidden_dim=16, num_heads=2, attn_drop=0., proj_drop=0., linear_drop=0)
+        dp2 = DataParallel(net2, bucket_mb=0.001)
+        flat2 = torch.full((net2._flat_numel,), float(rank + 1))
+        dp2.bucketer.begin(flat2)
+        assert "conv2d." not in dp2.bucketer.group_starts
+        dp2.bucketer.on_ready("conv2d.")                 # must be a no-op, not a KeyError
+        for st in reversed(net2.engine.sched):
+            if st[0] in ("block", "skip"):
+                dp2.bucketer.on_ready(st[1])
+        dp2.bucketer.on_ready("PE.")
+        dp2.bucketer.finish()
+        assert torch.allclose(flat2, torch.full_like(flat2, 1.5))
         q.put((rank, "ok"))
     except Exception as e:       # noqa: BLE001
         q.put((rank, f"fail: {e!r}"))

@@ -81,9 +81,9 @@ def test_oracle_matches_reference_golden(name):
     model.load_state_dict(fill_state_dict(model.state_dict()))
     x, y = make_input(B, kw["num_channels"], kw["im_size"])
     got = pack(run_case(model, x, y, train=True), full=name.startswith("tiny"))
-    assert set(got) | {"n_params"} == {k for k in gold.files if "_cond:" not in k}
+    assert set(got) | {"n_params"} == {k for k in gold.files if "_cond:" not in k and not k.startswith("r64:")}
     for k in gold.files:
-        if k == "n_params" or "_cond:" in k:
+        if k == "n_params" or "_cond:" in k or k.startswith("r64:"):      # r64: the reference evaluated in fp64
             continue
         g, o = gold[k], got[k]
         scale = max(np.abs(g).max(), 1e-30)

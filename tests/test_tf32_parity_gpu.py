@@ -1,0 +1,80 @@
+"""Parity of the BENCHMARKED configuration (TF32 tensor-core contractions, bf16 or fp32 attention maps, streamed
+Re-Attention where it applies) against the reference's golden vectors: eval forward, eval-mode gradients and
+TRAIN-mode (dropout p = 0) outputs, loss, dx, every parameter gradient and the BatchNorm buffers.
+Protocol and tolerances: tests/_parity.py."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from _parity import CONFIGS, build_net, parity_rows, summarize   # noqa: E402
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+@pytest.fixture
+def tf32():
+    import vit_unet_b200 as vu
+    vu.set_precision("tf32")
+    yield vu
+    vu.set_precision("fp32"); vu.set_bf16_maps(True); vu.set_bf16_probs(False)
+
+
+@pytest.mark.parametrize("bf16_maps", [True, False])
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_tf32_path_matches_reference_golden(tf32, name, bf16_maps):
+    tf32.set_bf16_maps(bf16_maps)
+    net, x, y = build_net(name, _quiet)
+    rows = parity_rows(name, net, x, y)
+    bad = [r for r in rows if r[3] == "FAIL"]
+    assert not bad, f"{len(bad)} of {len(rows)} tensors out of tolerance; worst: {summarize(bad)}"
+    checked = [r for r in rows if r[3] == "ok"]
+    assert len(checked) >= 0.5 * len(rows), "more than half of the tensors fell into the chaotic regime"
+
+
+def test_tf32_centred_bf16_probabilities(tf32):
+    """VU_BF16_PROBS variant (train-mode probabilities kept as centred bf16) on the level-2 block shape."""
+    tf32.set_bf16_maps(True); tf32.set_bf16_probs(True)
+    net, x, y = build_net("l2block_head", _quiet)
+    rows = parity_rows("l2block_head", net, x, y)
+    bad = [r for r in rows if r[3] == "FAIL"]
+    assert not bad, summarize(bad)
+
+
+def test_tf32_dropout_masks_agree_between_forward_and_backward(tf32):
+    """Dropout ON (attention 0.25 / projection 0.25): the masks are regenerated in every kernel, never stored.  If any
+    backward kernel regenerated a different mask than its forward twin, the gradient would not be the derivative of
+    the loss the forward computed: check against central differences of the CUDA forward (same seed => same masks)
+    on the level-2 block shape the tensor-core map kernels run at."""
+    vu = tf32
+    _, kw, _ = CONFIGS["l2block_head"]
+    kw = dict(kw, attn_drop=0.25, proj_drop=0.25, size_bottleneck=1)
+    from make_golden import fill_state_dict, make_input
+    net = _quiet(vu.HViT_UNet, **kw)
+    net.load_state_dict(fill_state_dict(net.state_dict()))
+    net.to("cuda").train()
+    x, y = make_input(2, 3, 224)
+    x, y = x.cuda(), y.cuda()
+
+    def loss():
+        torch.manual_seed(11)
+        return vu.mse_loss(net(x), y)
+    net.zero_grad(); loss().backward()
+    pd = dict(net.named_parameters())
+    for pname, idx in (("BottleNeck.0.ReAttn.proj.bias", 17), ("BottleNeck.0.ReAttn.var_norm.weight", 3),
+                       ("BottleNeck.0.ReAttn.reatten_matrix.weight", 10), ("BottleNeck.0.ReAttn.vconv2d.weight", 5)):
+        prm = pd[pname]
+        g = prm.grad.view(-1)[idx].item()
+        with torch.no_grad():
+            eps = 2e-2 * max(1.0, abs(prm.view(-1)[idx].item()))
+            prm.view(-1)[idx] += eps; lp = loss().item()
+            prm.view(-1)[idx] -= 2 * eps; lm = loss().item()
+            prm.view(-1)[idx] += eps
+        fd = (lp - lm) / (2 * eps)
+        assert abs(fd - g) <= 0.1 * max(abs(g), abs(fd)) + 2e-5, (pname, fd, g)

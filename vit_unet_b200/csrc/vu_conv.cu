@@ -3,6 +3,8 @@
 //   * PatchEncoder conv (README variant) and the reconstruction conv: whole-image 'same' conv (model.py:428)
 // One thread per pixel, all C output channels of all fused convs in registers; the 9*C input taps come from
 // L1 (each input float is reused 9*C*nconv times), so HBM sees one read of x and one write per output.
+#include <mutex>
+
 #include "vu_common.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -12,7 +14,8 @@ namespace vu {
 
 // Filter weights / biases of the launch in flight live in __constant__ memory: after full unrolling every weight is
 // an immediate constant-bank operand of its FFMA (no LDS / register per weight).  They are refreshed with a
-// stream-ordered device-to-device cudaMemcpyToSymbolAsync before each launch (972 B at most).
+// stream-ordered device-to-device cudaMemcpyToSymbolAsync before each launch (972 B at most); FilterGuard (below)
+// orders the (upload, launch) pairs of different streams / host threads on the same device.
 __constant__ float c_w[3 * 4 * 4 * 9];
 __constant__ float c_b[3 * 4];
 
@@ -477,6 +480,26 @@ static bool launch_patch_conv(int p, const float* s0, const float* s1, const flo
   return false;
 }
 
+// c_w / c_b are per-device globals, and a stream-ordered upload only orders work inside ONE stream.  FilterGuard
+// makes every (upload, launch) pair on a device wait for the previous conv kernel that read the filters, whatever
+// stream or host thread launched it: a per-device mutex around the enqueue + an event recorded after each launch that
+// the next user's stream waits on (a no-op when it is the same stream).  Two streams or threads can therefore run the
+// model on one GPU without seeing each other's filters.
+struct FilterSlot { std::mutex mu; cudaEvent_t ev = nullptr; bool recorded = false; };
+static FilterSlot g_filter_slot[64];
+struct FilterGuard {
+  FilterSlot* slot; cudaStream_t s; std::unique_lock<std::mutex> lk;
+  explicit FilterGuard(cudaStream_t st) : s(st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) dev = 0;
+    slot = &g_filter_slot[dev];
+    lk = std::unique_lock<std::mutex>(slot->mu);
+    if (!slot->ev) cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming);
+    if (slot->recorded) cudaStreamWaitEvent(s, slot->ev, 0);
+  }
+  ~FilterGuard() { if (slot->ev && cudaEventRecord(slot->ev, s) == cudaSuccess) slot->recorded = true; }
+};
+
 static int upload_filters(const char* fn, const float* w, const float* bias, int nconv, int C, cudaStream_t s) {
   if (cudaMemcpyToSymbolAsync(c_w, w, sizeof(float) * nconv * C * C * 9, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
     return check_launch(fn);
@@ -524,6 +547,7 @@ extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const flo
   int threads = 256;
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
+  FilterGuard guard(s);           // released (event recorded) after the launch below, on every return path
   rc = upload_filters(fn, w, bias, nconv, C, s); if (rc) return rc;
   if (g.fast && p_x == p_out && C <= 3 && p_x >= 4 && !getenv("VU_CONV_GENERIC")) {
     const int64_t patches = (int64_t)B * (H / p_x) * (W / p_x);
@@ -553,6 +577,7 @@ extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const flo
   int threads = 256;
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
+  FilterGuard guard(s);
   rc = upload_filters(fn, w, nullptr, nconv, C, s); if (rc) return rc;
   if (g.fast && p_dy == p_dx && C <= 3 && p_dy >= 4 && !getenv("VU_CONV_GENERIC")) {
     const int64_t patches = (int64_t)B * (H / p_dy) * (W / p_dy);

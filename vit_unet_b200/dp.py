@@ -45,7 +45,9 @@ class GradBucketer:
         """All gradients of parameter group `prefix` and of every later group are final."""
         if self.world == 1 or self._flat is None:
             return
-        start = self.group_starts[prefix]
+        start = self.group_starts.get(prefix)
+        if start is None:             # the model has no parameters under this prefix (e.g. no output conv)
+            return
         if start < self._sent_from and self._sent_from - start >= self.bucket_numel:
             self._launch(start, self._sent_from)
 
@@ -86,23 +88,30 @@ class DataParallel(torch.nn.Module):
         self.bucketer = GradBucketer(starts, module._flat_numel, int(bucket_mb * (1 << 20) / 4), process_group)
         module._dp = self.bucketer
         if broadcast_from is not None and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            gsrc = dist.get_global_rank(process_group, broadcast_from) if process_group is not None else broadcast_from
             for t in list(pd.values()) + [b for _, b in module.named_buffers()]:
-                dist.broadcast(t.data, src=broadcast_from, group=process_group)
+                dist.broadcast(t.data, src=gsrc, group=process_group)
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
 
     def sync_buffers(self, src: int = 0) -> None:
-        """Broadcast rank `src`'s buffers (Re-Attention BatchNorm running_mean / running_var / num_batches_tracked) to
-        every rank.  BatchNorm statistics are per-rank during training (standard non-sync-BN data parallelism,
-        SURVEY 8(e)); call this before evaluating or checkpointing so all ranks agree on one set of running stats."""
-        if not (dist.is_initialized() and dist.get_world_size(self.bucketer.pg) > 1):
+        """COLLECTIVE -- every rank of the process group must call it.  Broadcast the buffers (Re-Attention BatchNorm
+        running_mean / running_var / num_batches_tracked) of group-rank `src` to every rank.  BatchNorm statistics
+        are per-rank during training (standard non-sync-BN data parallelism); call this on all ranks
+        before evaluating or checkpointing so they agree on one set of running stats.  `src` is a rank INSIDE the
+        process group (0 = its first member), so sub-groups that do not contain global rank 0 work."""
+        pg = self.bucketer.pg
+        if not (dist.is_initialized() and dist.get_world_size(pg) > 1):
             return
+        gsrc = dist.get_global_rank(pg, src) if pg is not None else src
         for _, b in self.module.named_buffers():
-            dist.broadcast(b.data, src=src, group=self.bucketer.pg)
+            dist.broadcast(b.data, src=gsrc, group=pg)
 
-    def state_dict(self, *a, sync_from: Optional[int] = 0, **k):
-        """The wrapped model's state_dict (the reference's key layout, no 'module.' prefix), after sync_buffers()."""
+    def state_dict(self, *a, sync_from: Optional[int] = None, **k):
+        """The wrapped model's state_dict (the reference's key layout, no 'module.' prefix).  No collective runs by
+        default, so the usual ``if rank == 0: torch.save(model.state_dict())`` cannot hang; call ``sync_buffers()``
+        on EVERY rank first (or pass ``sync_from=r`` on every rank) to checkpoint one agreed set of BN statistics."""
         if sync_from is not None:
             self.sync_buffers(sync_from)
         return self.module.state_dict(*a, **k)

@@ -22,6 +22,7 @@ class FusedAdamW(torch.optim.Optimizer):
             raise ValueError("invalid AdamW hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._flat = None          # (model, flat_param, flat_m, flat_v, step)
+        self._warned = False
 
     # ------------------------------------------------------------------------------------------ flat path
     def flatten(self, model) -> "FusedAdamW":
@@ -34,8 +35,34 @@ class FusedAdamW(torch.optim.Optimizer):
             view = flat[off:off + p.numel()].view(p.shape)
             view.copy_(p.data)
             p.data = view
-        self._flat = dict(model=model, p=flat, m=torch.zeros_like(flat), v=torch.zeros_like(flat), step=0)
+        m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+        step = torch.zeros((), dtype=torch.int64)          # ONE shared step counter (host tensor, updated in place)
+        for name, off in zip(model._param_names, model._flat_offsets):
+            p = pd[name]
+            old = self.state.get(p, {})
+            st = dict(step=step, m=m[off:off + p.numel()].view(p.shape), v=v[off:off + p.numel()].view(p.shape))
+            if old:                                         # flatten() after some per-tensor steps: keep the moments
+                st["m"].copy_(old["m"]); st["v"].copy_(old["v"]); step.fill_(int(old["step"]))
+            self.state[p] = st
+        # self.state[p]['m'/'v'] are VIEWS of the flat moment buffers and every parameter shares one step tensor, so
+        # state_dict()/load_state_dict() round-trip the flat path and the per-tensor fall-back continues from the
+        # same moments instead of restarting at zero.
+        self._flat = dict(model=model, p=flat, m=m, v=v, step=step)
+        self._warned = False
         return self
+
+    def load_state_dict(self, state_dict):
+        """torch's loader replaces the per-parameter state tensors; copy them back INTO the flat buffers."""
+        if self._flat is None:
+            return super().load_state_dict(state_dict)
+        views = {p: dict(st) for p, st in self.state.items()}
+        super().load_state_dict(state_dict)
+        step = self._flat["step"]
+        for p, old in views.items():
+            new = self.state.get(p)
+            if new:
+                old["m"].copy_(new["m"]); old["v"].copy_(new["v"]); step.fill_(int(new["step"]))
+            self.state[p] = old
 
     def _flat_grads_alias(self) -> bool:
         f = self._flat
@@ -60,8 +87,15 @@ class FusedAdamW(torch.optim.Optimizer):
             f, grp = self._flat, self.param_groups[0]
             f["step"] += 1
             ops.adamw(f["p"], f["model"].flat_grad(), f["m"], f["v"], grp["lr"], grp["betas"][0], grp["betas"][1],
-                      grp["eps"], grp["weight_decay"], f["step"])
+                      grp["eps"], grp["weight_decay"], int(f["step"]))
             return loss
+        if self._flat is not None and not self._warned:
+            import warnings
+            warnings.warn("FusedAdamW: gradients no longer alias the model's flat gradient buffer (zero_grad("
+                          "set_to_none=False), gradient accumulation or model.to() after flatten()); using one launch "
+                          "per parameter on the same moment buffers", stacklevel=2)
+            self._warned = True
+        shared_step_done = False
         for grp in self.param_groups:
             for p in grp["params"]:
                 if p.grad is None:
@@ -70,11 +104,16 @@ class FusedAdamW(torch.optim.Optimizer):
                     raise RuntimeError("FusedAdamW runs on CUDA tensors only (no CPU fallback)")
                 st = self.state[p]
                 if not st:
-                    st["step"] = self._flat["step"] if self._flat is not None else 0
+                    st["step"] = torch.zeros((), dtype=torch.int64)
                     st["m"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["v"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] += 1
+                if self._flat is not None and st["step"] is self._flat["step"]:
+                    if not shared_step_done:                 # one shared counter: advance it once per step()
+                        st["step"] += 1
+                        shared_step_done = True
+                else:
+                    st["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 ops.adamw(p.data, g, st["m"], st["v"], grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],
-                          grp["weight_decay"], st["step"])
+                          grp["weight_decay"], int(st["step"]))
         return loss
