@@ -178,6 +178,69 @@ def run_reference(args):
     print_line(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------- eager-PyTorch-on-GPU arm
+def run_eager(args):
+    """SURVEY.md 8(d), second baseline: "what a user of the reference gets today" -- the SAME plain-PyTorch model
+    (oracle port of vit_unet/torch/model.py) moved to one B200 and run eagerly through cuBLAS / cuDNN, with TF32 matmuls
+    off (stock default) and on.  Same workload, loss, dropout and timing rules as the CUDA arm; none of this repo's
+    kernels are loaded.  Reported next to the CUDA arm, never as its value."""
+    from oracle import vit_unet_oracle as O
+    rank, world, local = _dist_env(args)
+    if rank != 0:
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    wl = WORKLOADS[args.workload]
+    preset = {"base_train": "base", "lite_infer": "lite", "large_train": "large", "base1ch_dice": "base"}[args.workload]
+    B = args.eager_batch
+    res = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = O.get_vit_unet(preset, variant="head", **({"num_channels": 1} if args.workload == "base1ch_dice" else {}))
+        m.to(dev).train(wl["train"])
+        x, y = _synthetic(B)
+        if args.workload == "base1ch_dice":
+            x, y = (x[:, :1] * 0.224 + 0.456).contiguous(), (y[:, :1] > 0.5).float().contiguous()
+        x, y = x.to(dev), y.to(dev)
+        loss_fn = O.dice_loss if wl["loss"] == "dice" else torch.nn.functional.l1_loss
+
+        def step():
+            if not wl["train"]:
+                with torch.no_grad():
+                    return (m(x) - y).abs().mean()
+            m.zero_grad(set_to_none=True)
+            loss = loss_fn(m(x), y)
+            loss.backward()
+            return loss
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        res["tf32" if tf32 else "fp32"] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms,
+                                           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        del m, x, y
+        torch.cuda.empty_cache()
+    best = max(res.values(), key=lambda r: r["images_per_s"])
+    line = {"impl": "eager", "metric": METRIC if args.workload == "base_train" else wl["name"] + " images/s",
+            "value": best["images_per_s"], "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32/f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": B,
+                       "where": "one B200, stock eager PyTorch (cuBLAS / cuDNN / ATen kernels) running the oracle port of the "
+                                "reference model; value = the faster of TF32-off / TF32-on"},
+            "eager": res, "gpu_launches": 0}
+    print_line(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
     import torch.distributed as dist
@@ -356,7 +419,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference", "eager"],
+                    help="cuda: this repo; reference: the reference's CPU path (oracle port); eager: the same plain-PyTorch "
+                         "model run eagerly on one B200 through cuBLAS/cuDNN (SURVEY 8(d) second baseline)")
+    ap.add_argument("--eager-batch", type=int, default=64, help="batch of the eager-PyTorch arm (it materialises every "
+                    "(B,h,N,N) map in fp32 and keeps them for autograd: ~1 GB per image for Base)")
     ap.add_argument("--workload", default="base_train", choices=["base_train", "lite_infer", "large_train", "base1ch_dice"],
                     help="base_train is the headline (BASELINE.json metric); the others are extra modes")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (SURVEY 8(d) C3: 64..256; ~40 GB of the 180 GB at 256)")
@@ -378,6 +445,8 @@ def main():
     print_line = lambda text: (out.write(text + "\n"), out.flush())
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager":
+        run_eager(args)
     else:
         run_cuda(args)
 

@@ -5,7 +5,7 @@ Public surface (mirrors ``vit_unet.torch.model`` of the reference):
     l1_loss, mse_loss, dice_loss           fused losses
     set_precision('fp32' | 'tf32')         CUDA-core exact path / tcgen05 tensor-core path
 """
-from .engine import get_precision, set_bf16_maps, set_bf16_probs, set_map_l2_budget, set_precision
+from .engine import get_precision, set_bf16_maps, set_bf16_probs, set_map_l2_budget, set_precision, set_streamed
 from .losses import DiceLoss, L1Loss, MSELoss, dice_loss, l1_loss, mse_loss
 from .model import HViT_UNet, ViT_UNet, get_vit_unet
 from .optim import FusedAdamW

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitunet_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class VuError(RuntimeError):
@@ -56,6 +56,7 @@ SIGNATURES = {
     "vu_reattn_bwd_reduce": [_p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bwd_params": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "vu_reattn_bwd_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _f, _u64, _u32, _p],
+    "vu_reattn_stream_fwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _u64, _u32, _p],
     "vu_ln_stats": [_p, _i, _l, _f, _p, _p, _p],
     "vu_ln_apply": [_p, _p, _p, _p, _p, _i, _l, _p],
     "vu_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p],
@@ -72,6 +73,7 @@ _SPECIAL = {
     "vu_last_error": ([], C.c_char_p),
     "vu_device_sm_count": ([_i], C.c_int),
     "vu_reattn_tensor_core_path": ([_i, _i, _i], C.c_int),
+    "vu_reattn_stream_supported": ([_i, _i, _i], C.c_int),
 }
 
 _lib = None

@@ -38,6 +38,15 @@ _BF16_PROBS = {"value": os.environ.get("VU_BF16_PROBS", "0") == "1"}
 _KEEP_MIXED_MAP = {"value": os.environ.get("VU_KEEP_MIXED_MAP", "1") == "1"}
 
 
+# streamed Re-Attention forward (vu_reattn_stream.cu) on the tensor-core path where the shape is supported: no
+# (B,h,N,N) map is written in inference; in training only the centred bf16 probabilities the backward pass reads
+_STREAMED = {"value": os.environ.get("VU_STREAMED", "1") == "1"}
+
+
+def set_streamed(on: bool) -> None:
+    _STREAMED["value"] = bool(on)
+
+
 def set_bf16_maps(on: bool) -> None:
     _BF16_MAPS["value"] = bool(on)
 
@@ -167,6 +176,11 @@ class Engine:
         c = self._map_chunk(B, h, N, ld)
         keep_P = saved is not None
         bf16 = prec == ops.PREC_TF32 and _BF16_MAPS["value"] and N % 8 == 0
+        # streamed forward: always for inference; with a backward pass to feed only where the materialised backward
+        # kernels accept centred bf16 probabilities (8 heads, bf16 maps)
+        if (prec == ops.PREC_TF32 and _STREAMED["value"] and c >= B and ops.reattn_stream_supported(h, hd, N)
+                and (not keep_P or (bf16 and ops.reattn_tensor_core_path(h, N, ld)))):
+            return self._attn_fwd_streamed(P, pre, xq, xkv, q, k, v, l, B, train, seed, sid, residual, saved)
         # train mode on the tensor-core map path: probabilities are kept as CENTRED bf16 (P - 1/N), scores are a
         # per-slice fp32 scratch -- the saved map and every later pass over it cost half the bytes
         pc16 = bf16 and train and _BF16_PROBS["value"] and ops.reattn_tensor_core_path(h, N, ld)
@@ -243,6 +257,46 @@ class Engine:
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums, seed=seed, sid=sid,
                          adrop=adrop, pdrop=pdrop, train=train, chunk=c, bf16=bf16, A=A)
+        return y
+
+    def _attn_fwd_streamed(self, P, pre, xq, xkv, q, k, v, l, B, train, seed, sid, residual, saved):
+        """softmax -> dropout -> head mixing + BatchNorm -> A.V without the (B,h,N,N) maps (vu_reattn_stream.cu)."""
+        g = self.g
+        N, D, h = g.N(l), g.D(l), g.heads
+        hd = D // h
+        scale = float(hd) ** -0.5
+        adrop = g.attn_drop if train else 0.0
+        keep_P = saved is not None
+        vt = ops.heads_transpose_bf16(v, B, N, D, h)
+        fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
+        sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device) if (train or keep_P) else None
+        O = _empty((B, N, D), xq)
+        Pm = torch.empty((B, h, N, N), dtype=torch.bfloat16, device=xq.device) if keep_P else None
+
+        def finalize():
+            ops.reattn_bn_finalize(sums if train else None, B * N * N, h, N, P[pre + "reatten_matrix.weight"].reshape(h, h),
+                                   P[pre + "reatten_matrix.bias"], P[pre + "var_norm.weight"], P[pre + "var_norm.bias"],
+                                   P[pre + "var_norm.running_mean"], P[pre + "var_norm.running_var"],
+                                   P.get(pre + "var_norm.num_batches_tracked"), 1e-5, 0.1, train, fold, bn_saved)
+        if train or keep_P:
+            rowc = _empty((B, h, N), xq)
+            # keep-bits of the dropout mask: generated (hashed) once by the statistics launch, re-read by the apply launch
+            mask = torch.empty(B * N * N * h // 8, dtype=torch.uint8, device=xq.device) if adrop > 0 else None
+            ops.reattn_stream_fwd(ops.STREAM_STATS, q, k, None, None, None, rowc, sums, Pm, B, h, N, hd, scale, adrop, seed, sid,
+                                  mask=mask)
+            finalize()
+            ops.reattn_stream_fwd(ops.STREAM_APPLY, q, k, vt, O, fold, rowc, None, None, B, h, N, hd, scale, adrop, seed, sid,
+                                  mask=mask)
+        else:
+            finalize()
+            ops.reattn_stream_fwd(ops.STREAM_EVAL, q, k, vt, O, fold, None, None, None, B, h, N, hd, scale)
+        y = _empty((B, N, D), xq)
+        pdrop = g.proj_drop if train else 0.0
+        self._gemm_tokens(O, P[pre + "proj.weight"], y, B * N, D, D, bias=P[pre + "proj.bias"],
+                          residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
+        if saved is not None:
+            saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums if train else None,
+                         seed=seed, sid=sid, adrop=adrop, pdrop=pdrop, train=train, chunk=B, bf16=True, A=None)
         return y
 
     def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):

@@ -274,6 +274,27 @@ def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, sca
           _stream(), nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
+# ----------------------------------------------------------------------------------------- streamed re-attention
+STREAM_EVAL, STREAM_STATS, STREAM_APPLY = 0, 1, 2
+
+
+def reattn_stream_supported(h: int, hd: int, N: int) -> bool:
+    return bool(_lib.load().vu_reattn_stream_supported(h, hd, N))
+
+
+def reattn_stream_fwd(mode, q, k, vt, o, fold, rowc, sums, pc, B, h, N, hd, scale, drop_p=0.0, seed=0, sid=0,
+                      mask=None):
+    """Streamed Re-Attention forward (no (B,h,N,N) map): see include/vit_unet_b200.h vu_reattn_stream_fwd."""
+    ldn = vt.shape[-1] if vt is not None else 0
+    sweeps = {STREAM_EVAL: 2, STREAM_STATS: 2, STREAM_APPLY: 1}[mode]
+    pv = 0 if mode == STREAM_STATS else 1
+    _call("vu_reattn_stream_fwd", mode, _chk(q, "q"), _chk(k, "k"), _opt(vt, "vt", torch.bfloat16), _opt(o, "o"),
+          _opt(fold, "fold"), _opt(rowc, "rowc"), _opt(sums, "sums", torch.float64), _opt(pc, "pc", torch.bfloat16),
+          _opt(mask, "mask", torch.uint8), B, h, N, hd, ldn, scale, drop_p, seed, sid, _stream(),
+          flops=2.0 * B * h * N * N * hd * (sweeps + pv) + (2.0 * h * B * h * N * N if pv else 0.0),
+          nbytes=4.0 * B * N * h * hd * (2 + pv) + 2.0 * B * N * h * hd * pv + (2.0 * B * h * N * N if pc is not None else 0.0))
+
+
 # ----------------------------------------------------------------------------------------- layer norm
 LN_SCRATCH = 2 + 2 * _lib.LN_SPLIT      # floats of scratch per image for ln_stats / ln_bwd
 
