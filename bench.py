@@ -255,6 +255,10 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=dev)
     vu.set_precision(args.precision)
     B = args.batch
+    if args.global_batch:                   # strong scaling (fixed global batch, e.g. 1024 -> 128 per GPU at N=8)
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} must be divisible by the {world} ranks")
+        B = args.global_batch // world
     torch.manual_seed(0)
     wl = WORKLOADS[args.workload]
     kw = dict(BASE_KW, **wl["kw"])
@@ -386,7 +390,8 @@ def run_cuda(args):
     roof["step_tensor_frac"] = roof["step_tflops"] / peaks["tflops"]
 
     line = {"metric": METRIC if args.workload == "base_train" else wl["name"] + " images/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": wl["name"],
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
@@ -427,6 +432,8 @@ def main():
     ap.add_argument("--workload", default="base_train", choices=["base_train", "lite_infer", "large_train", "base1ch_dice"],
                     help="base_train is the headline (BASELINE.json metric); the others are extra modes")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (SURVEY 8(d) C3: 64..256; ~40 GB of the 180 GB at 256)")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed GLOBAL batch split over the ranks "
+                    "(overrides --batch; reported with scaling=strong)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
     ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "tf32"), choices=["fp32", "tf32"],
                     help="tf32: tcgen05 tensor-core contractions (default, the performance mode); fp32: CUDA-core exact mode")

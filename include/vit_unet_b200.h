@@ -150,20 +150,21 @@ int vu_reattn_bwd_rows(const void* P, void* dA_dS, int map_fmt, int B, int h, in
 
 /* ---- streamed Re-Attention (vu_reattn_stream.cu): the same math as the chain softmax -> dropout -> mix/BN -> A.V
  * (model.py:155-161, :251-256) WITHOUT materialising the (B,h,N,N) maps, for the fine levels (many tokens, small
- * heads): (h, hd) in {(8,8), (8,24), (8,32), (4,12), (4,48)}, N % 16 == 0.  q, k: (B,N,h*hd) fp32; vt: per-head
+ * heads): (h, hd) in {(8,8), (8,24), (4,12), (4,48)}, N % 16 == 0.  q, k: (B,N,h*hd) fp32; vt: per-head
  * transposed bf16 values (B,h,hd,ldn) from vu_heads_transpose_bf16; o: (B,N,h*hd) fp32 (pre-projection output).
  * Scores run as TF32 warp MMAs, A.V as bf16 warp MMAs (the tensor-core precision class, VU_PREC_TF32).
  * mode 0: eval forward, one launch (fold = running-statistics affine from vu_reattn_bn_finalize(train=0)).
  * mode 1: train statistics: rowc[b,h,i] = log2-domain softmax constant of every row, sums += centred moments of the
  *         dropped maps (same definition as vu_softmax_stats); pc != NULL also writes the centred bf16 probabilities
  *         (B,h,N,N) consumed by the materialised backward kernels (VU_MAP_P_CENTRED_BF16).
- * mode 2: train apply: o = (fold . dropout(softmax)) v with the row constants of mode 1 and the batch-statistics fold.
+ * mode 2: train apply: o = (fold . dropout(softmax)) v with the row constants of mode 1 and the batch-statistics fold;
+ *         amap != NULL also writes the mixed map A as bf16 (B,h,N,N) for the backward product dV = A^T dO.
  * Dropout masks are those of the materialised kernels, element for element (same counter-hash keying).  mask
  * (optional, B * N * N * h / 8 bytes): mode 1 caches the keep-bits it generated, mode 2 reads them instead of
  * hashing again (the hash is ~40 % of the apply sweep's instructions); NULL = regenerate. */
 int vu_reattn_stream_supported(int h, int hd, int N);
 int vu_reattn_stream_fwd(int mode, const float* q, const float* k, const void* vt, float* o, const float* fold,
-                         float* rowc, double* sums, void* pc, void* mask, int B, int h, int N, int hd, int ldn,
+                         float* rowc, double* sums, void* pc, void* amap, void* mask, int B, int h, int N, int hd, int ldn,
                          float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 
 /* ---------------------------------------------------------------- LayerNorm over (N,D) (model.py:193-196,204,206) */
@@ -181,6 +182,9 @@ enum { VU_LOSS_L1 = 0, VU_LOSS_MSE = 1, VU_LOSS_DICE = 2 };
 /* sums[4] (double, zeroed here): L1 {sum|d|}, MSE {sum d^2}, DICE {sum xy, sum x, sum y}; loss[0] = the scalar */
 int vu_loss_fwd(int kind, const float* pred, const float* target, int64_t n, double* sums, float* loss,
                 void* stream);
+/* loss[0] from sums alone (n = GLOBAL element count): lets data-parallel ranks all-reduce `sums` between the
+ * reduction and the scalar, so soft-Dice stays the reference's whole-batch ratio (README.md:96-101). */
+int vu_loss_finalize(int kind, int64_t n, const double* sums, float* loss, void* stream);
 /* dpred = gscale[0] * dloss/dpred  (gscale: device scalar, the upstream gradient) */
 int vu_loss_bwd(int kind, const float* pred, const float* target, int64_t n, const double* sums,
                 const float* gscale, float* dpred, void* stream);

@@ -474,3 +474,28 @@ def test_psnr_and_input_pipeline(ops):
     img = torch.randint(0, 256, (3, 20, 24, 3), dtype=torch.uint8, generator=g)
     exp = ((img.float() / 255.0 - 0.456) / 0.224).permute(0, 3, 1, 2)
     _close(ops.u8hwc_to_chw(img.cuda(), 1 / 255.0, 0.456, 0.224), exp, rtol=1e-5, name="u8hwc->chw")
+
+
+def test_dice_global_batch_semantics_from_partial_sums(ops):
+    """Data-parallel soft-Dice (README.md:96-101 is a whole-batch ratio): adding the per-shard sums and finalising once
+    equals the Dice of the whole batch, and the shard gradients computed from the GLOBAL sums are the rows of the
+    whole-batch gradient (what losses.dice_loss(group=...) does with a 3-double all-reduce)."""
+    g = torch.Generator().manual_seed(4)
+    pred, tgt = torch.rand(4, 1, 32, 32, generator=g).cuda(), (torch.rand(4, 1, 32, 32, generator=g) > 0.6).float().cuda()
+    full = torch.empty(4, dtype=torch.float64, device="cuda"); lf = torch.empty((), device="cuda")
+    ops.loss_fwd("dice", pred, tgt, full, lf)
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+    for a, b in ((pred[:2].contiguous(), tgt[:2].contiguous()), (pred[2:].contiguous(), tgt[2:].contiguous())):
+        s = torch.empty(4, dtype=torch.float64, device="cuda"); l = torch.empty((), device="cuda")
+        ops.loss_fwd("dice", a, b, s, l)
+        sums += s
+    lg = torch.empty((), device="cuda")
+    ops.loss_finalize("dice", pred.numel(), sums, lg)
+    assert abs(lg.item() - lf.item()) <= 1e-6
+    exp = 1 - (2 * (pred.double() * tgt.double()).sum() + 1) / (pred.double().sum() + tgt.double().sum() + 1)
+    assert abs(lg.item() - exp.item()) <= 1e-6
+    one = torch.ones(1, device="cuda")
+    dfull = torch.empty_like(pred); ops.loss_bwd("dice", pred, tgt, full, one, dfull)
+    dpart = torch.empty(2, 1, 32, 32, device="cuda")
+    ops.loss_bwd("dice", pred[2:].contiguous(), tgt[2:].contiguous(), sums, one, dpart)
+    assert torch.allclose(dpart, dfull[2:], rtol=1e-6, atol=1e-9)

@@ -147,6 +147,17 @@ extern "C" int vu_loss_fwd(int kind, const float* pred, const float* target, int
   return check_launch(fn);
 }
 
+// Second half of vu_loss_fwd on its own: the scalar from (possibly all-reduced) sums.  Data-parallel soft-Dice is a
+// ratio of GLOBAL sums (README.md:96-101 flattens the whole batch), so the ranks add their three sums first.
+extern "C" int vu_loss_finalize(int kind, int64_t n, const double* sums, float* loss, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_loss_finalize";
+  VU_REQUIRE(kind >= VU_LOSS_L1 && kind <= VU_LOSS_DICE, fn, "unknown loss kind");
+  VU_REQUIRE(sums && loss && n > 0, fn, "bad arguments");
+  loss_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(kind, n, sums, loss);
+  return check_launch(fn);
+}
+
 extern "C" int vu_loss_bwd(int kind, const float* pred, const float* target, int64_t n, const double* sums,
                            const float* gscale, float* dpred, void* stream) {
   using namespace vu;

@@ -43,6 +43,7 @@ struct Args {
   float* rowc;                              // (B, H, N) softmax constants c = m + log2 l (written by STATS, read by APPLY)
   double* sums;                             // H + H*H centred moments (STATS)
   __nv_bfloat16* pc;                        // optional (B, H, N, N) centred probabilities P - 1/N for the backward pass
+  __nv_bfloat16* amap;                      // optional (B, H, N, N) mixed map A written by APPLY (backward: dV = A^T dO)
   uint2* mask;                              // dropout keep-bits cached by STATS for APPLY: (B, N/16, N/16, 32 lanes) x 64 bits
   int N, D, ldn;
   float sl2;                                // hd^-1/2 * log2(e)
@@ -418,6 +419,11 @@ stream_fwd_kernel(const Args g) {
           uint32_t af[4];
           af[0] = pack_bf16(a[0][0], a[0][1]); af[1] = pack_bf16(a[0][2], a[0][3]);
           af[2] = pack_bf16(a[1][0], a[1][1]); af[3] = pack_bf16(a[1][2], a[1][3]);
+          if (MODE == MODE_APPLY && g.amap) {      // keys 4tig..4tig+3 of rows gid / gid+8: one 8-byte store each
+            __nv_bfloat16* ap = g.amap + (((size_t)b * H + h) * N + rowa) * N + t * KT + st * 16 + 4 * tig;
+            *reinterpret_cast<uint2*>(ap) = make_uint2(af[0], af[2]);
+            *reinterpret_cast<uint2*>(ap + (size_t)8 * N) = make_uint2(af[1], af[3]);
+          }
 #pragma unroll
           for (int nt = 0; nt < KS; ++nt) {
             const uint2 bv = *reinterpret_cast<const uint2*>(vrow + (h * HD + nt * 8) * VP);
@@ -455,7 +461,7 @@ static int launch_fwd(const Args& a, int B, cudaStream_t st, const char* fn) {
 }
 
 static bool supported(int h, int hd, int N) {
-  const bool shape = (h == 8 && (hd == 8 || hd == 24 || hd == 32)) || (h == 4 && (hd == 12 || hd == 48));
+  const bool shape = (h == 8 && (hd == 8 || hd == 24)) || (h == 4 && (hd == 12 || hd == 48));
   return shape && N % 16 == 0 && N >= 64 && N <= 8192;
 }
 
@@ -465,7 +471,6 @@ static bool supported(int h, int hd, int N) {
 #define VU_RS_DISPATCH(h, hd, CALL)                                                 \
   if (h == 8 && hd == 24) { constexpr int HH = 8, HDD = 24; CALL; }                 \
   else if (h == 8 && hd == 8) { constexpr int HH = 8, HDD = 8; CALL; }              \
-  else if (h == 8 && hd == 32) { constexpr int HH = 8, HDD = 32; CALL; }            \
   else if (h == 4 && hd == 12) { constexpr int HH = 4, HDD = 12; CALL; }            \
   else { constexpr int HH = 4, HDD = 48; CALL; }
 
@@ -476,7 +481,7 @@ extern "C" int vu_reattn_stream_supported(int h, int hd, int N) { return vu::rs:
 //           optionally writes the centred bf16 probabilities pc (B,h,N,N) that the backward pass consumes;
 //       2 = train apply (sweep C) with the fold of the batch statistics and the row constants of mode 1.
 extern "C" int vu_reattn_stream_fwd(int mode, const float* q, const float* k, const void* vt, float* o, const float* fold,
-                                    float* rowc, double* sums, void* pc, void* mask, int B, int h, int N, int hd, int ldn,
+                                    float* rowc, double* sums, void* pc, void* amap, void* mask, int B, int h, int N, int hd, int ldn,
                                     float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_stream_fwd";
@@ -489,10 +494,10 @@ extern "C" int vu_reattn_stream_fwd(int mode, const float* q, const float* k, co
                             "apply needs vt (ldn % 8 == 0), o and fold");
   if (mode != 0) VU_REQUIRE(rowc, fn, "train modes need the row-constant buffer");
   if (mode == 1) VU_REQUIRE(sums && (!pc || (uintptr_t)pc % 8 == 0), fn, "statistics need sums; pc must be 8-byte aligned");
-  VU_REQUIRE((uintptr_t)mask % 8 == 0, fn, "mask must be 8-byte aligned");
+  VU_REQUIRE((uintptr_t)mask % 8 == 0 && (uintptr_t)amap % 8 == 0, fn, "mask / amap must be 8-byte aligned");
   rs::Args a;
   a.q = q; a.k = k; a.vt = (const __nv_bfloat16*)vt; a.o = o; a.fold = fold; a.rowc = rowc; a.sums = sums;
-  a.pc = (__nv_bfloat16*)pc; a.mask = (uint2*)mask; a.N = N; a.D = h * hd; a.ldn = ldn;
+  a.pc = (__nv_bfloat16*)pc; a.amap = (__nv_bfloat16*)amap; a.mask = (uint2*)mask; a.N = N; a.D = h * hd; a.ldn = ldn;
   a.sl2 = scale * 1.4426950408889634f;
   const bool drop = mode != 0 && drop_p > 0.f;
   a.thresh = drop ? drop_threshold(drop_p) : 0u;

@@ -272,6 +272,7 @@ class Engine:
         sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device) if (train or keep_P) else None
         O = _empty((B, N, D), xq)
         Pm = torch.empty((B, h, N, N), dtype=torch.bfloat16, device=xq.device) if keep_P else None
+        A = None
 
         def finalize():
             ops.reattn_bn_finalize(sums if train else None, B * N * N, h, N, P[pre + "reatten_matrix.weight"].reshape(h, h),
@@ -285,8 +286,11 @@ class Engine:
             ops.reattn_stream_fwd(ops.STREAM_STATS, q, k, None, None, None, rowc, sums, Pm, B, h, N, hd, scale, adrop, seed, sid,
                                   mask=mask)
             finalize()
+            # the mixed map is kept (bf16) for the backward product dV = A^T dO: one write here instead of a recompute there
+            A = (torch.empty((B, h, N, N), dtype=torch.bfloat16, device=xq.device)
+                 if (keep_P and _KEEP_MIXED_MAP["value"]) else None)
             ops.reattn_stream_fwd(ops.STREAM_APPLY, q, k, vt, O, fold, rowc, None, None, B, h, N, hd, scale, adrop, seed, sid,
-                                  mask=mask)
+                                  mask=mask, amap=A)
         else:
             finalize()
             ops.reattn_stream_fwd(ops.STREAM_EVAL, q, k, vt, O, fold, None, None, None, B, h, N, hd, scale)
@@ -296,7 +300,7 @@ class Engine:
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums if train else None,
-                         seed=seed, sid=sid, adrop=adrop, pdrop=pdrop, train=train, chunk=B, bf16=True, A=None)
+                         seed=seed, sid=sid, adrop=adrop, pdrop=pdrop, train=train, chunk=B, bf16=True, A=A)
         return y
 
     def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):

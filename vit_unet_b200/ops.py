@@ -283,16 +283,16 @@ def reattn_stream_supported(h: int, hd: int, N: int) -> bool:
 
 
 def reattn_stream_fwd(mode, q, k, vt, o, fold, rowc, sums, pc, B, h, N, hd, scale, drop_p=0.0, seed=0, sid=0,
-                      mask=None):
+                      mask=None, amap=None):
     """Streamed Re-Attention forward (no (B,h,N,N) map): see include/vit_unet_b200.h vu_reattn_stream_fwd."""
     ldn = vt.shape[-1] if vt is not None else 0
     sweeps = {STREAM_EVAL: 2, STREAM_STATS: 2, STREAM_APPLY: 1}[mode]
     pv = 0 if mode == STREAM_STATS else 1
     _call("vu_reattn_stream_fwd", mode, _chk(q, "q"), _chk(k, "k"), _opt(vt, "vt", torch.bfloat16), _opt(o, "o"),
           _opt(fold, "fold"), _opt(rowc, "rowc"), _opt(sums, "sums", torch.float64), _opt(pc, "pc", torch.bfloat16),
-          _opt(mask, "mask", torch.uint8), B, h, N, hd, ldn, scale, drop_p, seed, sid, _stream(),
+          _opt(amap, "amap", torch.bfloat16), _opt(mask, "mask", torch.uint8), B, h, N, hd, ldn, scale, drop_p, seed, sid, _stream(),
           flops=2.0 * B * h * N * N * hd * (sweeps + pv) + (2.0 * h * B * h * N * N if pv else 0.0),
-          nbytes=4.0 * B * N * h * hd * (2 + pv) + 2.0 * B * N * h * hd * pv + (2.0 * B * h * N * N if pc is not None else 0.0))
+          nbytes=4.0 * B * N * h * hd * (2 + pv) + 2.0 * B * N * h * hd * pv + (2.0 * B * h * N * N if pc is not None else 0.0) + (2.0 * B * h * N * N if amap is not None else 0.0))
 
 
 # ----------------------------------------------------------------------------------------- layer norm
@@ -320,6 +320,10 @@ def ln_bwd(g, x, stats, w, dx, dw, db, scratch, B, n):
 def loss_fwd(kind, pred, target, sums, loss):
     _call("vu_loss_fwd", LOSS_KINDS[kind], _chk(pred, "pred"), _chk(target, "target"), pred.numel(),
           _chk(sums, "sums", torch.float64), _chk(loss, "loss"), _stream(), nbytes=8.0 * pred.numel())
+
+
+def loss_finalize(kind, n, sums, loss):
+    _call("vu_loss_finalize", LOSS_KINDS[kind], n, _chk(sums, "sums", torch.float64), _chk(loss, "loss"), _stream())
 
 
 def loss_bwd(kind, pred, target, sums, gscale, dpred):
