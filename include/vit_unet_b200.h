@@ -167,6 +167,18 @@ int vu_reattn_stream_fwd(int mode, const float* q, const float* k, const void* v
                          float* rowc, double* sums, void* pc, void* amap, void* mask, int B, int h, int N, int hd, int ldn,
                          float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 
+/* streamed backward: pc = centred bf16 probabilities (B,h,N,N) written by vu_reattn_stream_fwd mode 1, mask = its
+ * cached keep-bits (or NULL: re-hash), dO / v: (B,N,h*hd) fp32.  dA = dO v^T is formed on the fly, never stored.
+ * _bwd_reduce: red[h + h*h] (double, caller zeroes) += { sum dA_h, sum dA_h (Pd_g - 1/N) }  (as vu_reattn_mix_reduce).
+ * _bwd_ds: dS (bf16 (B,h,N,N), the gradient of the pre-softmax scores: softmax / dropout / mixing / BatchNorm
+ * backward, as dA -> vu_reattn_bwd_rows) and dq = dS k (B,N,h*hd) with kt = per-head transposed bf16 keys. */
+int vu_reattn_stream_bwd_reduce(const void* pc, const void* mask, const float* dO, const float* v, double* red,
+                                int B, int h, int N, int hd, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
+int vu_reattn_stream_bwd_ds(const void* pc, const void* mask, const float* dO, const float* v, const void* kt, void* ds,
+                            float* dq, const float* W, const float* bconv, const float* gamma, const float* saved,
+                            const float* coef, int train, int B, int h, int N, int hd, int ldn, float drop_p,
+                            uint64_t seed, uint32_t stream_id, void* stream);
+
 /* ---------------------------------------------------------------- LayerNorm over (N,D) (model.py:193-196,204,206) */
 #define VU_LN_SPLIT 8      /* CTAs cooperating on one image's statistics */
 /* stats[b] = {mean, rstd} over the n = N*D elements of image b; scratch: 2*VU_LN_SPLIT*B floats */

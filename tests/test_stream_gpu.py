@@ -138,3 +138,70 @@ def test_stream_refuses_unsupported_shapes(ops):
     with pytest.raises(VuError):
         ops.reattn_stream_fwd(ops.STREAM_EVAL, q, q, torch.zeros(1, 8, 24, 104, dtype=torch.bfloat16, device="cuda"),
                               torch.zeros_like(q), torch.zeros(72, device="cuda"), None, None, None, 1, 8, 100, 24, 0.2)
+
+
+# ------------------------------------------------------------------------------------------------ streamed backward
+def _bn_params(h, seed):
+    W = _rand(h, h, seed=seed + 1) / h ** 0.5
+    bconv = _rand(h, seed=seed + 2) * 0.05
+    gamma = 1.0 + 0.3 * _rand(h, seed=seed + 3)
+    beta = 0.002 * _rand(h, seed=seed + 4)
+    rmean = 0.01 * _rand(h, seed=seed + 5) + 1.0 / 784
+    rvar = (1e-6 * (1.0 + 0.25 * _rand(h, seed=seed + 6))).abs()
+    return [t.contiguous() for t in (W, bconv, gamma, beta, rmean, rvar)]
+
+
+@pytest.mark.parametrize("train", [True, False])
+@pytest.mark.parametrize("p", [0.0, 0.25])
+@pytest.mark.parametrize("h,hd,N", [(8, 24, 784), (8, 24, 128), (4, 12, 336)])
+def test_stream_backward_matches_materialised_chain(ops, h, hd, N, p, train):
+    """vu_reattn_stream_bwd_reduce / _bwd_ds against the exact fp32 materialised kernels (scores -> softmax_stats ->
+    bn_finalize -> dA = dO v^T -> bwd_reduce -> bwd_params -> bwd_rows -> dq = dS k) on the same inputs and dropout seed."""
+    if p > 0 and not train:
+        pytest.skip("dropout is a train-mode feature")
+    B, seed, sid = 2, 99, 3
+    D, scale = h * hd, hd ** -0.5
+    q, k, v, _ = _inputs(B, h, hd, N, seed=30)
+    dO = _rand(B, N, D, seed=40)
+    W, bconv, gamma, beta, rmean, rvar = _bn_params(h, 50)
+    # ---- materialised reference chain (fp32 kernels)
+    S = torch.empty(B, h, N, N, device="cuda")
+    ops.gemm(q, k, S, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=N, batch_outer=B, batch_inner=h, sA=(N * D, hd),
+             sB=(N * D, hd), sC=(h * N * N, N * N), precision=ops.PREC_FP32)
+    sums_m = torch.zeros(h + h * h, dtype=torch.float64, device="cuda")
+    ops.softmax_stats(S, B, h, N, N, scale, p, seed, sid, sums_m, precision=ops.PREC_FP32)       # S -> P
+    fold_m, bn_m = torch.empty(h * h + h, device="cuda"), torch.empty(2 * h, device="cuda")
+    ops.reattn_bn_finalize(sums_m if train else None, B * N * N, h, N, W, bconv, gamma, beta, rmean.clone(), rvar.clone(),
+                           None, 1e-5, 0.1, train, fold_m, bn_m)
+    dA = torch.empty(B, h, N, N, device="cuda")
+    ops.gemm(dO, v, dA, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=N, batch_outer=B, batch_inner=h, sA=(N * D, hd),
+             sB=(N * D, hd), sC=(h * N * N, N * N), precision=ops.PREC_FP32)
+    red_m = torch.zeros(h + h * h, dtype=torch.float64, device="cuda")
+    ops.reattn_bwd_reduce(S, dA, B, h, N, N, p, seed, sid, red_m)
+    coef_m = torch.empty(2 * h, device="cuda")
+    dW, db, dg, dbt = (torch.zeros(h * h, device="cuda"), torch.zeros(h, device="cuda"), torch.zeros(h, device="cuda"),
+                       torch.zeros(h, device="cuda"))
+    ops.reattn_bwd_params(red_m, sums_m if train else None, B, h, N, W, bconv, gamma, bn_m, train, coef_m, dW, db, dg, dbt)
+    ops.reattn_bwd_rows(S, dA, B, h, N, N, W, bconv, gamma, bn_m, coef_m, train, scale, p, seed, sid)     # dA -> dS in place
+    dq_m = torch.einsum("bhij,bhje->bihe", dA.double(), _heads(k, h)).reshape(B, N, D)
+    # ---- streamed chain
+    rowc = torch.empty(B, h, N, device="cuda")
+    sums = torch.zeros_like(sums_m)
+    pc = torch.empty(B, h, N, N, dtype=torch.bfloat16, device="cuda")
+    mask = torch.zeros(B * N * N * h // 8, dtype=torch.uint8, device="cuda") if p > 0 else None
+    ops.reattn_stream_fwd(ops.STREAM_STATS, q, k, None, None, None, rowc, sums, pc, B, h, N, hd, scale, p, seed, sid, mask=mask)
+    red = torch.zeros_like(red_m)
+    ops.reattn_stream_bwd_reduce(pc, mask, dO, v, red, B, h, N, hd, p, seed, sid)
+    _close(red[:h], red_m[:h], 5e-3, "s1")
+    _close(red[h:], red_m[h:], 2e-2, "X'")
+    kt = ops.heads_transpose_bf16(k, B, N, D, h)
+    dS = torch.empty(B, h, N, N, dtype=torch.bfloat16, device="cuda")
+    dq = torch.empty(B, N, D, device="cuda")
+    # same coefficients on both sides: this compares the kernels, not the amplification of the reductions' rounding
+    ops.reattn_stream_bwd_ds(pc, mask, dO, v, kt, dS, dq, W, bconv, gamma, bn_m, coef_m, train, B, h, N, hd, p, seed, sid)
+    _close(dS.float(), dA, 2e-2, "dS")
+    _close(dq, dq_m, 2e-2, "dq")
+    if p > 0:      # re-hashing instead of the cached keep-bits gives the same gradients
+        dS2, dq2 = torch.empty_like(dS), torch.empty_like(dq)
+        ops.reattn_stream_bwd_ds(pc, None, dO, v, kt, dS2, dq2, W, bconv, gamma, bn_m, coef_m, train, B, h, N, hd, p, seed, sid)
+        assert torch.equal(dS2, dS) and torch.equal(dq2, dq)

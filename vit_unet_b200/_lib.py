@@ -57,6 +57,8 @@ SIGNATURES = {
     "vu_reattn_bwd_params": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "vu_reattn_bwd_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _f, _u64, _u32, _p],
     "vu_reattn_stream_fwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _u64, _u32, _p],
+    "vu_reattn_stream_bwd_reduce": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p],
+    "vu_reattn_stream_bwd_ds": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _u32, _p],
     "vu_ln_stats": [_p, _i, _l, _f, _p, _p, _p],
     "vu_ln_apply": [_p, _p, _p, _p, _p, _i, _l, _p],
     "vu_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p],

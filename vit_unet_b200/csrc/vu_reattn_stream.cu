@@ -460,6 +460,416 @@ static int launch_fwd(const Args& a, int B, cudaStream_t st, const char* fn) {
   return check_launch(fn);
 }
 
+// ======================================================================================= backward (streamed)
+// The backward pass reads the centred bf16 probabilities Pc = P - 1/N that the statistics launch wrote (2 bytes per
+// map element, no Q / K tiles and no exp needed) and recomputes everything else on the fly:
+//   stream_bwd_reduce_kernel   dA = dO v^T (TF32 MMAs, never stored);  red[h] += sum dA_h;  red[H + h H + g] += sum dA_h (Pd_g - 1/N)
+//                              -> vu_reattn_bwd_params: BatchNorm-backward means + all parameter gradients of the mixing stage
+//   stream_bwd_ds_kernel       sweep 1: dA again, dM_h = k_h (dA_h - m1_h - Mhat_h m2_h), dPd_g = sum_h W_hg dM_h,
+//                              dP_g = keep dPd_g / (1-p) -> bf16 into the dS buffer, delta_g = sum_j dP_g P_g per row;
+//                              sweep 2: dS_g = scale P_g (dP_g - delta_g) -> bf16 map (dK = dS^T q runs as a tcgen05 GEMM)
+//                              and dq += dS k on the tensor cores (dS fragments are the MMA A operand, k^T tiles in smem).
+// Same CTA shape and key permutation as the forward kernel (a lane owns 4 consecutive keys of two rows, all heads).
+struct BwdArgs {
+  const __nv_bfloat16* pc;                  // (B, H, N, N) centred probabilities
+  const uint2* mask;                        // keep-bits cached by the forward statistics launch (NULL: re-hash)
+  const float* dO; const float* v;          // (B, N, D) fp32
+  const __nv_bfloat16* kt;                  // (B, H, hd, ldn) bf16 transposed keys (ds kernel)
+  __nv_bfloat16* ds;                        // (B, H, N, N) bf16: dP after sweep 1, dS after sweep 2
+  float* dq;                                // (B, N, D)
+  double* red;                              // H + H*H (reduce kernel)
+  const float* W; const float* bconv; const float* gamma; const float* saved; const float* coef;   // ds kernel
+  int N, D, ldn, train;
+  float scale;                              // hd^-1/2
+  uint32_t thresh; float dscale; uint32_t key; float cN;
+};
+
+// keep-bits of this lane's (2 rows x H heads x 4 keys) for one 16-key step: cached, or regenerated with the same hash
+template <int H>
+__device__ __forceinline__ uint2 step_keep_bits(const BwdArgs& g, int b, int rowa, int lane, int step, uint32_t ctr_r0,
+                                                uint32_t ctr_r1, uint32_t nn4) {
+  if (!g.thresh) return make_uint2(0xffffffffu, 0xffffffffu);
+  if (g.mask) return __ldg(g.mask + (((size_t)b * (g.N >> 4) + (rowa >> 4)) * (g.N >> 4) + step) * 32 + lane);
+  uint32_t bits[2] = {0u, 0u};
+  const uint32_t j4 = (uint32_t)(step * 4);
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint4 rr = Philox::gen_k(g.key, (r ? ctr_r1 : ctr_r0) + (uint32_t)h * nn4 + j4);
+      bits[r] |= ((uint32_t)(rr.x >= g.thresh) | ((uint32_t)(rr.y >= g.thresh) << 1) | ((uint32_t)(rr.z >= g.thresh) << 2) |
+                  ((uint32_t)(rr.w >= g.thresh) << 3)) << (4 * h);
+    }
+  return make_uint2(bits[0], bits[1]);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <int H, int HD>
+struct BwdPlan {
+  static constexpr int D = H * HD, QP = D + 4, KS = (HD + 7) / 8;
+  static constexpr size_t do_bytes = (size_t)WARPS * 16 * QP * 4;
+  static constexpr size_t v_bytes = (size_t)KT * QP * 4;           // one stage of fp32 value rows (B operand of dA = dO v^T)
+  static constexpr size_t kt_bytes = (size_t)(D + 8) * VP;         // one stage of bf16 k^T rows (B operand of dq += dS k)
+  static constexpr size_t reduce_total = do_bytes + 2 * v_bytes + 16;
+  static constexpr size_t ds_total = do_bytes + 2 * (v_bytes > kt_bytes ? v_bytes : kt_bytes) + (size_t)(3 * H * H + 4 * H) * 4 + 16;
+};
+
+template <int H, int HD>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+stream_bwd_reduce_kernel(const BwdArgs g) {
+  using P = BwdPlan<H, HD>;
+  constexpr int D = P::D, QP = P::QP;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* Gs = reinterpret_cast<float*>(smem);                 // resident dO rows of the CTA
+  float* Vs = Gs + WARPS * 16 * QP;                           // 2 stages of value rows
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int N = g.N, b = blockIdx.y, row0 = blockIdx.x * (WARPS * 16);
+  const float* __restrict__ gb = g.dO + (size_t)b * N * D;
+  const float* __restrict__ vb = g.v + (size_t)b * N * D;
+  const int ntiles = (N + KT - 1) / KT;
+  auto load_v = [&](int tile, int stage) {
+    float* dst = Vs + stage * KT * QP;
+    const int key0 = tile * KT;
+    for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
+      const int kr = c / (D / 4), q4 = c - kr * (D / 4);
+      const bool ok = key0 + kr < N;
+      cp_async16(dst + kr * QP + 4 * q4, ok ? vb + (size_t)(key0 + kr) * D + 4 * q4 : vb, ok);
+    }
+  };
+  for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
+    const int r = c / (D / 4), q4 = c - r * (D / 4);
+    const bool ok = row0 + r < N;
+    cp_async16(Gs + r * QP + 4 * q4, ok ? gb + (size_t)(row0 + r) * D + 4 * q4 : gb, ok);
+  }
+  load_v(0, 0);
+  cp_async_commit();
+  for (int r = tid; r < WARPS * 16; r += WARPS * 32) *reinterpret_cast<float4*>(Gs + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = tid; r < 2 * KT; r += WARPS * 32) *reinterpret_cast<float4*>(Vs + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const bool active = row0 + warp * 16 < N;
+  const float* Gw = Gs + warp * 16 * QP;
+  const int rowa = row0 + warp * 16 + gid;
+  const uint32_t nn4 = (uint32_t)(((size_t)N * N) >> 2);
+  const uint32_t ctr_r0 = (uint32_t)((((size_t)b * H * N + rowa) * N) >> 2) + tig;
+  const uint32_t ctr_r1 = ctr_r0 + 8u * (uint32_t)(N >> 2);
+  const float keep_off = g.cN * g.dscale - g.cN;              // kept: (pc + cN) dscale - cN = pc dscale + keep_off; dropped: -cN
+  float x[H][H], s1[H];                                       // x[h][g] = sum dA_h (Pd_g - cN)
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    s1[h] = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < H; ++gg) x[h][gg] = 0.f;
+  }
+  for (int t = 0; t < ntiles; ++t) {
+    cp_async_wait<0>();
+    __syncthreads();
+    if (t + 1 < ntiles) { load_v(t + 1, (t + 1) & 1); cp_async_commit(); }
+    if (!active) continue;
+    const float* Vst = Vs + (t & 1) * KT * QP;
+    const int steps = min(KT / 16, (N - t * KT) / 16);
+    for (int st = 0; st < steps; ++st) {
+      const int step = t * (KT / 16) + st;
+      uint2 pw[H][2];                                         // centred probabilities of (head, row): 4 keys as 4 bf16
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          pw[h][r] = __ldg(reinterpret_cast<const uint2*>(g.pc + (((size_t)b * H + h) * N + rowa + 8 * r) * N + step * 16 + 4 * tig));
+      const uint2 bits = step_keep_bits<H>(g, b, rowa, lane, step, ctr_r0, ctr_r1, nn4);
+      float dA[H][2][4];
+      scores_step<H, HD>(dA, Gw, Vst + st * 16 * QP, lane);
+      // positions e of a lane: (u, c) -> row (c >> 1), key 4 tig + 2 u + (c & 1); pdc[g][u][c] in the same order as dA
+#pragma unroll
+      for (int gg = 0; gg < H; ++gg) {
+        float pdc[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t w = (r ? bits.y : bits.x) >> (4 * gg);
+          const float c0 = bf16_lo(pw[gg][r].x), c1 = bf16_hi(pw[gg][r].x), c2 = bf16_lo(pw[gg][r].y), c3 = bf16_hi(pw[gg][r].y);
+          pdc[0][2 * r] = (w & 1u) ? fmaf(c0, g.dscale, keep_off) : -g.cN;
+          pdc[0][2 * r + 1] = (w & 2u) ? fmaf(c1, g.dscale, keep_off) : -g.cN;
+          pdc[1][2 * r] = (w & 4u) ? fmaf(c2, g.dscale, keep_off) : -g.cN;
+          pdc[1][2 * r + 1] = (w & 8u) ? fmaf(c3, g.dscale, keep_off) : -g.cN;
+        }
+#pragma unroll
+        for (int h = 0; h < H; h += 2)
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ffma2(x[h][gg], x[h + 1][gg], dA[h][u][e], dA[h + 1][u][e], pdc[u][e]);
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) s1[h] += (dA[h][u][0] + dA[h][u][1]) + (dA[h][u][2] + dA[h][u][3]);
+    }
+  }
+  __syncthreads();
+  constexpr int NV = H + H * H;
+  double* red = reinterpret_cast<double*>(smem);
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    const float v = warp_sum(s1[h]);
+    if (lane == 0) red[h * WARPS + warp] = (double)v;
+#pragma unroll
+    for (int gg = 0; gg < H; ++gg) {
+      const float w = warp_sum(x[h][gg]);
+      if (lane == 0) red[(H + h * H + gg) * WARPS + warp] = (double)w;
+    }
+  }
+  __syncthreads();
+  if (tid < NV) {
+    double v = 0.0;
+    for (int w = 0; w < WARPS; ++w) v += red[tid * WARPS + w];
+    atomicAdd(g.red + tid, v);
+  }
+}
+
+template <int H, int HD, bool TRAIN>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+stream_bwd_ds_kernel(const BwdArgs g) {
+  using P = BwdPlan<H, HD>;
+  constexpr int D = P::D, QP = P::QP, KS = P::KS;
+  constexpr size_t stage_bytes = P::v_bytes > P::kt_bytes ? P::v_bytes : P::kt_bytes;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* Gs = reinterpret_cast<float*>(smem);
+  unsigned char* St = reinterpret_cast<unsigned char*>(Gs + WARPS * 16 * QP);       // 2 stages: fp32 value rows (sweep 1) / bf16 k^T rows (sweep 2)
+  float* We = reinterpret_cast<float*>(St + 2 * stage_bytes);   // e[h][g] (H*H), Wb[g][h] (H*H, mix-back, transposed), kh[H], c0[H]
+  float* Wb = We + H * H;
+  float* Kh = Wb + H * H;
+  float* C0 = Kh + H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int N = g.N, b = blockIdx.y, row0 = blockIdx.x * (WARPS * 16);
+  const float* __restrict__ gb = g.dO + (size_t)b * N * D;
+  const float* __restrict__ vb = g.v + (size_t)b * N * D;
+  const __nv_bfloat16* __restrict__ ktb = g.kt + (size_t)b * D * g.ldn;
+  const int ntiles = (N + KT - 1) / KT;
+  auto load_v = [&](int tile, int stage) {
+    float* dst = reinterpret_cast<float*>(St + stage * stage_bytes);
+    const int key0 = tile * KT;
+    for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
+      const int kr = c / (D / 4), q4 = c - kr * (D / 4);
+      const bool ok = key0 + kr < N;
+      cp_async16(dst + kr * QP + 4 * q4, ok ? vb + (size_t)(key0 + kr) * D + 4 * q4 : vb, ok);
+    }
+  };
+  auto load_kt = [&](int tile, int stage) {
+    unsigned char* dst = St + stage * stage_bytes;
+    const int key0 = tile * KT;
+    for (int c = tid; c < D * (KT / 8); c += WARPS * 32) {
+      const int row = c / (KT / 8), q8 = c - row * (KT / 8);
+      const bool ok = key0 + 8 * q8 < N;
+      cp_async16(dst + row * VP + 16 * q8, ok ? (const void*)(ktb + (size_t)row * g.ldn + key0 + 8 * q8) : (const void*)ktb, ok);
+    }
+  };
+  for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
+    const int r = c / (D / 4), q4 = c - r * (D / 4);
+    const bool ok = row0 + r < N;
+    cp_async16(Gs + r * QP + 4 * q4, ok ? gb + (size_t)(row0 + r) * D + 4 * q4 : gb, ok);
+  }
+  load_v(0, 0);
+  cp_async_commit();
+  for (int r = tid; r < WARPS * 16; r += WARPS * 32) *reinterpret_cast<float4*>(Gs + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
+  // folded coefficients (one thread per (h, g)):
+  //   dM_h = kh_h dA_h + c0_h + sum_g e_hg pk_g          pk_g = keep ? p_g : 0
+  //   kh = gamma invstd; e_hg = -kh m2 invstd W_hg dscale; c0_h = -kh (m1 + m2 invstd (b_h - mean_h))     (train)
+  //   x_g = sum_h Wb[g][h] dM_h = dPd_g / (1-p),  Wb[g][h] = W[h][g] dscale
+  for (int i = tid; i < H * H; i += WARPS * 32) {
+    const int h = i / H, gg = i - h * H;
+    const float invstd = g.saved[H + h], kh = g.gamma[h] * invstd;
+    const float m2 = TRAIN ? g.coef[H + h] : 0.f;
+    We[h * H + gg] = -kh * m2 * invstd * g.W[h * H + gg] * g.dscale;
+    Wb[gg * H + h] = g.W[h * H + gg] * g.dscale;
+    if (gg == 0) {
+      Kh[h] = kh;
+      C0[h] = TRAIN ? -kh * (g.coef[h] + m2 * invstd * (g.bconv[h] - g.saved[h])) : 0.f;
+    }
+  }
+  const bool active = row0 + warp * 16 < N;
+  const float* Gw = Gs + warp * 16 * QP;
+  const int rowa = row0 + warp * 16 + gid;
+  const uint32_t nn4 = (uint32_t)(((size_t)N * N) >> 2);
+  const uint32_t ctr_r0 = (uint32_t)((((size_t)b * H * N + rowa) * N) >> 2) + tig;
+  const uint32_t ctr_r1 = ctr_r0 + 8u * (uint32_t)(N >> 2);
+  float delta[H][2];
+#pragma unroll
+  for (int h = 0; h < H; ++h) { delta[h][0] = 0.f; delta[h][1] = 0.f; }
+
+  // ---------------------------------------------------------------- sweep 1: dP (bf16 -> ds buffer) and the row dots
+  for (int t = 0; t < ntiles; ++t) {
+    cp_async_wait<0>();
+    __syncthreads();
+    // the first k^T tile of sweep 2 is prefetched behind the last value tile
+    if (t + 1 < ntiles) load_v(t + 1, (t + 1) & 1); else load_kt(0, (t + 1) & 1);
+    cp_async_commit();
+    if (!active) continue;
+    const float* Vst = reinterpret_cast<const float*>(St + (t & 1) * stage_bytes);
+    const int steps = min(KT / 16, (N - t * KT) / 16);
+    for (int st = 0; st < steps; ++st) {
+      const int step = t * (KT / 16) + st;
+      uint2 pw[H][2];
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          pw[h][r] = __ldg(reinterpret_cast<const uint2*>(g.pc + (((size_t)b * H + h) * N + rowa + 8 * r) * N + step * 16 + 4 * tig));
+      const uint2 bits = step_keep_bits<H>(g, b, rowa, lane, step, ctr_r0, ctr_r1, nn4);
+      float dM[H][2][4];
+      scores_step<H, HD>(dM, Gw, Vst + st * 16 * QP, lane);           // dA
+      float pk[H][2][4];                                              // keep ? p : 0
+#pragma unroll
+      for (int gg = 0; gg < H; ++gg)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t w = (r ? bits.y : bits.x) >> (4 * gg);
+          pk[gg][0][2 * r] = (w & 1u) ? bf16_lo(pw[gg][r].x) + g.cN : 0.f;
+          pk[gg][0][2 * r + 1] = (w & 2u) ? bf16_hi(pw[gg][r].x) + g.cN : 0.f;
+          pk[gg][1][2 * r] = (w & 4u) ? bf16_lo(pw[gg][r].y) + g.cN : 0.f;
+          pk[gg][1][2 * r + 1] = (w & 8u) ? bf16_hi(pw[gg][r].y) + g.cN : 0.f;
+        }
+      // dM_h = kh dA_h + c0_h + sum_g e_hg pk_g   (in place over dA)
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float kh = Kh[h], c0 = C0[h];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dM[h][u][e] = fmaf(kh, dM[h][u][e], c0);
+        if (TRAIN) {
+#pragma unroll
+          for (int q4 = 0; q4 < H / 4; ++q4) {
+            const float4 w = *reinterpret_cast<const float4*>(We + h * H + 4 * q4);
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                ffma2(dM[h][u][0], dM[h][u][1], pk[4 * q4 + gi][u][0], pk[4 * q4 + gi][u][1], wv[gi]);
+                ffma2(dM[h][u][2], dM[h][u][3], pk[4 * q4 + gi][u][2], pk[4 * q4 + gi][u][3], wv[gi]);
+              }
+          }
+        }
+      }
+      // x_g = sum_h Wb[g][h] dM_h;  dP_g = keep ? x_g : 0 (bf16 -> ds);  delta_g += x_g pk_g
+#pragma unroll
+      for (int gg = 0; gg < H; ++gg) {
+        float xg[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { xg[u][0] = 0.f; xg[u][1] = 0.f; xg[u][2] = 0.f; xg[u][3] = 0.f; }
+#pragma unroll
+        for (int q4 = 0; q4 < H / 4; ++q4) {
+          const float4 w = *reinterpret_cast<const float4*>(Wb + gg * H + 4 * q4);
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int hi = 0; hi < 4; ++hi)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              ffma2(xg[u][0], xg[u][1], dM[4 * q4 + hi][u][0], dM[4 * q4 + hi][u][1], wv[hi]);
+              ffma2(xg[u][2], xg[u][3], dM[4 * q4 + hi][u][2], dM[4 * q4 + hi][u][3], wv[hi]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t w = (r ? bits.y : bits.x) >> (4 * gg);
+          delta[gg][r] = fmaf(xg[0][2 * r], pk[gg][0][2 * r], delta[gg][r]);
+          delta[gg][r] = fmaf(xg[0][2 * r + 1], pk[gg][0][2 * r + 1], delta[gg][r]);
+          delta[gg][r] = fmaf(xg[1][2 * r], pk[gg][1][2 * r], delta[gg][r]);
+          delta[gg][r] = fmaf(xg[1][2 * r + 1], pk[gg][1][2 * r + 1], delta[gg][r]);
+          uint2 o;
+          o.x = pack_bf16((w & 1u) ? xg[0][2 * r] : 0.f, (w & 2u) ? xg[0][2 * r + 1] : 0.f);
+          o.y = pack_bf16((w & 4u) ? xg[1][2 * r] : 0.f, (w & 8u) ? xg[1][2 * r + 1] : 0.f);
+          *reinterpret_cast<uint2*>(g.ds + (((size_t)b * H + gg) * N + rowa + 8 * r) * N + step * 16 + 4 * tig) = o;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float d = delta[h][r];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      delta[h][r] = d;
+    }
+
+  // ---------------------------------------------------------------- sweep 2: dS = scale P (dP - delta) -> map, dq += dS k
+  float dq[H][KS][4];
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int nt = 0; nt < KS; ++nt) { dq[h][nt][0] = 0.f; dq[h][nt][1] = 0.f; dq[h][nt][2] = 0.f; dq[h][nt][3] = 0.f; }
+  for (int t = 0; t < ntiles; ++t) {
+    const int item = ntiles + t;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (t + 1 < ntiles) { load_kt(t + 1, (item + 1) & 1); cp_async_commit(); }
+    if (!active) continue;
+    const unsigned char* Kst = St + (item & 1) * stage_bytes;
+    const int steps = min(KT / 16, (N - t * KT) / 16);
+    for (int st = 0; st < steps; ++st) {
+      const int step = t * (KT / 16) + st;
+      const unsigned char* krow = Kst + gid * VP + st * 32 + tig * 8;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        uint32_t af[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const size_t off = (((size_t)b * H + h) * N + rowa + 8 * r) * N + step * 16 + 4 * tig;
+          const uint2 pw = __ldg(reinterpret_cast<const uint2*>(g.pc + off));
+          const uint2 dw = *reinterpret_cast<const uint2*>(g.ds + off);          // written by this very lane in sweep 1
+          const float d = delta[h][r];
+          const float s0 = g.scale * (bf16_lo(pw.x) + g.cN) * (bf16_lo(dw.x) - d), s1 = g.scale * (bf16_hi(pw.x) + g.cN) * (bf16_hi(dw.x) - d);
+          const float s2 = g.scale * (bf16_lo(pw.y) + g.cN) * (bf16_lo(dw.y) - d), s3 = g.scale * (bf16_hi(pw.y) + g.cN) * (bf16_hi(dw.y) - d);
+          const uint32_t lo = pack_bf16(s0, s1), hi = pack_bf16(s2, s3);
+          *reinterpret_cast<uint2*>(g.ds + off) = make_uint2(lo, hi);
+          af[r] = lo; af[2 + r] = hi;            // reg0/1: keys 4tig, +1 of rows gid / gid+8; reg2/3: keys 4tig+2, +3
+        }
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt) {
+          const uint2 bv = *reinterpret_cast<const uint2*>(krow + (h * HD + nt * 8) * VP);
+          mma_bf16(dq[h][nt], af, bv.x, bv.y);
+        }
+      }
+    }
+  }
+  if (active) {
+    float* ob = g.dq + ((size_t)b * N + rowa) * D;
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int nt = 0; nt < KS; ++nt) {
+        const int e = nt * 8 + 2 * tig;
+        if (e < HD) {
+          *reinterpret_cast<float2*>(ob + h * HD + e) = make_float2(dq[h][nt][0], dq[h][nt][1]);
+          *reinterpret_cast<float2*>(ob + (size_t)8 * D + h * HD + e) = make_float2(dq[h][nt][2], dq[h][nt][3]);
+        }
+      }
+  }
+}
+
+template <int H, int HD>
+static int launch_bwd_reduce(const BwdArgs& a, int B, cudaStream_t st, const char* fn) {
+  const size_t smem = BwdPlan<H, HD>::reduce_total;
+  static uint64_t seen = 0;
+  if (first_use_on_device(seen))
+    cudaFuncSetAttribute(stream_bwd_reduce_kernel<H, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const dim3 grid((unsigned)cdiv(a.N, WARPS * 16), (unsigned)B);
+  stream_bwd_reduce_kernel<H, HD><<<grid, WARPS * 32, smem, st>>>(a);
+  return check_launch(fn);
+}
+template <int H, int HD, bool TRAIN>
+static int launch_bwd_ds(const BwdArgs& a, int B, cudaStream_t st, const char* fn) {
+  const size_t smem = BwdPlan<H, HD>::ds_total;
+  static uint64_t seen = 0;
+  if (first_use_on_device(seen))
+    cudaFuncSetAttribute(stream_bwd_ds_kernel<H, HD, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const dim3 grid((unsigned)cdiv(a.N, WARPS * 16), (unsigned)B);
+  stream_bwd_ds_kernel<H, HD, TRAIN><<<grid, WARPS * 32, smem, st>>>(a);
+  return check_launch(fn);
+}
+
 static bool supported(int h, int hd, int N) {
   const bool shape = (h == 8 && (hd == 8 || hd == 24)) || (h == 4 && (hd == 12 || hd == 48));
   return shape && N % 16 == 0 && N >= 64 && N <= 8192;
@@ -510,5 +920,60 @@ extern "C" int vu_reattn_stream_fwd(int mode, const float* q, const float* k, co
     if (pc) { VU_RS_DISPATCH(h, hd, return (rs::launch_fwd<HH, HDD, rs::MODE_STATS, true>(a, B, st, fn))); }
     else { VU_RS_DISPATCH(h, hd, return (rs::launch_fwd<HH, HDD, rs::MODE_STATS, false>(a, B, st, fn))); }
   } else { VU_RS_DISPATCH(h, hd, return (rs::launch_fwd<HH, HDD, rs::MODE_APPLY, false>(a, B, st, fn))); }
+  return VU_OK;
+}
+
+static void fill_bwd_args(vu::rs::BwdArgs& a, const void* pc, const void* mask, const float* dO, const float* v, int h, int N,
+                          int hd, float drop_p, uint64_t seed, uint32_t stream_id) {
+  using namespace vu;
+  a = rs::BwdArgs();
+  a.pc = (const __nv_bfloat16*)pc; a.mask = (const uint2*)mask; a.dO = dO; a.v = v;
+  a.N = N; a.D = h * hd; a.scale = 1.0f / sqrtf((float)hd);
+  a.thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  a.dscale = drop_p > 0.f ? drop_keep_scale(drop_p) : 1.0f;
+  a.key = Philox::key(seed, stream_id);
+  a.cN = 1.0f / (float)N;
+}
+
+// red[h + h*h] (double, caller zeroes) += { sum dA_h , sum dA_h (Pd_g - 1/N) } with dA = dO v^T formed on the fly
+// (the streamed twin of vu_reattn_mix_reduce / vu_reattn_bwd_reduce: no dA map is read or written).
+extern "C" int vu_reattn_stream_bwd_reduce(const void* pc, const void* mask, const float* dO, const float* v, double* red,
+                                           int B, int h, int N, int hd, float drop_p, uint64_t seed, uint32_t stream_id,
+                                           void* stream) {
+  using namespace vu;
+  const char* fn = "vu_reattn_stream_bwd_reduce";
+  VU_REQUIRE(pc && dO && v && red && B > 0 && B <= 65535, fn, "null pointer or bad batch");
+  VU_REQUIRE(rs::supported(h, hd, N), fn, "unsupported (heads, head_dim, tokens): see vu_reattn_stream_supported");
+  VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
+  VU_REQUIRE((uintptr_t)pc % 8 == 0 && (uintptr_t)mask % 8 == 0 && (uintptr_t)dO % 16 == 0 && (uintptr_t)v % 16 == 0, fn, "misaligned pointer");
+  rs::BwdArgs a; fill_bwd_args(a, pc, mask, dO, v, h, N, hd, drop_p, seed, stream_id);
+  a.red = red;
+  cudaStream_t st = as_stream(stream);
+  VU_RS_DISPATCH(h, hd, return (rs::launch_bwd_reduce<HH, HDD>(a, B, st, fn)));
+  return VU_OK;
+}
+
+// dS (bf16 map, (B,h,N,N)) and dq (B,N,h*hd) from the centred probabilities, dO and v: the streamed twin of
+// dA = dO v^T  +  vu_reattn_bwd_rows  +  dq = dS k.   kt: per-head transposed bf16 keys (vu_heads_transpose_bf16).
+// coef: BatchNorm-backward means from vu_reattn_bwd_params (train); saved: {mean, invstd} from vu_reattn_bn_finalize.
+extern "C" int vu_reattn_stream_bwd_ds(const void* pc, const void* mask, const float* dO, const float* v, const void* kt,
+                                       void* ds, float* dq, const float* W, const float* bconv, const float* gamma,
+                                       const float* saved, const float* coef, int train, int B, int h, int N, int hd,
+                                       int ldn, float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_reattn_stream_bwd_ds";
+  VU_REQUIRE(pc && dO && v && kt && ds && dq && W && bconv && gamma && saved && B > 0 && B <= 65535, fn, "null pointer or bad batch");
+  VU_REQUIRE(!train || coef, fn, "train mode needs the BN-backward coefficients");
+  VU_REQUIRE(rs::supported(h, hd, N), fn, "unsupported (heads, head_dim, tokens): see vu_reattn_stream_supported");
+  VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
+  VU_REQUIRE(ldn % 8 == 0 && ldn >= N, fn, "kt needs ldn % 8 == 0");
+  VU_REQUIRE((uintptr_t)pc % 8 == 0 && (uintptr_t)mask % 8 == 0 && (uintptr_t)dO % 16 == 0 && (uintptr_t)v % 16 == 0 &&
+             (uintptr_t)kt % 16 == 0 && (uintptr_t)ds % 8 == 0 && (uintptr_t)dq % 8 == 0, fn, "misaligned pointer");
+  rs::BwdArgs a; fill_bwd_args(a, pc, mask, dO, v, h, N, hd, drop_p, seed, stream_id);
+  a.kt = (const __nv_bfloat16*)kt; a.ds = (__nv_bfloat16*)ds; a.dq = dq; a.ldn = ldn; a.train = train;
+  a.W = W; a.bconv = bconv; a.gamma = gamma; a.saved = saved; a.coef = coef;
+  cudaStream_t st = as_stream(stream);
+  if (train) { VU_RS_DISPATCH(h, hd, return (rs::launch_bwd_ds<HH, HDD, true>(a, B, st, fn))); }
+  else { VU_RS_DISPATCH(h, hd, return (rs::launch_bwd_ds<HH, HDD, false>(a, B, st, fn))); }
   return VU_OK;
 }

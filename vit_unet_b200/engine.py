@@ -41,10 +41,12 @@ _KEEP_MIXED_MAP = {"value": os.environ.get("VU_KEEP_MIXED_MAP", "1") == "1"}
 # streamed Re-Attention forward (vu_reattn_stream.cu) on the tensor-core path where the shape is supported: no
 # (B,h,N,N) map is written in inference; in training only the centred bf16 probabilities the backward pass reads
 _STREAMED = {"value": os.environ.get("VU_STREAMED", "1") == "1"}
+_STREAMED_BWD = {"value": os.environ.get("VU_STREAMED_BWD", "1") == "1"}     # streamed backward kernels too (else: materialised)
 
 
-def set_streamed(on: bool) -> None:
+def set_streamed(on: bool, backward: bool = True) -> None:
     _STREAMED["value"] = bool(on)
+    _STREAMED_BWD["value"] = bool(on and backward)
 
 
 def set_bf16_maps(on: bool) -> None:
@@ -272,7 +274,7 @@ class Engine:
         sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device) if (train or keep_P) else None
         O = _empty((B, N, D), xq)
         Pm = torch.empty((B, h, N, N), dtype=torch.bfloat16, device=xq.device) if keep_P else None
-        A = None
+        A, mask = None, None
 
         def finalize():
             ops.reattn_bn_finalize(sums if train else None, B * N * N, h, N, P[pre + "reatten_matrix.weight"].reshape(h, h),
@@ -287,8 +289,7 @@ class Engine:
                                   mask=mask)
             finalize()
             # the mixed map is kept (bf16) for the backward product dV = A^T dO: one write here instead of a recompute there
-            A = (torch.empty((B, h, N, N), dtype=torch.bfloat16, device=xq.device)
-                 if (keep_P and _KEEP_MIXED_MAP["value"]) else None)
+            A = torch.empty((B, h, N, N), dtype=torch.bfloat16, device=xq.device) if keep_P else None
             ops.reattn_stream_fwd(ops.STREAM_APPLY, q, k, vt, O, fold, rowc, None, None, B, h, N, hd, scale, adrop, seed, sid,
                                   mask=mask, amap=A)
         else:
@@ -300,7 +301,8 @@ class Engine:
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums if train else None,
-                         seed=seed, sid=sid, adrop=adrop, pdrop=pdrop, train=train, chunk=B, bf16=True, A=A)
+                         seed=seed, sid=sid, adrop=adrop, pdrop=pdrop, train=train, chunk=B, bf16=True, A=A, streamed=True,
+                         mask=mask)
         return y
 
     def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):
@@ -323,9 +325,41 @@ class Engine:
         self._wgrad(dyd, O, G[pre + "proj.weight"], M, D, D)
         ops.colsum(dyd, M, D, D, G[pre + "proj.bias"], accumulate=True)
         del dyd
-        # recompute the mixed map, then dV = A^T dO ; dA = dO V^T
         Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
         bm = P[pre + "reatten_matrix.bias"]
+        if sv.get("streamed") and _STREAMED_BWD["value"]:
+            # streamed backward (vu_reattn_stream.cu): dA = dO v^T is formed on the fly in both kernels and never stored;
+            # the maps that cross HBM are the saved centred probabilities (read), the saved mixed map (dV = A^T dO) and dS
+            # (written once, read by dK = dS^T q)
+            gamma = P[pre + "var_norm.weight"]
+            mask, A_kept = sv.get("mask"), sv["A"]
+            red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
+            ops.reattn_stream_bwd_reduce(Pm, mask, dO, v, red, B, h, N, hd, adrop, seed, sid)
+            dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
+            dOt = ops.heads_transpose_bf16(dO, B, N, D, h)
+            ldn = dOt.shape[-1]
+
+            def map_gemm_t(Amap, Bt, Cout):          # Cout (B,N,D head-sliced) = Amap^T @ tokens of the head
+                ops.gemm(Amap, Bt, Cout, N, hd, N, trans_a=True, trans_b=True, lda=N, ldb=ldn, ldc=D, batch_outer=B,
+                         batch_inner=h, sA=(h * N * N, N * N), sB=(h * hd * ldn, hd * ldn), sC=(N * D, hd), precision=prec)
+            map_gemm_t(A_kept, dOt, dv)
+            sv["A"] = None
+            del A_kept, dOt
+            coef = _empty((2 * h,), dy)
+            ops.reattn_bwd_params(red, sv["sums"], B, h, N, Wm, bm, gamma, sv["bn"], train, coef,
+                                  G[pre + "reatten_matrix.weight"], G[pre + "reatten_matrix.bias"],
+                                  G[pre + "var_norm.weight"], G[pre + "var_norm.bias"])
+            kt = ops.heads_transpose_bf16(k, B, N, D, h)
+            dS = torch.empty((B, h, N, N), dtype=torch.bfloat16, device=dy.device)
+            ops.reattn_stream_bwd_ds(Pm, mask, dO, v, kt, dS, dq, Wm, bm, gamma, sv["bn"], coef, train, B, h, N, hd,
+                                     adrop, seed, sid)
+            del kt, dO
+            qt = ops.heads_transpose_bf16(q, B, N, D, h)
+            map_gemm_t(dS, qt, dk)
+            del dS, qt
+            self._qkv_conv_bwd(P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc)
+            return
+        # recompute the mixed map, then dV = A^T dO ; dA = dO V^T
         # Same image slices as forward (identical dropout RNG streams).  Phase A per slice: dA = dO V^T, one pass over
         # (P, dA) -> recomputed mixed map A + backward reductions, dV = A^T dO.  Then the closed-form parameter
         # gradients / BatchNorm-backward means.  Phase B per slice: dA again (a K = head_dim GEMM, cheaper than an HBM
@@ -382,6 +416,12 @@ class Engine:
             map_gemm(dA, False, kt if bf16 else None, k, dq, b0, bc)
             map_gemm(dA, True, qt if bf16 else None, q, dk, b0, bc)
         del dO, dA
+        self._qkv_conv_bwd(P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc)
+
+    def _qkv_conv_bwd(self, P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc):
+        """backward of the three per-patch 3x3 convs (model.py:152-154): data gradients accumulate into dx, weights into G"""
+        g = self.g
+        dy = dq
         wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
         xq, xkv = sv["xq"], sv["xkv"]
         C, S = g.C, g.S

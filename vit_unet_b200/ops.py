@@ -295,6 +295,20 @@ def reattn_stream_fwd(mode, q, k, vt, o, fold, rowc, sums, pc, B, h, N, hd, scal
           nbytes=4.0 * B * N * h * hd * (2 + pv) + 2.0 * B * N * h * hd * pv + (2.0 * B * h * N * N if pc is not None else 0.0) + (2.0 * B * h * N * N if amap is not None else 0.0))
 
 
+def reattn_stream_bwd_reduce(pc, mask, dO, v, red, B, h, N, hd, drop_p, seed, sid):
+    _call("vu_reattn_stream_bwd_reduce", _chk(pc, "pc", torch.bfloat16), _opt(mask, "mask", torch.uint8), _chk(dO, "dO"),
+          _chk(v, "v"), _chk(red, "red", torch.float64), B, h, N, hd, drop_p, seed, sid, _stream(),
+          flops=2.0 * B * h * N * N * hd + 2.0 * h * B * h * N * N, nbytes=2.0 * B * h * N * N + 8.0 * B * N * h * hd)
+
+
+def reattn_stream_bwd_ds(pc, mask, dO, v, kt, dS, dq, W, bconv, gamma, saved, coef, train, B, h, N, hd, drop_p, seed, sid):
+    _call("vu_reattn_stream_bwd_ds", _chk(pc, "pc", torch.bfloat16), _opt(mask, "mask", torch.uint8), _chk(dO, "dO"),
+          _chk(v, "v"), _chk(kt, "kt", torch.bfloat16), _chk(dS, "dS", torch.bfloat16), _chk(dq, "dq"), _chk(W, "W"),
+          _chk(bconv, "bconv"), _chk(gamma, "gamma"), _chk(saved, "saved"), _opt(coef, "coef"), int(train), B, h, N, hd,
+          kt.shape[-1], drop_p, seed, sid, _stream(),
+          flops=4.0 * B * h * N * N * hd + 4.0 * h * B * h * N * N, nbytes=(2.0 * 2 + 2.0 * 3) * B * h * N * N + 14.0 * B * N * h * hd)
+
+
 # ----------------------------------------------------------------------------------------- layer norm
 LN_SCRATCH = 2 + 2 * _lib.LN_SPLIT      # floats of scratch per image for ln_stats / ln_bwd
 
