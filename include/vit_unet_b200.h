@@ -212,6 +212,15 @@ int vu_psnr(const float* pred, const float* target, int B, int64_t n, float data
 int vu_u8hwc_to_chw(const uint8_t* src, float* dst, int B, int C, int H, int W, float scale, float mean, float std,
                     void* stream);
 
+/* N4 continued: cv2.resize(INTER_LINEAR) of a uint8 HWC batch (dataset.py:59-60), and a fused affine warp (albumentations
+ * ShiftScaleRotate with BORDER_CONSTANT, run_denoising.py:52-55) + Normalize + HWC->CHW float.  mats: B x 6 floats, the
+ * map from OUTPUT to SOURCE pixel coordinates (NULL = identity); interp 1 bilinear / 0 nearest; round_u8 rounds the
+ * sample to a grey level as cv2 does for uint8 images; dst = ((sample * scale) - mean) / std * post. */
+int vu_resize_u8hwc(const uint8_t* src, uint8_t* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, void* stream);
+int vu_warp_u8hwc_to_chw(const uint8_t* src, float* dst, const float* mats, int B, int C, int Hs, int Ws, int Hd, int Wd,
+                         int interp, float border, int round_u8, float scale, float mean, float std, float post,
+                         void* stream);
+
 /* ---------------------------------------------------------------- misc */
 /* out = in * keep / (1-p), keep from the same counter-based stream the GEMM epilogue uses (index = flat element) */
 int vu_dropout(const float* in, float* out, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream);

@@ -8,6 +8,7 @@ Public surface (mirrors ``vit_unet.torch.model`` of the reference):
 from .engine import get_precision, set_bf16_maps, set_bf16_probs, set_map_l2_budget, set_precision, set_streamed
 from .losses import DiceLoss, L1Loss, MSELoss, dice_loss, l1_loss, mse_loss
 from .model import HViT_UNet, ViT_UNet, get_vit_unet
+from .input_pipeline import DenoisingBatchPipeline
 from .optim import FusedAdamW
 
 __all__ = ["ViT_UNet", "HViT_UNet", "get_vit_unet", "l1_loss", "mse_loss", "dice_loss", "L1Loss", "MSELoss",

@@ -67,6 +67,8 @@ SIGNATURES = {
     "vu_loss_bwd": [_i, _p, _p, _l, _p, _p, _p, _p],
     "vu_psnr": [_p, _p, _i, _l, _f, _p, _p, _p],
     "vu_u8hwc_to_chw": [_p, _p, _i, _i, _i, _i, _f, _f, _f, _p],
+    "vu_resize_u8hwc": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "vu_warp_u8hwc_to_chw": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _f, _f, _f, _f, _p],
     "vu_dropout": [_p, _p, _l, _f, _u64, _u32, _p],
     "vu_axpby": [_p, _p, _l, _f, _f, _p],
     "vu_adamw": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _f, _p],

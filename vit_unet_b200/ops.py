@@ -366,6 +366,25 @@ def u8hwc_to_chw(src, scale=1.0 / 255.0, mean=0.0, std=1.0):
     return dst
 
 
+def resize_u8hwc(src, Hd, Wd):
+    """cv2.resize(INTER_LINEAR) of a uint8 (B,H,W,C) batch on the device."""
+    B, Hs, Ws, Cc = src.shape
+    dst = torch.empty((B, Hd, Wd, Cc), dtype=torch.uint8, device=src.device)
+    _call("vu_resize_u8hwc", _chk(src, "src", torch.uint8), _chk(dst, "dst", torch.uint8), B, Cc, Hs, Ws, Hd, Wd, _stream(),
+          nbytes=float(src.numel() + dst.numel()))
+    return dst
+
+
+def warp_u8hwc_to_chw(src, mats, Hd, Wd, bilinear=True, border=0.0, round_u8=True, scale=1.0 / 255.0, mean=0.0, std=1.0,
+                      post=1.0):
+    """uint8 (B,H,W,C) -> float32 (B,C,Hd,Wd) through per-image inverse affine maps `mats` (B,6) or the identity."""
+    B, Hs, Ws, Cc = src.shape
+    dst = torch.empty((B, Cc, Hd, Wd), dtype=torch.float32, device=src.device)
+    _call("vu_warp_u8hwc_to_chw", _chk(src, "src", torch.uint8), _chk(dst, "dst"), _opt(mats, "mats"), B, Cc, Hs, Ws, Hd, Wd,
+          int(bilinear), border, int(round_u8), scale, mean, std, post, _stream(), nbytes=float(src.numel() + 4 * dst.numel()))
+    return dst
+
+
 def dropout(x, out, p, seed, sid):
     _call("vu_dropout", _chk(x, "in"), _chk(out, "out"), x.numel(), p, seed, sid, _stream(), nbytes=8.0 * x.numel())
     return out
