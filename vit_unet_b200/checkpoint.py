@@ -74,3 +74,46 @@ def head_to_readme(sd: Dict[str, torch.Tensor], *, num_channels: int, im_size: i
     out["PE.conv2d.weight"] = w
     out["PE.conv2d.bias"] = torch.zeros(C, dtype=w.dtype, device=w.device)
     return out
+
+
+# ------------------------------------------------------------------ best-checkpoint.bin (run_denoising.py:88,100)
+# The reference trains through benatools' TorchFitterBase (not vendored, not installable here): `fitter.fit(...)`
+# writes `<folder>/best-checkpoint.bin` and `fitter.load(path)` restores it (run_denoising.py:84-100).  The file is a
+# torch.save'd dict; the keys below are the ones that class is known to write (model / optimizer / scheduler state,
+# best loss, epoch).  load_checkpoint also accepts a bare state_dict, and either LayerNorm layout (README <-> HEAD).
+def save_checkpoint(path, model, optimizer=None, scheduler=None, best_summary_loss=None, epoch=0, sync=True):
+    """Write a best-checkpoint.bin.  `model` may be a vit_unet_b200.dp.DataParallel wrapper: with sync=True EVERY rank
+    must call this (the BatchNorm running statistics of rank 0 are broadcast first), and only rank 0 writes."""
+    import torch.distributed as dist
+    from .dp import DataParallel
+    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    if isinstance(model, DataParallel) and sync:
+        model.sync_buffers(0)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    if rank != 0:
+        return None
+    blob = {"model_state_dict": sd,
+            "optimizer_state_dict": optimizer.state_dict() if optimizer is not None else None,
+            "scheduler_state_dict": scheduler.state_dict() if scheduler is not None else None,
+            "best_summary_loss": best_summary_loss, "epoch": epoch}
+    torch.save(blob, path)
+    return path
+
+
+def load_checkpoint(path, model, optimizer=None, scheduler=None, geometry=None, map_location="cpu"):
+    """Restore a best-checkpoint.bin (or a bare state_dict) into `model` (plain or DataParallel-wrapped).  When the file
+    holds the OTHER variant's layout (shared LN vs LN1/LN2) it is converted with readme_to_head / head_to_readme; pass
+    geometry=dict(num_channels=, im_size=, patch_size=, depth=) for that.  Returns the checkpoint dict."""
+    blob = torch.load(path, map_location=map_location, weights_only=False)
+    sd = blob["model_state_dict"] if isinstance(blob, dict) and "model_state_dict" in blob else blob
+    want = set(model.state_dict().keys())
+    if set(sd.keys()) != want:
+        if geometry is None:
+            raise ValueError("checkpoint layout differs from the model's (README vs HEAD variant?); pass geometry= to convert")
+        sd = head_to_readme(sd, **geometry) if any(".LN1." in k for k in sd) else readme_to_head(sd, **geometry)
+    model.load_state_dict(sd)
+    if optimizer is not None and isinstance(blob, dict) and blob.get("optimizer_state_dict") is not None:
+        optimizer.load_state_dict(blob["optimizer_state_dict"])
+    if scheduler is not None and isinstance(blob, dict) and blob.get("scheduler_state_dict") is not None:
+        scheduler.load_state_dict(blob["scheduler_state_dict"])
+    return blob
