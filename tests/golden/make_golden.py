@@ -142,32 +142,37 @@ def load_reference_module():
     return mod
 
 
-def _fwd_bwd(model, x, y):
+def _fwd_bwd(model, x, y, loss_kind="l1"):
     model.zero_grad(set_to_none=True)
     xin = x.clone().requires_grad_(True)
     out = model(xin)
-    loss = torch.nn.functional.l1_loss(out, y)
+    loss = torch.nn.functional.l1_loss(out, y) if loss_kind == "l1" else torch.nn.functional.mse_loss(out, y)
     loss.backward()
     return dict(out=out.detach().clone(), loss=loss.detach().clone(), dx=xin.grad.detach().clone(),
                 grads={k: p.grad.detach().clone() for k, p in model.named_parameters()})
 
 
-def run_case(model, x, y, train: bool):
+def run_case(model, x, y, train: bool, loss_kind: str = "l1"):
     """eval forward; eval-mode fwd+bwd (BatchNorm on running statistics: the well-conditioned gradient check);
-    train-mode fwd+bwd with L1 loss and dropout p=0 (batch statistics + running-stat update)."""
+    train-mode fwd+bwd with dropout p=0 (batch statistics + running-stat update).
+    loss_kind "l1": tags evg / trn (the benchmark's loss; its gradient sign(out - y) / n is DISCONTINUOUS in the output,
+    so per-pixel gradients of a reduced-precision path can differ by whole terms where out ~ y).
+    loss_kind "mse": tags mev / mtr (run_denoising.py:80, the loss the reference trains with; smooth, so gradients of a
+    tensor-core path can be held to the reference element by element)."""
     res = {}
     model.eval()
     with torch.no_grad():
         res["eval_out"] = model(x).detach().clone()
+    ev, tr = ("evg", "trn") if loss_kind == "l1" else ("mev", "mtr")
     if train:
-        res["evg"] = _fwd_bwd(model, x, y)
+        res[ev] = _fwd_bwd(model, x, y, loss_kind)
         model.train()
-        res["trn"] = _fwd_bwd(model, x, y)
+        res[tr] = _fwd_bwd(model, x, y, loss_kind)
         res["buffers_after"] = {k: b.detach().clone() for k, b in model.named_buffers()}
     return res
 
 
-def conditioning(model, x, y, ref64=None):
+def conditioning(model, x, y, ref64=None, loss_kind="l1"):
     """How far the fp32 model is from its own fp64 evaluation (max-relative errors), per mode and per tensor.
 
     Train-mode BatchNorm over near-uniform attention maps amplifies fp32 round-off by orders of magnitude per
@@ -182,10 +187,10 @@ def conditioning(model, x, y, ref64=None):
     def rel(u, v):
         return float(((u.double() - v).abs().max() / v.abs().max().clamp_min(1e-300)).item())
     out = {}
-    for tag, train in (("evg", False), ("trn", True)):
+    for tag, train in ((("evg", False), ("trn", True)) if loss_kind == "l1" else (("mev", False), ("mtr", True))):
         model.train(train); m64.train(train)
-        a = _fwd_bwd(model, x, y)
-        b = _fwd_bwd(m64, x.double(), y.double())
+        a = _fwd_bwd(model, x, y, loss_kind)
+        b = _fwd_bwd(m64, x.double(), y.double(), loss_kind)
         if ref64 is not None:
             ref64[tag] = b
         out[f"{tag}_cond:out"] = rel(a["out"], b["out"])
@@ -212,7 +217,7 @@ def pack(res: dict, full: bool) -> dict:
         out[key + "_sum"] = np.float64(t.double().sum().item())
         out[key] = t.numpy().copy() if full else _sub(t)
     put("eval_out", res["eval_out"])
-    for tag in ("evg", "trn"):
+    for tag in ("evg", "trn", "mev", "mtr"):
         if tag not in res:
             continue
         r = res[tag]
@@ -252,6 +257,19 @@ def main():
         # the tensor-core path are measured against where fp32 itself is not reproducible (Base train mode)
         for k, v in pack({"eval_out": res["eval_out"], **r64}, full).items():
             if k.startswith(("evg_", "trn_")) and not k.endswith("_sum") and "_gnorm:" not in k:
+                out["r64:" + k] = np.asarray(v, dtype=np.float64)
+        # the same with the MSE loss the reference trains with (always subsampled; BN buffers are those of the L1 run)
+        model.load_state_dict(fill_state_dict(model.state_dict()))
+        mres = run_case(model, x, y, train=True, loss_kind="mse")
+        for k, v in pack(mres, False).items():
+            if k.startswith(("mev_", "mtr_")):
+                out[k] = v
+        model.load_state_dict(fill_state_dict(model.state_dict()))
+        m64 = {}
+        for k, v in conditioning(model, x, y, m64, loss_kind="mse").items():
+            out[k] = np.float64(v)
+        for k, v in pack({"eval_out": res["eval_out"], **m64}, False).items():
+            if k.startswith(("mev_", "mtr_")) and not k.endswith("_sum") and "_gnorm:" not in k:
                 out["r64:" + k] = np.asarray(v, dtype=np.float64)
         out["n_params"] = np.int64(sum(p.numel() for p in model.parameters()))
         path = os.path.join(HERE, f"{name}.npz")

@@ -65,7 +65,7 @@ def test_best_checkpoint_save_and_reload(tmp_path):
     assert blob["epoch"] == 3 and blob["best_summary_loss"] == 0.5
     net2.eval()
     with torch.no_grad():
-        assert torch.equal(net2(x.cuda()), ref)                # weights AND BatchNorm running statistics restored
+        assert torch.allclose(net2(x.cuda()), ref, rtol=1e-6, atol=1e-7)   # weights AND BatchNorm running statistics restored
     assert int(opt2._flat["step"]) == 2
     assert torch.equal(opt2._flat["m"], opt._flat["m"]) and torch.equal(opt2._flat["v"], opt._flat["v"])
     # the README-variant module loads the same file through the layout conversion (LN1 == LN2 is required: refused here)

@@ -151,7 +151,8 @@ def test_matches_reference_golden(name):
     got = pack(run_case(_Wrap(net), x, y, train=True), full=name.startswith("tiny"))
     cond = _gold_cond(name)
     for k in gold.files:
-        if k == "n_params" or "_cond:" in k or k.endswith("_sum") or "_gnorm:" in k or k.startswith("r64:"):
+        if (k == "n_params" or "_cond:" in k or k.endswith("_sum") or "_gnorm:" in k or k.startswith("r64:")
+                or k.startswith(("mev_", "mtr_"))):
             continue
         kk = k
         for tag in ("evg_g:", "trn_g:", "buf:"):

@@ -18,7 +18,7 @@ for prec, maps in (("fp32", False), ("tf32", False), ("tf32", True)):
     vu.set_precision(prec); vu.set_bf16_maps(maps)
     for name in names:
         net, x, y = build_net(name, quiet)
-        rows = parity_rows(name, net, x, y)
+        rows = parity_rows(name, net, x, y, l1_grads=True)
         by = {}
         for k, e, t, st in rows:
             grp = k.split(":")[0] if ":" in k else k
