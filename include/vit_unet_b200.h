@@ -179,6 +179,10 @@ int vu_reattn_stream_bwd_ds(const void* pc, const void* mask, const float* dO, c
                             const float* coef, int train, int B, int h, int N, int hd, int ldn, float drop_p,
                             uint64_t seed, uint32_t stream_id, void* stream);
 
+/* number of VU_PREC_TF32 GEMM requests that ran on the CUDA-core kernel because an operand was not TMA-addressable
+ * (also logged to stderr the first few times; VU_LOG_FALLBACKS=1 logs all) */
+int vu_gemm_tf32_fallbacks(void);
+
 /* ---------------------------------------------------------------- LayerNorm over (N,D) (model.py:193-196,204,206) */
 #define VU_LN_SPLIT 8      /* CTAs cooperating on one image's statistics */
 /* stats[b] = {mean, rstd} over the n = N*D elements of image b; scratch: 2*VU_LN_SPLIT*B floats */

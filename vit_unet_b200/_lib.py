@@ -79,6 +79,7 @@ _SPECIAL = {
     "vu_device_sm_count": ([_i], C.c_int),
     "vu_reattn_tensor_core_path": ([_i, _i, _i], C.c_int),
     "vu_reattn_stream_supported": ([_i, _i, _i], C.c_int),
+    "vu_gemm_tf32_fallbacks": ([], C.c_int),
 }
 
 _lib = None

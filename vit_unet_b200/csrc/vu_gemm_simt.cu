@@ -6,6 +6,10 @@
 // a TMxTN micro-tile split into 4-wide column/row groups so that every shared-memory read is a conflict-free
 // LDS.128.  Both operands may be transposed in memory; batch index z = (zo, zi) with independent strides so that
 // head-sliced views of (B,N,h,hd) tensors need no copies.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+
 #include "vu_common.cuh"
 
 namespace vu {
@@ -260,6 +264,7 @@ int gemm_simt(const vu_gemm_desc& d, cudaStream_t s) {
   return check_launch("vu_gemm");
 }
 
+static std::atomic<long> g_tf32_fallbacks{0};
 int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled);   // vu_gemm_tc.cu
 int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled);   // vu_gemm_scores.cu
 
@@ -308,13 +313,22 @@ extern "C" int vu_gemm(const vu_gemm_desc* d, void* stream) {
     rc = gemm_tc(*d, s, &handled);
     if (rc != VU_OK || handled) return rc;
     VU_REQUIRE(!any_bf16, fn, "bfloat16 GEMM could not be mapped onto the tensor-core kernel");
-    // shapes the tensor-core kernel does not cover fall through to the CUDA-core kernel (same numerics class
-    // or better); this is a kernel choice inside the CUDA path, not a CPU fallback.
+    // shapes the tensor-core kernel does not cover (an operand TMA cannot address: base or stride not 16-byte aligned)
+    // fall through to the CUDA-core kernel (same numerics class or better) -- a ~7x slower kernel choice inside the CUDA
+    // path, not a CPU fallback.  It is COUNTED (vu_gemm_tf32_fallbacks) and the first occurrence of each shape class is
+    // logged to stderr, so a performance cliff cannot hide.
+    const long n = ++g_tf32_fallbacks;
+    if (n <= 4 || getenv("VU_LOG_FALLBACKS"))
+      fprintf(stderr, "[vit_unet_b200] vu_gemm: TF32 request M=%d N=%d K=%d (lda=%lld ldb=%lld, trans %d/%d) is not TMA-addressable; "
+              "running the CUDA-core kernel (%ld so far)\n", d->M, d->N, d->K, (long long)d->lda, (long long)d->ldb,
+              d->trans_a, d->trans_b, n);
   } else {
     VU_REQUIRE(d->precision == VU_PREC_FP32, fn, "unknown precision");
   }
   return gemm_simt(*d, s);
 }
+
+extern "C" int vu_gemm_tf32_fallbacks(void) { return (int)vu::g_tf32_fallbacks.load(); }
 
 extern "C" int vu_colsum(const float* X, int64_t M, int N, int64_t ld, float* out, int accumulate, void* stream) {
   using namespace vu;

@@ -400,5 +400,10 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
          wd, step, grad_scale, _stream())
 
 
+def gemm_tf32_fallbacks() -> int:
+    """TF32 GEMM requests that ran on the CUDA-core kernel (operand not TMA-addressable); 0 on the benchmarked path."""
+    return int(_lib.load().vu_gemm_tf32_fallbacks())
+
+
 def sm_count(device: int = 0) -> int:
     return _lib.load().vu_device_sm_count(device)
