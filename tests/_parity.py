@@ -22,7 +22,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 YARD = 10
 CHAOS = 1e-2
 OUT_BASE = 1e-2
-GRAD_BASE = 3e-2
+GRAD_BASE = 3e-2          # TF32 contractions, fp32 attention maps: measured <= 2.8e-2 (B200, r2_parity_table)
+GRAD_BASE_BF16 = 1e-1     # + bf16 storage of the mixed / gradient maps (2^-9 per element, few-token levels average little):
+                          #   measured <= 9.7e-2 on the tiny configs, <= 3e-3 at the Base level-2 shapes
+CHAOS_TC = 1e-4           # a tensor whose fp32 reference is itself > 1e-4 from fp64 amplifies the 2^-11 input rounding of a
+                          #   tensor-core path by the same factor (x 8192) to O(1): reported, finiteness only
 
 
 class _Wrap(torch.nn.Module):        # run_case drives a CPU-style module; hop to the device at the boundary
@@ -43,7 +47,7 @@ def build_net(name, quiet):
     return net, x, y
 
 
-def parity_rows(name, net, x, y, l1_grads=False):
+def parity_rows(name, net, x, y, l1_grads=False, grad_base=GRAD_BASE, chaos=CHAOS / YARD):
     """[(key, err, tol, status)] with status in {'ok', 'FAIL', 'chaotic'}; err relative to max|ref|.
 
     Two passes over the golden file: the L1-loss run (tags evg / trn: the benchmark's loss) contributes the eval output,
@@ -87,16 +91,16 @@ def parity_rows(name, net, x, y, l1_grads=False):
             if rest in ("out", "loss"):
                 c, base = cond[f"{tag}_cond:out"], OUT_BASE
             elif rest == "dx":
-                c, base = cond[f"{tag}_cond:dx"], GRAD_BASE
+                c, base = cond[f"{tag}_cond:dx"], grad_base
             else:
                 pname = rest[2:]
                 if tag in ("trn", "mtr") and pname.endswith("reatten_matrix.bias"):
                     continue          # exactly 0 in theory under train-mode BN; round-off on both sides
-                c, base = cond[f"{tag}_cond:{pname}"], GRAD_BASE
+                c, base = cond[f"{tag}_cond:{pname}"], grad_base
         tol = base + YARD * c
         if not np.isfinite(o).all():
             rows.append((k, float("inf"), tol, "FAIL"))
-        elif c > CHAOS / YARD:
+        elif c > chaos:
             rows.append((k, err, tol, "chaotic"))
         else:
             rows.append((k, err, tol, "ok" if err <= tol else "FAIL"))

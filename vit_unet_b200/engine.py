@@ -38,10 +38,13 @@ _BF16_PROBS = {"value": os.environ.get("VU_BF16_PROBS", "0") == "1"}
 _KEEP_MIXED_MAP = {"value": os.environ.get("VU_KEEP_MIXED_MAP", "1") == "1"}
 
 
-# streamed Re-Attention forward (vu_reattn_stream.cu) on the tensor-core path where the shape is supported: no
-# (B,h,N,N) map is written in inference; in training only the centred bf16 probabilities the backward pass reads
-_STREAMED = {"value": os.environ.get("VU_STREAMED", "1") == "1"}
-_STREAMED_BWD = {"value": os.environ.get("VU_STREAMED_BWD", "1") == "1"}     # streamed backward kernels too (else: materialised)
+# streamed Re-Attention (vu_reattn_stream.cu) on the tensor-core path where the shape is supported: no (B,h,N,N) map is
+# written in inference; in training only the centred bf16 probabilities, the mixed map and dS cross HBM.  OPT-IN
+# (set_streamed / VU_STREAMED=1): measured on B200 (tools/block_bench.py, 256 images, Base level-2 block) the streamed
+# kernels run at 7 warps per SM (all heads of a position live in one lane: 240-255 registers) and are latency-bound --
+# forward 5.3 ms vs 4.4 ms materialised, backward 12.0 vs 5.8 ms -- while using 40 % less memory (7.6 vs 12.3 GB).
+_STREAMED = {"value": os.environ.get("VU_STREAMED", "0") == "1"}
+_STREAMED_BWD = {"value": os.environ.get("VU_STREAMED_BWD", "1") == "1"}     # with it: the streamed backward kernels too
 
 
 def set_streamed(on: bool, backward: bool = True) -> None:
