@@ -254,6 +254,8 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     vu.set_precision(args.precision)
+    if args.streamed is not None:
+        vu.set_streamed(bool(args.streamed), inference=bool(args.streamed))
     B = args.batch
     if args.global_batch:                   # strong scaling (fixed global batch, e.g. 1024 -> 128 per GPU at N=8)
         if args.global_batch % world:
@@ -399,6 +401,8 @@ def run_cuda(args):
                                if wl["train"] else "eval forward under no_grad (batch-sharded, no collective)",
                        "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)" if args.dropout is None else f"OVERRIDDEN to {args.dropout}", "precision": args.precision,
                        "maps": ("P fp32; mixed map A and gradient map dA/dS bf16 where N % 8 == 0; 8-head map kernels on TF32 warp MMAs" if (args.precision == "tf32" and os.environ.get("VU_BF16_MAPS", "1") == "1") else "fp32"),
+                       "reattention": ("streamed (no attention maps)" if (args.streamed == 1 or (args.streamed is None and not wl["train"]))
+                                       else "materialised maps") + " at the levels vu_reattn_stream_supported covers",
                        "l2": "per-step working set (saved activations + attention maps, GBs) >> 126 MB L2"},
             "clocks": clocks.summary(), "roofline": roof,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.nbytes + y_pin.nbytes),
@@ -437,6 +441,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
     ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "tf32"), choices=["fp32", "tf32"],
                     help="tf32: tcgen05 tensor-core contractions (default, the performance mode); fp32: CUDA-core exact mode")
+    ap.add_argument("--streamed", type=int, default=None, help="1/0: force the streamed Re-Attention kernels on/off "
+                    "(default: on for no-grad inference, off for training steps; see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=None, help="override attn/proj dropout (experiments; default = preset 0.2)")
     ap.add_argument("--min-warmup", type=int, default=3, help="lower only for profiler runs (numbers under ncu are never bench values)")

@@ -45,11 +45,18 @@ _KEEP_MIXED_MAP = {"value": os.environ.get("VU_KEEP_MIXED_MAP", "1") == "1"}
 # forward 5.3 ms vs 4.4 ms materialised, backward 12.0 vs 5.8 ms -- while using 40 % less memory (7.6 vs 12.3 GB).
 _STREAMED = {"value": os.environ.get("VU_STREAMED", "0") == "1"}
 _STREAMED_BWD = {"value": os.environ.get("VU_STREAMED_BWD", "1") == "1"}     # with it: the streamed backward kernels too
+# INFERENCE (nothing saved for backward) is different: there the streamed kernel replaces fp32 map round trips of up to
+# 157 MB per image and block (Lite level 2: 3136 tokens) and needs no batch slicing, so it is on by default
+_STREAMED_INFER = {"value": os.environ.get("VU_STREAMED_INFER", "1") == "1"}
 
 
-def set_streamed(on: bool, backward: bool = True) -> None:
+def set_streamed(on: bool, backward: bool = True, inference=None) -> None:
+    """Streamed Re-Attention for training steps (forward, and with `backward` the backward kernels); `inference`
+    (default: unchanged) switches the streamed no-grad forward, which is on by default."""
     _STREAMED["value"] = bool(on)
     _STREAMED_BWD["value"] = bool(on and backward)
+    if inference is not None:
+        _STREAMED_INFER["value"] = bool(inference)
 
 
 def set_bf16_maps(on: bool) -> None:
@@ -183,7 +190,8 @@ class Engine:
         bf16 = prec == ops.PREC_TF32 and _BF16_MAPS["value"] and N % 8 == 0
         # streamed forward: always for inference; with a backward pass to feed only where the materialised backward
         # kernels accept centred bf16 probabilities (8 heads, bf16 maps)
-        if (prec == ops.PREC_TF32 and _STREAMED["value"] and c >= B and ops.reattn_stream_supported(h, hd, N)
+        stream_on = _STREAMED["value"] or (_STREAMED_INFER["value"] and not keep_P and not train)
+        if (prec == ops.PREC_TF32 and stream_on and c >= B and ops.reattn_stream_supported(h, hd, N)
                 and (not keep_P or (bf16 and ops.reattn_tensor_core_path(h, N, ld)))):
             return self._attn_fwd_streamed(P, pre, xq, xkv, q, k, v, l, B, train, seed, sid, residual, saved)
         # train mode on the tensor-core map path: probabilities are kept as CENTRED bf16 (P - 1/N), scores are a

@@ -160,9 +160,14 @@ class _ViTUNetBase(nn.Module):
     map_budget_bytes = 16 << 30       # transient attention-map budget for no-grad inference (HBM is 180 GB)
 
     def _eval_chunk(self, B: int) -> int:
+        from . import engine as _e
         g = self.engine.g
-        n = g.N(g.depth)
-        per_image = 2 * g.heads * n * ((n + 3) // 4 * 4) * 4
+        per_image = 1
+        for l in range(g.depth + 1):         # levels whose maps are materialised (the streamed inference kernel writes none)
+            n, hd = g.N(l), g.D(l) // g.heads
+            if (_e.get_precision() == "tf32" and _e._STREAMED_INFER["value"] and ops.reattn_stream_supported(g.heads, hd, n)):
+                continue
+            per_image = max(per_image, 2 * g.heads * n * ((n + 3) // 4 * 4) * 4)
         return max(1, min(B, self.map_budget_bytes // per_image))
 
     def flat_grad(self):
