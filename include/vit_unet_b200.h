@@ -160,7 +160,7 @@ int vu_reattn_bwd_rows(const void* P, void* dA_dS, int map_fmt, int B, int h, in
  * mode 2: train apply: o = (fold . dropout(softmax)) v with the row constants of mode 1 and the batch-statistics fold;
  *         amap != NULL also writes the mixed map A as bf16 (B,h,N,N) for the backward product dV = A^T dO.
  * Dropout masks are those of the materialised kernels, element for element (same counter-hash keying).  mask
- * (optional, B * N * N * h / 8 bytes): mode 1 caches the keep-bits it generated, mode 2 reads them instead of
+ * (optional, B * (N/16)^2 * 256 bytes = 64 bits per lane of every (image, 16-row unit, 16-key step)): mode 1 caches the keep-bits it generated, mode 2 reads them instead of
  * hashing again (the hash is ~40 % of the apply sweep's instructions); NULL = regenerate. */
 int vu_reattn_stream_supported(int h, int hd, int N);
 int vu_reattn_stream_fwd(int mode, const float* q, const float* k, const void* vt, float* o, const float* fold,

@@ -25,6 +25,8 @@ OUT_BASE = 1e-2
 GRAD_BASE = 3e-2          # TF32 contractions, fp32 attention maps: measured <= 2.8e-2 (B200, r2_parity_table)
 GRAD_BASE_BF16 = 1e-1     # + bf16 storage of the mixed / gradient maps (2^-9 per element, few-token levels average little):
                           #   measured <= 9.7e-2 on the tiny configs, <= 3e-3 at the Base level-2 shapes
+OUT_BASE_TRAIN_BF16 = 3e-2   # TRAIN-mode outputs with bf16 maps: BatchNorm batch statistics of the tiny configs are taken over as
+                             #   few as 2 x 4 x 4 map values per head; measured <= 2.0e-2 (tiny_head_1ch), <= 1.7e-3 at Base shapes
 CHAOS_TC = 1e-4           # a tensor whose fp32 reference is itself > 1e-4 from fp64 amplifies the 2^-11 input rounding of a
                           #   tensor-core path by the same factor (x 8192) to O(1): reported, finiteness only
 
@@ -47,7 +49,7 @@ def build_net(name, quiet):
     return net, x, y
 
 
-def parity_rows(name, net, x, y, l1_grads=False, grad_base=GRAD_BASE, chaos=CHAOS / YARD):
+def parity_rows(name, net, x, y, l1_grads=False, grad_base=GRAD_BASE, chaos=CHAOS / YARD, train_out_base=OUT_BASE):
     """[(key, err, tol, status)] with status in {'ok', 'FAIL', 'chaotic'}; err relative to max|ref|.
 
     Two passes over the golden file: the L1-loss run (tags evg / trn: the benchmark's loss) contributes the eval output,
@@ -85,11 +87,11 @@ def parity_rows(name, net, x, y, l1_grads=False, grad_base=GRAD_BASE, chaos=CHAO
         if k == "eval_out":
             c, base = 0.0, OUT_BASE
         elif k.startswith("buf:"):
-            c, base = cond["trn_cond:out"], OUT_BASE
+            c, base = cond["trn_cond:out"], train_out_base
         else:
             tag, rest = k[:3], k[4:]
             if rest in ("out", "loss"):
-                c, base = cond[f"{tag}_cond:out"], OUT_BASE
+                c, base = cond[f"{tag}_cond:out"], (train_out_base if tag in ("trn", "mtr") else OUT_BASE)
             elif rest == "dx":
                 c, base = cond[f"{tag}_cond:dx"], grad_base
             else:

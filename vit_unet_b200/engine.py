@@ -295,7 +295,7 @@ class Engine:
         if train or keep_P:
             rowc = _empty((B, h, N), xq)
             # keep-bits of the dropout mask: generated (hashed) once by the statistics launch, re-read by the apply launch
-            mask = torch.empty(B * N * N * h // 8, dtype=torch.uint8, device=xq.device) if adrop > 0 else None
+            mask = torch.empty(ops.stream_mask_bytes(B, N), dtype=torch.uint8, device=xq.device) if adrop > 0 else None
             ops.reattn_stream_fwd(ops.STREAM_STATS, q, k, None, None, None, rowc, sums, Pm, B, h, N, hd, scale, adrop, seed, sid,
                                   mask=mask)
             finalize()

@@ -278,6 +278,12 @@ def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, sca
 STREAM_EVAL, STREAM_STATS, STREAM_APPLY = 0, 1, 2
 
 
+def stream_mask_bytes(B: int, N: int) -> int:
+    """size of the cached dropout keep-bit buffer: 64 bits per lane of every (image, 16-row unit, 16-key step),
+    whatever the head count (bit 4*head + key; 4-head models use the low half)"""
+    return B * (N // 16) * (N // 16) * 32 * 8
+
+
 def reattn_stream_supported(h: int, hd: int, N: int) -> bool:
     return bool(_lib.load().vu_reattn_stream_supported(h, hd, N))
 
