@@ -54,23 +54,37 @@ def _peaks():
     return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+# kernel class of the live table -> regex over the ncu kernel names of profiles/r02_step_traffic.json
+_NCU_CLASS = {
+    "gemm_tcgen05_tf32:tokens": r"gemm_tf32_tc_kernel<.*, 0>$",          # fp32-operand tcgen05 GEMMs (a few L0/L1 map products included)
+    "gemm_tcgen05_tf32:map_in": r"gemm_tf32_tc_kernel<.*, 1>$",          # bf16-operand (map-reading) tcgen05 GEMMs
+    "gemm_tcgen05_tf32:map_out": r"gemm_tf32_tc_kernel<.*, 0>$",
+    "gemm_mma_tf32:map_out": r"scores_mma_kernel", "vu_reattn_bwd_rows": r"reattn_bwd_rows", "vu_softmax_stats": r"softmax_stats",
+    "vu_reattn_mix_reduce": r"reattn_mix_reduce", "vu_reattn_mix": r"reattn_mix_mma_kernel|reattn_mix_kernel",
+    "vu_reattn_stream_fwd": r"stream_fwd_kernel", "vu_reattn_stream_bwd_ds": r"stream_bwd_ds", "vu_reattn_stream_bwd_reduce": r"stream_bwd_reduce",
+}
+
+
 def _ncu_traffic(kernel_class, batch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch (the Base L2-level
-    attention block, where 92 % of the map bytes live), from this round's committed `ncu --set full` capture
-    (profiles/ncu_traffic.json, captured at 32 images), scaled linearly to `batch` images.  None if absent."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if not os.path.exists(path) or ":tokens" in kernel_class:      # the committed capture is one attention block
-        return None, None
+    """HBM traffic from this round's committed ncu capture of ONE benchmarked step (profiles/r02_step_traffic.json, made by
+    tools/ncu_step.sh + profiles/make_step_summary.py: dram__bytes_read.sum + dram__bytes_write.sum of every kernel),
+    scaled linearly from the captured batch to `batch`.  Returns (bytes per launch of the class, bytes per step of the
+    class, bytes per step of ALL kernels, note) or Nones when the capture is absent."""
+    import re
+    path = os.path.join(ROOT, "profiles", "r02_step_traffic.json")
+    if not os.path.exists(path):
+        return None, None, None, None
     d = json.load(open(path))
-    # kernel class of the live table -> substring of the ncu kernel name (profiles/make_summary.py keys)
-    sub = {"gemm_tcgen05": "gemm_tf32_tc", "gemm_mma": "scores_mma", "vu_reattn_bwd_rows": "reattn_bwd_rows",
-           "vu_reattn_mix_reduce": "reattn_mix_reduce", "vu_reattn_mix": "reattn_mix_mma", "vu_softmax_stats": "softmax_stats"}
-    want = next((v for k, v in sub.items() if kernel_class.startswith(k)), kernel_class.replace("vu_", ""))
-    cands = [v for k, v in d.items() if want in k]
-    if not cands:
-        return None, None
-    e = max(cands, key=lambda v: v["bytes_per_launch"])
-    return e["bytes_per_image"] * batch, f"largest launch ({e['shape']}), ncu capture at {e['captured_batch']} images scaled to {batch}"
+    scale = batch / float(d["batch"])
+    rx = next((v for k, v in _NCU_CLASS.items() if kernel_class.startswith(k)), re.escape(kernel_class.replace("vu_", "")))
+    hit = [v for k, v in d["kernels"].items() if re.search(rx, k)]
+    total = d["step_dram_bytes"] * scale
+    if not hit:
+        return None, None, total, "no kernel of the capture matches this class"
+    cls_bytes = sum(v["dram_bytes"] for v in hit) * scale
+    n = sum(v["launches"] for v in hit)
+    return cls_bytes / n, cls_bytes, total, (f"ncu capture of one Base step at {d['batch']} images (profiles/r02_step.md), kernels matching /{rx}/: "
+                                             f"{n} launches per step, scaled to {batch} images")
 
 
 def _synthetic(B, gen_seed=0):
@@ -384,10 +398,18 @@ def run_cuda(args):
                      "kernel_ms_per_step": top["ms"] / args.steps, "kernel_share_of_step": top["ms"] / ms,
                      "launches_timed": top["launches"], "all_kernels_ms_per_step": k["total_kernel_ms"] / args.steps,
                      "by_kernel": by})
-        tr, note = _ncu_traffic(top_name, B)
-        if tr is not None:
-            roof["traffic"] = tr
-            roof["traffic_note"] = note
+        if args.workload == "base_train":
+            tr, cls_b, step_b, note = _ncu_traffic(top_name, B)
+            if tr is not None:
+                roof["traffic"] = tr                      # dram bytes per launch of the dominant kernel class (average)
+                roof["traffic_per_step"] = cls_b
+                roof["traffic_note"] = note
+            if step_b is not None:
+                alg = sum(v.get("alg_bytes", 0.0) for v in by.values()) / args.steps
+                roof["step_dram_bytes"] = step_b          # every kernel of the step, from the same capture
+                roof["step_algorithmic_bytes"] = alg      # sum of the ops' algorithmic bytes (what the maths must move)
+                roof["step_compulsory_bytes"] = 87e6 * B  # ~87 MB per image if no attention map ever touched HBM
+                roof["wasted_traffic_ratio"] = step_b / (87e6 * B)
     roof["step_tflops"] = value / world * wl["flops"] / 1e12
     roof["step_tensor_frac"] = roof["step_tflops"] / peaks["tflops"]
 

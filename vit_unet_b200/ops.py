@@ -84,7 +84,7 @@ class KernelTimer:
         for k, v in agg.items():
             sec = max(v["ms"], 1e-9) * 1e-3
             tf, gbs = v["flops"] / sec / 1e12, v["bytes"] / sec / 1e9
-            by[k] = {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 4), "launches": v["launches"],
+            by[k] = {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 4), "launches": v["launches"], "alg_bytes": v["bytes"],
                      "tflops": round(tf, 2), "gbs": round(gbs, 1), "tensor_frac": round(tf / peak_tflops, 4),
                      "hbm_frac": round(gbs / peak_gbs, 4)}
         return {"by_kernel": by, "total_kernel_ms": total}
