@@ -10,7 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from _parity import (CHAOS_TC, CONFIGS, GRAD_BASE, GRAD_BASE_BF16, OUT_BASE, OUT_BASE_TRAIN_BF16, build_net, parity_rows,
+from _parity import (CHAOS_TC, CONFIGS, GRAD_BASE, GRAD_BASE_BF16, GRAD_BASE_L2, OUT_BASE, OUT_BASE_TRAIN_BF16, build_net, parity_rows,
                      summarize)   # noqa: E402
 
 
@@ -32,7 +32,8 @@ def tf32():
 def test_tf32_path_matches_reference_golden(tf32, name, bf16_maps):
     tf32.set_bf16_maps(bf16_maps)
     net, x, y = build_net(name, _quiet)
-    rows = parity_rows(name, net, x, y, grad_base=GRAD_BASE_BF16 if bf16_maps else GRAD_BASE, chaos=CHAOS_TC,
+    gb = GRAD_BASE_L2 if name.startswith("l2block") else (GRAD_BASE_BF16 if bf16_maps else GRAD_BASE)
+    rows = parity_rows(name, net, x, y, grad_base=gb, chaos=CHAOS_TC,
                        train_out_base=OUT_BASE_TRAIN_BF16 if bf16_maps else OUT_BASE)
     bad = [r for r in rows if r[3] == "FAIL"]
     assert not bad, f"{len(bad)} of {len(rows)} tensors out of tolerance; worst: {summarize(bad)}"
@@ -48,7 +49,8 @@ def test_tf32_streamed_attention_matches_reference_golden(tf32, name):
     tf32.set_bf16_maps(True); tf32.set_streamed(True)
     try:
         net, x, y = build_net(name, _quiet)
-        rows = parity_rows(name, net, x, y, grad_base=GRAD_BASE_BF16, chaos=CHAOS_TC, train_out_base=OUT_BASE_TRAIN_BF16)
+        gb = GRAD_BASE_L2 if name.startswith("l2block") else GRAD_BASE_BF16
+        rows = parity_rows(name, net, x, y, grad_base=gb, chaos=CHAOS_TC, train_out_base=OUT_BASE_TRAIN_BF16)
     finally:
         tf32.set_streamed(False)
     bad = [r for r in rows if r[3] == "FAIL"]
@@ -59,7 +61,7 @@ def test_tf32_centred_bf16_probabilities(tf32):
     """VU_BF16_PROBS variant (train-mode probabilities kept as centred bf16) on the level-2 block shape."""
     tf32.set_bf16_maps(True); tf32.set_bf16_probs(True)
     net, x, y = build_net("l2block_head", _quiet)
-    rows = parity_rows("l2block_head", net, x, y, grad_base=GRAD_BASE_BF16, chaos=CHAOS_TC, train_out_base=OUT_BASE_TRAIN_BF16)
+    rows = parity_rows("l2block_head", net, x, y, grad_base=GRAD_BASE_L2, chaos=CHAOS_TC, train_out_base=OUT_BASE_TRAIN_BF16)
     bad = [r for r in rows if r[3] == "FAIL"]
     assert not bad, summarize(bad)
 
