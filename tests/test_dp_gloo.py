@@ -58,6 +58,15 @@ def _worker(rank, world, port, q):
         assert len(spans) > 1 and spans[0][1] == net._flat_numel and spans[-1][0] == 0
         assert all(spans[i][0] == spans[i + 1][1] for i in range(len(spans) - 1))
         assert order[0] == "PE." and order[-1] == "conv2d."
+        # the projection weight of every attention opens its own notification point (early bucket for the largest tensor)
+        pd = dict(zip(net._param_names, net._flat_offsets))
+        assert b.group_starts["Encoders.0.ReAttn.proj."] == pd["Encoders.0.ReAttn.proj.weight"]
+        assert b.group_starts["SkipConnections.0.proj."] == pd["SkipConnections.0.proj.weight"]
+        b.begin(flat)
+        b.bucket_numel = 1
+        b.on_ready("Encoders.0.ReAttn.proj.")
+        assert b.launched == [(pd["Encoders.0.ReAttn.proj.weight"], net._flat_numel)]
+        b.finish()
         # BatchNorm running statistics drift apart per rank during training; checkpointing broadcasts rank 0's
         bufs = dict(net.named_buffers())
         name = next(n for n in bufs if n.endswith("var_norm.running_mean"))

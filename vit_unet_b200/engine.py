@@ -336,6 +336,7 @@ class Engine:
         self._wgrad(dyd, O, G[pre + "proj.weight"], M, D, D)
         ops.colsum(dyd, M, D, D, G[pre + "proj.bias"], accumulate=True)
         del dyd
+        self._notify(pre + "proj.")        # [proj.weight, end of the flat gradient buffer) is final: an early all-reduce bucket
         Wm = P[pre + "reatten_matrix.weight"].reshape(h, h)
         bm = P[pre + "reatten_matrix.bias"]
         if sv.get("streamed") and _STREAMED_BWD["value"]:
