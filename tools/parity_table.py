@@ -14,9 +14,11 @@ def quiet(fn, *a, **k):
 
 
 names = sys.argv[1:] or list(CONFIGS)
-for prec, maps in (("fp32", False), ("tf32", False), ("tf32", True)):
-    vu.set_precision(prec); vu.set_bf16_maps(maps)
+for prec, maps, streamed in (("fp32", False, False), ("tf32", False, False), ("tf32", True, False), ("tf32", True, True)):
+    vu.set_precision(prec); vu.set_bf16_maps(maps); vu.set_streamed(streamed)
     for name in names:
+        if streamed and not name.startswith(("l2block", "base", "lite")):
+            continue
         net, x, y = build_net(name, quiet)
         rows = parity_rows(name, net, x, y, l1_grads=True)
         by = {}
@@ -29,7 +31,7 @@ for prec, maps in (("fp32", False), ("tf32", False), ("tf32", True)):
             a[2] += 1
             if e >= a[0]:
                 a[0], a[1] = e, k
-        print(f"== {name} prec={prec} bf16_maps={maps}")
+        print(f"== {name} prec={prec} bf16_maps={maps} streamed={streamed}")
         for grp, (e, k, n, nch, ech) in by.items():
             print(f"   {grp:10s} worst {e:.3e} ({k}) over {n} tensors; chaotic {nch} (max {ech:.2e})")
         fails = [r for r in rows if r[3] == "FAIL"]
