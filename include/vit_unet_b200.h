@@ -117,11 +117,9 @@ int vu_reattn_tensor_core_path(int h, int N, int ld);
  * Pc == NULL: P overwrites S in place (fp32).  Pc != NULL: centred bf16 probabilities are written to Pc (same
  * (B,h,N,ld) indexing), S is left untouched and the moments are those of the ROUNDED map.
  * precision = VU_PREC_TF32 lets the moments of 8-head maps without pad columns be accumulated by TF32 warp MMAs
- * (centred inputs, fp32 accumulation); VU_PREC_FP32 keeps the exact CUDA-core sums.
- * keep_mask (optional, tensor-core map path only, B*h*N*N/4 bytes): the keep-bits this kernel hashes are cached there,
- * one byte per key quad; vu_reattn_mix / _mix_reduce / _bwd_rows given the same buffer read them instead of hashing. */
+ * (centred inputs, fp32 accumulation); VU_PREC_FP32 keeps the exact CUDA-core sums. */
 int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
-                     uint32_t stream_id, double* sums, int precision, void* keep_mask, void* stream);
+                     uint32_t stream_id, double* sums, int precision, void* stream);
 /* fold conv1x1 + BatchNorm into one affine:  fold[h*h + h] = {alpha'[h][g], beta'[h]};
  * saved[2h] = {mean_h, invstd_h}.  train=1: batch statistics from `sums` (+ running-stat update,
  * momentum, unbiased variance, num_batches_tracked += 1); train=0: running statistics. model.py:136,159 */
@@ -131,15 +129,14 @@ int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, int N, const
                           float* fold, float* saved, void* stream);
 /* A_h = sum_g alpha'[h,g]*drop(P_g) + beta'[h].  map_fmt: see VU_MAP_* (P fp32 or centred bf16; A fp32 or bf16). */
 int vu_reattn_mix(const void* P, void* A, int map_fmt, const float* fold, int B, int h, int N, int ld,
-                  float drop_p, uint64_t seed, uint32_t stream_id, const void* keep_mask, void* stream);
+                  float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 /* backward reductions: red[h + h*h] (double, caller zeroes) += { s1_h = sum dA_h,  X'_{hg} = sum dA_h (Pd_g - c) } */
 int vu_reattn_bwd_reduce(const float* P, const float* dA, int B, int h, int N, int ld, float drop_p, uint64_t seed,
                          uint32_t stream_id, double* red, void* stream);
 /* fused backward pass: A = mix(P) (as vu_reattn_mix) AND the reductions of vu_reattn_bwd_reduce, one read of P, dA.
  * A == NULL (tensor-core map path only): the caller kept the forward map, only the reductions are computed. */
 int vu_reattn_mix_reduce(const void* P, const void* dA, void* A, int map_fmt, const float* fold, int B, int h, int N,
-                         int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red, const void* keep_mask,
-                         void* stream);
+                         int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red, void* stream);
 /* closed-form parameter gradients from (red, sums): dW[h*h], dbconv[h], dgamma[h], dbeta[h] are ACCUMULATED
  * (atomic; caller zeroes); coef[2h] = BatchNorm-backward means {mean dA_h, mean dA_h*Ahat_h} for vu_reattn_bwd_rows.
  * sums may be NULL when train == 0. */
@@ -149,8 +146,7 @@ int vu_reattn_bwd_params(const double* red, const double* sums, int B, int h, in
 /* in place dA -> dS (gradient of the pre-softmax scores) */
 int vu_reattn_bwd_rows(const void* P, void* dA_dS, int map_fmt, int B, int h, int N, int ld, const float* W,
                        const float* bconv, const float* gamma, const float* saved, const float* coef,
-                       int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, const void* keep_mask,
-                       void* stream);
+                       int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream);
 
 /* ---- streamed Re-Attention (vu_reattn_stream.cu): the same math as the chain softmax -> dropout -> mix/BN -> A.V
  * (model.py:155-161, :251-256) WITHOUT materialising the (B,h,N,N) maps, for the fine levels (many tokens, small

@@ -499,37 +499,3 @@ def test_dice_global_batch_semantics_from_partial_sums(ops):
     dpart = torch.empty(2, 1, 32, 32, device="cuda")
     ops.loss_bwd("dice", pred[2:].contiguous(), tgt[2:].contiguous(), sums, one, dpart)
     assert torch.allclose(dpart, dfull[2:], rtol=1e-6, atol=1e-9)
-
-
-def test_cached_keep_bits_equal_rehashed_masks(ops):
-    """Tensor-core map path: softmax_stats caches the keep-bits it hashes (one byte per key quad); mix / mix_reduce /
-    bwd_rows given that cache produce bit-identical results to regenerating the mask by hashing."""
-    B, h, N, p, seed, sid = 2, 8, 128, 0.3, 77, 9
-    g = torch.Generator().manual_seed(6)
-    S0 = torch.randn(B, h, N, N, generator=g).cuda()
-    fold = (torch.randn(h * h + h, generator=g) * 0.3).cuda()
-    W = (torch.randn(h, h, generator=g) / h ** 0.5).cuda().contiguous()
-    bconv, gamma = (torch.randn(h, generator=g) * 0.05).cuda(), (1 + 0.3 * torch.randn(h, generator=g)).cuda()
-    saved = torch.cat([torch.full((h,), 1.0 / N), torch.full((h,), 50.0)]).cuda()
-    coef = (torch.randn(2 * h, generator=g) * 1e-3).cuda()
-    dA0 = torch.randn(B, h, N, N, generator=g).cuda().bfloat16()
-    outs = []
-    for cached in (False, True):
-        mask = torch.zeros(B * h * N * N // 4 + 256, dtype=torch.uint8, device="cuda") if cached else None
-        S = S0.clone()
-        Pc = torch.empty(B, h, N, N, dtype=torch.bfloat16, device="cuda")
-        sums = torch.zeros(h + h * h, dtype=torch.float64, device="cuda")
-        ops.softmax_stats(S, B, h, N, N, 0.2, p, seed, sid, sums, precision=ops.PREC_TF32, Pc=Pc, mask=mask)
-        A = torch.empty(B, h, N, N, dtype=torch.bfloat16, device="cuda")
-        ops.reattn_mix(Pc, A, fold, B, h, N, N, p, seed, sid, tf32=True, mask=mask)
-        red = torch.zeros(h + h * h, dtype=torch.float64, device="cuda")
-        ops.reattn_mix_reduce(Pc, dA0, None, fold, B, h, N, N, p, seed, sid, red, tf32=True, mask=mask)
-        dA = dA0.clone()
-        ops.reattn_bwd_rows(Pc, dA, B, h, N, N, W, bconv, gamma, saved, coef, True, 0.2, p, seed, sid, tf32=True, mask=mask)
-        outs.append((sums.clone(), A.clone(), red.clone(), dA.clone()))
-        if cached:
-            kept = (mask[:B * h * N * N // 4].to(torch.int32).unsqueeze(1) >> torch.arange(4, device="cuda")) & 1
-            assert abs(kept.float().mean().item() - (1 - p)) < 0.01
-    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][3], outs[1][3])
-    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-12, atol=0) or torch.allclose(outs[0][0], outs[1][0], rtol=1e-6)
-    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-6, atol=1e-9)

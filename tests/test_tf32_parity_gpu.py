@@ -24,7 +24,7 @@ def tf32():
     import vit_unet_b200 as vu
     vu.set_precision("tf32")
     yield vu
-    vu.set_precision("fp32"); vu.set_bf16_maps(True); vu.set_bf16_probs(False, long_rows=True, mask_cache=True); vu.set_streamed(False)
+    vu.set_precision("fp32"); vu.set_bf16_maps(True); vu.set_bf16_probs(False); vu.set_streamed(False)
 
 
 @pytest.mark.parametrize("bf16_maps", [True, False])
@@ -55,15 +55,6 @@ def test_tf32_streamed_attention_matches_reference_golden(tf32, name):
         tf32.set_streamed(False)
     bad = [r for r in rows if r[3] == "FAIL"]
     assert not bad, f"{len(bad)} of {len(rows)} tensors out of tolerance; worst: {summarize(bad)}"
-
-
-def test_tf32_fp32_probabilities_and_rehashed_masks(tf32):
-    """The non-default storage at the level-2 shape: fp32 probabilities, dropout mask re-hashed in every kernel."""
-    tf32.set_bf16_maps(True); tf32.set_bf16_probs(False, long_rows=False, mask_cache=False)
-    net, x, y = build_net("l2block_head", _quiet)
-    rows = parity_rows("l2block_head", net, x, y, grad_base=GRAD_BASE_L2, chaos=CHAOS_TC, train_out_base=OUT_BASE_TRAIN_BF16)
-    bad = [r for r in rows if r[3] == "FAIL"]
-    assert not bad, summarize(bad)
 
 
 def test_tf32_centred_bf16_probabilities(tf32):

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitunet_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 7
 
 
 class VuError(RuntimeError):
@@ -48,14 +48,14 @@ SIGNATURES = {
     "vu_gemm": [C.POINTER(GemmDesc), _p],
     "vu_colsum": [_p, _l, _i, _l, _p, _i, _p],
     "vu_softmax_rows": [_p, _l, _i, _i, _f, _p],
-    "vu_softmax_stats": [_p, _p, _i, _i, _i, _i, _f, _f, _u64, _u32, _p, _i, _p, _p],
-    "vu_reattn_mix_reduce": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p, _p],
+    "vu_softmax_stats": [_p, _p, _i, _i, _i, _i, _f, _f, _u64, _u32, _p, _i, _p],
+    "vu_reattn_mix_reduce": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_stats": [_p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bn_finalize": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p],
-    "vu_reattn_mix": [_p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
+    "vu_reattn_mix": [_p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p],
     "vu_reattn_bwd_reduce": [_p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
     "vu_reattn_bwd_params": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
-    "vu_reattn_bwd_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _f, _u64, _u32, _p, _p],
+    "vu_reattn_bwd_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _f, _u64, _u32, _p],
     "vu_reattn_stream_fwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _u64, _u32, _p],
     "vu_reattn_stream_bwd_reduce": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p],
     "vu_reattn_stream_bwd_ds": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _u32, _p],

@@ -60,10 +60,6 @@ softmax_rows_kernel(float* __restrict__ S, int64_t rows, int N, int ld, float sc
 struct QuadCtx {
   uint32_t thresh; float dscale; uint64_t seed; uint32_t stream; float c; int N;
   uint32_t key;          // Philox::key(seed, stream), computed on the host
-  // optional cache of the keep-bits on the tensor-core map path (one byte per key quad, indexed by the quad's
-  // counter = flat element index / 4): the statistics kernel, which hashes anyway, WRITES it (mask_out); the three
-  // later kernels READ it (mask_in) instead of hashing again (the hash + compares are ~25 instructions per quad)
-  const uint8_t* mask_in; uint8_t* mask_out;
 };
 __device__ __forceinline__ float4 load_pd(const float* __restrict__ p, uint64_t flat_idx, const QuadCtx& q) {
   float4 v = *reinterpret_cast<const float4*>(p);
@@ -543,7 +539,6 @@ static int grid_for(int64_t work_items, int threads, int per_sm) {
 }
 static QuadCtx make_ctx(float drop_p, uint64_t seed, uint32_t stream_id, int N) {
   QuadCtx q;
-  q.mask_in = nullptr; q.mask_out = nullptr;
   q.thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
   q.dscale = drop_keep_scale(drop_p); q.seed = seed; q.stream = stream_id; q.c = 1.0f / (float)N; q.N = N;
   q.key = Philox::key(seed, stream_id);
@@ -605,7 +600,7 @@ extern "C" int vu_reattn_bn_finalize(const double* sums, int64_t count, int h, i
 }
 
 extern "C" int vu_reattn_mix(const void* Pv, void* A, int map_fmt, const float* fold, int B, int h, int N, int ld,
-                             float drop_p, uint64_t seed, uint32_t stream_id, const void* keep_mask, void* stream) {
+                             float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_mix";
   const int map_bf16 = map_fmt & VU_MAP_BF16, p_bf16 = map_fmt & VU_MAP_P_CENTRED_BF16;
@@ -615,8 +610,6 @@ extern "C" int vu_reattn_mix(const void* Pv, void* A, int map_fmt, const float* 
   VU_REQUIRE(drop_p >= 0.f && drop_p < 1.f, fn, "drop_p must be in [0,1)");
   VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
-  VU_REQUIRE(!keep_mask || ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)), fn, "keep_mask is a cache of the tensor-core map path");
-  q.mask_in = (const uint8_t*)keep_mask;
   if ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)) {
     VU_REQUIRE(B <= 65535, fn, "at most 65535 images per call on the tensor-core map path");
     const int64_t tiles = cdiv((int64_t)N * N / 4, 8);          // per image; grid = (x, B)
@@ -659,8 +652,7 @@ extern "C" int vu_reattn_bwd_params(const double* red, const double* sums, int B
 
 extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int B, int h, int N, int ld, const float* W,
                                   const float* bconv, const float* gamma, const float* saved, const float* coef,
-                                  int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id,
-                                  const void* keep_mask, void* stream) {
+                                  int train, float scale, float drop_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_bwd_rows";
   const int map_bf16 = map_fmt & VU_MAP_BF16, p_bf16 = map_fmt & VU_MAP_P_CENTRED_BF16;
@@ -670,8 +662,6 @@ extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int 
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
   VU_REQUIRE(!map_bf16 || ld % 8 == 0, fn, "bf16 maps need ld % 8 == 0");
   VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
-  VU_REQUIRE(!keep_mask || ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)), fn, "keep_mask is a cache of the tensor-core map path");
-  q.mask_in = (const uint8_t*)keep_mask;
   if ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)) {
     cudaStream_t st = as_stream(stream);
     __nv_bfloat16* d = (__nv_bfloat16*)dA_dS;
@@ -716,7 +706,7 @@ extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int 
 }
 
 extern "C" int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld, float scale, float drop_p, uint64_t seed,
-                                uint32_t stream_id, double* sums, int precision, void* keep_mask, void* stream) {
+                                uint32_t stream_id, double* sums, int precision, void* stream) {
   using namespace vu;
   const char* fn = "vu_softmax_stats";
   VU_REQUIRE(VU_MAP_ARGS_OK(S) && sums, fn, "bad arguments (maps need ld % 4 == 0 and 16-byte alignment)");
@@ -726,8 +716,6 @@ extern "C" int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld,
   const bool use_mma = precision == VU_PREC_TF32 && mma_path(h, N, ld);
   VU_REQUIRE(!Pc || (use_mma && (uintptr_t)Pc % 16 == 0), fn,
              "centred bf16 output needs VU_PREC_TF32, h == 8, ld == N, N % 8 == 0 and 16-byte alignment");
-  VU_REQUIRE(!keep_mask || use_mma, fn, "keep_mask is a cache of the tensor-core map path");
-  q.mask_out = (uint8_t*)keep_mask;
   if (use_mma) {
     if (N > 256 && N <= 1024) {          // asynchronous row pipeline (cp.async.bulk ring in shared memory)
       constexpr int ST = 2;
@@ -760,7 +748,7 @@ extern "C" int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld,
 
 extern "C" int vu_reattn_mix_reduce(const void* Pv, const void* dA, void* A, int map_fmt, const float* fold, int B, int h,
                                     int N, int ld, float drop_p, uint64_t seed, uint32_t stream_id, double* red,
-                                    const void* keep_mask, void* stream) {
+                                    void* stream) {
   using namespace vu;
   const char* fn = "vu_reattn_mix_reduce";
   const int map_bf16 = map_fmt & VU_MAP_BF16, p_bf16 = map_fmt & VU_MAP_P_CENTRED_BF16;
@@ -773,8 +761,6 @@ extern "C" int vu_reattn_mix_reduce(const void* Pv, const void* dA, void* A, int
   VU_REQUIRE(A != dA, fn, "A and dA must be distinct buffers");
   VU_REQUIRE(!p_bf16 || (map_bf16 && mma_path(h, N, ld)), fn, "centred bf16 probabilities need bf16 maps, h == 8, ld == N, N % 8 == 0");
   QuadCtx q = make_ctx(drop_p, seed, stream_id, N);
-  VU_REQUIRE(!keep_mask || ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)), fn, "keep_mask is a cache of the tensor-core map path");
-  q.mask_in = (const uint8_t*)keep_mask;
   if ((map_bf16 || (map_fmt & VU_MAP_TF32_MIX)) && mma_path(h, N, ld)) {
     VU_REQUIRE(B <= 65535, fn, "at most 65535 images per call on the tensor-core map path");
     const int64_t tiles = cdiv((int64_t)N * N / 4, 8);          // per image; grid = (x, B)

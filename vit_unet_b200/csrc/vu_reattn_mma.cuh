@@ -62,14 +62,9 @@ __device__ __forceinline__ void frag_bwd(const float* __restrict__ F, int e, int
 // dropout of one quad in place (ctr = low 32 bits of element index / 4); returns the keep bits (bit t = component t)
 __device__ __forceinline__ uint32_t drop_quad(float4& v, uint32_t ctr, const QuadCtx& q) {
   if (!q.thresh) return 0xFu;
-  uint32_t m;
-  if (q.mask_in) {                 // keep-bits cached by the statistics kernel (warp-uniform branch)
-    m = q.mask_in[ctr];
-  } else {
-    const uint4 rr = Philox::gen_k(q.key, ctr);
-    m = (rr.x >= q.thresh ? 1u : 0u) | (rr.y >= q.thresh ? 2u : 0u) | (rr.z >= q.thresh ? 4u : 0u) | (rr.w >= q.thresh ? 8u : 0u);
-    if (q.mask_out) q.mask_out[ctr] = (uint8_t)m;
-  }
+  const uint4 rr = Philox::gen_k(q.key, ctr);
+  const uint32_t m = (rr.x >= q.thresh ? 1u : 0u) | (rr.y >= q.thresh ? 2u : 0u) | (rr.z >= q.thresh ? 4u : 0u) |
+                     (rr.w >= q.thresh ? 8u : 0u);
   v.x = (m & 1u) ? v.x * q.dscale : 0.f; v.y = (m & 2u) ? v.y * q.dscale : 0.f;
   v.z = (m & 4u) ? v.z * q.dscale : 0.f; v.w = (m & 8u) ? v.w * q.dscale : 0.f;
   return m;

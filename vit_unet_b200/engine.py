@@ -36,8 +36,6 @@ _BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "1") == "1"}      # on by 
 # the map kernels are issue-bound rather than HBM-bound once the mixing runs on the tensor cores)
 _BF16_PROBS = {"value": os.environ.get("VU_BF16_PROBS", "0") == "1"}
 _KEEP_MIXED_MAP = {"value": os.environ.get("VU_KEEP_MIXED_MAP", "1") == "1"}
-_BF16_PROBS_LONG = {"value": os.environ.get("VU_BF16_PROBS_LONG", "1") == "1"}     # centred bf16 probabilities where N >= 256
-_MASK_CACHE = {"value": os.environ.get("VU_MASK_CACHE", "1") == "1"}               # cached attention-dropout keep-bits
 
 
 # streamed Re-Attention (vu_reattn_stream.cu) on the tensor-core path where the shape is supported: no (B,h,N,N) map is
@@ -65,15 +63,9 @@ def set_bf16_maps(on: bool) -> None:
     _BF16_MAPS["value"] = bool(on)
 
 
-def set_bf16_probs(on: bool, long_rows=None, mask_cache=None) -> None:
-    """Store the train-mode attention probabilities as centred bf16 (P - 1/N) wherever the tensor-core map path applies
-    (`on`), or only where rows are long (`long_rows`, N >= 256: the default); `mask_cache` switches the cached
-    attention-dropout keep-bits (default on)."""
+def set_bf16_probs(on: bool) -> None:
+    """Store the train-mode attention probabilities as centred bf16 (P - 1/N) where the tensor-core map path applies."""
     _BF16_PROBS["value"] = bool(on)
-    if long_rows is not None:
-        _BF16_PROBS_LONG["value"] = bool(long_rows)
-    if mask_cache is not None:
-        _MASK_CACHE["value"] = bool(mask_cache)
 
 
 def set_map_l2_budget(megabytes: float) -> None:
@@ -204,15 +196,7 @@ class Engine:
             return self._attn_fwd_streamed(P, pre, xq, xkv, q, k, v, l, B, train, seed, sid, residual, saved)
         # train mode on the tensor-core map path: probabilities are kept as CENTRED bf16 (P - 1/N), scores are a
         # per-slice fp32 scratch -- the saved map and every later pass over it cost half the bytes
-        tc_maps = ops.reattn_tensor_core_path(h, N, ld)
-        # centred bf16 probabilities: on request everywhere the tensor-core map kernels run, and by default for long rows
-        # (N >= 256: the BatchNorm statistics average over >= 65k values per image and head; measured +1.4 % images/s and
-        # half the saved-map memory; the few-token levels keep fp32 probabilities)
-        pc16 = bf16 and train and tc_maps and (_BF16_PROBS["value"] or (_BF16_PROBS_LONG["value"] and N >= 256))
-        # keep-bits of the attention dropout: hashed once by the statistics kernel, cached (one byte per key quad) and
-        # re-read by mix / mix_reduce / bwd_rows (the hash costs 3-5 ms per step when every kernel regenerates it)
-        kmask = (torch.empty(B * h * N * ld // 4 + 256, dtype=torch.uint8, device=xq.device)
-                 if (train and adrop > 0 and c >= B and tc_maps and prec == ops.PREC_TF32 and _MASK_CACHE["value"]) else None)
+        pc16 = bf16 and train and _BF16_PROBS["value"] and ops.reattn_tensor_core_path(h, N, ld)
         if pc16:
             Pm = torch.empty((B, h, N, ld), dtype=torch.bfloat16, device=xq.device)
             Sc = _empty((c, h, N, ld), xq)
@@ -231,7 +215,7 @@ class Engine:
 
         def mix_pv(b0, bc, src, ci):
             ops.reattn_mix(src, A[:bc], fold, bc, h, N, ld, adrop, seed, sid + _CHUNK_STREAM * ci,
-                           tf32=prec == ops.PREC_TF32, mask=kmask)
+                           tf32=prec == ops.PREC_TF32)
             if bf16:
                 ops.gemm(A[:bc], vt[b0:b0 + bc], O[b0:b0 + bc], N, hd, N, trans_b=True, lda=ld, ldb=ldn, ldc=D,
                          batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(h * hd * ldn, hd * ldn),
@@ -253,11 +237,11 @@ class Engine:
                 if pc16:
                     scores(b0, bc, Sc[:bc])
                     ops.softmax_stats(Sc[:bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums,
-                                      precision=prec, Pc=Pm[b0:b0 + bc], mask=kmask)
+                                      precision=prec, Pc=Pm[b0:b0 + bc])
                 else:
                     scores(b0, bc, Pm[b0:b0 + bc])
                     ops.softmax_stats(Pm[b0:b0 + bc], bc, h, N, ld, scale, adrop, seed, sid + _CHUNK_STREAM * ci, sums,
-                                      precision=prec, mask=kmask)
+                                      precision=prec)
             finalize()
             for ci, b0 in enumerate(range(0, B, c)):
                 bc = min(c, B - b0)
@@ -285,7 +269,7 @@ class Engine:
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums, seed=seed, sid=sid,
-                         adrop=adrop, pdrop=pdrop, train=train, chunk=c, bf16=bf16, A=A, kmask=kmask)
+                         adrop=adrop, pdrop=pdrop, train=train, chunk=c, bf16=bf16, A=A)
         return y
 
     def _attn_fwd_streamed(self, P, pre, xq, xkv, q, k, v, l, B, train, seed, sid, residual, saved):
@@ -426,7 +410,7 @@ class Engine:
             bc = min(c, B - b0)
             grad_map(b0, bc)
             ops.reattn_mix_reduce(Pm[b0:b0 + bc], dA[:bc], None if A_kept is not None else A[:bc], sv["fold"], bc, h, N, ld,
-                                  adrop, seed, sid + _CHUNK_STREAM * ci, red, tf32=prec == ops.PREC_TF32, mask=sv.get("kmask"))
+                                  adrop, seed, sid + _CHUNK_STREAM * ci, red, tf32=prec == ops.PREC_TF32)
             map_gemm(A, True, dOt if bf16 else None, dO, dv, b0, bc)
         sv["A"] = None
         del A, A_kept
@@ -440,7 +424,7 @@ class Engine:
             if not single:
                 grad_map(b0, bc)
             ops.reattn_bwd_rows(Pm[b0:b0 + bc], dA[:bc], bc, h, N, ld, Wm, bm, gamma, sv["bn"], coef, train, scale,
-                                adrop, seed, sid + _CHUNK_STREAM * ci, tf32=prec == ops.PREC_TF32, mask=sv.get("kmask"))
+                                adrop, seed, sid + _CHUNK_STREAM * ci, tf32=prec == ops.PREC_TF32)
             map_gemm(dA, False, kt if bf16 else None, k, dq, b0, bc)
             map_gemm(dA, True, qt if bf16 else None, q, dk, b0, bc)
         del dO, dA

@@ -214,14 +214,14 @@ def softmax_rows(S, rows, N, ld, scale):
     _call("vu_softmax_rows", _chk(S, "S"), rows, N, ld, scale, _stream(), nbytes=8.0 * rows * N)
 
 
-def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums, precision=PREC_FP32, Pc=None, mask=None):
-    """in place (Pc is None) or S -> centred bf16 Pc; mask: optional keep-bit cache written here (B*h*N*N/4 bytes)"""
+def softmax_stats(S, B, h, N, ld, scale, drop_p, seed, sid, sums, precision=PREC_FP32, Pc=None):
+    """in place (Pc is None) or S -> centred bf16 Pc"""
     pc = _chk(Pc, "Pc", torch.bfloat16) if Pc is not None else None
     _call("vu_softmax_stats", _chk(S, "S"), pc, B, h, N, ld, scale, drop_p, seed, sid, _chk(sums, "sums", torch.float64),
-          int(precision), _opt(mask, "mask", torch.uint8), _stream(), nbytes=(4.0 + (2.0 if Pc is not None else 4.0)) * B * h * N * N)
+          int(precision), _stream(), nbytes=(4.0 + (2.0 if Pc is not None else 4.0)) * B * h * N * N)
 
 
-def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red, tf32=False, mask=None):
+def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red, tf32=False):
     pd, bf = _map(dA, "dA")
     pa, bf2 = _map(A, "A") if A is not None else (None, bf)       # A None: reductions only (tensor-core path)
     if bf != bf2:
@@ -229,7 +229,7 @@ def reattn_mix_reduce(P, dA, A, fold, B, h, N, ld, drop_p, seed, sid, red, tf32=
     pp, fmt, pb = _pmap(P, bf, tf32)
     eb = 2.0 if bf else 4.0
     _call("vu_reattn_mix_reduce", pp, pd, pa, fmt, _chk(fold, "fold"), B, h, N, ld,
-          drop_p, seed, sid, _chk(red, "red", torch.float64), _opt(mask, "mask", torch.uint8), _stream(),
+          drop_p, seed, sid, _chk(red, "red", torch.float64), _stream(),
           nbytes=(pb + eb * (2 if A is not None else 1)) * B * h * N * N,
           flops=(4.0 if A is not None else 2.0) * h * B * h * N * N)
 
@@ -247,11 +247,10 @@ def reattn_bn_finalize(sums, count, h, N, W, bconv, gamma, beta, rmean, rvar, nb
          _chk(fold, "fold"), _chk(saved, "saved"), _stream())
 
 
-def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid, tf32=False, mask=None):
+def reattn_mix(P, A, fold, B, h, N, ld, drop_p, seed, sid, tf32=False):
     pa, bf = _map(A, "A")
     pp, fmt, pb = _pmap(P, bf, tf32)
-    _call("vu_reattn_mix", pp, pa, fmt, _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _opt(mask, "mask", torch.uint8),
-          _stream(),
+    _call("vu_reattn_mix", pp, pa, fmt, _chk(fold, "fold"), B, h, N, ld, drop_p, seed, sid, _stream(),
           nbytes=(pb + (2.0 if bf else 4.0)) * B * h * N * N, flops=2.0 * h * B * h * N * N)
 
 
@@ -267,12 +266,12 @@ def reattn_bwd_params(red, sums, B, h, N, W, bconv, gamma, saved, train, coef, d
          _stream())
 
 
-def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid, tf32=False, mask=None):
+def reattn_bwd_rows(P, dA, B, h, N, ld, W, bconv, gamma, saved, coef, train, scale, drop_p, seed, sid, tf32=False):
     pd, bf = _map(dA, "dA")
     pp, fmt, pb = _pmap(P, bf, tf32)
     _call("vu_reattn_bwd_rows", pp, pd, fmt, B, h, N, ld, _chk(W, "W"), _chk(bconv, "bconv"),
           _chk(gamma, "gamma"), _chk(saved, "saved"), _chk(coef, "coef"), int(train), scale, drop_p, seed, sid,
-          _opt(mask, "mask", torch.uint8), _stream(), nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
+          _stream(), nbytes=(pb + 2 * (2.0 if bf else 4.0)) * B * h * N * N, flops=4.0 * h * B * h * N * N)
 
 
 # ----------------------------------------------------------------------------------------- streamed re-attention
