@@ -24,7 +24,7 @@ def tf32():
     import vit_unet_b200 as vu
     vu.set_precision("tf32")
     yield vu
-    vu.set_precision("fp32"); vu.set_bf16_maps(True); vu.set_bf16_probs(False); vu.set_streamed(False)
+    vu.set_precision("fp32"); vu.set_bf16_maps(True); vu.set_bf16_probs(False, long_rows=True); vu.set_streamed(False)
 
 
 @pytest.mark.parametrize("bf16_maps", [True, False])
@@ -55,6 +55,15 @@ def test_tf32_streamed_attention_matches_reference_golden(tf32, name):
         tf32.set_streamed(False)
     bad = [r for r in rows if r[3] == "FAIL"]
     assert not bad, f"{len(bad)} of {len(rows)} tensors out of tolerance; worst: {summarize(bad)}"
+
+
+def test_tf32_fp32_probabilities_at_long_rows(tf32):
+    """The non-default storage at the level-2 shape: fp32 probabilities (centred bf16 is the default for N >= 256)."""
+    tf32.set_bf16_maps(True); tf32.set_bf16_probs(False, long_rows=False)
+    net, x, y = build_net("l2block_head", _quiet)
+    rows = parity_rows("l2block_head", net, x, y, grad_base=GRAD_BASE_L2, chaos=CHAOS_TC, train_out_base=OUT_BASE_TRAIN_BF16)
+    bad = [r for r in rows if r[3] == "FAIL"]
+    assert not bad, summarize(bad)
 
 
 def test_tf32_centred_bf16_probabilities(tf32):
@@ -91,9 +100,10 @@ def test_tf32_dropout_masks_agree_between_forward_and_backward(tf32):
         prm = pd[pname]
         g = prm.grad.view(-1)[idx].item()
         with torch.no_grad():
-            eps = 2e-2 * max(1.0, abs(prm.view(-1)[idx].item()))
+            eps = 5e-2 * max(1.0, abs(prm.view(-1)[idx].item()))
             prm.view(-1)[idx] += eps; lp = loss().item()
             prm.view(-1)[idx] -= 2 * eps; lm = loss().item()
             prm.view(-1)[idx] += eps
         fd = (lp - lm) / (2 * eps)
-        assert abs(fd - g) <= 0.1 * max(abs(g), abs(fd)) + 2e-5, (pname, fd, g)
+        # the loss is an fp32 scalar ~0.5: a central difference over 2 eps = 0.1 resolves the derivative to ~3e-6 / 0.1
+        assert abs(fd - g) <= 0.1 * max(abs(g), abs(fd)) + 6e-5, (pname, fd, g)

@@ -36,6 +36,7 @@ _BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "1") == "1"}      # on by 
 # the map kernels are issue-bound rather than HBM-bound once the mixing runs on the tensor cores)
 _BF16_PROBS = {"value": os.environ.get("VU_BF16_PROBS", "0") == "1"}
 _KEEP_MIXED_MAP = {"value": os.environ.get("VU_KEEP_MIXED_MAP", "1") == "1"}
+_BF16_PROBS_LONG = {"value": os.environ.get("VU_BF16_PROBS_LONG", "1") == "1"}     # centred bf16 probabilities where N >= 256
 
 
 # streamed Re-Attention (vu_reattn_stream.cu) on the tensor-core path where the shape is supported: no (B,h,N,N) map is
@@ -63,9 +64,12 @@ def set_bf16_maps(on: bool) -> None:
     _BF16_MAPS["value"] = bool(on)
 
 
-def set_bf16_probs(on: bool) -> None:
-    """Store the train-mode attention probabilities as centred bf16 (P - 1/N) where the tensor-core map path applies."""
+def set_bf16_probs(on: bool, long_rows=None) -> None:
+    """Store the train-mode attention probabilities as centred bf16 (P - 1/N) wherever the tensor-core map path applies
+    (`on`), or only where rows are long (`long_rows`, N >= 256: the default)."""
     _BF16_PROBS["value"] = bool(on)
+    if long_rows is not None:
+        _BF16_PROBS_LONG["value"] = bool(long_rows)
 
 
 def set_map_l2_budget(megabytes: float) -> None:
@@ -196,7 +200,14 @@ class Engine:
             return self._attn_fwd_streamed(P, pre, xq, xkv, q, k, v, l, B, train, seed, sid, residual, saved)
         # train mode on the tensor-core map path: probabilities are kept as CENTRED bf16 (P - 1/N), scores are a
         # per-slice fp32 scratch -- the saved map and every later pass over it cost half the bytes
-        pc16 = bf16 and train and _BF16_PROBS["value"] and ops.reattn_tensor_core_path(h, N, ld)
+        # centred bf16 probabilities: on request everywhere the tensor-core map kernels run, and by default for long rows
+        # (N >= 256: the BatchNorm statistics average over >= 65k values per image and head; measured +0.7 .. 1.4 % images/s
+        # and half the saved-map memory; the few-token levels keep fp32 probabilities).
+        # Negative result kept out of the tree: caching the dropout keep-bits (one byte per key quad, written by the
+        # statistics kernel, read by mix / mix_reduce / bwd_rows instead of re-hashing) LOST 3.6 % -- the scattered byte
+        # loads cost these HBM-bound kernels more than the ~25 integer instructions of the hash (93.3 vs 90.0 ms per step)
+        pc16 = (bf16 and train and ops.reattn_tensor_core_path(h, N, ld)
+                and (_BF16_PROBS["value"] or (_BF16_PROBS_LONG["value"] and N >= 256)))
         if pc16:
             Pm = torch.empty((B, h, N, ld), dtype=torch.bfloat16, device=xq.device)
             Sc = _empty((c, h, N, ld), xq)
