@@ -424,7 +424,7 @@ def run_cuda(args):
                        "step": ("zero_grad + forward + loss + backward" + (" + bucketed NCCL grad all-reduce" if world > 1 else ""))
                                if wl["train"] else "eval forward under no_grad (batch-sharded, no collective)",
                        "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)" if args.dropout is None else f"OVERRIDDEN to {args.dropout}", "precision": args.precision,
-                       "maps": ("P fp32; mixed map A and gradient map dA/dS bf16 where N % 8 == 0; 8-head map kernels on TF32 warp MMAs" if (args.precision == "tf32" and os.environ.get("VU_BF16_MAPS", "1") == "1") else "fp32"),
+                       "maps": ("P centred bf16 where N >= 256 (else fp32); mixed map A and gradient map dA/dS bf16 where N % 8 == 0; 8-head map kernels on TF32 warp MMAs" if (args.precision == "tf32" and os.environ.get("VU_BF16_MAPS", "1") == "1") else "fp32"),
                        "reattention": ("streamed (no attention maps)" if (args.streamed == 1 or (args.streamed is None and not wl["train"]))
                                        else "materialised maps") + " at the levels vu_reattn_stream_supported covers",
                        "l2": "per-step working set (saved activations + attention maps, GBs) >> 126 MB L2"},
@@ -432,7 +432,8 @@ def run_cuda(args):
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.nbytes + y_pin.nbytes),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": loss_host,
                     "input_pipeline": "pinned host -> device every step, double-buffered on a copy stream (copy of step i+1 overlaps step i)"},
-            "gpu_launches": launches}
+            "gpu_launches": launches,
+            "gemm_tf32_fallbacks": ops.gemm_tf32_fallbacks()}      # TF32 requests that ran on the CUDA-core GEMM (0 = none)
     if world == 1 and not args.no_cpu_baseline and args.workload == "base_train":
         cores = os.cpu_count() or 1
         sec, _ = cpu_reference_step_time(args.cpu_batch, 2, 1, cores)
