@@ -116,6 +116,15 @@ struct Plan {
   static constexpr size_t total(bool with_v) { return q_bytes + 2 * k_bytes + (with_v ? 2 * v_bytes : 0) + w_bytes + 16; }
 };
 
+// Shared-memory row of key kr (0 .. KT-1) of a tile: inside every 16-key block the keys are stored in MMA order -- rows
+// 0..7 = n-tile 0 (keys 0,1,4,5,8,9,12,13), rows 8..15 = n-tile 1 (keys 2,3,6,7,10,11,14,15) -- so that each ldmatrix
+// 8x8 block reads EIGHT CONSECUTIVE rows (conflict-free with the padded pitch); with keys in natural order the blocks
+// would pick rows {0,1,4,5,8,9,12,13}, and rows 8 apart share their banks (2-way conflicts, measured 78 M per launch).
+__device__ __forceinline__ int key_row(int kr) {
+  const int k = kr & 15;
+  return (kr & ~15) + (((k >> 1) & 1) << 3) + ((k >> 2) << 1) + (k & 1);
+}
+
 // Scores of one 16-key step for all heads: s[g][u][0..3] (u = n-tile of the pair).  Lane (gid, tig) ends up with rows
 // gid / gid + 8 and keys 4 tig .. 4 tig + 3 of the step: (u, c) -> key 4 tig + 2 u + c.
 template <int H, int HD>
@@ -124,8 +133,9 @@ __device__ __forceinline__ void scores_step(float (&s)[H][2][4], const float* Qw
   const int m = lane >> 3, r = lane & 7;
   // A (queries): matrix m -> rows (m & 1) * 8 + r, k offset (m >> 1) * 4
   const float* qa = Qw + ((m & 1) * 8 + r) * P::QP + (m >> 1) * 4;
-  // B (keys), two n-tiles: matrix m -> tile u = m >> 1, k half m & 1; n index r -> key 4 (r / 2) + 2 u + (r % 2)
-  const float* ka = Kst + (4 * (r >> 1) + 2 * (m >> 1) + (r & 1)) * P::QP + (m & 1) * 4;
+  // B (keys), two n-tiles: matrix m -> tile u = m >> 1, k half m & 1; n index r -> key 4 (r / 2) + 2 u + (r % 2), which
+  // key_row() stored at row 8 u + r of the 16-key block
+  const float* ka = Kst + ((m >> 1) * 8 + r) * P::QP + (m & 1) * 4;
 #pragma unroll
   for (int g = 0; g < H; ++g) {
 #pragma unroll
@@ -142,8 +152,11 @@ __device__ __forceinline__ void scores_step(float (&s)[H][2][4], const float* Qw
   }
 }
 
+// (4 heads of 12): 140-153 registers without a cap -- just above the 146 that let TWO 7-warp CTAs share an SM; capped.
+template <int H, int HD> constexpr int kMinCtas = (H == 4 && HD == 12) ? 2 : 1;
+
 template <int H, int HD, int MODE, bool WRITE_PC>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+__global__ void __launch_bounds__(WARPS * 32, kMinCtas<H, HD>)
 stream_fwd_kernel(const Args g) {
   using P = Plan<H, HD>;
   constexpr int D = P::D, QP = P::QP, KS = P::KS;
@@ -166,7 +179,7 @@ stream_fwd_kernel(const Args g) {
     for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
       const int kr = c / (D / 4), q4 = c - kr * (D / 4);
       const bool ok = key0 + kr < N;
-      cp_async16(dst + kr * QP + 4 * q4, ok ? kb + (size_t)(key0 + kr) * D + 4 * q4 : kb, ok);
+      cp_async16(dst + key_row(kr) * QP + 4 * q4, ok ? kb + (size_t)(key0 + kr) * D + 4 * q4 : kb, ok);
     }
   };
   auto load_v = [&](int tile, int stage) {
@@ -541,7 +554,7 @@ stream_bwd_reduce_kernel(const BwdArgs g) {
     for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
       const int kr = c / (D / 4), q4 = c - kr * (D / 4);
       const bool ok = key0 + kr < N;
-      cp_async16(dst + kr * QP + 4 * q4, ok ? vb + (size_t)(key0 + kr) * D + 4 * q4 : vb, ok);
+      cp_async16(dst + key_row(kr) * QP + 4 * q4, ok ? vb + (size_t)(key0 + kr) * D + 4 * q4 : vb, ok);
     }
   };
   for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
@@ -658,7 +671,7 @@ stream_bwd_ds_kernel(const BwdArgs g) {
     for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
       const int kr = c / (D / 4), q4 = c - kr * (D / 4);
       const bool ok = key0 + kr < N;
-      cp_async16(dst + kr * QP + 4 * q4, ok ? vb + (size_t)(key0 + kr) * D + 4 * q4 : vb, ok);
+      cp_async16(dst + key_row(kr) * QP + 4 * q4, ok ? vb + (size_t)(key0 + kr) * D + 4 * q4 : vb, ok);
     }
   };
   auto load_kt = [&](int tile, int stage) {
