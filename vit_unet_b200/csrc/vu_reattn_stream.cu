@@ -19,7 +19,7 @@
 //
 // Status (B200, DESIGN.md section 5, profiles/r02_stream.md): parity-green against the reference goldens in eval and
 // train mode, forward and backward.  The no-grad forward is the default wherever the shape is covered (Lite inference
-// 3.07x, Base inference 1.34x over the materialised chain).  For TRAINING steps the kernels are opt-in: a lane holds
+// 3.9x, Base inference 1.4x over the materialised chain).  For TRAINING steps the kernels are opt-in: a lane holds
 // all heads of its 8 positions (64 registers) plus 96 output / 72 reduction accumulators -> 240-255 registers, one
 // 7-warp CTA per SM, 15-42 % issue utilisation (latency-bound), and the materialised map kernels (23-68 % occupancy,
 // 4.5-6.7 TB/s) are faster despite moving 15x the bytes.

@@ -43,7 +43,7 @@ _BF16_PROBS_LONG = {"value": os.environ.get("VU_BF16_PROBS_LONG", "1") == "1"}  
 # written in inference; in training only the centred bf16 probabilities, the mixed map and dS cross HBM.  OPT-IN
 # (set_streamed / VU_STREAMED=1): measured on B200 (tools/block_bench.py, 256 images, Base level-2 block) the streamed
 # kernels run at 7 warps per SM (all heads of a position live in one lane: 240-255 registers) and are latency-bound --
-# forward 5.3 ms vs 4.4 ms materialised, backward 12.0 vs 5.8 ms -- while using 40 % less memory (7.6 vs 12.3 GB).
+# forward 4.9 ms vs 4.4 ms materialised, backward 12.6 vs 5.7 ms -- while using 40 % less memory (7.6 vs 12.3 GB).
 _STREAMED = {"value": os.environ.get("VU_STREAMED", "0") == "1"}
 _STREAMED_BWD = {"value": os.environ.get("VU_STREAMED_BWD", "1") == "1"}     # with it: the streamed backward kernels too
 # INFERENCE (nothing saved for backward) is different: there the streamed kernel replaces fp32 map round trips of up to
