@@ -14,6 +14,7 @@ The first bucket is the reconstruction conv + the last skip connection (a 3072^2
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -77,9 +78,23 @@ class GradBucketer:
 class DataParallel(torch.nn.Module):
     """Wraps a vit_unet_b200 model: same call surface, gradients averaged across ranks during backward."""
 
-    def __init__(self, module, process_group=None, bucket_mb: float = 32.0, broadcast_from: Optional[int] = 0):
+    def __init__(self, module, process_group=None, bucket_mb: float = 32.0, broadcast_from: Optional[int] = 0,
+                 high_priority: Optional[bool] = None):
         super().__init__()
         self.module = module
+        # The all-reduce kernels run next to persistent compute kernels that occupy every SM; on a high-priority stream
+        # their CTAs are scheduled as soon as a slot frees instead of queueing behind the compute grid (timeline:
+        # tools/dp_timeline.py).  Default: a dedicated NCCL group with high-priority streams when none is given
+        # (VU_DP_HIGH_PRIORITY=0 keeps the default group).
+        if high_priority is None:
+            high_priority = os.environ.get("VU_DP_HIGH_PRIORITY", "1") == "1"
+        if (process_group is None and high_priority and dist.is_initialized() and dist.get_backend() == "nccl"
+                and dist.get_world_size() > 1):
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                process_group = dist.new_group(backend="nccl", pg_options=opts)
+            except (AttributeError, TypeError, RuntimeError):     # older / newer torch spellings: fall back to the default group
+                process_group = None
         pd = dict(module.named_parameters())
         starts: Dict[str, int] = {}
         for name, off in zip(module._param_names, module._flat_offsets):
