@@ -22,13 +22,14 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 YARD = 10
 CHAOS = 1e-2
 OUT_BASE = 1e-2
-GRAD_BASE = 3e-2          # TF32 contractions, fp32 attention maps: measured <= 2.8e-2 (B200, r2_parity_table)
-GRAD_BASE_BF16 = 1.5e-1   # + bf16 storage of the mixed / gradient maps (2^-9 per element) on the TINY configs, whose BatchNorm
+GRAD_BASE = 5e-2          # TF32 contractions, fp32 attention maps: measured <= 2.8e-2 (B200, profiles/r02_parity.md); the margin
+                          #   covers the run-to-run spread of the atomically accumulated reductions
+GRAD_BASE_BF16 = 2.5e-1   # + bf16 storage of the mixed / gradient maps (2^-9 per element) on the TINY configs, whose BatchNorm
                           #   normalises over a few hundred map values (16 / 64 tokens, batch 2-3) and whose q/k conv gradients
                           #   are differences of nearly equal terms: measured 9.7e-2 .. 1.3e-1 (run-to-run: atomics order)
 GRAD_BASE_L2 = 1e-2       # the Base / Lite / 1-channel LEVEL-2 shapes the benchmark spends its time at (l2block_* configs,
                           #   784 tokens): measured <= 3e-3 with either map storage, streamed or materialised
-OUT_BASE_TRAIN_BF16 = 3e-2   # TRAIN-mode outputs with bf16 maps: BatchNorm batch statistics of the tiny configs are taken over as
+OUT_BASE_TRAIN_BF16 = 5e-2   # TRAIN-mode outputs with bf16 maps: BatchNorm batch statistics of the tiny configs are taken over as
                              #   few as 2 x 4 x 4 map values per head; measured <= 2.0e-2 (tiny_head_1ch), <= 1.7e-3 at Base shapes
 CHAOS_TC = 1e-4           # a tensor whose fp32 reference is itself > 1e-4 from fp64 amplifies the 2^-11 input rounding of a
                           #   tensor-core path by the same factor (x 8192) to O(1): reported, finiteness only
