@@ -158,6 +158,38 @@ def test_model_tf32_within_1e2():
     assert (psnr(a) - psnr(b)).abs().max().item() < 0.01
 
 
+def test_lite_streamed_inference_within_1e2_and_psnr():
+    """BASELINE configs[1] path: Lite eval forward under no_grad on the tensor-core path = streamed Re-Attention at the
+    3136- and 784-token levels (4 heads of 12 / 48), tcgen05 token GEMMs.  1e-2 relative, PSNR delta < 0.01 dB, and the
+    streamed forward agrees with the materialised one."""
+    import contextlib, io
+    import vit_unet_b200 as vu
+    from make_golden import CONFIGS, fill_state_dict, make_input
+    from oracle import vit_unet_oracle as O
+    _, kw, _ = CONFIGS["lite_head"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref, net = O.HViT_UNet(**kw), vu.HViT_UNet(**kw)
+    sd = fill_state_dict(ref.state_dict())
+    ref.load_state_dict(sd); net.load_state_dict(sd); net.to("cuda")
+    x, clean = make_input(2, 3, 224, seed=3)
+    ref.eval(); net.eval()
+    vu.set_precision("tf32")
+    try:
+        with torch.no_grad():
+            a = ref(x)
+            b = net(x.cuda()).cpu()                       # streamed (default for inference)
+            vu.set_streamed(False, inference=False)
+            c = net(x.cuda()).cpu()                       # materialised
+    finally:
+        vu.set_streamed(False, inference=True); vu.set_precision("fp32")
+    for out, tag in ((b, "streamed"), (c, "materialised")):
+        rel = ((a - out).abs().max() / a.abs().max()).item()
+        assert rel <= 1e-2, (tag, rel)
+    psnr = lambda o: 10 * torch.log10(4.0 / ((o - clean) ** 2).flatten(1).mean(1))
+    assert (psnr(a) - psnr(b)).abs().max().item() < 0.01
+    assert ((b - c).abs().max() / c.abs().max()).item() <= 5e-3
+
+
 # ------------------------------------------------------------------------------------------------ bf16 operands
 @pytest.mark.parametrize("M,N,K", [(128, 32, 64), (784, 24, 784), (300, 72, 200), (256, 128, 512)])
 @pytest.mark.parametrize("ta", [False, True])
