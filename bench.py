@@ -38,6 +38,8 @@ WORKLOADS = {
                        name="ViT_UNet Base denoising training step, L1 loss, 3x224x224 (BASELINE configs[2])"),
     "lite_infer": dict(kw=dict(depth_te=1, patch_size=16, hidden_dim=64, num_heads=4), train=False, loss="l1", flops=9.311e9,
                        name="ViT_UNet Lite inference (eval forward), 3x224x224 (BASELINE configs[1])"),
+    "lite_train": dict(kw=dict(depth_te=1, patch_size=16, hidden_dim=64, num_heads=4), train=True, loss="l1", flops=27.9e9,
+                       name="ViT_UNet Lite denoising training step, L1 loss (README usage line: run_denoising.py --model_string lite)"),
     "base_infer": dict(kw={}, train=False, loss="l1", flops=7.755e9,
                        name="ViT_UNet Base inference (eval forward), 3x224x224"),
     "large_train": dict(kw=dict(depth_te=4, size_bottleneck=4), train=True, loss="l1", flops=42.4e9,
@@ -207,7 +209,7 @@ def run_eager(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     wl = WORKLOADS[args.workload]
-    preset = {"base_train": "base", "lite_infer": "lite", "base_infer": "base", "large_train": "large", "base1ch_dice": "base"}[args.workload]
+    preset = {"base_train": "base", "lite_infer": "lite", "lite_train": "lite", "base_infer": "base", "large_train": "large", "base1ch_dice": "base"}[args.workload]
     B = args.eager_batch
     res = {}
     for tf32 in (False, True):
@@ -458,7 +460,7 @@ def main():
                          "model run eagerly on one B200 through cuBLAS/cuDNN (SURVEY 8(d) second baseline)")
     ap.add_argument("--eager-batch", type=int, default=64, help="batch of the eager-PyTorch arm (it materialises every "
                     "(B,h,N,N) map in fp32 and keeps them for autograd: ~1 GB per image for Base)")
-    ap.add_argument("--workload", default="base_train", choices=["base_train", "lite_infer", "base_infer", "large_train", "base1ch_dice"],
+    ap.add_argument("--workload", default="base_train", choices=["base_train", "lite_infer", "lite_train", "base_infer", "large_train", "base1ch_dice"],
                     help="base_train is the headline (BASELINE.json metric); the others are extra modes")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (SURVEY 8(d) C3: 64..256; ~40 GB of the 180 GB at 256)")
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed GLOBAL batch split over the ranks "

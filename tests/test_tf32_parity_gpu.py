@@ -42,7 +42,7 @@ def test_tf32_path_matches_reference_golden(tf32, name, bf16_maps):
         assert len(checked) >= 0.5 * len(rows), "more than half of the tensors fell into the chaotic regime"
 
 
-@pytest.mark.parametrize("name", ["l2block_head", "l2block_1ch", "base_head"])
+@pytest.mark.parametrize("name", ["l2block_head", "l2block_1ch", "l2block_lite", "lite_head", "base_head"])
 def test_tf32_streamed_attention_matches_reference_golden(tf32, name):
     """The streamed Re-Attention kernels (forward AND backward; opt-in: set_streamed) on the configs whose finest level
     they cover, against the same golden vectors."""

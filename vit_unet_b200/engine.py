@@ -195,8 +195,10 @@ class Engine:
         # streamed forward: always for inference; with a backward pass to feed only where the materialised backward
         # kernels accept centred bf16 probabilities (8 heads, bf16 maps)
         stream_on = _STREAMED["value"] or (_STREAMED_INFER["value"] and not keep_P and not train)
-        if (prec == ops.PREC_TF32 and stream_on and c >= B and ops.reattn_stream_supported(h, hd, N)
-                and (not keep_P or (bf16 and ops.reattn_tensor_core_path(h, N, ld)))):
+        # with a backward pass to feed: either the streamed backward kernels take over (any supported head count), or the
+        # materialised tensor-core backward reads the centred bf16 probabilities (8 heads only)
+        bwd_ok = (not keep_P or _STREAMED_BWD["value"] or (bf16 and ops.reattn_tensor_core_path(h, N, ld)))
+        if prec == ops.PREC_TF32 and stream_on and c >= B and ops.reattn_stream_supported(h, hd, N) and bwd_ok:
             return self._attn_fwd_streamed(P, pre, xq, xkv, q, k, v, l, B, train, seed, sid, residual, saved)
         # train mode on the tensor-core map path: probabilities are kept as CENTRED bf16 (P - 1/N), scores are a
         # per-slice fp32 scratch -- the saved map and every later pass over it cost half the bytes
