@@ -152,13 +152,13 @@ def _bn_params(h, seed):
 
 @pytest.mark.parametrize("train", [True, False])
 @pytest.mark.parametrize("p", [0.0, 0.25])
-@pytest.mark.parametrize("h,hd,N", [(8, 24, 784), (8, 24, 128), (4, 12, 336)])
+@pytest.mark.parametrize("h,hd,N", [(8, 24, 784), (8, 24, 128), (4, 12, 336), (4, 48, 336), (8, 8, 208), (4, 12, 3136)])
 def test_stream_backward_matches_materialised_chain(ops, h, hd, N, p, train):
     """vu_reattn_stream_bwd_reduce / _bwd_ds against the exact fp32 materialised kernels (scores -> softmax_stats ->
     bn_finalize -> dA = dO v^T -> bwd_reduce -> bwd_params -> bwd_rows -> dq = dS k) on the same inputs and dropout seed."""
     if p > 0 and not train:
         pytest.skip("dropout is a train-mode feature")
-    B, seed, sid = 2, 99, 3
+    B, seed, sid = (1 if N > 1024 else 2), 99, 3
     D, scale = h * hd, hd ** -0.5
     q, k, v, _ = _inputs(B, h, hd, N, seed=30)
     dO = _rand(B, N, D, seed=40)

@@ -191,7 +191,8 @@ def test_lite_streamed_inference_within_1e2_and_psnr():
 
 
 # ------------------------------------------------------------------------------------------------ bf16 operands
-@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (784, 24, 784), (300, 72, 200), (256, 128, 512)])
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (784, 24, 784), (300, 72, 200), (256, 128, 512), (784, 48, 784),
+                                    (3136, 12, 3136), (336, 64, 336), (784, 8, 784)])
 @pytest.mark.parametrize("ta", [False, True])
 def test_tc_gemm_bf16_operands(ops, M, N, K, ta):
     """kind::f16 path: bf16 A (K-major or MN-major) x bf16 K-major B -> fp32 C."""

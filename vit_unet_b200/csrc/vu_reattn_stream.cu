@@ -81,6 +81,16 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// mma.sync reads fp32 bit patterns as TF32 by TRUNCATION (a -2^-11 relative bias on every operand).  Sums with heavy
+// cancellation (sum dA over a map, the BatchNorm moments) turn that bias into O(1) relative errors, so every fp32 tile
+// is rounded to nearest in shared memory right after it lands: one integer add per element (the low 13 bits that
+// remain are ignored by the tensor core).  Each thread rounds exactly the 16-byte chunks it copied itself, after its own
+// cp.async group completed and before the barrier that publishes the tile.
+__device__ __forceinline__ void round_tf32_chunk(float* p) {
+  uint4 v = *reinterpret_cast<uint4*>(p);
+  v.x += 0x1000u; v.y += 0x1000u; v.z += 0x1000u; v.w += 0x1000u;
+  *reinterpret_cast<uint4*>(p) = v;
+}
 __device__ __forceinline__ float ex2(float x) {             // MUFU.EX2 (2^-22 relative), flushes denormal results to 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -192,16 +202,29 @@ stream_fwd_kernel(const Args g) {
     }
   };
 
+  auto round_k = [&](int stage) {          // same chunk ownership as load_k
+    float* dst = Ks + stage * KT * QP;
+    for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
+      const int kr = c / (D / 4), q4 = c - kr * (D / 4);
+      round_tf32_chunk(dst + key_row(kr) * QP + 4 * q4);
+    }
+  };
   // ---- prologue: resident Q rows of the CTA, the fold, zeroed pads; first K (and V) tile in flight
   for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
     const int r = c / (D / 4), q4 = c - r * (D / 4);
     const bool ok = row0 + r < N;
     cp_async16(Qs + r * QP + 4 * q4, ok ? qb + (size_t)(row0 + r) * D + 4 * q4 : qb, ok);
   }
+  cp_async_commit();                        // group 1: the Q rows (rounded below while the first K tile is in flight)
   constexpr int FIRST_HAS_V = (MODE == MODE_APPLY);
   load_k(0, 0);
   if (FIRST_HAS_V) load_v(0, 0);
   cp_async_commit();
+  cp_async_wait<1>();
+  for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
+    const int r = c / (D / 4), q4 = c - r * (D / 4);
+    round_tf32_chunk(Qs + r * QP + 4 * q4);
+  }
   for (int r = tid; r < WARPS * 16; r += WARPS * 32) *reinterpret_cast<float4*>(Qs + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = tid; r < 2 * KT; r += WARPS * 32) *reinterpret_cast<float4*>(Ks + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (HAS_C) {
@@ -220,8 +243,9 @@ stream_fwd_kernel(const Args g) {
 
   int item = 0;                                              // running index over (sweep, tile) -> stage = item & 1
   auto next_tile = [&](int t, int sweep_has_v, bool more, int next_t, int next_has_v) {
-    // wait for tile `item`, make it visible, then prefetch the following one into the other stage
+    // wait for tile `item`, round it to TF32, make it visible, then prefetch the following one into the other stage
     cp_async_wait<0>();
+    round_k(item & 1);
     __syncthreads();
     if (more) {
       load_k(next_t, (item + 1) & 1);
@@ -557,13 +581,26 @@ stream_bwd_reduce_kernel(const BwdArgs g) {
       cp_async16(dst + key_row(kr) * QP + 4 * q4, ok ? vb + (size_t)(key0 + kr) * D + 4 * q4 : vb, ok);
     }
   };
+  auto round_v = [&](int stage) {
+    float* dst = Vs + stage * KT * QP;
+    for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
+      const int kr = c / (D / 4), q4 = c - kr * (D / 4);
+      round_tf32_chunk(dst + key_row(kr) * QP + 4 * q4);
+    }
+  };
   for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
     const int r = c / (D / 4), q4 = c - r * (D / 4);
     const bool ok = row0 + r < N;
     cp_async16(Gs + r * QP + 4 * q4, ok ? gb + (size_t)(row0 + r) * D + 4 * q4 : gb, ok);
   }
+  cp_async_commit();
   load_v(0, 0);
   cp_async_commit();
+  cp_async_wait<1>();
+  for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
+    const int r = c / (D / 4), q4 = c - r * (D / 4);
+    round_tf32_chunk(Gs + r * QP + 4 * q4);
+  }
   for (int r = tid; r < WARPS * 16; r += WARPS * 32) *reinterpret_cast<float4*>(Gs + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = tid; r < 2 * KT; r += WARPS * 32) *reinterpret_cast<float4*>(Vs + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -583,6 +620,7 @@ stream_bwd_reduce_kernel(const BwdArgs g) {
   }
   for (int t = 0; t < ntiles; ++t) {
     cp_async_wait<0>();
+    round_v(t & 1);
     __syncthreads();
     if (t + 1 < ntiles) { load_v(t + 1, (t + 1) & 1); cp_async_commit(); }
     if (!active) continue;
@@ -683,13 +721,26 @@ stream_bwd_ds_kernel(const BwdArgs g) {
       cp_async16(dst + row * VP + 16 * q8, ok ? (const void*)(ktb + (size_t)row * g.ldn + key0 + 8 * q8) : (const void*)ktb, ok);
     }
   };
+  auto round_v = [&](int stage) {
+    float* dst = reinterpret_cast<float*>(St + stage * stage_bytes);
+    for (int c = tid; c < KT * (D / 4); c += WARPS * 32) {
+      const int kr = c / (D / 4), q4 = c - kr * (D / 4);
+      round_tf32_chunk(dst + key_row(kr) * QP + 4 * q4);
+    }
+  };
   for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
     const int r = c / (D / 4), q4 = c - r * (D / 4);
     const bool ok = row0 + r < N;
     cp_async16(Gs + r * QP + 4 * q4, ok ? gb + (size_t)(row0 + r) * D + 4 * q4 : gb, ok);
   }
+  cp_async_commit();
   load_v(0, 0);
   cp_async_commit();
+  cp_async_wait<1>();
+  for (int c = tid; c < WARPS * 16 * (D / 4); c += WARPS * 32) {
+    const int r = c / (D / 4), q4 = c - r * (D / 4);
+    round_tf32_chunk(Gs + r * QP + 4 * q4);
+  }
   for (int r = tid; r < WARPS * 16; r += WARPS * 32) *reinterpret_cast<float4*>(Gs + r * QP + D) = make_float4(0.f, 0.f, 0.f, 0.f);
   // folded coefficients (one thread per (h, g)):
   //   dM_h = kh_h dA_h + c0_h + sum_g e_hg pk_g          pk_g = keep ? p_g : 0
@@ -719,6 +770,7 @@ stream_bwd_ds_kernel(const BwdArgs g) {
   // ---------------------------------------------------------------- sweep 1: dP (bf16 -> ds buffer) and the row dots
   for (int t = 0; t < ntiles; ++t) {
     cp_async_wait<0>();
+    round_v(t & 1);
     __syncthreads();
     // the first k^T tile of sweep 2 is prefetched behind the last value tile
     if (t + 1 < ntiles) load_v(t + 1, (t + 1) & 1); else load_kt(0, (t + 1) & 1);
