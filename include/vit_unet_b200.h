@@ -84,14 +84,16 @@ typedef struct vu_gemm_desc {
   float drop_p;           /* >0: inverted dropout on act(...) keyed by (drop_seed, drop_stream, m*N+n) */
   uint64_t drop_seed; uint32_t drop_stream;
   int precision;          /* VU_PREC_* */
-  /* element types (tensor-core path only): 0 = float32, 1 = bfloat16.  A and B must agree; a bf16 B operand must be
-   * K-major (trans_b = 1); a bf16 C supports alpha/bias only.  ld* and batch strides count elements of that type. */
-  int a_bf16, b_bf16, c_bf16;
+  /* element types (tensor-core path only): 0 = float32, 1 = bfloat16.  A and B must agree (either may be K- or
+   * MN-major); a bf16 C takes every fused epilogue but cannot be accumulated into (no accumulate / split_k);
+   * aux_bf16: aux_in / aux_out are bfloat16 (bf16 operands only).  bias and residual are always float32.
+   * ld* and batch strides count elements of the tensor's own type. */
+  int a_bf16, b_bf16, c_bf16, aux_bf16;
 } vu_gemm_desc;
 
 int vu_gemm(const vu_gemm_desc* d_host, void* stream);
-/* out[n] (+)= sum_m X[m*ld+n]   (bias gradients) */
-int vu_colsum(const float* X, int64_t M, int N, int64_t ld, float* out, int accumulate, void* stream);
+/* out[n] (+)= sum_m X[m*ld+n]   (bias gradients); X float32, or bfloat16 when x_bf16 != 0 */
+int vu_colsum(const void* X, int x_bf16, int64_t M, int N, int64_t ld, float* out, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------- Re-Attention core (model.py:155-161) */
 /* maps are (B, h, N, ld) fp32 with ld >= N, ld % 4 == 0 */
@@ -187,10 +189,13 @@ int vu_gemm_tf32_fallbacks(void);
 #define VU_LN_SPLIT 8      /* CTAs cooperating on one image's statistics */
 /* stats[b] = {mean, rstd} over the n = N*D elements of image b; scratch: 2*VU_LN_SPLIT*B floats */
 int vu_ln_stats(const float* x, int B, int64_t n, float eps, float* stats, float* scratch, void* stream);
-int vu_ln_apply(const float* x, const float* stats, const float* w, const float* b, float* out,
+/* out_bf16 (optional, NULL = none): a bfloat16 copy of the result written in the same pass -- the A operand of the next
+ * tensor-core GEMM in the bf16 mode (the fp32 result stays the residual stream) */
+int vu_ln_apply(const float* x, const float* stats, const float* w, const float* b, float* out, void* out_bf16,
                 int B, int64_t n, void* stream);
-/* dx = LN backward; dw/db += (atomic; caller zeroes or accumulates: the README variant shares one LN) */
-int vu_ln_bwd(const float* g, const float* x, const float* stats, const float* w, float* dx,
+/* dx = LN backward; dw/db += (atomic; caller zeroes or accumulates: the README variant shares one LN);
+ * dx_bf16 (optional): bfloat16 copy of dx for the following data- / weight-gradient GEMMs */
+int vu_ln_bwd(const float* g, const float* x, const float* stats, const float* w, float* dx, void* dx_bf16,
               float* dw, float* db, float* scratch /* (2 + 2*VU_LN_SPLIT)*B floats */, int B, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------- losses (run_denoising.py:80, README.md:91-101) */
@@ -226,8 +231,12 @@ int vu_warp_u8hwc_to_chw(const uint8_t* src, float* dst, const float* mats, int 
                          void* stream);
 
 /* ---------------------------------------------------------------- misc */
-/* out = in * keep / (1-p), keep from the same counter-based stream the GEMM epilogue uses (index = flat element) */
-int vu_dropout(const float* in, float* out, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream);
+/* out = in * keep / (1-p), keep from the same counter-based stream the GEMM epilogue uses (index = flat element);
+ * out is float32, or bfloat16 when out_bf16 != 0 (p == 0: a plain conversion) */
+int vu_dropout(const float* in, void* out, int out_bf16, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream);
+/* bf16 mode: dst (bfloat16 [R][C], optional) and dst_t (bfloat16 [C][R], optional) = src (float32 [R][C]) -- the per-step
+ * copies of an nn.Linear weight: W as the K-major B operand of y = x W^T, W^T as the K-major B operand of dx = dy W */
+int vu_cast_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream);
 /* y = a*x + b*y elementwise */
 int vu_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);
 /* fused AdamW over one flat parameter buffer (torch.optim.AdamW semantics; run_denoising.py:81) */

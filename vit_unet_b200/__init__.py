@@ -3,7 +3,7 @@
 Public surface (mirrors ``vit_unet.torch.model`` of the reference):
     ViT_UNet, HViT_UNet, get_vit_unet      nn.Modules executed by hand-written CUDA kernels
     l1_loss, mse_loss, dice_loss           fused losses
-    set_precision('fp32' | 'tf32')         CUDA-core exact path / tcgen05 tensor-core path
+    set_precision('fp32' | 'tf32' | 'bf16')   CUDA-core exact path / tcgen05 TF32 path / bf16 storage + bf16 tcgen05 products
 """
 from .engine import get_precision, set_bf16_maps, set_bf16_probs, set_map_l2_budget, set_precision, set_streamed
 from .losses import DiceLoss, L1Loss, MSELoss, dice_loss, l1_loss, mse_loss

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitunet_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class VuError(RuntimeError):
@@ -30,7 +30,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float), ("act", C.c_int), ("accumulate", C.c_int), ("split_k", C.c_int),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint64), ("drop_stream", C.c_uint32),
         ("precision", C.c_int),
-        ("a_bf16", C.c_int), ("b_bf16", C.c_int), ("c_bf16", C.c_int),
+        ("a_bf16", C.c_int), ("b_bf16", C.c_int), ("c_bf16", C.c_int), ("aux_bf16", C.c_int),
     ]
 
 
@@ -46,7 +46,7 @@ SIGNATURES = {
     "vu_conv3x3_bwd_data": [_p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "vu_conv3x3_bwd_weight": [_p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     "vu_gemm": [C.POINTER(GemmDesc), _p],
-    "vu_colsum": [_p, _l, _i, _l, _p, _i, _p],
+    "vu_colsum": [_p, _i, _l, _i, _l, _p, _i, _p],
     "vu_softmax_rows": [_p, _l, _i, _i, _f, _p],
     "vu_softmax_stats": [_p, _p, _i, _i, _i, _i, _f, _f, _u64, _u32, _p, _i, _p],
     "vu_reattn_mix_reduce": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _f, _u64, _u32, _p, _p],
@@ -60,8 +60,8 @@ SIGNATURES = {
     "vu_reattn_stream_bwd_reduce": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _u64, _u32, _p],
     "vu_reattn_stream_bwd_ds": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _u32, _p],
     "vu_ln_stats": [_p, _i, _l, _f, _p, _p, _p],
-    "vu_ln_apply": [_p, _p, _p, _p, _p, _i, _l, _p],
-    "vu_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p],
+    "vu_ln_apply": [_p, _p, _p, _p, _p, _p, _i, _l, _p],
+    "vu_ln_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p],
     "vu_loss_fwd": [_i, _p, _p, _l, _p, _p, _p],
     "vu_loss_finalize": [_i, _l, _p, _p, _p],
     "vu_loss_bwd": [_i, _p, _p, _l, _p, _p, _p, _p],
@@ -69,7 +69,8 @@ SIGNATURES = {
     "vu_u8hwc_to_chw": [_p, _p, _i, _i, _i, _i, _f, _f, _f, _p],
     "vu_resize_u8hwc": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "vu_warp_u8hwc_to_chw": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _f, _f, _f, _f, _p],
-    "vu_dropout": [_p, _p, _l, _f, _u64, _u32, _p],
+    "vu_dropout": [_p, _p, _i, _l, _f, _u64, _u32, _p],
+    "vu_cast_bf16": [_p, _p, _p, _i, _i, _p],
     "vu_axpby": [_p, _p, _l, _f, _f, _p],
     "vu_adamw": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _f, _p],
 }

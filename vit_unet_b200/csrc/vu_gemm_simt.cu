@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "vu_common.cuh"
 
 namespace vu {
@@ -270,15 +272,16 @@ int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled);   // vu_g
 
 // column sums: out[n] (+)= sum_m X[m*ld + n].  grid (N/32, chunks of M); smem transpose-free: each warp
 // owns 32 columns, threads stride over rows, partials combined with atomics.
+template <typename TX>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ X, int64_t M, int N, int64_t ld, float* __restrict__ out, int64_t rows_per_block) {
+colsum_kernel(const TX* __restrict__ X, int64_t M, int N, int64_t ld, float* __restrict__ out, int64_t rows_per_block) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float acc = 0.f;
   if (n < N)
-    for (int64_t r = r0 + warp; r < r1; r += 8) acc += X[r * ld + n];
+    for (int64_t r = r0 + warp; r < r1; r += 8) acc += (float)X[r * ld + n];
   red[warp][lane] = acc;
   __syncthreads();
   if (warp == 0) {
@@ -330,7 +333,7 @@ extern "C" int vu_gemm(const vu_gemm_desc* d, void* stream) {
 
 extern "C" int vu_gemm_tf32_fallbacks(void) { return (int)vu::g_tf32_fallbacks.load(); }
 
-extern "C" int vu_colsum(const float* X, int64_t M, int N, int64_t ld, float* out, int accumulate, void* stream) {
+extern "C" int vu_colsum(const void* X, int x_bf16, int64_t M, int N, int64_t ld, float* out, int accumulate, void* stream) {
   using namespace vu;
   const char* fn = "vu_colsum";
   VU_REQUIRE(X && out && M > 0 && N > 0 && ld >= N, fn, "bad arguments");
@@ -341,6 +344,7 @@ extern "C" int vu_colsum(const float* X, int64_t M, int N, int64_t ld, float* ou
   int64_t chunks = std::min<int64_t>(cdiv(M, 64), std::max<int64_t>(1, (int64_t)sm_count() * 4 / cdiv(N, 32)));
   int64_t rpb = cdiv(M, chunks);
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, rpb));
-  colsum_kernel<<<grid, 256, 0, s>>>(X, M, N, ld, out, rpb);
+  if (x_bf16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, out, rpb);
+  else colsum_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(X), M, N, ld, out, rpb);
   return check_launch(fn);
 }

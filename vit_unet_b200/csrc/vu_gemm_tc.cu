@@ -36,7 +36,8 @@ struct TcArgs {
   float alpha; int act; int accumulate; int split_k; int k_per_split;
   float drop_scale; uint32_t drop_thresh; uint64_t drop_seed; uint32_t drop_stream;
   uint32_t mn_lbo, mn_sbo;      // MN-major descriptor strides (bytes)
-  int c_bf16;                   // C is __nv_bfloat16 (plain store / accumulate only)
+  int c_bf16;                   // C is __nv_bfloat16 (no accumulate / split-K; the fused epilogues apply)
+  int aux_bf16;                 // aux_in / aux_out are __nv_bfloat16
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -130,13 +131,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, b
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
 }
 
-// BF16 = true: both operands are __nv_bfloat16 (kind::f16, 64 elements per 128-byte k-block, UMMA_K = 16); the B
-// operand must then be K-major (the engine keeps transposed bf16 copies of q/k/v/dO for that), A may be MN-major
-// with the ordinary SWIZZLE_128B atoms (64 elements x 8 k-rows; two 8 KB slabs per stage).
+// BF16 = true: both operands are __nv_bfloat16 (kind::f16, 64 elements per 128-byte k-block, UMMA_K = 16).  Either
+// operand may be MN-major with the ordinary SWIZZLE_128B atoms (64 elements x 8 k-rows; ROWS / 64 slabs of 8 KB per
+// stage, LBO = 8192 between slabs, SBO = 1024 between 8-k-row groups): the weight-gradient products dW = dY^T X read
+// both token tensors as they lie in memory.  An MN-major bf16 B needs BLOCK_N >= 64 (one slab is 64 columns wide).
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool BF16>
 __global__ void __launch_bounds__(192, 3)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
-  static_assert(!(BF16 && B_MN), "bf16 B operands are K-major");
+  static_assert(!(BF16 && B_MN) || BLOCK_N >= 64, "an MN-major bf16 B tile is made of 64-column slabs");
   constexpr int KB = BF16 ? 64 : 32;                    // elements per 128-byte k-block
   constexpr uint32_t A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 4;
   constexpr uint32_t B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
@@ -197,7 +199,10 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int sl = 0; sl < TC_BLOCK_M / 32; ++sl) tma_load_4d(a_dst + sl * 4096, &tmA, full_bar + s, m0 + sl * 32, k0, zi, zo);
         }
         if (!B_MN) tma_load_4d(b_dst, &tmB, full_bar + s, k0, n0, zi, zo);
-        else {
+        else if (BF16) {
+#pragma unroll
+          for (int sl = 0; sl < BLOCK_N / 64; ++sl) tma_load_4d(b_dst + sl * 8192, &tmB, full_bar + s, n0 + sl * 64, k0, zi, zo);
+        } else {
 #pragma unroll
           for (int sl = 0; sl < BLOCK_N / 32; ++sl) tma_load_4d(b_dst + sl * 4096, &tmB, full_bar + s, n0 + sl * 32, k0, zi, zo);
         }
@@ -218,7 +223,9 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t ad = !A_MN ? make_smem_desc(a_base + kk * 32, 16, 1024, 2)
                               : (BF16 ? make_smem_desc(a_base + kk * 2048, 8192, 1024, 2)
                                       : make_smem_desc(a_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1));
-          const uint64_t bd = B_MN ? make_smem_desc(b_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1) : make_smem_desc(b_base + kk * 32, 16, 1024, 2);
+          const uint64_t bd = !B_MN ? make_smem_desc(b_base + kk * 32, 16, 1024, 2)
+                              : (BF16 ? make_smem_desc(b_base + kk * 2048, 8192, 1024, 2)
+                                      : make_smem_desc(b_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1));
           if (BF16) umma_bf16(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
           else umma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
         }
@@ -271,7 +278,10 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     const bool vec_r = g.residual && ((uintptr_t)(g.residual + coff) % 16 == 0) && (g.ldr % 4 == 0) && nv == 4;
     const float* axp = g.aux_in ? g.aux_in : g.aux_out;
-    const bool vec_x = axp && ((uintptr_t)(axp + coff) % 16 == 0) && (g.ldaux % 4 == 0) && nv == 4;
+    // aux rows as one vector access: float4 (fp32) or 4 x bf16 = 8 bytes
+    const bool vec_x = axp && nv == 4 && (g.ldaux % 4 == 0) &&
+                       (g.aux_bf16 ? ((uintptr_t)(reinterpret_cast<const __nv_bfloat16*>(axp) + coff) % 8 == 0)
+                                   : ((uintptr_t)(axp + coff) % 16 == 0));
 #pragma unroll 1
     for (int r0 = 0; r0 < 32; r0 += RPI) {
       const int row = r0 + lane / LPR;
@@ -279,18 +289,6 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (m >= g.M || nv <= 0) continue;
       const float4 t4 = *reinterpret_cast<const float4*>(stage + row * LDS + cl);
       float v[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
-      if (g.c_bf16) {          // bf16 map output: plain store (host side rejects epilogues other than alpha/bias)
-        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + coff + (int64_t)m * g.ldc + n;
-        if (nv == 4 && ((uintptr_t)cb % 8 == 0)) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(cb) = pk;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < nv) cb[j] = __float2bfloat16_rn(v[j]);
-        }
-        continue;
-      }
       float* dst = C + (int64_t)m * g.ldc + n;
       if (g.split_k > 1) {
         if (g.residual && ks == 0) {
@@ -301,24 +299,50 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
         continue;
       }
+      const int64_t xoff = coff + (int64_t)m * g.ldaux + n;
       if (g.act == VU_ACT_GELU) {
         if (g.aux_out) {
-          float* ax = g.aux_out + coff + (int64_t)m * g.ldaux + n;
-          if (vec_x) *reinterpret_cast<float4*>(ax) = make_float4(v[0], v[1], v[2], v[3]);
-          else {
+          if (g.aux_bf16) {
+            __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(g.aux_out) + xoff;
+            if (vec_x) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+              uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(ax) = pk;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = v[j];
+              for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* ax = g.aux_out + xoff;
+            if (vec_x) *reinterpret_cast<float4*>(ax) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = v[j];
+            }
           }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = gelu_exact(v[j]);
       } else if (g.act == VU_ACT_GELU_BWD) {
-        const float* ax = g.aux_in + coff + (int64_t)m * g.ldaux + n;
         float a[4] = {0.f, 0.f, 0.f, 0.f};
-        if (vec_x) { float4 t = *reinterpret_cast<const float4*>(ax); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
-        else {
+        if (g.aux_bf16) {
+          const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + xoff;
+          if (vec_x) {
+            const uint2 pk = *reinterpret_cast<const uint2*>(ax);
+            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+            a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < nv) a[j] = ax[j];
+            for (int j = 0; j < 4; ++j) if (j < nv) a[j] = __bfloat162float(ax[j]);
+          }
+        } else {
+          const float* ax = g.aux_in + xoff;
+          if (vec_x) { float4 t = *reinterpret_cast<const float4*>(ax); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) a[j] = ax[j];
+          }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] *= gelu_exact_grad(a[j]);
@@ -338,7 +362,17 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rp[j];
         }
       }
-      if (vec_c) {
+      if (g.c_bf16) {          // bf16 output (host side rejects accumulate / split-K)
+        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + coff + (int64_t)m * g.ldc + n;
+        if (nv == 4 && ((uintptr_t)cb % 8 == 0)) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(cb) = pk;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) cb[j] = __float2bfloat16_rn(v[j]);
+        }
+      } else if (vec_c) {
         float4 o = make_float4(v[0], v[1], v[2], v[3]);
         if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
         *reinterpret_cast<float4*>(dst) = o;
@@ -418,7 +452,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
     }                                                                                                             \
     kfn<<<grid, block, smem, s>>>(tmA, tmB, g);                                                                   \
   } while (0)
-  if constexpr (BF16) {
+  if constexpr (BF16 && BLOCK_N < 64) {
+    if (b_mn) return fail_arg("vu_gemm", "MN-major bf16 B operand needs a 64-column tile");
     if (!a_mn) VU_TC_LAUNCH(false, false);
     else VU_TC_LAUNCH(true, false);
   } else {
@@ -437,12 +472,13 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   if ((d.a_bf16 != 0) != (d.b_bf16 != 0)) return fail_arg("vu_gemm", "A and B must have the same element type");
   const bool a_mn = d.trans_a != 0;        // A(m,k) = A[k*lda + m]  -> m contiguous
   const bool b_mn = d.trans_b == 0;        // B(k,n) = B[k*ldb + n]  -> n contiguous
-  if (bf16 && b_mn) return fail_arg("vu_gemm", "bf16 B operand must be K-major (trans_b = 1)");
-  if (d.c_bf16 && (d.residual || d.aux_in || d.aux_out || d.act != VU_ACT_NONE || d.drop_p > 0.f || d.split_k > 1 || d.accumulate))
-    return fail_arg("vu_gemm", "bf16 output supports only alpha/bias epilogues");
+  if (d.c_bf16 && (d.split_k > 1 || d.accumulate))
+    return fail_arg("vu_gemm", "bf16 output cannot be accumulated into (no accumulate / split_k)");
+  if (d.aux_bf16 && !bf16) return fail_arg("vu_gemm", "bf16 aux tensors need bf16 operands");
   const int bi = d.batch_inner > 0 ? d.batch_inner : 1, bo = d.batch_outer > 0 ? d.batch_outer : 1;
   const int kb_elems = bf16 ? 64 : TC_BLOCK_K;
   int block_n = d.N <= 32 ? 32 : (d.N <= 64 ? 64 : 128);
+  if (bf16 && b_mn && block_n < 64) block_n = 64;      // one MN-major bf16 slab is 64 columns (TMA zero-fills past N)
   const int kps0 = (int)cdiv(cdiv(d.K, d.split_k > 1 ? d.split_k : 1), kb_elems) * kb_elems;
   const bool one_kb_narrow = !bf16 && block_n == 128 && kps0 <= kb_elems && getenv("VU_TC_QK128") == nullptr;
   if (one_kb_narrow) block_n = 64;      // box width of the B operand must match the kernel's BLOCK_N
@@ -452,7 +488,7 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   else ok = encode_operand(&tmA, d.A, d.M, d.K, d.lda, bi, d.sAi, bo, d.sAo, bf16 ? 64 : 32, kb_elems, true, bf16);
   if (!ok) return bf16 ? fail_arg("vu_gemm", "bf16 operand A is not TMA-addressable (16-byte alignment of base/strides)") : VU_OK;
   if (!b_mn) ok = encode_operand(&tmB, d.B, d.K, d.N, d.ldb, bi, d.sBi, bo, d.sBo, kb_elems, block_n, false, bf16);
-  else ok = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, 32, kb_elems, true, bf16);
+  else ok = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, bf16 ? 64 : 32, kb_elems, true, bf16);
   if (!ok) return bf16 ? fail_arg("vu_gemm", "bf16 operand B is not TMA-addressable (16-byte alignment of base/strides)") : VU_OK;
 
   TcArgs g;
@@ -469,6 +505,7 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   g.drop_seed = d.drop_seed; g.drop_stream = d.drop_stream;
   g.mn_lbo = 4096; g.mn_sbo = 512;
   g.c_bf16 = d.c_bf16 != 0;
+  g.aux_bf16 = d.aux_bf16 != 0;
   const int nbatch = bi * bo;
   int rc;
   if (bf16) {
@@ -479,8 +516,14 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
     if (block_n == 32 && st32 == 2) rc = launch_tc<32, 2, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     else if (block_n == 32 && st32 == 3) rc = launch_tc<32, 3, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     else if (block_n == 32) rc = launch_tc<32, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
-    else if (block_n == 64) rc = launch_tc<64, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
-    else rc = launch_tc<128, 3, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    // token GEMMs in the bf16 mode: short contractions (<= 32 k-blocks of 64) are output-bound -> two stages, more CTAs per SM
+    else if (block_n == 64) {
+      if (g.k_per_split <= 2048) rc = launch_tc<64, 2, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+      else rc = launch_tc<64, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    } else {
+      if (g.k_per_split <= 2048) rc = launch_tc<128, 2, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+      else rc = launch_tc<128, 3, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+    }
   } else if (block_n == 32) {
     if (g.k_per_split <= 1024) rc = launch_tc<32, 2>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     else rc = launch_tc<32, 4>(tmA, tmB, g, a_mn, b_mn, nbatch, s);

@@ -1,5 +1,7 @@
 // Fused scalar losses + their gradients (MSELoss: run_denoising.py:80; soft-Dice: README.md:91-101; L1 named by
 // the benchmark configs), plus dropout regeneration, axpby and a fused AdamW step (run_denoising.py:81).
+#include <cuda_bf16.h>
+
 #include "vu_common.cuh"
 
 namespace vu {
@@ -45,17 +47,57 @@ loss_bwd_kernel(int kind, const float* __restrict__ p, const float* __restrict__
   }
 }
 
+// TOut = float or __nv_bfloat16 (the bf16 mode hands the masked gradient straight to the tensor-core GEMMs; thresh == 0
+// makes it a plain fp32 -> bf16 conversion)
+template <typename TOut>
 __global__ void __launch_bounds__(256)
-dropout_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, uint32_t thresh, float scale,
+dropout_kernel(const float* __restrict__ in, TOut* __restrict__ out, int64_t n, uint32_t thresh, float scale,
                uint64_t seed, uint32_t stream) {
+  const bool vec = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % (4 * sizeof(TOut)) == 0);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (int64_t)gridDim.x * blockDim.x) {
-    uint4 r = Philox::gen(seed, stream, (uint64_t)q);
+    uint4 r = thresh ? Philox::gen(seed, stream, (uint64_t)q) : make_uint4(0u, 0u, 0u, 0u);
     uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    if (vec && q * 4 + 3 < n) {
+      const float4 t = *reinterpret_cast<const float4*>(in + q * 4);
+      float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = rr[k] >= thresh ? v[k] * scale : 0.f;
+      if constexpr (sizeof(TOut) == 4) *reinterpret_cast<float4*>(out + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + q * 4) = pk;
+      }
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int64_t i = q * 4 + k;
-      if (i < n) out[i] = rr[k] >= thresh ? in[i] * scale : 0.f;
+      if (i < n) out[i] = (TOut)(rr[k] >= thresh ? in[i] * scale : 0.f);
     }
+  }
+}
+
+// dst (bf16, [R][Cc]) and / or dstT (bf16, [Cc][R]) = src (fp32, [R][Cc]): the per-step bf16 copies of the Linear weights
+// (W for the forward products, W^T as the K-major B operand of the data-gradient products).  32x32 tiles through smem.
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstT, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    const float v = (r < R && c < Cc) ? src[(int64_t)r * Cc + c] : 0.f;
+    tile[ty + i][tx] = v;
+    if (dst && r < R && c < Cc) dst[(int64_t)r * Cc + c] = __float2bfloat16_rn(v);
+  }
+  if (!dstT) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (c < Cc && r < R) dstT[(int64_t)c * R + r] = __float2bfloat16_rn(tile[tx][ty + i]);
   }
 }
 
@@ -168,12 +210,28 @@ extern "C" int vu_loss_bwd(int kind, const float* pred, const float* target, int
   return check_launch(fn);
 }
 
-extern "C" int vu_dropout(const float* in, float* out, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream) {
+extern "C" int vu_dropout(const float* in, void* out, int out_bf16, int64_t n, float p, uint64_t seed, uint32_t stream_id,
+                          void* stream) {
   using namespace vu;
   const char* fn = "vu_dropout";
   VU_REQUIRE(in && out && n > 0 && p >= 0.f && p < 1.f, fn, "bad arguments");
   uint32_t th = p > 0.f ? drop_threshold(p) : 0u;
-  dropout_kernel<<<ew_grid(cdiv(n, 4)), 256, 0, as_stream(stream)>>>(in, out, n, th, drop_keep_scale(p), seed, stream_id);
+  if (out_bf16)
+    dropout_kernel<__nv_bfloat16><<<ew_grid(cdiv(n, 4)), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n, th,
+                                                                                  drop_keep_scale(p), seed, stream_id);
+  else
+    dropout_kernel<float><<<ew_grid(cdiv(n, 4)), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<float*>(out), n, th,
+                                                                          drop_keep_scale(p), seed, stream_id);
+  return check_launch(fn);
+}
+
+extern "C" int vu_cast_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream) {
+  using namespace vu;
+  const char* fn = "vu_cast_bf16";
+  VU_REQUIRE(src && (dst || dst_t) && R > 0 && C > 0, fn, "bad arguments");
+  dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(R, 32));
+  cast_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                        reinterpret_cast<__nv_bfloat16*>(dst_t), R, C);
   return check_launch(fn);
 }
 

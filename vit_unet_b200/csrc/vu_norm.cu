@@ -1,8 +1,18 @@
 // LayerNorm over the whole (N, D) token matrix of an image (normalized_shape=(num_patches, projection_dim),
 // model.py:193-196,204,206): a per-image reduction over n = C*H*W elements with an (N,D)-shaped affine.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "vu_common.cuh"
 
 namespace vu {
+
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, float a, float b, float c, float d) {   // p 8-byte aligned
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
 
 // grid (VU_LN_SPLIT, B): every CTA reduces one slice of an image with two passes (mean, then centred sum of
 // squares -- the slice is L1/L2 resident for the second pass); slices are merged exactly (Chan et al.) by a tiny
@@ -67,7 +77,8 @@ __global__ void ln_stats_finalize_kernel(const float* __restrict__ part, int B, 
 template <int V>
 __global__ void __launch_bounds__(256)
 ln_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w,
-                const float* __restrict__ bias, float* __restrict__ out, int64_t n, int64_t total) {
+                const float* __restrict__ bias, float* __restrict__ out, __nv_bfloat16* __restrict__ out16, int64_t n,
+                int64_t total) {
   for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V; e < total; e += (int64_t)gridDim.x * blockDim.x * V) {
     int64_t b = e / n; int64_t r = e - b * n;
     float mean = __ldg(stats + 2 * b), rstd = __ldg(stats + 2 * b + 1);
@@ -79,8 +90,11 @@ ln_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, co
       o.x = fmaf((t.x - mean) * rstd, ww.x, bb.x); o.y = fmaf((t.y - mean) * rstd, ww.y, bb.y);
       o.z = fmaf((t.z - mean) * rstd, ww.z, bb.z); o.w = fmaf((t.w - mean) * rstd, ww.w, bb.w);
       *reinterpret_cast<float4*>(out + e) = o;
+      if (out16) store4_bf16(out16 + e, o.x, o.y, o.z, o.w);
     } else {
-      out[e] = fmaf((x[e] - mean) * rstd, w[r], bias[r]);
+      const float o = fmaf((x[e] - mean) * rstd, w[r], bias[r]);
+      out[e] = o;
+      if (out16) out16[e] = __float2bfloat16_rn(o);
     }
   }
 }
@@ -121,7 +135,8 @@ template <int V>
 __global__ void __launch_bounds__(256)
 ln_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
                     const float* __restrict__ w, const float* __restrict__ scratch, float* __restrict__ dx,
-                    float* __restrict__ dw, float* __restrict__ db, int B, int64_t n, int b_per_chunk) {
+                    __nv_bfloat16* __restrict__ dx16, float* __restrict__ dw, float* __restrict__ db, int B, int64_t n,
+                    int b_per_chunk) {
   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (e >= n) return;
   const int b0 = blockIdx.y * b_per_chunk, b1 = min(B, b0 + b_per_chunk);
@@ -144,8 +159,13 @@ ln_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, co
       o[k] = rstd * (gv[k] * ww[k] - c1 - xh * c2);
       aw[k] = fmaf(gv[k], xh, aw[k]); ab[k] += gv[k];
     }
-    if (V == 4) *reinterpret_cast<float4*>(dx + (int64_t)b * n + e) = make_float4(o[0], o[1], o[2], o[3]);
-    else dx[(int64_t)b * n + e] = o[0];
+    if (V == 4) {
+      *reinterpret_cast<float4*>(dx + (int64_t)b * n + e) = make_float4(o[0], o[1], o[2], o[3]);
+      if (dx16) store4_bf16(dx16 + (int64_t)b * n + e, o[0], o[1], o[2], o[3]);
+    } else {
+      dx[(int64_t)b * n + e] = o[0];
+      if (dx16) dx16[(int64_t)b * n + e] = __float2bfloat16_rn(o[0]);
+    }
   }
 #pragma unroll
   for (int k = 0; k < V; ++k) { atomicAdd(dw + e + k, aw[k]); atomicAdd(db + e + k, ab[k]); }
@@ -166,20 +186,22 @@ extern "C" int vu_ln_stats(const float* x, int B, int64_t n, float eps, float* s
 }
 
 extern "C" int vu_ln_apply(const float* x, const float* stats, const float* w, const float* b, float* out,
-                           int B, int64_t n, void* stream) {
+                           void* out_bf16, int B, int64_t n, void* stream) {
   using namespace vu;
   const char* fn = "vu_ln_apply";
   VU_REQUIRE(x && stats && w && b && out && B > 0 && n > 0, fn, "bad arguments");
   int64_t total = n * B;
-  bool vec = (n % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)b % 16 == 0);
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  bool vec = (n % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)w % 16 == 0) &&
+             ((uintptr_t)b % 16 == 0) && ((uintptr_t)o16 % 8 == 0);
   int64_t work = vec ? total / 4 : total;
   int blocks = (int)std::min<int64_t>(cdiv(work, 256), (int64_t)sm_count() * 16);
-  if (vec) ln_apply_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(x, stats, w, b, out, n, total);
-  else ln_apply_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(x, stats, w, b, out, n, total);
+  if (vec) ln_apply_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(x, stats, w, b, out, o16, n, total);
+  else ln_apply_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(x, stats, w, b, out, o16, n, total);
   return check_launch(fn);
 }
 
-extern "C" int vu_ln_bwd(const float* g, const float* x, const float* stats, const float* w, float* dx,
+extern "C" int vu_ln_bwd(const float* g, const float* x, const float* stats, const float* w, float* dx, void* dx_bf16,
                          float* dw, float* db, float* scratch, int B, int64_t n, void* stream) {
   using namespace vu;
   const char* fn = "vu_ln_bwd";
@@ -191,13 +213,15 @@ extern "C" int vu_ln_bwd(const float* g, const float* x, const float* stats, con
   ln_bwd_stats_kernel<<<dim3(S, B), 512, 0, s>>>(g, x, stats, w, n, len, part);
   ln_bwd_finalize_kernel<<<(unsigned)cdiv(B, 128), 128, 0, s>>>(part, B, S, scratch);
   int rc = check_launch(fn); if (rc) return rc;
-  bool vec = (n % 4 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dx % 16 == 0);
+  __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+  bool vec = (n % 4 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
+             ((uintptr_t)dx16 % 8 == 0);
   int64_t work = vec ? n / 4 : n;
   int gx = (int)cdiv(work, 256);
   int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(B, cdiv((int64_t)sm_count() * 8, gx)));
   int bpc = (int)cdiv(B, chunks);
   dim3 grid(gx, (unsigned)cdiv(B, bpc));
-  if (vec) ln_bwd_apply_kernel<4><<<grid, 256, 0, s>>>(g, x, stats, w, scratch, dx, dw, db, B, n, bpc);
-  else ln_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(g, x, stats, w, scratch, dx, dw, db, B, n, bpc);
+  if (vec) ln_bwd_apply_kernel<4><<<grid, 256, 0, s>>>(g, x, stats, w, scratch, dx, dx16, dw, db, B, n, bpc);
+  else ln_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(g, x, stats, w, scratch, dx, dx16, dw, db, B, n, bpc);
   return check_launch(fn);
 }

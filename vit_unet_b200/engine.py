@@ -76,13 +76,20 @@ def set_map_l2_budget(megabytes: float) -> None:
     _MAP_L2_BYTES["value"] = int(megabytes * (1 << 20))
 
 
+PREC_BF16 = 2       # engine-level mode; at the C ABI the bf16-operand GEMMs are VU_PREC_TF32 requests with a_bf16 / b_bf16 set
+
+
 def set_precision(mode: str) -> None:
-    """'fp32': CUDA-core FMA everywhere (1e-5 parity).  'tf32': tcgen05 tensor cores for the contractions."""
-    _PRECISION["value"] = {"fp32": ops.PREC_FP32, "tf32": ops.PREC_TF32}[mode]
+    """'fp32': CUDA-core FMA everywhere (1e-5 parity).  'tf32': tcgen05 tensor cores for the contractions, fp32 storage.
+    'bf16': the tensor-core path with bf16 storage and bf16 (kind::f16) tcgen05 products for the token GEMMs: every GEMM
+    operand that is not the residual stream (attention output, LayerNorm output copy, FeedForward hidden, the gradients
+    entering the data- and weight-gradient products) and the per-step copies of the Linear weights are bfloat16; the
+    residual stream, LayerNorm / BatchNorm statistics, master weights and all gradients of parameters stay fp32."""
+    _PRECISION["value"] = {"fp32": ops.PREC_FP32, "tf32": ops.PREC_TF32, "bf16": PREC_BF16}[mode]
 
 
 def get_precision() -> str:
-    return "tf32" if _PRECISION["value"] == ops.PREC_TF32 else "fp32"
+    return {ops.PREC_FP32: "fp32", ops.PREC_TF32: "tf32", PREC_BF16: "bf16"}[_PRECISION["value"]]
 
 
 @dataclass
@@ -153,11 +160,36 @@ class Engine:
         self.g = geom
         self.sched = geom.schedule()
         self.on_grads_ready = None     # callback(first_param_index) used by the data-parallel wrapper
+        self.precision = None          # per-module override of the global precision mode (ViT_UNet(dtype=torch.bfloat16))
+        self._w16 = {}                 # bf16 copies of the Linear weights of the forward pass in flight (bf16 mode)
 
     # ------------------------------------------------------------------------------------------- helpers
+    def _mode(self) -> int:
+        return self.precision if self.precision is not None else _PRECISION["value"]
+
+    def _prec(self) -> int:
+        """precision class handed to the C ABI: the bf16 mode runs on the tensor-core (VU_PREC_TF32) entry points"""
+        m = self._mode()
+        return ops.PREC_TF32 if m == PREC_BF16 else m
+
+    def _b16(self) -> bool:
+        return self._mode() == PREC_BF16
+
     def _gemm_tokens(self, A, W, out, M, N, K, **kw):
         """out[M,N] = A[M,K] @ W[N,K]^T (+epilogue): the nn.Linear shape."""
-        return ops.gemm(A, W, out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, precision=_PRECISION["value"], **kw)
+        return ops.gemm(A, W, out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, precision=self._prec(), **kw)
+
+    def _weight16(self, P, name, transposed=False):
+        """bf16 copy of Linear weight `name` (out,in), or of its transpose (in,out): made once per forward pass, kept with
+        the saved tensors for the backward pass (the master weight stays fp32)"""
+        ent = self._w16.get(name)
+        if ent is None:
+            ent = ops.cast_bf16(P[name], want_t=self._w16_need_t, want_n=True)
+            self._w16[name] = ent
+        if transposed and ent[1] is None:
+            ent = (ent[0], ops.cast_bf16(P[name], want_t=True, want_n=False)[1])
+            self._w16[name] = ent
+        return ent[1] if transposed else ent[0]
 
     @staticmethod
     def _map_chunk(B, h, N, ld):
@@ -172,7 +204,7 @@ class Engine:
         g = self.g
         N, D, h, p = g.N(l), g.D(l), g.heads, g.p(l)
         hd, ld = D // h, ops.pad4(N)
-        prec = _PRECISION["value"]
+        prec, b16 = self._prec(), self._b16()
         wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
         q, k, v = _empty((B, N, D), xq), _empty((B, N, D), xq), _empty((B, N, D), xq)
         if xq is xkv:
@@ -216,7 +248,8 @@ class Engine:
         else:
             Pm = _empty((B if (keep_P or train) else c, h, N, ld), xq)
         A = torch.empty((c, h, N, ld), dtype=torch.bfloat16 if bf16 else torch.float32, device=xq.device)
-        O = _empty((B, N, D), xq)
+        # bf16 mode: the attention output is only ever a GEMM operand (proj forward, proj weight gradient) -> bf16
+        O = torch.empty((B, N, D), dtype=torch.bfloat16, device=xq.device) if b16 else _empty((B, N, D), xq)
         vt = ops.heads_transpose_bf16(v, B, N, D, h) if bf16 else None        # (B,h,hd,ldn): K-major B operand of A.V
         ldn = vt.shape[-1] if bf16 else 0
         fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
@@ -278,7 +311,8 @@ class Engine:
             Pm = None
         y = _empty((B, N, D), xq)
         pdrop = g.proj_drop if train else 0.0
-        self._gemm_tokens(O, P[pre + "proj.weight"], y, B * N, D, D, bias=P[pre + "proj.bias"],
+        Wp = self._weight16(P, pre + "proj.weight") if b16 else P[pre + "proj.weight"]
+        self._gemm_tokens(O, Wp, y, B * N, D, D, bias=P[pre + "proj.bias"],
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums, seed=seed, sid=sid,
@@ -321,7 +355,11 @@ class Engine:
             ops.reattn_stream_fwd(ops.STREAM_EVAL, q, k, vt, O, fold, None, None, None, B, h, N, hd, scale)
         y = _empty((B, N, D), xq)
         pdrop = g.proj_drop if train else 0.0
-        self._gemm_tokens(O, P[pre + "proj.weight"], y, B * N, D, D, bias=P[pre + "proj.bias"],
+        Wp = P[pre + "proj.weight"]
+        if self._b16():       # the streamed kernels write fp32 rows: one conversion pass (6 bytes per token element)
+            O = ops.dropout(O, torch.empty((B, N, D), dtype=torch.bfloat16, device=xq.device), 0.0, 0, 0)
+            Wp = self._weight16(P, pre + "proj.weight")
+        self._gemm_tokens(O, Wp, y, B * N, D, D, bias=P[pre + "proj.bias"],
                           residual=residual, drop_p=pdrop, drop_seed=seed, drop_stream=sid + 1)
         if saved is not None:
             saved.update(xq=xq, xkv=xkv, q=q, k=k, v=v, Pm=Pm, O=O, fold=fold, bn=bn_saved, sums=sums if train else None,
@@ -334,18 +372,23 @@ class Engine:
         g = self.g
         N, D, h, p = g.N(l), g.D(l), g.heads, g.p(l)
         hd, ld = D // h, ops.pad4(N)
-        prec = _PRECISION["value"]
+        prec, b16 = self._prec(), self._b16()
         M = B * N
         q, k, v, Pm, O = sv["q"], sv["k"], sv["v"], sv["Pm"], sv["O"]
         seed, sid, adrop, pdrop, train = sv["seed"], sv["sid"], sv["adrop"], sv["pdrop"], sv["train"]
-        if pdrop > 0:
+        if b16:            # masked gradient straight to bf16: the A operand of dO = dyd Wp and of dWp = dyd^T O
+            dyd = ops.dropout(dy, torch.empty(dy.shape, dtype=torch.bfloat16, device=dy.device), pdrop, seed, sid + 1)
+        elif pdrop > 0:
             dyd = ops.dropout(dy, torch.empty_like(dy), pdrop, seed, sid + 1)
         else:
             dyd = dy
-        Wp = P[pre + "proj.weight"]
         # proj: dO = dyd @ Wp ; dWp = dyd^T @ O ; dbp = colsum(dyd)
         dO = _empty((B, N, D), dy)
-        ops.gemm(dyd, Wp, dO, M, D, D, trans_b=False, lda=D, ldb=D, ldc=D, precision=prec)
+        if b16:
+            ops.gemm(dyd, self._weight16(P, pre + "proj.weight", transposed=True), dO, M, D, D, trans_b=True, lda=D, ldb=D,
+                     ldc=D, precision=prec)
+        else:
+            ops.gemm(dyd, P[pre + "proj.weight"], dO, M, D, D, trans_b=False, lda=D, ldb=D, ldc=D, precision=prec)
         self._wgrad(dyd, O, G[pre + "proj.weight"], M, D, D)
         ops.colsum(dyd, M, D, D, G[pre + "proj.bias"], accumulate=True)
         del dyd
@@ -474,7 +517,7 @@ class Engine:
         tiles = ((N + 127) // 128) * ((K + 127) // 128)
         split = max(1, min(64, (2 * 148) // max(tiles, 1), M // 512))
         ops.gemm(dY, X, dW, N, K, M, trans_a=True, trans_b=False, lda=N, ldb=K, ldc=K, accumulate=True,
-                 split_k=split, precision=_PRECISION["value"])
+                 split_k=split, precision=self._prec())
 
     # ------------------------------------------------------------------------------------------- block
     def _ln_names(self, pre):
@@ -492,14 +535,22 @@ class Engine:
         st1 = _empty((B, 2), x)
         ops.ln_stats(y1, B, n, 1e-5, st1)
         x1 = _empty((B, N, D), x)
-        ops.ln_apply(y1, st1, P[ln1 + "weight"], P[ln1 + "bias"], x1, B, n)
+        b16 = self._b16()
+        # bf16 mode: LayerNorm also writes a bf16 copy of its result (the A operand of the first FeedForward product and
+        # of its weight gradient); the fp32 result stays the residual stream.  The hidden tensors are bf16.
+        x1b = torch.empty((B, N, D), dtype=torch.bfloat16, device=x.device) if b16 else None
+        ops.ln_apply(y1, st1, P[ln1 + "weight"], P[ln1 + "bias"], x1, B, n, out16=x1b)
         ldrop = g.linear_drop if train else 0.0        # Dropout after GELU and after the second Linear (model.py:105,107)
-        pre_act, act = _empty((M, Hd), x), _empty((M, Hd), x)
-        self._gemm_tokens(x1, P[pre + "FeedForward.net.0.weight"], act, M, Hd, D,
+        hdt = torch.bfloat16 if b16 else torch.float32
+        pre_act = torch.empty((M, Hd), dtype=hdt, device=x.device) if saved is not None else None
+        act = torch.empty((M, Hd), dtype=hdt, device=x.device)
+        W1 = self._weight16(P, pre + "FeedForward.net.0.weight") if b16 else P[pre + "FeedForward.net.0.weight"]
+        W2 = self._weight16(P, pre + "FeedForward.net.3.weight") if b16 else P[pre + "FeedForward.net.3.weight"]
+        self._gemm_tokens(x1b if b16 else x1, W1, act, M, Hd, D,
                           bias=P[pre + "FeedForward.net.0.bias"], act=ops.ACT_GELU, aux_out=pre_act, ldaux=Hd,
                           drop_p=ldrop, drop_seed=seed, drop_stream=sid + 2)
         y2 = _empty((B, N, D), x)
-        self._gemm_tokens(act, P[pre + "FeedForward.net.3.weight"], y2, M, D, Hd,
+        self._gemm_tokens(act, W2, y2, M, D, Hd,
                           bias=P[pre + "FeedForward.net.3.bias"], residual=x1,
                           drop_p=ldrop, drop_seed=seed, drop_stream=sid + 3)
         st2 = _empty((B, 2), x)
@@ -507,32 +558,47 @@ class Engine:
         x2 = _empty((B, N, D), x)
         ops.ln_apply(y2, st2, P[ln2 + "weight"], P[ln2 + "bias"], x2, B, n)
         if saved is not None:
-            saved.update(attn=sv_attn, y1=y1, st1=st1, x1=x1, pre_act=pre_act, act=act, y2=y2, st2=st2, ldrop=ldrop,
-                         seed=seed, sid=sid)
+            saved.update(attn=sv_attn, y1=y1, st1=st1, x1=x1b if b16 else x1, pre_act=pre_act, act=act, y2=y2, st2=st2,
+                         ldrop=ldrop, seed=seed, sid=sid)
         return x2
 
     def _block_bwd(self, P, G, pre, dx2, l, B, sv):
         g = self.g
         N, D, Hd = g.N(l), g.D(l), g.Hd(l)
         n, M = N * D, B * N
-        prec = _PRECISION["value"]
+        prec, b16 = self._prec(), self._b16()
         ln1, ln2 = self._ln_names(pre)
         scratch = _empty((B, ops.LN_SCRATCH), dx2)
         dy2 = torch.empty_like(dx2)
-        ops.ln_bwd(dx2, sv["y2"], sv["st2"], P[ln2 + "weight"], dy2, G[ln2 + "weight"], G[ln2 + "bias"], scratch, B, n)
-        W1, W2 = P[pre + "FeedForward.net.0.weight"], P[pre + "FeedForward.net.3.weight"]
-        # FF2: dpre = drop(dy2d @ W2) * gelu'(pre) ; dW2 = dy2d^T act ; db2 = colsum(dy2d), dy2d = drop-mask(dy2)
         ldrop, seed, sid = sv["ldrop"], sv["seed"], sv["sid"]
-        dy2d = ops.dropout(dy2, torch.empty_like(dy2), ldrop, seed, sid + 3) if ldrop > 0 else dy2
-        dpre = _empty((M, Hd), dx2)
-        ops.gemm(dy2d, W2, dpre, M, Hd, D, trans_b=False, lda=D, ldb=Hd, ldc=Hd, act=ops.ACT_GELU_BWD,
-                 aux_in=sv["pre_act"], ldaux=Hd, drop_p=ldrop, drop_seed=seed, drop_stream=sid + 2, precision=prec)
+        # bf16 mode: LayerNorm backward also emits the bf16 copy of dy2 that the FeedForward gradient products read
+        dy2b = torch.empty(dx2.shape, dtype=torch.bfloat16, device=dx2.device) if (b16 and ldrop == 0) else None
+        ops.ln_bwd(dx2, sv["y2"], sv["st2"], P[ln2 + "weight"], dy2, G[ln2 + "weight"], G[ln2 + "bias"], scratch, B, n,
+                   dx16=dy2b)
+        # FF2: dpre = drop(dy2d @ W2) * gelu'(pre) ; dW2 = dy2d^T act ; db2 = colsum(dy2d), dy2d = drop-mask(dy2)
+        if b16:
+            dy2d = dy2b if ldrop == 0 else ops.dropout(dy2, torch.empty(dy2.shape, dtype=torch.bfloat16, device=dy2.device),
+                                                      ldrop, seed, sid + 3)
+            dpre = torch.empty((M, Hd), dtype=torch.bfloat16, device=dx2.device)
+            ops.gemm(dy2d, self._weight16(P, pre + "FeedForward.net.3.weight", transposed=True), dpre, M, Hd, D, trans_b=True,
+                     lda=D, ldb=D, ldc=Hd, act=ops.ACT_GELU_BWD, aux_in=sv["pre_act"], ldaux=Hd, drop_p=ldrop, drop_seed=seed,
+                     drop_stream=sid + 2, precision=prec)
+        else:
+            W1, W2 = P[pre + "FeedForward.net.0.weight"], P[pre + "FeedForward.net.3.weight"]
+            dy2d = ops.dropout(dy2, torch.empty_like(dy2), ldrop, seed, sid + 3) if ldrop > 0 else dy2
+            dpre = _empty((M, Hd), dx2)
+            ops.gemm(dy2d, W2, dpre, M, Hd, D, trans_b=False, lda=D, ldb=Hd, ldc=Hd, act=ops.ACT_GELU_BWD,
+                     aux_in=sv["pre_act"], ldaux=Hd, drop_p=ldrop, drop_seed=seed, drop_stream=sid + 2, precision=prec)
         self._wgrad(dy2d, sv["act"], G[pre + "FeedForward.net.3.weight"], M, D, Hd)
         ops.colsum(dy2d, M, D, D, G[pre + "FeedForward.net.3.bias"], accumulate=True)
-        del dy2d
+        del dy2d, dy2b
         # FF1: dx1 = dpre @ W1 + dy2 ; dW1 = dpre^T x1 ; db1 = colsum(dpre)
         dx1 = torch.empty_like(dx2)
-        ops.gemm(dpre, W1, dx1, M, D, Hd, trans_b=False, lda=Hd, ldb=D, ldc=D, residual=dy2, precision=prec)
+        if b16:
+            ops.gemm(dpre, self._weight16(P, pre + "FeedForward.net.0.weight", transposed=True), dx1, M, D, Hd, trans_b=True,
+                     lda=Hd, ldb=Hd, ldc=D, residual=dy2, precision=prec)
+        else:
+            ops.gemm(dpre, W1, dx1, M, D, Hd, trans_b=False, lda=Hd, ldb=D, ldc=D, residual=dy2, precision=prec)
         self._wgrad(dpre, sv["x1"], G[pre + "FeedForward.net.0.weight"], M, Hd, D)
         ops.colsum(dpre, M, Hd, Hd, G[pre + "FeedForward.net.0.bias"], accumulate=True)
         del dy2, dpre
@@ -549,6 +615,8 @@ class Engine:
         B = X.shape[0]
         C, S = g.C, g.S
         saved: Optional[dict] = {"steps": [], "B": B} if save else None
+        self._w16 = {}                  # bf16 weight copies of THIS pass (the optimizer changes the masters between passes)
+        self._w16_need_t = bool(save)   # the transposed copies serve the data-gradient products of the backward pass
         src = X
         if g.pe_conv:
             src = torch.empty_like(X)
@@ -590,6 +658,8 @@ class Engine:
             ops.repatch(x, out, B, C, S, S, g.p0, 0)
         if save:
             saved["x_last"] = x
+            saved["w16"] = self._w16
+        self._w16 = {}
         return out, saved
 
     def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], saved: dict, dout: torch.Tensor,
@@ -597,6 +667,7 @@ class Engine:
         """Fills G (zero-initialised gradient tensors keyed like P).  Returns dX or None."""
         g = self.g
         B, C, S = saved["B"], g.C, g.S
+        self._w16 = saved.get("w16", {})
         dx = _empty((B, g.N(0), g.D(0)), dout)
         if g.out_conv:
             w = P["conv2d.weight"].contiguous()
@@ -643,6 +714,7 @@ class Engine:
             dX = _empty((B, C, S, S), dx)
             ops.repatch(dx, dX, B, C, S, S, g.p0, 0)
         self._notify("PE.")
+        self._w16 = {}
         return dX
 
     def _notify(self, prefix: str):

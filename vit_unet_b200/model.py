@@ -165,7 +165,7 @@ class _ViTUNetBase(nn.Module):
         per_image = 1
         for l in range(g.depth + 1):         # levels whose maps are materialised (the streamed inference kernel writes none)
             n, hd = g.N(l), g.D(l) // g.heads
-            if (_e.get_precision() == "tf32" and _e._STREAMED_INFER["value"] and ops.reattn_stream_supported(g.heads, hd, n)):
+            if (self.engine._prec() == ops.PREC_TF32 and _e._STREAMED_INFER["value"] and ops.reattn_stream_supported(g.heads, hd, n)):
                 continue
             per_image = max(per_image, 2 * g.heads * n * ((n + 3) // 4 * 4) * 4)
         return max(1, min(B, self.map_budget_bytes // per_image))
@@ -243,8 +243,8 @@ class ViT_UNet(_ViTUNetBase):
         assert preprocessing in ['conv', 'fourier', 'none'], "Preprocessing can only be 'conv', 'fourier' or 'none'."
         if preprocessing == "fourier":
             raise NotImplementedError("preprocessing='fourier' is out of scope (the reference discards the output)")
-        if dtype != torch.float32:
-            raise NotImplementedError("only dtype=torch.float32 parameters are supported")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise NotImplementedError("dtype must be torch.float32 or torch.bfloat16")
         side = int(math.isqrt(num_patches))
         assert side * side == num_patches, "num_patches must be a perfect square"
         self.depth, self.depth_te, self.size_bottleneck = depth, depth_te, size_bottleneck
@@ -259,8 +259,11 @@ class ViT_UNet(_ViTUNetBase):
         p_final = patch_size // (2 ** depth)
         self.PE = _PEParams(num_patches * 4 ** depth, num_channels * p_final ** 2, num_channels,
                             conv=(preprocessing == "conv"))
+        # dtype=torch.bfloat16 (the notebook forwards it to Linear / LayerNorm, ViT_UNet.ipynb c22:L10,13, c27:L27-29)
+        # selects the bf16 storage / compute mode of the engine for THIS module: bf16 tcgen05 products and bf16 saved
+        # activations, fp32 master parameters (so optimizers and checkpoints are unchanged), fp32 inputs and outputs
         self._build_blocks(depth, depth_te, size_bottleneck, num_patches, self.projection_dim, num_channels,
-                           hidden_dim, num_heads, linear_drop, shared_ln=True, dtype=dtype)
+                           hidden_dim, num_heads, linear_drop, shared_ln=True, dtype=None)
         if preprocessing == "conv":
             self.conv2d = nn.Conv2d(num_channels, num_channels, 3, padding="same")
         self._finish_init(Geometry(C=num_channels, S=self.im_size, p0=patch_size, depth=depth, depth_te=depth_te,
@@ -268,6 +271,9 @@ class ViT_UNet(_ViTUNetBase):
                                    shared_ln=True, pe_conv=(preprocessing == "conv"), table_p=p_final,
                                    out_conv=(preprocessing == "conv"), attn_drop=attn_drop, proj_drop=proj_drop,
                                    linear_drop=linear_drop))
+        if dtype == torch.bfloat16:
+            from .engine import PREC_BF16
+            self.engine.precision = PREC_BF16
 
     def forward(self, X: torch.Tensor) -> torch.Tensor:
         self._check_input(X)

@@ -174,7 +174,10 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
     d.A, d.B, d.C = _chk(A, "A", A.dtype if d.a_bf16 else torch.float32), _chk(Bm, "B", Bm.dtype if d.b_bf16 else torch.float32), \
         _chk(Cm, "C", Cm.dtype if d.c_bf16 else torch.float32)
     d.bias, d.residual = _opt(bias, "bias"), _opt(residual, "residual")
-    d.aux_in, d.aux_out = _opt(aux_in, "aux_in"), _opt(aux_out, "aux_out")
+    aux = aux_in if aux_in is not None else aux_out
+    d.aux_bf16 = int(aux is not None and aux.dtype == torch.bfloat16)
+    adt = torch.bfloat16 if d.aux_bf16 else torch.float32
+    d.aux_in, d.aux_out = _opt(aux_in, "aux_in", adt), _opt(aux_out, "aux_out", adt)
     d.M, d.N, d.K = M, N, K
     d.trans_a, d.trans_b = int(trans_a), int(trans_b)
     d.lda, d.ldb, d.ldc, d.ldr, d.ldaux = lda, ldb, ldc, ldr or ldc, ldaux or ldc
@@ -186,7 +189,8 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
     d.drop_p, d.drop_seed, d.drop_stream = drop_p, drop_seed, drop_stream
     d.precision = precision
     nb = batch_outer * batch_inner
-    kind = "gemm_tcgen05_tf32" if precision == PREC_TF32 else "gemm_simt_fp32"
+    # class names of the live roofline table: the batched map products keep their round-1 names whatever the operand type
+    kind = ("gemm_tcgen05_bf16" if (d.a_bf16 and nb == 1) else "gemm_tcgen05_tf32") if precision == PREC_TF32 else "gemm_simt_fp32"
     if (precision == PREC_TF32 and not trans_a and trans_b and K <= 128 and ((N + 7) // 8 * 8) * (K + 8) * 4 <= 200 * 1024
             and M >= 64 and N >= 64 and not d.a_bf16
             and bias is None and residual is None and aux_in is None and aux_out is None and act == ACT_NONE
@@ -205,7 +209,9 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
 
 
 def colsum(X, M, N, ld, out, accumulate=False):
-    _call("vu_colsum", _chk(X, "X"), M, N, ld, _chk(out, "out"), int(accumulate), _stream(), nbytes=4.0 * M * N)
+    bf = X.dtype == torch.bfloat16
+    _call("vu_colsum", _chk(X, "X", X.dtype if bf else torch.float32), int(bf), M, N, ld, _chk(out, "out"), int(accumulate),
+          _stream(), nbytes=(2.0 if bf else 4.0) * M * N)
     return out
 
 
@@ -326,14 +332,16 @@ def ln_stats(x, B, n, eps, stats, scratch=None):
           nbytes=4.0 * B * n)
 
 
-def ln_apply(x, stats, w, b, out, B, n):
-    _call("vu_ln_apply", _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(b, "b"), _chk(out, "out"), B, n,
-          _stream(), nbytes=8.0 * B * n + 8.0 * n)
+def ln_apply(x, stats, w, b, out, B, n, out16=None):
+    """out16: optional bf16 copy of the result (bf16 mode: the next GEMM's A operand)"""
+    _call("vu_ln_apply", _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(b, "b"), _chk(out, "out"),
+          _opt(out16, "out16", torch.bfloat16), B, n, _stream(), nbytes=(8.0 + (2.0 if out16 is not None else 0.0)) * B * n + 8.0 * n)
 
 
-def ln_bwd(g, x, stats, w, dx, dw, db, scratch, B, n):
+def ln_bwd(g, x, stats, w, dx, dw, db, scratch, B, n, dx16=None):
     _call("vu_ln_bwd", _chk(g, "g"), _chk(x, "x"), _chk(stats, "stats"), _chk(w, "w"), _chk(dx, "dx"),
-          _chk(dw, "dw"), _chk(db, "db"), _chk(scratch, "scratch"), B, n, _stream(), nbytes=12.0 * B * n + 12.0 * n)
+          _opt(dx16, "dx16", torch.bfloat16), _chk(dw, "dw"), _chk(db, "db"), _chk(scratch, "scratch"), B, n, _stream(),
+          nbytes=(12.0 + (2.0 if dx16 is not None else 0.0)) * B * n + 12.0 * n)
 
 
 # ----------------------------------------------------------------------------------------- losses / misc
@@ -392,8 +400,21 @@ def warp_u8hwc_to_chw(src, mats, Hd, Wd, bilinear=True, border=0.0, round_u8=Tru
 
 
 def dropout(x, out, p, seed, sid):
-    _call("vu_dropout", _chk(x, "in"), _chk(out, "out"), x.numel(), p, seed, sid, _stream(), nbytes=8.0 * x.numel())
+    """out fp32, or bf16 (bf16 mode: masked gradient as a GEMM operand; p == 0 is a plain conversion)"""
+    bf = out.dtype == torch.bfloat16
+    _call("vu_dropout", _chk(x, "in"), _chk(out, "out", out.dtype if bf else torch.float32), int(bf), x.numel(), p, seed, sid,
+          _stream(), nbytes=(6.0 if bf else 8.0) * x.numel())
     return out
+
+
+def cast_bf16(w, want_t=True, want_n=True):
+    """fp32 (R,C) -> (bf16 (R,C) or None, bf16 (C,R) or None): per-step copies of a Linear weight for the bf16 mode"""
+    R, Cc = w.shape
+    dn = torch.empty((R, Cc), dtype=torch.bfloat16, device=w.device) if want_n else None
+    dt = torch.empty((Cc, R), dtype=torch.bfloat16, device=w.device) if want_t else None
+    _call("vu_cast_bf16", _chk(w, "w"), _opt(dn, "dst", torch.bfloat16), _opt(dt, "dst_t", torch.bfloat16), R, Cc, _stream(),
+          nbytes=(4.0 + 2.0 * (int(want_n) + int(want_t))) * R * Cc)
+    return dn, dt
 
 
 def axpby(x, y, a, b):
