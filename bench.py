@@ -43,7 +43,7 @@ WORKLOADS = {
     "base_infer": dict(kw={}, train=False, loss="l1", flops=7.755e9,
                        name="ViT_UNet Base inference (eval forward), 3x224x224"),
     "large_train": dict(kw=dict(depth_te=4, size_bottleneck=4), train=True, loss="l1", flops=42.4e9,
-                        name="ViT_UNet Large denoising training step, L1 loss (BASELINE configs[3] architecture, TF32 not bf16)"),
+                        name="ViT_UNet Large denoising training step, L1 loss (BASELINE configs[3]; pass --dtype bf16 for its bf16 storage / compute mode)"),
     "base1ch_dice": dict(kw=dict(num_channels=1), train=True, loss="dice", flops=5.46e9,
                          name="ViT_UNet Base 1-channel segmentation step, soft-Dice loss (BASELINE configs[4])"),
 }
@@ -60,6 +60,7 @@ def _peaks():
 
 # kernel class of the live table -> regex over the ncu kernel names of profiles/r02_step_traffic.json
 _NCU_CLASS = {
+    "gemm_tcgen05_bf16:tokens": r"gemm_tf32_tc_kernel<(64|128), .*, 1>$",  # bf16 mode: token GEMMs on bf16 operands
     "gemm_tcgen05_tf32:tokens": r"gemm_tf32_tc_kernel<.*, 0>$",          # fp32-operand tcgen05 GEMMs (a few L0/L1 map products included)
     "gemm_tcgen05_tf32:map_in": r"gemm_tf32_tc_kernel<.*, 1>$",          # bf16-operand (map-reading) tcgen05 GEMMs
     "gemm_tcgen05_tf32:map_out": r"gemm_tf32_tc_kernel<.*, 0>$",
@@ -420,13 +421,13 @@ def run_cuda(args):
     line = {"metric": METRIC if args.workload == "base_train" else wl["name"] + " images/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.global_batch else "weak",
-            "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": wl["name"],
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "step": ("zero_grad + forward + loss + backward" + (" + bucketed NCCL grad all-reduce" if world > 1 else ""))
                                if wl["train"] else "eval forward under no_grad (batch-sharded, no collective)",
                        "dropout": "attn 0.2 / proj 0.2 / linear 0 (preset)" if args.dropout is None else f"OVERRIDDEN to {args.dropout}", "precision": args.precision,
-                       "maps": ("P centred bf16 where N >= 256 (else fp32); mixed map A and gradient map dA/dS bf16 where N % 8 == 0; 8-head map kernels on TF32 warp MMAs" if (args.precision == "tf32" and os.environ.get("VU_BF16_MAPS", "1") == "1") else "fp32"),
+                       "maps": ("P centred bf16 where N >= 256 (else fp32); mixed map A and gradient map dA/dS bf16 where N % 8 == 0; 8-head map kernels on TF32 warp MMAs" if (args.precision in ("tf32", "bf16") and os.environ.get("VU_BF16_MAPS", "1") == "1") else "fp32"),
                        "reattention": ("streamed (no attention maps)" if (args.streamed == 1 or (args.streamed is None and not wl["train"]))
                                        else "materialised maps") + " at the levels vu_reattn_stream_supported covers",
                        "l2": "per-step working set (saved activations + attention maps, GBs) >> 126 MB L2"},
@@ -466,8 +467,11 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed GLOBAL batch split over the ranks "
                     "(overrides --batch; reported with scaling=strong)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
-    ap.add_argument("--precision", default=os.environ.get("VU_PRECISION", "tf32"), choices=["fp32", "tf32"],
-                    help="tf32: tcgen05 tensor-core contractions (default, the performance mode); fp32: CUDA-core exact mode")
+    ap.add_argument("--precision", "--dtype", dest="precision", default=os.environ.get("VU_PRECISION", "tf32"),
+                    choices=["fp32", "tf32", "bf16"],
+                    help="tf32: tcgen05 tensor-core contractions on fp32 storage (default); bf16: bf16 storage of every GEMM operand / "
+                         "saved activation outside the residual stream + bf16 tcgen05 token GEMMs (BASELINE configs[3]); "
+                         "fp32: CUDA-core exact mode")
     ap.add_argument("--streamed", type=int, default=None, help="1/0: force the streamed Re-Attention kernels on/off "
                     "(default: on for no-grad inference, off for training steps; see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -47,18 +47,20 @@ int vu_heads_transpose_bf16(const float* src, void* dst, int B, int N, int D, in
 
 /* ---------------------------------------------------------------- 3x3 convs (model.py:137-139,152-154,428) */
 /* nconv (1..3) bias-optional 3x3 C->C convs sharing one input.  Zero padding at the borders of
- * `border_p`-sized patches (border_p == 0: image borders).  w: [nconv][C][C][3][3], bias: [nconv][C] or NULL.
- * x is read in layout p_x; out_k written in layout p_out. */
-int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const float* bias, int nconv,
+ * `border_p`-sized patches (border_p == 0: image borders).  Filters [C][C][3][3] per conv: w1 == NULL -> all convs
+ * contiguous at w ([nconv][C][C][3][3]); else conv k reads its own block w / w1 / w2 (the q/k/v nn.Conv2d weights
+ * where they lie, no concatenation pass).  bias: [nconv][C] or NULL.  x is read in layout p_x; out_k written in p_out. */
+int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const float* w1, const float* w2, const float* bias, int nconv,
                    float* out0, float* out1, float* out2, int p_out, int border_p,
                    int B, int C, int H, int W, void* stream);
 /* dx[p_dx] (+)= sum_k conv_transpose(dy_k[p_dy], w_k) */
 int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const float* dy2, int p_dy,
-                        const float* w, int nconv, float* dx, int p_dx, int border_p,
+                        const float* w, const float* w1, const float* w2, int nconv, float* dx, int p_dx, int border_p,
                         int B, int C, int H, int W, int accumulate, void* stream);
-/* dw[nconv][C][C][3][3] += ..., dbias[nconv][C] += ... (atomic accumulation: caller zeroes) */
+/* dw_k[C][C][3][3] += ..., dbias[nconv][C] += ... (atomic accumulation: caller zeroes).  dw1 == NULL: the blocks of all
+ * convs are contiguous at dw; else conv k accumulates into dw / dw1 / dw2 (separate slots of a flat gradient buffer). */
 int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, const float* dy1, const float* dy2,
-                          int p_dy, int nconv, float* dw, float* dbias, int border_p,
+                          int p_dy, int nconv, float* dw, float* dw1, float* dw2, float* dbias, int border_p,
                           int B, int C, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------- GEMM (model.py:155,161,162; :103,106) */
@@ -237,6 +239,8 @@ int vu_dropout(const float* in, void* out, int out_bf16, int64_t n, float p, uin
 /* bf16 mode: dst (bfloat16 [R][C], optional) and dst_t (bfloat16 [C][R], optional) = src (float32 [R][C]) -- the per-step
  * copies of an nn.Linear weight: W as the K-major B operand of y = x W^T, W^T as the K-major B operand of dx = dy W */
 int vu_cast_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream);
+/* stream-ordered zero fill (cudaMemsetAsync) of `bytes` bytes: accumulators and gradient buffers */
+int vu_zero(void* p, int64_t bytes, void* stream);
 /* y = a*x + b*y elementwise */
 int vu_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream);
 /* fused AdamW over one flat parameter buffer (torch.optim.AdamW semantics; run_denoising.py:81) */

@@ -5,17 +5,20 @@ import torch
 from vit_unet_b200 import ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+BF16 = len(sys.argv) > 2 and sys.argv[2] == "bf16"      # bf16 mode: bf16 operands, K-major transposed weight copy for dgrad
 prec = ops.PREC_TF32
 shapes = []
 for name, N_tok, D, Hd in (("L0", 49, 3072, 128), ("L1", 196, 768, 64), ("L2", 784, 192, 32)):
     M = B * N_tok
-    shapes += [(f"{name} proj fwd  NT", M, D, D, False, True), (f"{name} proj dgrad NN", M, D, D, False, False),
+    shapes += [(f"{name} proj fwd  NT", M, D, D, False, True), (f"{name} proj dgrad NN", M, D, D, False, BF16),
                (f"{name} proj wgrad TN", D, D, M, True, False), (f"{name} FF1 fwd NT", M, Hd, D, False, True),
                (f"{name} FF2 fwd NT", M, D, Hd, False, True), (f"{name} FF1 wgrad TN", Hd, D, M, True, False)]
 tot_ms = 0
 for name, M, N, K, ta, tb in shapes:
     A = torch.randn((K, M) if ta else (M, K), device="cuda")
     Bm = torch.randn((N, K) if tb else (K, N), device="cuda")
+    if BF16:
+        A, Bm = A.bfloat16(), Bm.bfloat16()
     C = torch.zeros(M, N, device="cuda")
     split = 1
     if ta:

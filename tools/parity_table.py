@@ -13,14 +13,17 @@ def quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
-names = sys.argv[1:] or list(CONFIGS)
-for prec, maps, streamed in (("fp32", False, False), ("tf32", False, False), ("tf32", True, False), ("tf32", True, True)):
+names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CONFIGS)
+MODES = (("fp32", False, False), ("tf32", False, False), ("tf32", True, False), ("tf32", True, True), ("bf16", True, False))
+if "--bf16" in sys.argv:
+    MODES = (("bf16", True, False),)
+for prec, maps, streamed in MODES:
     vu.set_precision(prec); vu.set_bf16_maps(maps); vu.set_streamed(streamed)
     for name in names:
         if streamed and not name.startswith(("l2block", "base", "lite")):
             continue
         net, x, y = build_net(name, quiet)
-        rows = parity_rows(name, net, x, y, l1_grads=True)
+        rows = parity_rows(name, net, x, y, l1_grads=(prec == "fp32"), chaos=(1e-3 if prec == "fp32" else 1e-4))
         by = {}
         for k, e, t, st in rows:
             grp = k.split(":")[0] if ":" in k else k

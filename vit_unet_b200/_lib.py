@@ -42,9 +42,9 @@ SIGNATURES = {
     "vu_heads_transpose_bf16": [_p, _p, _i, _i, _i, _i, _i, _p],
     "vu_pe_fwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     "vu_pe_bwd_table": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
-    "vu_conv3x3_fwd": [_p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "vu_conv3x3_bwd_data": [_p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
-    "vu_conv3x3_bwd_weight": [_p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    "vu_conv3x3_fwd": [_p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "vu_conv3x3_bwd_data": [_p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vu_conv3x3_bwd_weight": [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vu_gemm": [C.POINTER(GemmDesc), _p],
     "vu_colsum": [_p, _i, _l, _i, _l, _p, _i, _p],
     "vu_softmax_rows": [_p, _l, _i, _i, _f, _p],
@@ -72,6 +72,7 @@ SIGNATURES = {
     "vu_dropout": [_p, _p, _i, _l, _f, _u64, _u32, _p],
     "vu_cast_bf16": [_p, _p, _p, _i, _i, _p],
     "vu_axpby": [_p, _p, _l, _f, _f, _p],
+    "vu_zero": [_p, _l, _p],
     "vu_adamw": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _f, _p],
 }
 _SPECIAL = {
@@ -86,7 +87,7 @@ _SPECIAL = {
 _lib = None
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
-_KERNELS_PER_CALL = {"vu_ln_bwd": 3, "vu_ln_stats": 2, "vu_loss_fwd": 2, "vu_psnr": 3}
+_KERNELS_PER_CALL = {"vu_ln_bwd": 3, "vu_ln_stats": 2, "vu_loss_fwd": 2, "vu_psnr": 3, "vu_zero": 0}
 LN_SPLIT = 8
 _launches = 0
 

@@ -140,8 +140,8 @@ conv3x3_bwd_data_kernel(const float* __restrict__ d0, const float* __restrict__ 
 template <int C, bool WIDE>
 __global__ void __launch_bounds__(128, 3)
 conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ d0, const float* __restrict__ d1,
-                          const float* __restrict__ d2, float* __restrict__ dw, float* __restrict__ dbias,
-                          ConvGeom g) {
+                          const float* __restrict__ d2, float* __restrict__ dw0, float* __restrict__ dw1,
+                          float* __restrict__ dw2, float* __restrict__ dbias, ConvGeom g) {
   constexpr int NCO = WIDE ? C : 1;
   constexpr int NACC = NCO * (C * 9 + 1);
   const int k = WIDE ? blockIdx.y : blockIdx.y / C;
@@ -207,7 +207,8 @@ conv3x3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__
     for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += red[threadIdx.x][wv];
     const int c = threadIdx.x / (C * 9 + 1), e = threadIdx.x % (C * 9 + 1);
     const int co = co0 + c;
-    if (e < C * 9) atomicAdd(dw + ((int64_t)(k * C + co) * C) * 9 + e, s);
+    float* dw = k == 0 ? dw0 : (k == 1 ? dw1 : dw2);        // gradient block [C][C][3][3] of conv k
+    if (e < C * 9) atomicAdd(dw + ((int64_t)co * C) * 9 + e, s);
     else if (dbias) atomicAdd(dbias + k * C + co, s);
   }
 }
@@ -240,8 +241,8 @@ struct WgTile {
 template <int C, int P>
 __global__ void __launch_bounds__(128, 3)
 conv3x3_wgrad_patch_kernel(const float* __restrict__ x, const float* __restrict__ d0, const float* __restrict__ d1,
-                           const float* __restrict__ d2, float* __restrict__ dw, float* __restrict__ dbias,
-                           int64_t total_units) {
+                           const float* __restrict__ d2, float* __restrict__ dw0, float* __restrict__ dw1,
+                           float* __restrict__ dw2, float* __restrict__ dbias, int64_t total_units) {
   using T = WgTile<C, P>;
   constexpr int NACC = C * (C * 9 + 1);
   __shared__ __align__(16) float xs[T::SMEM];
@@ -340,19 +341,20 @@ conv3x3_wgrad_patch_kernel(const float* __restrict__ x, const float* __restrict_
   if (tid < NACC) {
     const float sum = (red[tid][0] + red[tid][1]) + (red[tid][2] + red[tid][3]);
     const int co = tid / (C * 9 + 1), e = tid % (C * 9 + 1);
-    if (e < C * 9) atomicAdd(dw + ((int64_t)(k * C + co) * C) * 9 + e, sum);
+    float* dw = k == 0 ? dw0 : (k == 1 ? dw1 : dw2);
+    if (e < C * 9) atomicAdd(dw + ((int64_t)co * C) * 9 + e, sum);
     else if (dbias) atomicAdd(dbias + k * C + co, sum);
   }
 }
 
 template <int C, int P>
 static void launch_wgrad_patch(const float* x, const float* d0, const float* d1, const float* d2, int nconv,
-                               float* dw, float* dbias, int64_t patches, cudaStream_t s) {
+                               float* dw0, float* dw1, float* dw2, float* dbias, int64_t patches, cudaStream_t s) {
   using T = WgTile<C, P>;
   const int64_t units = patches * T::UPP, items = (units + T::K - 1) / T::K;
   const int per_sm = nconv == 3 ? 1 : (nconv == 2 ? 2 : 3);        // 3 resident CTAs per SM over (x, y)
   const int bx = (int)std::min<int64_t>(items, (int64_t)sm_count() * per_sm);
-  conv3x3_wgrad_patch_kernel<C, P><<<dim3(bx, nconv), 128, 0, s>>>(x, d0, d1, d2, dw, dbias, units);
+  conv3x3_wgrad_patch_kernel<C, P><<<dim3(bx, nconv), 128, 0, s>>>(x, d0, d1, d2, dw0, dw1, dw2, dbias, units);
 }
 
 // ------------------------------------------------------------------ forward / backward-data, patch-tiled fast paths
@@ -500,9 +502,18 @@ struct FilterGuard {
   ~FilterGuard() { if (slot->ev && cudaEventRecord(slot->ev, s) == cudaSuccess) slot->recorded = true; }
 };
 
-static int upload_filters(const char* fn, const float* w, const float* bias, int nconv, int C, cudaStream_t s) {
-  if (cudaMemcpyToSymbolAsync(c_w, w, sizeof(float) * nconv * C * C * 9, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-    return check_launch(fn);
+// w1 == NULL (and nconv > 1): the filters of all convs are contiguous at w0; else conv k's filters are at w_k -- the three
+// nn.Conv2d weights are uploaded straight from their own parameter tensors (no concatenation pass)
+static int upload_filters(const char* fn, const float* w0, const float* w1, const float* w2, const float* bias, int nconv,
+                          int C, cudaStream_t s) {
+  const size_t one = sizeof(float) * C * C * 9;
+  if (nconv == 1 || !w1) {
+    if (cudaMemcpyToSymbolAsync(c_w, w0, one * nconv, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return check_launch(fn);
+  } else {
+    const float* ws[3] = {w0, w1, w2};
+    for (int k = 0; k < nconv; ++k)
+      if (cudaMemcpyToSymbolAsync(c_w, ws[k], one, one * k, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return check_launch(fn);
+  }
   if (bias) {
     if (cudaMemcpyToSymbolAsync(c_b, bias, sizeof(float) * nconv * C, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
       return check_launch(fn);
@@ -536,19 +547,20 @@ static int make_geom(const char* fn, ConvGeom& g, int p_in, int p_out, int borde
     default: { constexpr int CC = 4; __VA_ARGS__; } break; \
   }
 
-extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const float* bias, int nconv,
-                              float* out0, float* out1, float* out2, int p_out, int border_p,
+extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const float* w1, const float* w2, const float* bias,
+                              int nconv, float* out0, float* out1, float* out2, int p_out, int border_p,
                               int B, int C, int H, int W, void* stream) {
   using namespace vu;
   const char* fn = "vu_conv3x3_fwd";
   VU_REQUIRE(x && w && out0 && nconv >= 1 && nconv <= 3, fn, "null pointer or nconv outside 1..3");
   VU_REQUIRE((nconv < 2 || out1) && (nconv < 3 || out2), fn, "missing output pointer");
+  VU_REQUIRE(!w1 || nconv < 3 || w2, fn, "separate filter blocks: missing w2");
   ConvGeom g; int rc = make_geom(fn, g, p_x, p_out, border_p, B, C, H, W); if (rc) return rc;
   int threads = 256;
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
   FilterGuard guard(s);           // released (event recorded) after the launch below, on every return path
-  rc = upload_filters(fn, w, bias, nconv, C, s); if (rc) return rc;
+  rc = upload_filters(fn, w, w1, w2, bias, nconv, C, s); if (rc) return rc;
   if (g.fast && p_x == p_out && C <= 3 && p_x >= 4 && !getenv("VU_CONV_GENERIC")) {
     const int64_t patches = (int64_t)B * (H / p_x) * (W / p_x);
     bool done = false;
@@ -567,8 +579,8 @@ extern "C" int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const flo
 }
 
 extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const float* dy2, int p_dy,
-                                   const float* w, int nconv, float* dx, int p_dx, int border_p,
-                                   int B, int C, int H, int W, int accumulate, void* stream) {
+                                   const float* w, const float* w1, const float* w2, int nconv, float* dx, int p_dx,
+                                   int border_p, int B, int C, int H, int W, int accumulate, void* stream) {
   using namespace vu;
   const char* fn = "vu_conv3x3_bwd_data";
   VU_REQUIRE(dy0 && w && dx && nconv >= 1 && nconv <= 3, fn, "null pointer or nconv outside 1..3");
@@ -578,7 +590,8 @@ extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const flo
   int blocks = (int)std::min<int64_t>(cdiv(g.npix_total, threads), (int64_t)sm_count() * 32);
   cudaStream_t s = as_stream(stream);
   FilterGuard guard(s);
-  rc = upload_filters(fn, w, nullptr, nconv, C, s); if (rc) return rc;
+  VU_REQUIRE(!w1 || nconv < 3 || w2, fn, "separate filter blocks: missing w2");
+  rc = upload_filters(fn, w, w1, w2, nullptr, nconv, C, s); if (rc) return rc;
   if (g.fast && p_dy == p_dx && C <= 3 && p_dy >= 4 && !getenv("VU_CONV_GENERIC")) {
     const int64_t patches = (int64_t)B * (H / p_dy) * (W / p_dy);
     bool done = false;
@@ -597,7 +610,7 @@ extern "C" int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const flo
 }
 
 extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, const float* dy1,
-                                     const float* dy2, int p_dy, int nconv, float* dw, float* dbias,
+                                     const float* dy2, int p_dy, int nconv, float* dw, float* dw1, float* dw2, float* dbias,
                                      int border_p, int B, int C, int H, int W, void* stream) {
   using namespace vu;
   const char* fn = "vu_conv3x3_bwd_weight";
@@ -605,9 +618,13 @@ extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, 
   VU_REQUIRE((nconv < 2 || dy1) && (nconv < 3 || dy2), fn, "missing gradient pointer");
   ConvGeom g; int rc = make_geom(fn, g, p_x, p_dy, border_p, B, C, H, W); if (rc) return rc;
   cudaStream_t s = as_stream(stream);
+  // dw1 == NULL: the gradient blocks of all convs are contiguous at dw; else conv k accumulates into its own block dw_k
+  // (the three nn.Conv2d gradients live at their own offsets of the flat gradient buffer)
+  VU_REQUIRE(!dw1 || nconv < 3 || dw2, fn, "separate gradient blocks: missing dw2");
+  if (!dw1) { dw1 = dw + (int64_t)C * C * 9; dw2 = dw + (int64_t)2 * C * C * 9; }
   if (g.fast && p_x == p_dy && C <= 3 && (p_x == 4 || p_x == 8 || p_x == 16 || p_x == 32) && !getenv("VU_CONV_WGRAD_GENERIC")) {
     const int64_t patches = (int64_t)B * (H / p_x) * (W / p_x);
-#define VU_WG(CC, PPX) launch_wgrad_patch<CC, PPX>(x, dy0, dy1, dy2, nconv, dw, dbias, patches, s)
+#define VU_WG(CC, PPX) launch_wgrad_patch<CC, PPX>(x, dy0, dy1, dy2, nconv, dw, dw1, dw2, dbias, patches, s)
 #define VU_WG_P(CC) (p_x == 4 ? VU_WG(CC, 4) : p_x == 8 ? VU_WG(CC, 8) : p_x == 16 ? VU_WG(CC, 16) : VU_WG(CC, 32))
     if (C == 1) VU_WG_P(1); else if (C == 2) VU_WG_P(2); else VU_WG_P(3);
 #undef VU_WG_P
@@ -618,7 +635,7 @@ extern "C" int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, 
   int bx = (int)std::min<int64_t>(cdiv(g.npix_total, threads * 8), (int64_t)sm_count() * 6);
   if (bx < 1) bx = 1;
   VU_DISPATCH_C(C,
-    if (CC <= 3) conv3x3_bwd_weight_kernel<CC, (CC <= 3)><<<dim3(bx, nconv), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g);
-    else conv3x3_bwd_weight_kernel<CC, false><<<dim3(bx, nconv * C), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dbias, g));
+    if (CC <= 3) conv3x3_bwd_weight_kernel<CC, (CC <= 3)><<<dim3(bx, nconv), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dw1, dw2, dbias, g);
+    else conv3x3_bwd_weight_kernel<CC, false><<<dim3(bx, nconv * C), threads, 0, s>>>(x, dy0, dy1, dy2, dw, dw1, dw2, dbias, g));
   return check_launch(fn);
 }

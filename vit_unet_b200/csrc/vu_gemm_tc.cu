@@ -480,7 +480,9 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   int block_n = d.N <= 32 ? 32 : (d.N <= 64 ? 64 : 128);
   if (bf16 && b_mn && block_n < 64) block_n = 64;      // one MN-major bf16 slab is 64 columns (TMA zero-fills past N)
   const int kps0 = (int)cdiv(cdiv(d.K, d.split_k > 1 ? d.split_k : 1), kb_elems) * kb_elems;
-  const bool one_kb_narrow = !bf16 && block_n == 128 && kps0 <= kb_elems && getenv("VU_TC_QK128") == nullptr;
+  // one k-block contractions (K <= 32 floats / 64 bf16: the second FeedForward product and the first one's data gradient)
+  // are output-bound: 64-column tiles with a single stage let 6 CTAs share an SM
+  const bool one_kb_narrow = block_n == 128 && kps0 <= kb_elems && getenv("VU_TC_QK128") == nullptr;
   if (one_kb_narrow) block_n = 64;      // box width of the B operand must match the kernel's BLOCK_N
   CUtensorMap tmA, tmB;
   bool ok;
@@ -517,6 +519,7 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
     else if (block_n == 32 && st32 == 3) rc = launch_tc<32, 3, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     else if (block_n == 32) rc = launch_tc<32, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     // token GEMMs in the bf16 mode: short contractions (<= 32 k-blocks of 64) are output-bound -> two stages, more CTAs per SM
+    else if (one_kb_narrow) rc = launch_tc<64, 1, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
     else if (block_n == 64) {
       if (g.k_per_split <= 2048) rc = launch_tc<64, 2, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
       else rc = launch_tc<64, 4, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);

@@ -235,6 +235,13 @@ extern "C" int vu_cast_bf16(const float* src, void* dst, void* dst_t, int R, int
   return check_launch(fn);
 }
 
+extern "C" int vu_zero(void* p, int64_t bytes, void* stream) {
+  using namespace vu;
+  VU_REQUIRE(p && bytes >= 0, "vu_zero", "bad arguments");
+  if (bytes && cudaMemsetAsync(p, 0, (size_t)bytes, as_stream(stream)) != cudaSuccess) return check_launch("vu_zero");
+  return VU_OK;
+}
+
 extern "C" int vu_axpby(const float* x, float* y, int64_t n, float a, float b, void* stream) {
   using namespace vu;
   const char* fn = "vu_axpby";

@@ -207,13 +207,11 @@ class Engine:
         prec, b16 = self._prec(), self._b16()
         wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
         q, k, v = _empty((B, N, D), xq), _empty((B, N, D), xq), _empty((B, N, D), xq)
-        if xq is xkv:
-            wcat = torch.cat([wq.reshape(-1), wk.reshape(-1), wv.reshape(-1)])
-            ops.conv3x3_fwd(xq, p, wcat, None, [q, k, v], p, p, B, g.C, g.S, g.S)
+        if xq is xkv:         # the three filters are uploaded from their own parameter tensors (no concatenation pass)
+            ops.conv3x3_fwd(xq, p, [wq, wk, wv], None, [q, k, v], p, p, B, g.C, g.S, g.S)
         else:
-            ops.conv3x3_fwd(xq, p, wq.contiguous(), None, [q], p, p, B, g.C, g.S, g.S)
-            wcat = torch.cat([wk.reshape(-1), wv.reshape(-1)])
-            ops.conv3x3_fwd(xkv, p, wcat, None, [k, v], p, p, B, g.C, g.S, g.S)
+            ops.conv3x3_fwd(xq, p, wq, None, [q], p, p, B, g.C, g.S, g.S)
+            ops.conv3x3_fwd(xkv, p, [wk, wv], None, [k, v], p, p, B, g.C, g.S, g.S)
         # The (B,h,N,N) maps are processed in slices of `c` images sized so that the maps a kernel chain hands from
         # one launch to the next (S -> P -> A, ~2 live maps) stay resident in the 126 MB L2: HBM then sees P once on
         # the way out (it is saved for backward) and once on the way back in, instead of ~6 full passes.
@@ -253,7 +251,7 @@ class Engine:
         vt = ops.heads_transpose_bf16(v, B, N, D, h) if bf16 else None        # (B,h,hd,ldn): K-major B operand of A.V
         ldn = vt.shape[-1] if bf16 else 0
         fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
-        sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device) if train else None
+        sums = ops.zeros(h + h * h, torch.float64, xq.device) if train else None
 
         def scores(b0, bc, dst):
             ops.gemm(q[b0:b0 + bc], k[b0:b0 + bc], dst, N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld, batch_outer=bc,
@@ -329,7 +327,7 @@ class Engine:
         keep_P = saved is not None
         vt = ops.heads_transpose_bf16(v, B, N, D, h)
         fold, bn_saved = _empty((h * h + h,), xq), _empty((2 * h,), xq)
-        sums = torch.zeros(h + h * h, dtype=torch.float64, device=xq.device) if (train or keep_P) else None
+        sums = ops.zeros(h + h * h, torch.float64, xq.device) if (train or keep_P) else None
         O = _empty((B, N, D), xq)
         Pm = torch.empty((B, h, N, N), dtype=torch.bfloat16, device=xq.device) if keep_P else None
         A, mask = None, None
@@ -367,8 +365,9 @@ class Engine:
                          mask=mask)
         return y
 
-    def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc):
-        """dy: grad of proj output (pre-residual).  Accumulates into dxq_acc / dxkv_acc (may be the same tensor)."""
+    def _attn_bwd(self, P, G, pre, dy, l, B, sv, dxq_acc, dxkv_acc, acc_q=True, acc_kv=True):
+        """dy: grad of proj output (pre-residual).  Accumulates into dxq_acc / dxkv_acc (may be the same tensor); with
+        acc_* False the conv data gradient is WRITTEN instead (skip connection: no zero-filled accumulator needed)."""
         g = self.g
         N, D, h, p = g.N(l), g.D(l), g.heads, g.p(l)
         hd, ld = D // h, ops.pad4(N)
@@ -401,7 +400,7 @@ class Engine:
             # (written once, read by dK = dS^T q)
             gamma = P[pre + "var_norm.weight"]
             mask, A_kept = sv.get("mask"), sv["A"]
-            red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
+            red = ops.zeros(h + h * h, torch.float64, dy.device)
             ops.reattn_stream_bwd_reduce(Pm, mask, dO, v, red, B, h, N, hd, adrop, seed, sid)
             dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
             dOt = ops.heads_transpose_bf16(dO, B, N, D, h)
@@ -425,7 +424,7 @@ class Engine:
             qt = ops.heads_transpose_bf16(q, B, N, D, h)
             map_gemm_t(dS, qt, dk)
             del dS, qt
-            self._qkv_conv_bwd(P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc)
+            self._qkv_conv_bwd(P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc, acc_q, acc_kv)
             return
         # recompute the mixed map, then dV = A^T dO ; dA = dO V^T
         # Same image slices as forward (identical dropout RNG streams).  Phase A per slice: dA = dO V^T, one pass over
@@ -437,7 +436,7 @@ class Engine:
         gamma = P[pre + "var_norm.weight"]
         bf16 = sv["bf16"]
         mdt = torch.bfloat16 if bf16 else torch.float32
-        dA = torch.zeros((c, h, N, ld), dtype=mdt, device=dy.device) if ld != N else torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
+        dA = ops.zeros((c, h, N, ld), mdt, dy.device) if ld != N else torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
         A_kept = sv.get("A")
         A = A_kept if A_kept is not None else torch.empty((c, h, N, ld), dtype=mdt, device=dy.device)
         if bf16:     # per-head transposed bf16 copies: the K-major B operands of dV = A^T dO, dQ = dS K, dK = dS^T Q
@@ -455,7 +454,7 @@ class Engine:
                          ldb=D, ldc=D, batch_outer=bc, batch_inner=h, sA=(h * N * ld, N * ld), sB=(N * D, hd),
                          sC=(N * D, hd), precision=prec)
         dq, dk, dv = _empty((B, N, D), dy), _empty((B, N, D), dy), _empty((B, N, D), dy)
-        red = torch.zeros(h + h * h, dtype=torch.float64, device=dy.device)
+        red = ops.zeros(h + h * h, torch.float64, dy.device)
 
         def grad_map(b0, bc):
             ops.gemm(dO[b0:b0 + bc], v[b0:b0 + bc], dA[:bc], N, N, hd, trans_b=True, lda=D, ldb=D, ldc=ld,
@@ -484,33 +483,24 @@ class Engine:
             map_gemm(dA, False, kt if bf16 else None, k, dq, b0, bc)
             map_gemm(dA, True, qt if bf16 else None, q, dk, b0, bc)
         del dO, dA
-        self._qkv_conv_bwd(P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc)
+        self._qkv_conv_bwd(P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc, acc_q, acc_kv)
 
-    def _qkv_conv_bwd(self, P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc):
-        """backward of the three per-patch 3x3 convs (model.py:152-154): data gradients accumulate into dx, weights into G"""
+    def _qkv_conv_bwd(self, P, G, pre, sv, dq, dk, dv, p, B, dxq_acc, dxkv_acc, acc_q=True, acc_kv=True):
+        """backward of the three per-patch 3x3 convs (model.py:152-154): data gradients go into dx (accumulated, or written
+        when acc_* is False), weight gradients accumulate straight into their slots of the flat gradient buffer"""
         g = self.g
-        dy = dq
         wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
+        gq, gk, gv = G[pre + "qconv2d.weight"], G[pre + "kconv2d.weight"], G[pre + "vconv2d.weight"]
         xq, xkv = sv["xq"], sv["xkv"]
         C, S = g.C, g.S
-        nw = wq.numel()
         if xq is xkv:
-            wcat = torch.cat([wq.reshape(-1), wk.reshape(-1), wv.reshape(-1)])
-            ops.conv3x3_bwd_data([dq, dk, dv], p, wcat, dxq_acc, p, p, B, C, S, S, accumulate=True)
-            dw = torch.zeros(3 * nw, dtype=torch.float32, device=dy.device)
-            ops.conv3x3_bwd_weight(xq, p, [dq, dk, dv], p, dw, None, p, B, C, S, S)
-            G[pre + "qconv2d.weight"].view(-1).add_(dw[:nw])
-            G[pre + "kconv2d.weight"].view(-1).add_(dw[nw:2 * nw])
-            G[pre + "vconv2d.weight"].view(-1).add_(dw[2 * nw:])
+            ops.conv3x3_bwd_data([dq, dk, dv], p, [wq, wk, wv], dxq_acc, p, p, B, C, S, S, accumulate=acc_q)
+            ops.conv3x3_bwd_weight(xq, p, [dq, dk, dv], p, [gq, gk, gv], None, p, B, C, S, S)
         else:
-            ops.conv3x3_bwd_data([dq], p, wq.contiguous(), dxq_acc, p, p, B, C, S, S, accumulate=True)
-            wcat = torch.cat([wk.reshape(-1), wv.reshape(-1)])
-            ops.conv3x3_bwd_data([dk, dv], p, wcat, dxkv_acc, p, p, B, C, S, S, accumulate=True)
-            ops.conv3x3_bwd_weight(xq, p, [dq], p, G[pre + "qconv2d.weight"], None, p, B, C, S, S)
-            dw = torch.zeros(2 * nw, dtype=torch.float32, device=dy.device)
-            ops.conv3x3_bwd_weight(xkv, p, [dk, dv], p, dw, None, p, B, C, S, S)
-            G[pre + "kconv2d.weight"].view(-1).add_(dw[:nw])
-            G[pre + "vconv2d.weight"].view(-1).add_(dw[nw:])
+            ops.conv3x3_bwd_data([dq], p, wq, dxq_acc, p, p, B, C, S, S, accumulate=acc_q)
+            ops.conv3x3_bwd_data([dk, dv], p, [wk, wv], dxkv_acc, p, p, B, C, S, S, accumulate=acc_kv)
+            ops.conv3x3_bwd_weight(xq, p, [dq], p, gq, None, p, B, C, S, S)
+            ops.conv3x3_bwd_weight(xkv, p, [dk, dv], p, [gk, gv], None, p, B, C, S, S)
 
     def _wgrad(self, dY, X, dW, M, N, K):
         """dW[N,K] += dY[M,N]^T @ X[M,K]; split over the (long) token dimension for parallelism."""
@@ -620,7 +610,7 @@ class Engine:
         src = X
         if g.pe_conv:
             src = torch.empty_like(X)
-            ops.conv3x3_fwd(X, 0, P["PE.conv2d.weight"].contiguous(), P["PE.conv2d.bias"], [src], 0, 0, B, C, S, S)
+            ops.conv3x3_fwd(X, 0, P["PE.conv2d.weight"], P["PE.conv2d.bias"], [src], 0, 0, B, C, S, S)
         x = _empty((B, g.N(0), g.D(0)), X)
         ops.pe_fwd(src, 0, P["PE.position_embedding.weight"], g.table_p, x, g.p0, B, C, S, S)
         if save:
@@ -653,7 +643,7 @@ class Engine:
                 saved["steps"].append(sv)
         out = _empty((B, C, S, S), X)
         if g.out_conv:
-            ops.conv3x3_fwd(x, g.p0, P["conv2d.weight"].contiguous(), P["conv2d.bias"], [out], 0, 0, B, C, S, S)
+            ops.conv3x3_fwd(x, g.p0, P["conv2d.weight"], P["conv2d.bias"], [out], 0, 0, B, C, S, S)
         else:
             ops.repatch(x, out, B, C, S, S, g.p0, 0)
         if save:
@@ -670,8 +660,7 @@ class Engine:
         self._w16 = saved.get("w16", {})
         dx = _empty((B, g.N(0), g.D(0)), dout)
         if g.out_conv:
-            w = P["conv2d.weight"].contiguous()
-            ops.conv3x3_bwd_data([dout], 0, w, dx, g.p0, 0, B, C, S, S)
+            ops.conv3x3_bwd_data([dout], 0, P["conv2d.weight"], dx, g.p0, 0, B, C, S, S)
             ops.conv3x3_bwd_weight(saved["x_last"], g.p0, [dout], 0, G["conv2d.weight"], G["conv2d.bias"], 0, B, C, S, S)
         else:
             ops.repatch(dout, dx, B, C, S, S, 0, g.p0)
@@ -694,9 +683,8 @@ class Engine:
                 dx = ops.repatch(dx, y, B, C, S, S, g.p(l - 1), g.p(l))
             else:
                 _, pre, l = st
-                d_enc = torch.zeros_like(dx)
-                d_dec = torch.zeros_like(dx)
-                self._attn_bwd(P, G, pre, dx, l, B, sv, d_enc, d_dec)
+                d_enc, d_dec = torch.empty_like(dx), torch.empty_like(dx)     # written (not accumulated) by the conv backward
+                self._attn_bwd(P, G, pre, dx, l, B, sv, d_enc, d_dec, acc_q=False, acc_kv=False)
                 skip_grads[l] = d_enc
                 dx = d_dec
                 self._notify(pre)
@@ -709,7 +697,7 @@ class Engine:
             ops.conv3x3_bwd_weight(saved["X"], 0, [dsrc], 0, G["PE.conv2d.weight"], G["PE.conv2d.bias"], 0, B, C, S, S)
             if need_dx:
                 dX = _empty((B, C, S, S), dx)
-                ops.conv3x3_bwd_data([dsrc], 0, P["PE.conv2d.weight"].contiguous(), dX, 0, 0, B, C, S, S)
+                ops.conv3x3_bwd_data([dsrc], 0, P["PE.conv2d.weight"], dX, 0, 0, B, C, S, S)
         elif need_dx:
             dX = _empty((B, C, S, S), dx)
             ops.repatch(dx, dX, B, C, S, S, g.p0, 0)

@@ -80,7 +80,7 @@ class _ViTUNetFn(torch.autograd.Function):
         params = ctx.saved_tensors
         P = dict(zip(names, params))
         P.update(owner._buffer_dict())
-        flat = torch.zeros(owner._flat_numel, dtype=torch.float32, device=dout.device)
+        flat = ops.zeros(owner._flat_numel, torch.float32, dout.device)      # cudaMemsetAsync, no fill kernel
         G = {n: flat[o:o + p.numel()].view(p.shape) for n, p, o in zip(names, params, owner._flat_offsets)}
         owner._last_flat_grad = flat
         dp = owner._dp

@@ -137,10 +137,19 @@ def pe_bwd_table(dout, p_out, dtable, p_table, B, Cc, H, W, accumulate=False):
 
 
 # ----------------------------------------------------------------------------------------- convs
+def _filters(w, name):
+    """one contiguous tensor holding the filters of all fused convs, or a list of per-conv tensors -> three pointers"""
+    if isinstance(w, (list, tuple)):
+        ptrs = [_chk(t, f"{name}{i}") for i, t in enumerate(w)] + [None] * (3 - len(w))
+        return ptrs[0], ptrs[1], ptrs[2]
+    return _chk(w, name), None, None
+
+
 def conv3x3_fwd(x, p_x, w, bias, outs, p_out, border_p, B, Cc, H, W):
     n = len(outs)
     ptrs = [_chk(o, f"out{i}") for i, o in enumerate(outs)] + [None] * (3 - n)
-    _call("vu_conv3x3_fwd", _chk(x, "x"), p_x, _chk(w, "w"), _opt(bias, "bias"), n, ptrs[0], ptrs[1], ptrs[2],
+    w0, w1, w2 = _filters(w, "w")
+    _call("vu_conv3x3_fwd", _chk(x, "x"), p_x, w0, w1, w2, _opt(bias, "bias"), n, ptrs[0], ptrs[1], ptrs[2],
           p_out, border_p, B, Cc, H, W, _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W, flops=18.0 * n * Cc * Cc * B * H * W)
     return outs
 
@@ -148,18 +157,29 @@ def conv3x3_fwd(x, p_x, w, bias, outs, p_out, border_p, B, Cc, H, W):
 def conv3x3_bwd_data(dys, p_dy, w, dx, p_dx, border_p, B, Cc, H, W, accumulate=False):
     n = len(dys)
     ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
-    _call("vu_conv3x3_bwd_data", ptrs[0], ptrs[1], ptrs[2], p_dy, _chk(w, "w"), n, _chk(dx, "dx"), p_dx,
+    w0, w1, w2 = _filters(w, "w")
+    _call("vu_conv3x3_bwd_data", ptrs[0], ptrs[1], ptrs[2], p_dy, w0, w1, w2, n, _chk(dx, "dx"), p_dx,
           border_p, B, Cc, H, W, int(accumulate), _stream(), nbytes=(1 + n + int(accumulate)) * 4.0 * B * Cc * H * W,
           flops=18.0 * n * Cc * Cc * B * H * W)
     return dx
 
 
 def conv3x3_bwd_weight(x, p_x, dys, p_dy, dw, dbias, border_p, B, Cc, H, W):
+    """dw: one contiguous [nconv][C][C][3][3] tensor, or a list of per-conv gradient tensors (accumulated in place)"""
     n = len(dys)
     ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
-    _call("vu_conv3x3_bwd_weight", _chk(x, "x"), p_x, ptrs[0], ptrs[1], ptrs[2], p_dy, n, _chk(dw, "dw"),
+    d0, d1, d2 = _filters(dw, "dw")
+    _call("vu_conv3x3_bwd_weight", _chk(x, "x"), p_x, ptrs[0], ptrs[1], ptrs[2], p_dy, n, d0, d1, d2,
           _opt(dbias, "dbias"), border_p, B, Cc, H, W, _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W,
           flops=18.0 * n * Cc * Cc * B * H * W)
+
+
+def zeros(shape, dtype, device):
+    """torch.empty + a stream-ordered cudaMemsetAsync (accumulators, gradient buffers): no fill kernel"""
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if t.numel():
+        call("vu_zero", t.data_ptr(), t.numel() * t.element_size(), _stream())
+    return t
 
 
 # ----------------------------------------------------------------------------------------- GEMM
