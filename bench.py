@@ -467,11 +467,11 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed GLOBAL batch split over the ranks "
                     "(overrides --batch; reported with scaling=strong)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
-    ap.add_argument("--precision", "--dtype", dest="precision", default=os.environ.get("VU_PRECISION", "tf32"),
+    ap.add_argument("--precision", "--dtype", dest="precision", default=os.environ.get("VU_PRECISION", "bf16"),
                     choices=["fp32", "tf32", "bf16"],
-                    help="tf32: tcgen05 tensor-core contractions on fp32 storage (default); bf16: bf16 storage of every GEMM operand / "
-                         "saved activation outside the residual stream + bf16 tcgen05 token GEMMs (BASELINE configs[3]); "
-                         "fp32: CUDA-core exact mode")
+                    help="bf16 (default): bf16 storage of every GEMM operand / saved activation outside the residual stream + bf16 "
+                         "tcgen05 token GEMMs, fp32 residual stream / statistics / master weights / gradients; tf32: tcgen05 "
+                         "contractions on fp32 storage; fp32: CUDA-core exact mode")
     ap.add_argument("--streamed", type=int, default=None, help="1/0: force the streamed Re-Attention kernels on/off "
                     "(default: on for no-grad inference, off for training steps; see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -303,3 +303,21 @@ def test_model_bf16_maps_within_1e2():
     # per cent there, see make_golden.conditioning); every other tensor must agree to a few per cent
     bad = [(r, n, m) for r, n, m in rows if r > 5e-2 and not ("qconv2d" in n or "kconv2d" in n)]
     assert not bad, bad[-5:]
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("M,N,K", [(12800, 768, 64), (40000, 192, 192), (6272, 3072, 256), (25000, 64, 768)])
+def test_tc_gemm_persistent_many_tiles_per_cta(ops, M, N, K, bf16, monkeypatch):
+    """The opt-in persistent kernel (VU_TC_PERSISTENT=1: one CTA per SM walks the tiles, double-buffered TMEM
+    accumulators): several tiles per CTA (up to ~13 on 148 SMs) with bias + residual exercise the ring / accumulator
+    phase bookkeeping across tile boundaries."""
+    monkeypatch.setenv("VU_TC_PERSISTENT", "1")
+    A, W = _rand(M, K, seed=1), _rand(N, K, seed=2) / math.sqrt(K)
+    if bf16:
+        A, W = A.bfloat16(), W.bfloat16()
+    bias, res = _rand(N, seed=3), _rand(M, N, seed=4)
+    exp = A.double() @ W.double().t() + bias.double() + res.double()
+    out = torch.zeros(M, N, device="cuda")
+    ops.gemm(A.cuda(), W.cuda(), out, M, N, K, trans_b=True, lda=K, ldb=K, ldc=N, bias=bias.cuda(), residual=res.cuda(),
+             precision=ops.PREC_TF32)
+    _close(out, exp, 1e-4 if bf16 else TOL, name="persistent")

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvitunet_b200.so")
+LIB_PATH = os.environ.get("VU_LIB_PATH") or os.path.join(_HERE, "libvitunet_b200.so")     # VU_LIB_PATH: A/B builds of the kernels
 ABI_VERSION = 8
 
 

@@ -16,6 +16,7 @@
 // One 128 x BLOCK_N output tile per CTA; two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <algorithm>
 #include <cstdlib>
 
 #include "vu_common.cuh"
@@ -38,6 +39,7 @@ struct TcArgs {
   uint32_t mn_lbo, mn_sbo;      // MN-major descriptor strides (bytes)
   int c_bf16;                   // C is __nv_bfloat16 (no accumulate / split-K; the fused epilogues apply)
   int aux_bf16;                 // aux_in / aux_out are __nv_bfloat16
+  int tiles_m, tiles_n, total_tiles;   // persistent kernel: tile id -> (n tile fastest, m tile, batch * split)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -59,6 +61,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -131,11 +136,235 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, b
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
 }
 
+// Second half of the epilogue, shared by the one-tile-per-CTA kernel and the persistent kernel: the warp's 32 x BLOCK_N
+// sub-tile sits in shared memory (`stage`, row pitch BLOCK_N + 4 floats, alpha already applied); rows leave as coalesced
+// 16-byte-per-lane accesses through the fused epilogue (bias, GELU / GELU', dropout, residual, fp32 / bf16 / atomic store).
+template <int BLOCK_N, int UN>
+__device__ __forceinline__ void epilogue_rows(const TcArgs& g, const float* stage, const int lane, const int q, const int m0,
+                                              const int n0, const int z, const int ks, const int64_t coff) {
+  constexpr int LDS = BLOCK_N + 4;
+  float* C = g.C + coff;
+  constexpr int LPR = BLOCK_N / 4;                      // lanes covering one output row
+  constexpr int RPI = 32 / LPR;                         // rows handled per iteration
+  const int cl = (lane % LPR) * 4;                      // this lane's 4 columns inside the tile
+  const int n = n0 + cl;
+  const int nv = min(4, g.N - n);                       // <= 0: nothing to do for this lane
+  const bool vec_c = ((uintptr_t)C % 16 == 0) && (g.ldc % 4 == 0) && nv == 4;
+  float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (g.bias && (g.split_k <= 1 || ks == 0)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j < nv) bias4[j] = g.bias[n + j];
+  }
+  const uint32_t drop_key = Philox::key(g.drop_seed, g.drop_stream);
+  const bool vec_r = g.residual && ((uintptr_t)(g.residual + coff) % 16 == 0) && (g.ldr % 4 == 0) && nv == 4;
+  const float* axp = g.aux_in ? g.aux_in : g.aux_out;
+  // aux rows as one vector access: float4 (fp32) or 4 x bf16 = 8 bytes
+  const bool vec_x = axp && nv == 4 && (g.ldaux % 4 == 0) &&
+                     (g.aux_bf16 ? ((uintptr_t)(reinterpret_cast<const __nv_bfloat16*>(axp) + coff) % 8 == 0)
+                                 : ((uintptr_t)(axp + coff) % 16 == 0));
+  // ---- fast path: no activation, no split-K, whole aligned quads (every proj / FeedForward-2 / data-gradient / dense
+  // weight-gradient launch of the path).  The general row routine below costs ~100 executed instructions per row with one
+  // epilogue warp per scheduler and nothing to overlap them with -- measured 16 us per 128 x 128 tile, the whole lifetime
+  // of a thin GEMM's CTA.  Here a row is ~12 instructions, the loads of a batch of rows (residual, and C itself when
+  // accumulating) are issued together, and the addresses are strength-reduced.
+  {
+    const bool c_ok = g.c_bf16 ? ((uintptr_t)(reinterpret_cast<const __nv_bfloat16*>(g.C) + coff) % 8 == 0 && g.ldc % 4 == 0) : vec_c;
+    if (g.split_k <= 1 && g.act == VU_ACT_NONE && nv == 4 && c_ok && (!g.residual || vec_r) && !(g.accumulate && g.c_bf16) &&
+        (!g.drop_thresh || g.N % 4 == 0)) {
+      constexpr int ITER = 32 / RPI;                       // row iterations of this warp
+      constexpr int UB = ITER < UN ? ITER : UN;            // rows per batch of loads
+      const int r_in = lane / LPR;
+      const int mrow0 = m0 + q * 32 + r_in;
+      const float* sp = stage + r_in * LDS + cl;
+      const float4 b4 = make_float4(bias4[0], bias4[1], bias4[2], bias4[3]);
+      const float* rp = g.residual ? g.residual + coff + (int64_t)mrow0 * g.ldr + n : nullptr;
+      float* cp = C + (int64_t)mrow0 * g.ldc + n;
+      __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + coff + (int64_t)mrow0 * g.ldc + n;
+      const int64_t rstep = (int64_t)RPI * g.ldr, cstep = (int64_t)RPI * g.ldc;
+      const bool acc = g.accumulate != 0;
+      const uint64_t didx0 = (uint64_t)z * g.M * g.N + (uint64_t)mrow0 * g.N + n;      // dropout counter of the first row
+      const uint32_t dstep = (uint32_t)((RPI * g.N) >> 2);
+#pragma unroll 1
+      for (int ib = 0; ib < ITER; ib += UB) {
+        float4 rr[UB], cc[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const bool ok = mrow0 + (ib + u) * RPI < g.M;
+          rr[u] = (rp && ok) ? *reinterpret_cast<const float4*>(rp + (ib + u) * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+          cc[u] = (acc && ok) ? *reinterpret_cast<const float4*>(cp + (ib + u) * cstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          if (mrow0 + (ib + u) * RPI >= g.M) continue;
+          float4 t = *reinterpret_cast<const float4*>(sp + (ib + u) * RPI * LDS);
+          t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
+          if (g.drop_thresh) {
+            const uint4 r = Philox::gen_k(drop_key, (uint32_t)(didx0 >> 2) + (uint32_t)(ib + u) * dstep);
+            t.x = r.x >= g.drop_thresh ? t.x * g.drop_scale : 0.f; t.y = r.y >= g.drop_thresh ? t.y * g.drop_scale : 0.f;
+            t.z = r.z >= g.drop_thresh ? t.z * g.drop_scale : 0.f; t.w = r.w >= g.drop_thresh ? t.w * g.drop_scale : 0.f;
+          }
+          t.x += rr[u].x + cc[u].x; t.y += rr[u].y + cc[u].y; t.z += rr[u].z + cc[u].z; t.w += rr[u].w + cc[u].w;
+          if (g.c_bf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(cb + (ib + u) * cstep) = pk;
+          } else {
+            *reinterpret_cast<float4*>(cp + (ib + u) * cstep) = t;
+          }
+        }
+      }
+      return;
+    }
+  }
+  // One output row (this lane's 4 columns) through the fused epilogue.  pr / px: the residual and GELU' pre-activation
+  // quads of the row, loaded by the caller a whole batch of rows ahead (have_r / have_x), else fetched here.
+  auto process = [&](const int row, const bool have_r, const float4 pr, const bool have_x, const float4 px) {
+    const int m = m0 + q * 32 + row;
+    if (m >= g.M || nv <= 0) return;
+    const float4 t4 = *reinterpret_cast<const float4*>(stage + row * LDS + cl);
+    float v[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
+    float* dst = C + (int64_t)m * g.ldc + n;
+    if (g.split_k > 1) {
+      if (g.residual && ks == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nv) v[j] += g.residual[coff + (int64_t)m * g.ldr + n + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
+      return;
+    }
+    const int64_t xoff = coff + (int64_t)m * g.ldaux + n;
+    if (g.act == VU_ACT_GELU) {
+      if (g.aux_out) {
+        if (g.aux_bf16) {
+          __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(g.aux_out) + xoff;
+          if (vec_x) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(ax) = pk;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* ax = g.aux_out + xoff;
+          if (vec_x) *reinterpret_cast<float4*>(ax) = make_float4(v[0], v[1], v[2], v[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = v[j];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_exact(v[j]);
+    } else if (g.act == VU_ACT_GELU_BWD) {
+      float a[4] = {px.x, px.y, px.z, px.w};
+      if (have_x) {
+      } else if (g.aux_bf16) {
+        const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + xoff;
+        if (vec_x) {
+          const uint2 pk = *reinterpret_cast<const uint2*>(ax);
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+          a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) a[j] = __bfloat162float(ax[j]);
+        }
+      } else {
+        const float* ax = g.aux_in + xoff;
+        if (vec_x) { float4 t = *reinterpret_cast<const float4*>(ax); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nv) a[j] = ax[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= gelu_exact_grad(a[j]);
+    }
+    if (g.drop_thresh) {
+      const uint64_t idx0 = (uint64_t)z * g.M * g.N + (uint64_t)m * g.N + n;
+      if ((idx0 & 3) == 0) {       // the lane's 4 columns are one RNG quad: one hash instead of four
+        const uint4 r = Philox::gen_k(drop_key, (uint32_t)(idx0 >> 2));
+        v[0] = r.x >= g.drop_thresh ? v[0] * g.drop_scale : 0.f;
+        v[1] = r.y >= g.drop_thresh ? v[1] * g.drop_scale : 0.f;
+        v[2] = r.z >= g.drop_thresh ? v[2] * g.drop_scale : 0.f;
+        v[3] = r.w >= g.drop_thresh ? v[3] * g.drop_scale : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = Philox::keep(g.drop_seed, g.drop_stream, idx0 + j, g.drop_thresh) ? v[j] * g.drop_scale : 0.f;
+      }
+    }
+    if (g.residual) {
+      const float* rp = g.residual + coff + (int64_t)m * g.ldr + n;
+      if (have_r) { v[0] += pr.x; v[1] += pr.y; v[2] += pr.z; v[3] += pr.w; }
+      else if (vec_r) { float4 t = *reinterpret_cast<const float4*>(rp); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rp[j];
+      }
+    }
+    if (g.c_bf16) {          // bf16 output (host side rejects accumulate / split-K)
+      __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + coff + (int64_t)m * g.ldc + n;
+      if (nv == 4 && ((uintptr_t)cb % 8 == 0)) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(cb) = pk;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nv) cb[j] = __float2bfloat16_rn(v[j]);
+      }
+    } else if (vec_c) {
+      float4 o = make_float4(v[0], v[1], v[2], v[3]);
+      if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+      *reinterpret_cast<float4*>(dst) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nv) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
+    }
+  };
+  // Rows go through in batches of UN: the batch's residual / pre-activation quads are requested from global memory
+  // first (UN independent 16-byte loads per lane in flight), then the rows are finished.  With one load per row issued
+  // right where it is consumed the epilogue of an output-bound product (proj forward: bias + dropout + residual) ran at
+  // one memory latency per row: 251 us instead of 106 us for the same product without a residual (M = 200704, N = K = 192).
+  const bool pre_r = vec_r && g.split_k <= 1;
+  const bool pre_x = vec_x && g.act == VU_ACT_GELU_BWD;
+#pragma unroll 1
+  for (int rb = 0; rb < 32; rb += RPI * UN) {
+    float4 pr[UN], px[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int row = rb + u * RPI + lane / LPR;
+      const int m = m0 + q * 32 + row;
+      pr[u] = make_float4(0.f, 0.f, 0.f, 0.f); px[u] = pr[u];
+      if (m < g.M && nv > 0) {
+        if (pre_r) pr[u] = *reinterpret_cast<const float4*>(g.residual + coff + (int64_t)m * g.ldr + n);
+        if (pre_x) {
+          if (g.aux_bf16) {
+            const uint2 pk = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + coff + (int64_t)m * g.ldaux + n);
+            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+            px[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            px[u] = *reinterpret_cast<const float4*>(g.aux_in + coff + (int64_t)m * g.ldaux + n);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) process(rb + u * RPI + lane / LPR, pre_r, pr[u], pre_x, px[u]);
+  }
+}
+
 // BF16 = true: both operands are __nv_bfloat16 (kind::f16, 64 elements per 128-byte k-block, UMMA_K = 16).  Either
 // operand may be MN-major with the ordinary SWIZZLE_128B atoms (64 elements x 8 k-rows; ROWS / 64 slabs of 8 KB per
 // stage, LBO = 8192 between slabs, SBO = 1024 between 8-k-row groups): the weight-gradient products dW = dY^T X read
 // both token tensors as they lie in memory.  An MN-major bf16 B needs BLOCK_N >= 64 (one slab is 64 columns wide).
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool BF16>
+// EPI_UN: rows per batch of the epilogue's global loads (residual / GELU' pre-activation): 4 for launches that read such a
+// tensor, 1 (no batching, 71 instead of 96 registers -> one more resident CTA for the map-reading products) otherwise.
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool BF16, int EPI_UN>
 __global__ void __launch_bounds__(192, 3)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
   static_assert(!(BF16 && B_MN) || BLOCK_N >= 64, "an MN-major bf16 B tile is made of 64-column slabs");
@@ -241,9 +470,18 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // and every store of C is a fully coalesced 16 B-per-lane transaction.
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
     const int64_t coff = zo * g.sCo + zi * g.sCi;
-    float* C = g.C + coff;
     constexpr int LDS = BLOCK_N + 4;                      // padded staging row (floats)
     float* stage = reinterpret_cast<float*>(smem) + (size_t)q * 32 * LDS;
+    if (EPI_UN > 1 && g.residual && g.split_k <= 1) {
+      // the residual rows of this warp's 32 x BLOCK_N sub-tile are pulled into L2 while the main loop runs
+      const float* rbase = g.residual + coff + (int64_t)(m0 + q * 32) * g.ldr + n0;
+      constexpr int LINES = BLOCK_N / 32;                   // 128-byte lines per row
+      for (int i = lane; i < 32 * LINES; i += 32) {
+        const int rr = i / LINES, cc = (i - rr * LINES) * 32;
+        if (m0 + q * 32 + rr < g.M && n0 + cc < g.N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase + (int64_t)rr * g.ldr + cc));
+      }
+    }
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -265,122 +503,181 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         __uint_as_float(r[j4 + 2]) * g.alpha, __uint_as_float(r[j4 + 3]) * g.alpha);
     }
     __syncwarp();
-    constexpr int LPR = BLOCK_N / 4;                      // lanes covering one output row
-    constexpr int RPI = 32 / LPR;                         // rows handled per iteration
-    const int cl = (lane % LPR) * 4;                      // this lane's 4 columns inside the tile
-    const int n = n0 + cl;
-    const int nv = min(4, g.N - n);                       // <= 0: nothing to do for this lane
-    const bool vec_c = ((uintptr_t)C % 16 == 0) && (g.ldc % 4 == 0) && nv == 4;
-    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (g.bias && (g.split_k <= 1 || ks == 0)) {
+    epilogue_rows<BLOCK_N, EPI_UN>(g, stage, lane, q, m0, n0, z, ks, coff);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ persistent variant (token GEMMs)
+// One CTA per SM walks the output tiles (tile = blockIdx.x + i * gridDim.x, n tile fastest so that concurrently running
+// CTAs share A rows through L2).  The accumulator is DOUBLE-BUFFERED in TMEM (2 x BLOCK_N columns): while the four epilogue
+// warps drain tile i (TMEM -> registers -> their own staging rows in shared memory -> fused epilogue -> global), the MMA
+// warp already accumulates tile i+1 into the other buffer and the TMA warp keeps the STAGES-deep operand ring full across
+// tile boundaries.  Barrier init, tensor-map prefetch and the TMEM allocation are paid once per SM instead of once per
+// tile -- what the one-tile-per-CTA kernel loses on the thin (K <= 768) and output-bound shapes -- and the epilogue of a
+// large tile no longer idles the tensor pipe.  With one CTA per SM the epilogue can afford 8-row load batches (UN = 8).
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool BF16>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
+  static_assert(!(BF16 && B_MN) || BLOCK_N >= 64, "an MN-major bf16 B tile is made of 64-column slabs");
+  constexpr int KB = BF16 ? 64 : 32;
+  constexpr uint32_t A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 4;
+  constexpr uint32_t B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;              // two accumulators (64 -> 128, 128 -> 256 columns)
+  constexpr int LDS = BLOCK_N + 4;
+  constexpr uint32_t RING_BYTES = STAGES * (A_BYTES + B_BYTES);
+  constexpr uint32_t STAGING_BYTES = 4u * 32u * LDS * 4u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  float* staging = reinterpret_cast<float*>(smem + RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;            // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar + b, 1); mbar_init(tmem_empty_bar + b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile id -> coordinates (identical in the three roles)
+  auto decode = [&](int tile, int& m0, int& n0, int& z, int& ks, int& zo, int& zi, int& kbeg, int& nkb) {
+    const int tn = tile % g.tiles_n; tile /= g.tiles_n;
+    const int tm = tile % g.tiles_m; z = tile / g.tiles_m;
+    m0 = tm * TC_BLOCK_M; n0 = tn * BLOCK_N;
+    ks = 0;
+    if (g.split_k > 1) { ks = z % g.split_k; z /= g.split_k; }
+    zo = z / g.batch_inner; zi = z % g.batch_inner;
+    kbeg = ks * g.k_per_split;
+    const int kend = min(g.K, kbeg + g.k_per_split);
+    nkb = (kend - kbeg + KB - 1) / KB;
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      uint32_t it = 0;                                     // k-blocks issued so far (ring position across tiles)
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int m0, n0, z, ks, zo, zi, kbeg, nkb;
+        decode(tile, m0, n0, z, ks, zo, zi, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, A_BYTES + B_BYTES);
+          const int k0 = kbeg + kb * KB;
+          uint8_t* a_dst = sA + s * A_BYTES;
+          uint8_t* b_dst = sB + s * B_BYTES;
+          if (!A_MN) tma_load_4d(a_dst, &tmA, full_bar + s, k0, m0, zi, zo);
+          else if (BF16) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (j < nv) bias4[j] = g.bias[n + j];
+            for (int sl = 0; sl < TC_BLOCK_M / 64; ++sl) tma_load_4d(a_dst + sl * 8192, &tmA, full_bar + s, m0 + sl * 64, k0, zi, zo);
+          } else {
+#pragma unroll
+            for (int sl = 0; sl < TC_BLOCK_M / 32; ++sl) tma_load_4d(a_dst + sl * 4096, &tmA, full_bar + s, m0 + sl * 32, k0, zi, zo);
+          }
+          if (!B_MN) tma_load_4d(b_dst, &tmB, full_bar + s, k0, n0, zi, zo);
+          else if (BF16) {
+#pragma unroll
+            for (int sl = 0; sl < BLOCK_N / 64; ++sl) tma_load_4d(b_dst + sl * 8192, &tmB, full_bar + s, n0 + sl * 64, k0, zi, zo);
+          } else {
+#pragma unroll
+            for (int sl = 0; sl < BLOCK_N / 32; ++sl) tma_load_4d(b_dst + sl * 4096, &tmB, full_bar + s, n0 + sl * 32, k0, zi, zo);
+          }
+        }
+      }
     }
-    const bool vec_r = g.residual && ((uintptr_t)(g.residual + coff) % 16 == 0) && (g.ldr % 4 == 0) && nv == 4;
-    const float* axp = g.aux_in ? g.aux_in : g.aux_out;
-    // aux rows as one vector access: float4 (fp32) or 4 x bf16 = 8 bytes
-    const bool vec_x = axp && nv == 4 && (g.ldaux % 4 == 0) &&
-                       (g.aux_bf16 ? ((uintptr_t)(reinterpret_cast<const __nv_bfloat16*>(axp) + coff) % 8 == 0)
-                                   : ((uintptr_t)(axp + coff) % 16 == 0));
-#pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += RPI) {
-      const int row = r0 + lane / LPR;
-      const int m = m0 + q * 32 + row;
-      if (m >= g.M || nv <= 0) continue;
-      const float4 t4 = *reinterpret_cast<const float4*>(stage + row * LDS + cl);
-      float v[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
-      float* dst = C + (int64_t)m * g.ldc + n;
-      if (g.split_k > 1) {
-        if (g.residual && ks == 0) {
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN, BF16);
+    uint32_t it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++t) {
+      int m0, n0, z, ks, zo, zi, kbeg, nkb;
+      decode(tile, m0, n0, z, ks, zo, zi, kbeg, nkb);
+      const uint32_t buf = t & 1;
+      mbar_wait(tmem_empty_bar + buf, ((t >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator (2 tiles ago)
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += g.residual[coff + (int64_t)m * g.ldr + n + j];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
-        continue;
-      }
-      const int64_t xoff = coff + (int64_t)m * g.ldaux + n;
-      if (g.act == VU_ACT_GELU) {
-        if (g.aux_out) {
-          if (g.aux_bf16) {
-            __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(g.aux_out) + xoff;
-            if (vec_x) {
-              __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-              uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(ax) = pk;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else {
-            float* ax = g.aux_out + xoff;
-            if (vec_x) *reinterpret_cast<float4*>(ax) = make_float4(v[0], v[1], v[2], v[3]);
-            else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) if (j < nv) ax[j] = v[j];
-            }
+          for (int kk = 0; kk < TC_BLOCK_K / TC_UMMA_K; ++kk) {
+            const uint64_t ad = !A_MN ? make_smem_desc(a_base + kk * 32, 16, 1024, 2)
+                                : (BF16 ? make_smem_desc(a_base + kk * 2048, 8192, 1024, 2)
+                                        : make_smem_desc(a_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1));
+            const uint64_t bd = !B_MN ? make_smem_desc(b_base + kk * 32, 16, 1024, 2)
+                                : (BF16 ? make_smem_desc(b_base + kk * 2048, 8192, 1024, 2)
+                                        : make_smem_desc(b_base + kk * 1024, g.mn_lbo, g.mn_sbo, 1));
+            if (BF16) umma_bf16(tmem_d, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+            else umma_tf32(tmem_d, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
           }
+          umma_commit(empty_bar + s);
+          if (kb == nkb - 1) umma_commit(tmem_full_bar + buf);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = gelu_exact(v[j]);
-      } else if (g.act == VU_ACT_GELU_BWD) {
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-        if (g.aux_bf16) {
-          const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + xoff;
-          if (vec_x) {
-            const uint2 pk = *reinterpret_cast<const uint2*>(ax);
-            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
-            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
-            a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < nv) a[j] = __bfloat162float(ax[j]);
-          }
-        } else {
-          const float* ax = g.aux_in + xoff;
-          if (vec_x) { float4 t = *reinterpret_cast<const float4*>(ax); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
-          else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < nv) a[j] = ax[j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] *= gelu_exact_grad(a[j]);
+        __syncwarp();
       }
-      if (g.drop_thresh) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint64_t idx = (uint64_t)z * g.M * g.N + (uint64_t)m * g.N + (n + j);
-          v[j] = Philox::keep(g.drop_seed, g.drop_stream, idx, g.drop_thresh) ? v[j] * g.drop_scale : 0.f;
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;
+    float* stage = staging + (size_t)q * 32 * LDS;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++t) {
+      int m0, n0, z, ks, zo, zi, kbeg, nkb;
+      decode(tile, m0, n0, z, ks, zo, zi, kbeg, nkb);
+      const int64_t coff = zo * g.sCo + zi * g.sCi;
+      const uint32_t buf = t & 1;
+      if (g.residual && g.split_k <= 1) {                  // pull this warp's residual rows into L2 ahead of their use
+        const float* rbase = g.residual + coff + (int64_t)(m0 + q * 32) * g.ldr + n0;
+        constexpr int LINES = BLOCK_N / 32;
+        for (int i = lane; i < 32 * LINES; i += 32) {
+          const int rr = i / LINES, cc = (i - rr * LINES) * 32;
+          if (m0 + q * 32 + rr < g.M && n0 + cc < g.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase + (int64_t)rr * g.ldr + cc));
         }
       }
-      if (g.residual) {
-        const float* rp = g.residual + coff + (int64_t)m * g.ldr + n;
-        if (vec_r) { float4 t = *reinterpret_cast<const float4*>(rp); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-        else {
+      mbar_wait(tmem_full_bar + buf, (t >> 1) & 1);
+      tc_fence_after();
+      __syncwarp();                                        // the previous tile's rows have left this warp's staging area
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rp[j];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {           // two 16-column TMEM loads in flight per wait
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BLOCK_N + (uint32_t)c0, r0);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BLOCK_N + (uint32_t)c0 + 16u, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          *reinterpret_cast<float4*>(stage + lane * LDS + c0 + j4) =
+              make_float4(__uint_as_float(r0[j4]) * g.alpha, __uint_as_float(r0[j4 + 1]) * g.alpha,
+                          __uint_as_float(r0[j4 + 2]) * g.alpha, __uint_as_float(r0[j4 + 3]) * g.alpha);
+          *reinterpret_cast<float4*>(stage + lane * LDS + c0 + 16 + j4) =
+              make_float4(__uint_as_float(r1[j4]) * g.alpha, __uint_as_float(r1[j4 + 1]) * g.alpha,
+                          __uint_as_float(r1[j4 + 2]) * g.alpha, __uint_as_float(r1[j4 + 3]) * g.alpha);
         }
       }
-      if (g.c_bf16) {          // bf16 output (host side rejects accumulate / split-K)
-        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + coff + (int64_t)m * g.ldc + n;
-        if (nv == 4 && ((uintptr_t)cb % 8 == 0)) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(cb) = pk;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < nv) cb[j] = __float2bfloat16_rn(v[j]);
-        }
-      } else if (vec_c) {
-        float4 o = make_float4(v[0], v[1], v[2], v[3]);
-        if (g.accumulate) { float4 c = *reinterpret_cast<float4*>(dst); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-        *reinterpret_cast<float4*>(dst) = o;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nv) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + buf);    // accumulator free again: the MMA warp may start tile t + 2 in it
+      epilogue_rows<BLOCK_N, 8>(g, stage, lane, q, m0, n0, z, ks, coff);
     }
   }
   tc_fence_before();
@@ -442,15 +739,20 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
   constexpr size_t smem = (ring > staging ? ring : staging) + 1024 + 256;
   dim3 grid((unsigned)cdiv(g.N, BLOCK_N), (unsigned)cdiv(g.M, TC_BLOCK_M), (unsigned)(nbatch * g.split_k));
   dim3 block(192);
+  // launches whose epilogue reads a residual or a pre-activation tensor take the variant that batches those loads
+  const bool batched_epi = g.split_k <= 1 && (g.residual != nullptr || g.act == VU_ACT_GELU_BWD);
 #define VU_TC_LAUNCH(AMN, BMN)                                                                                   \
   do {                                                                                                            \
-    auto kfn = gemm_tf32_tc_kernel<BLOCK_N, STAGES, AMN, BMN, BF16>;                                                    \
+    auto kfn = gemm_tf32_tc_kernel<BLOCK_N, STAGES, AMN, BMN, BF16, 1>;                                                 \
+    auto kfn4 = gemm_tf32_tc_kernel<BLOCK_N, STAGES, AMN, BMN, BF16, 4>;                                                \
     static uint64_t seen = 0;                                                                                     \
     if (first_use_on_device(seen)) {                                                                              \
-      if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)       \
+      if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||     \
+          cudaFuncSetAttribute(kfn4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)      \
         return check_launch("vu_gemm(tc attr)");                                                                  \
     }                                                                                                             \
-    kfn<<<grid, block, smem, s>>>(tmA, tmB, g);                                                                   \
+    if (batched_epi) kfn4<<<grid, block, smem, s>>>(tmA, tmB, g);                                                 \
+    else kfn<<<grid, block, smem, s>>>(tmA, tmB, g);                                                              \
   } while (0)
   if constexpr (BF16 && BLOCK_N < 64) {
     if (b_mn) return fail_arg("vu_gemm", "MN-major bf16 B operand needs a 64-column tile");
@@ -464,6 +766,38 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
   }
 #undef VU_TC_LAUNCH
   return check_launch("vu_gemm(tc)");
+}
+
+// persistent launch: BLOCK_N in {64, 128}; stages fill what the 227 KB of shared memory leave after the staging rows
+template <int BLOCK_N, bool BF16>
+static int launch_tc_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, TcArgs g, bool a_mn, bool b_mn, int nbatch,
+                                cudaStream_t s) {
+  constexpr int STAGES = BLOCK_N == 128 ? 4 : 6;
+  constexpr size_t ring = (size_t)STAGES * (TC_BLOCK_M * TC_BLOCK_K * 4 + BLOCK_N * TC_BLOCK_K * 4);
+  constexpr size_t staging = (size_t)4 * 32 * (BLOCK_N + 4) * 4;
+  constexpr size_t smem = ring + staging + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "persistent GEMM: shared memory budget");
+  g.tiles_m = (int)cdiv(g.M, TC_BLOCK_M); g.tiles_n = (int)cdiv(g.N, BLOCK_N);
+  const int64_t total = (int64_t)g.tiles_m * g.tiles_n * nbatch * g.split_k;
+  if (total > 0x7fffffff) return fail_arg("vu_gemm", "too many tiles");
+  g.total_tiles = (int)total;
+  const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
+#define VU_TCP_LAUNCH(AMN, BMN)                                                                                  \
+  do {                                                                                                            \
+    auto kfn = gemm_tc_persistent_kernel<BLOCK_N, STAGES, AMN, BMN, BF16>;                                        \
+    static uint64_t seen = 0;                                                                                     \
+    if (first_use_on_device(seen)) {                                                                              \
+      if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)       \
+        return check_launch("vu_gemm(tc persistent attr)");                                                       \
+    }                                                                                                             \
+    kfn<<<grid, 192, smem, s>>>(tmA, tmB, g);                                                                     \
+  } while (0)
+  if (!a_mn && !b_mn) VU_TCP_LAUNCH(false, false);
+  else if (!a_mn && b_mn) VU_TCP_LAUNCH(false, true);
+  else if (a_mn && b_mn) VU_TCP_LAUNCH(true, true);
+  else VU_TCP_LAUNCH(true, false);
+#undef VU_TCP_LAUNCH
+  return check_launch("vu_gemm(tc persistent)");
 }
 
 int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
@@ -510,6 +844,31 @@ int gemm_tc(const vu_gemm_desc& d, cudaStream_t s, bool* handled) {
   g.aux_bf16 = d.aux_bf16 != 0;
   const int nbatch = bi * bo;
   int rc;
+  // OPT-IN (VU_TC_PERSISTENT=1, read per call): token GEMMs (no (image, head) batch) on the persistent kernel, 64-column
+  // tiles for N <= 192 (192 = 3 x 64 exactly).  Measured on B200 inside the Base step at 256 images (tools/ab_persistent.sh,
+  // bf16 mode): 8.75 ms per step for the token GEMMs against 7.76 ms with the one-tile-per-CTA kernel below -- once the
+  // epilogue's fast path made a tile's epilogue cheap, three resident CTAs per SM (12 epilogue warps, three independent
+  // MMA streams) beat one persistent CTA (4 epilogue warps, a 4-stage ring that covers only ~0.55 us of TMA latency);
+  // the persistent kernel wins only on the K = 768 projections (86 vs 94 us).  It would need 128 x 256 tiles / CTA pairs.
+  const char* pe = getenv("VU_TC_PERSISTENT");
+  const bool persistent_on = pe && pe[0] == '1';
+  if (persistent_on && nbatch == 1 && d.N > 32) {
+    const bool n64 = d.N <= 64 || d.N == 192 || (bf16 && b_mn && d.N < 128);
+    const int pbn = n64 ? 64 : 128;
+    bool okp = true;
+    if (pbn != block_n) {        // the B tensor map was encoded for another tile width: re-encode
+      if (!b_mn) okp = encode_operand(&tmB, d.B, d.K, d.N, d.ldb, bi, d.sBi, bo, d.sBo, kb_elems, pbn, false, bf16);
+      else okp = encode_operand(&tmB, d.B, d.N, d.K, d.ldb, bi, d.sBi, bo, d.sBo, bf16 ? 64 : 32, kb_elems, true, bf16);
+    }
+    if (okp) {
+      if (bf16) rc = pbn == 64 ? launch_tc_persistent<64, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s)
+                               : launch_tc_persistent<128, true>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+      else rc = pbn == 64 ? launch_tc_persistent<64, false>(tmA, tmB, g, a_mn, b_mn, nbatch, s)
+                          : launch_tc_persistent<128, false>(tmA, tmB, g, a_mn, b_mn, nbatch, s);
+      *handled = true;
+      return rc;
+    }
+  }
   if (bf16) {
     // map-reading products (N = head_dim <= 32, K = tokens): pure HBM streams of the bf16 map.  Two pipeline stages
     // (41 KB of shared memory) let 5 CTAs share an SM and hide each other's prologue / epilogue: 4.27 vs 3.89 TB/s

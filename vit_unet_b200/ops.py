@@ -91,6 +91,7 @@ class KernelTimer:
 
 
 _TIMER = {"t": None}
+_SHAPE_CLASSES = __import__("os").environ.get("VU_TIMER_SHAPES", "0") == "1"
 
 
 def set_kernel_timer(t):
@@ -221,6 +222,9 @@ def gemm(A, Bm, Cm, M, N, K, *, trans_a=False, trans_b=False, lda, ldb, ldc,
         cls = kind + (":map_out(QK^T,dA)" if N == M and K < N else ":map_in(PV,dV,dQ,dK)")
     else:
         cls = kind + ":tokens(proj,FF,dgrad,wgrad)"
+    if _SHAPE_CLASSES:           # VU_TIMER_SHAPES=1: one class per GEMM shape / epilogue (tools/step_gemm_shapes.py)
+        cls += f" M={M} N={N} K={K} t={int(trans_a)}{int(trans_b)} ep={'b' if bias is not None else ''}{'r' if residual is not None else ''}" \
+               f"{'g' if act == ACT_GELU else ('G' if act == ACT_GELU_BWD else '')}{'d' if drop_p > 0 else ''}{'a' if accumulate else ''} sk={split_k}"
     extra = (residual is not None) + int(accumulate) + (aux_in is not None) + (aux_out is not None)
     ea, eb, ec = (2.0 if d.a_bf16 else 4.0), (2.0 if d.b_bf16 else 4.0), (2.0 if d.c_bf16 else 4.0)
     _call("vu_gemm", C.byref(d), _stream(), flops=2.0 * M * N * K * nb,
