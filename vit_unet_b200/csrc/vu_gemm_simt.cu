@@ -272,23 +272,59 @@ int gemm_scores(const vu_gemm_desc& d, cudaStream_t s, bool* handled);   // vu_g
 
 // column sums: out[n] (+)= sum_m X[m*ld + n].  grid (N/32, chunks of M); smem transpose-free: each warp
 // owns 32 columns, threads stride over rows, partials combined with atomics.
+// column sums: out[n] (+)= sum_m X[m*ld + n].  A CTA covers 128 columns x a chunk of rows: every lane owns 4 consecutive
+// columns (one 16-byte fp32 / 8-byte bf16 load per row), the 8 warps take interleaved rows with 4 loads in flight each;
+// partials are combined through shared memory and one atomicAdd per column and CTA.
 template <typename TX>
+__device__ __forceinline__ float4 colsum_load4(const TX* p);
+template <>
+__device__ __forceinline__ float4 colsum_load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 colsum_load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 pk = *reinterpret_cast<const uint2*>(p);
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <typename TX, bool VEC>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const TX* __restrict__ X, int64_t M, int N, int64_t ld, float* __restrict__ out, int64_t rows_per_block) {
-  __shared__ float red[8][33];
+  __shared__ float red[8][132];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + lane;
+  const int n = blockIdx.x * 128 + lane * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  float acc = 0.f;
-  if (n < N)
-    for (int64_t r = r0 + warp; r < r1; r += 8) acc += (float)X[r * ld + n];
-  red[warp][lane] = acc;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (VEC) {
+    if (n < N) {             // N % 4 == 0: whole quads
+      int64_t r = r0 + warp;
+      for (; r + 24 < r1; r += 32) {
+        const float4 v0 = colsum_load4<TX>(X + r * ld + n), v1 = colsum_load4<TX>(X + (r + 8) * ld + n),
+                     v2 = colsum_load4<TX>(X + (r + 16) * ld + n), v3 = colsum_load4<TX>(X + (r + 24) * ld + n);
+        a0 += (v0.x + v1.x) + (v2.x + v3.x); a1 += (v0.y + v1.y) + (v2.y + v3.y);
+        a2 += (v0.z + v1.z) + (v2.z + v3.z); a3 += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; r < r1; r += 8) {
+        const float4 v = colsum_load4<TX>(X + r * ld + n);
+        a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+      }
+    }
+  } else {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      if (n < N) a0 += (float)X[r * ld + n];
+      if (n + 1 < N) a1 += (float)X[r * ld + n + 1];
+      if (n + 2 < N) a2 += (float)X[r * ld + n + 2];
+      if (n + 3 < N) a3 += (float)X[r * ld + n + 3];
+    }
+  }
+  *reinterpret_cast<float4*>(&red[warp][lane * 4]) = make_float4(a0, a1, a2, a3);
   __syncthreads();
-  if (warp == 0) {
+  if (threadIdx.x < 128) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][lane];
-    if (n < N) atomicAdd(out + n, s);
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < N) atomicAdd(out + c, s);
   }
 }
 
@@ -341,10 +377,19 @@ extern "C" int vu_colsum(const void* X, int x_bf16, int64_t M, int N, int64_t ld
   if (!accumulate) {
     if (cudaMemsetAsync(out, 0, sizeof(float) * N, s) != cudaSuccess) return check_launch(fn);
   }
-  int64_t chunks = std::min<int64_t>(cdiv(M, 64), std::max<int64_t>(1, (int64_t)sm_count() * 4 / cdiv(N, 32)));
+  int64_t chunks = std::min<int64_t>(cdiv(M, 64), std::max<int64_t>(1, (int64_t)sm_count() * 8 / cdiv(N, 128)));
   int64_t rpb = cdiv(M, chunks);
-  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, rpb));
-  if (x_bf16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, out, rpb);
-  else colsum_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(X), M, N, ld, out, rpb);
+  dim3 grid((unsigned)cdiv(N, 128), (unsigned)cdiv(M, rpb));
+  const int esz = x_bf16 ? 2 : 4;
+  const bool vec = N % 4 == 0 && ld % 4 == 0 && (uintptr_t)X % (4 * esz) == 0;
+  if (x_bf16) {
+    const __nv_bfloat16* Xb = reinterpret_cast<const __nv_bfloat16*>(X);
+    if (vec) colsum_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>(Xb, M, N, ld, out, rpb);
+    else colsum_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>(Xb, M, N, ld, out, rpb);
+  } else {
+    const float* Xf = reinterpret_cast<const float*>(X);
+    if (vec) colsum_kernel<float, true><<<grid, 256, 0, s>>>(Xf, M, N, ld, out, rpb);
+    else colsum_kernel<float, false><<<grid, 256, 0, s>>>(Xf, M, N, ld, out, rpb);
+  }
   return check_launch(fn);
 }

@@ -109,9 +109,23 @@ ln_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ x, co
   const float mean = stats[2 * b], rstd = stats[2 * b + 1];
   const float* gb = g + b * n; const float* xb = x + b * n;
   float a1 = 0.f, a2 = 0.f;
-  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
-    float gw = gb[i] * w[i];
-    a1 += gw; a2 = fmaf(gw, (xb[i] - mean) * rstd, a2);
+  const int64_t cnt = max((int64_t)0, end - beg);
+  if ((beg % 4 == 0) && (cnt % 4 == 0) && ((uintptr_t)gb % 16 == 0) && ((uintptr_t)xb % 16 == 0) && ((uintptr_t)w % 16 == 0)) {
+    const float4* g4 = reinterpret_cast<const float4*>(gb + beg);
+    const float4* x4 = reinterpret_cast<const float4*>(xb + beg);
+    const float4* w4 = reinterpret_cast<const float4*>(w + beg);
+    for (int64_t i = threadIdx.x; i < cnt / 4; i += blockDim.x) {
+      const float4 gg = g4[i], xx = x4[i], ww = __ldg(w4 + i);
+      const float g0 = gg.x * ww.x, g1 = gg.y * ww.y, g2 = gg.z * ww.z, g3 = gg.w * ww.w;
+      a1 += (g0 + g1) + (g2 + g3);
+      a2 = fmaf(g0, (xx.x - mean) * rstd, a2); a2 = fmaf(g1, (xx.y - mean) * rstd, a2);
+      a2 = fmaf(g2, (xx.z - mean) * rstd, a2); a2 = fmaf(g3, (xx.w - mean) * rstd, a2);
+    }
+  } else {
+    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      float gw = gb[i] * w[i];
+      a1 += gw; a2 = fmaf(gw, (xb[i] - mean) * rstd, a2);
+    }
   }
   double v[2] = {a1, a2};
   block_sum<2>(v, red);
