@@ -60,10 +60,11 @@ def _peaks():
 
 # kernel class of the live table -> regex over the ncu kernel names of profiles/r02_step_traffic.json
 _NCU_CLASS = {
-    "gemm_tcgen05_bf16:tokens": r"gemm_tf32_tc_kernel<(64|128), .*, 1>$",  # bf16 mode: token GEMMs on bf16 operands
-    "gemm_tcgen05_tf32:tokens": r"gemm_tf32_tc_kernel<.*, 0>$",          # fp32-operand tcgen05 GEMMs (a few L0/L1 map products included)
-    "gemm_tcgen05_tf32:map_in": r"gemm_tf32_tc_kernel<.*, 1>$",          # bf16-operand (map-reading) tcgen05 GEMMs
-    "gemm_tcgen05_tf32:map_out": r"gemm_tf32_tc_kernel<.*, 0>$",
+    # gemm_tf32_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, BF16, EPI_UN>
+    "gemm_tcgen05_bf16:tokens": r"gemm_tf32_tc_kernel<(64|128), \d, \d, \d, 1, \d>$",     # bf16 mode: token GEMMs on bf16 operands
+    "gemm_tcgen05_tf32:tokens": r"gemm_tf32_tc_kernel<\d+, \d, \d, \d, 0, \d>$",         # fp32-operand tcgen05 GEMMs (a few L0/L1 map products included)
+    "gemm_tcgen05_tf32:map_in": r"gemm_tf32_tc_kernel<32, \d, \d, \d, 1, \d>$",          # bf16-operand (map-reading) tcgen05 GEMMs
+    "gemm_tcgen05_tf32:map_out": r"gemm_tf32_tc_kernel<\d+, \d, \d, \d, 0, \d>$",
     "gemm_mma_tf32:map_out": r"scores_mma_kernel", "vu_reattn_bwd_rows": r"reattn_bwd_rows", "vu_softmax_stats": r"softmax_stats",
     "vu_reattn_mix_reduce": r"reattn_mix_reduce", "vu_reattn_mix": r"reattn_mix_mma_kernel|reattn_mix_kernel",
     "vu_reattn_stream_fwd": r"stream_fwd_kernel", "vu_reattn_stream_bwd_ds": r"stream_bwd_ds", "vu_reattn_stream_bwd_reduce": r"stream_bwd_reduce",

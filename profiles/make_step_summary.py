@@ -10,6 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+MODE = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 path = os.path.join(ROOT, "gpurun_out", "r2_step_kernels.csv")
 rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("=="))]
 hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
@@ -38,8 +39,8 @@ for _, m in ids.items():
     e["wr"] += m.get("dram__bytes_write.sum", (name, 0.0))[1]
 tot_ms = sum(e["ms"] for e in per.values())
 tot_b = sum(e["rd"] + e["wr"] for e in per.values())
-out = [f"# r02: every kernel of one benchmarked Base training step ({B} images, TF32 path, HEAD) under ncu\n",
-       f"Command: `sh tools/ncu_step.sh {B}` under gpurun (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum",
+out = [f"# r02: every kernel of one benchmarked Base training step ({B} images, {MODE} mode = the bench default, HEAD) under ncu\n",
+       f"Command: `sh tools/ncu_step.sh {B} {MODE}` under gpurun (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum",
        "--clock-control none --profile-from-start off`, tools/profile_step.py).  Serialised, cold-cache launches: compare SHARES.\n",
        f"Step total under ncu: {tot_ms:.1f} ms in {sum(e['n'] for e in per.values())} launches; DRAM traffic {tot_b / 1e9:.1f} GB per step "
        f"= {tot_b / B / 1e6:.0f} MB per image.\n",

@@ -6,7 +6,7 @@ import torch
 import vit_unet_b200 as vu
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-vu.set_precision("tf32")
+vu.set_precision(sys.argv[2] if len(sys.argv) > 2 else "bf16")      # the bench default
 with contextlib.redirect_stdout(io.StringIO()):
     net = vu.get_vit_unet("base")
 net.to("cuda").train()
