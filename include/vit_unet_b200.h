@@ -52,16 +52,19 @@ int vu_heads_transpose_bf16(const float* src, void* dst, int B, int N, int D, in
  * where they lie, no concatenation pass).  bias: [nconv][C] or NULL.  x is read in layout p_x; out_k written in p_out. */
 int vu_conv3x3_fwd(const float* x, int p_x, const float* w, const float* w1, const float* w2, const float* bias, int nconv,
                    float* out0, float* out1, float* out2, int p_out, int border_p,
-                   int B, int C, int H, int W, void* stream);
+                   int B, int C, int H, int W, int tf32, void* stream);
+/* tf32 != 0 (the tensor-core precision class, all three entry points): the per-patch convs (source, destination and border
+ * patch agree, patch >= 8, C <= 3) run as implicit GEMMs on TF32 warp MMAs (operands rounded to nearest TF32, fp32
+ * accumulation); 0 = exact fp32 FMAs. */
 /* dx[p_dx] (+)= sum_k conv_transpose(dy_k[p_dy], w_k) */
 int vu_conv3x3_bwd_data(const float* dy0, const float* dy1, const float* dy2, int p_dy,
                         const float* w, const float* w1, const float* w2, int nconv, float* dx, int p_dx, int border_p,
-                        int B, int C, int H, int W, int accumulate, void* stream);
+                        int B, int C, int H, int W, int accumulate, int tf32, void* stream);
 /* dw_k[C][C][3][3] += ..., dbias[nconv][C] += ... (atomic accumulation: caller zeroes).  dw1 == NULL: the blocks of all
  * convs are contiguous at dw; else conv k accumulates into dw / dw1 / dw2 (separate slots of a flat gradient buffer). */
 int vu_conv3x3_bwd_weight(const float* x, int p_x, const float* dy0, const float* dy1, const float* dy2,
                           int p_dy, int nconv, float* dw, float* dw1, float* dw2, float* dbias, int border_p,
-                          int B, int C, int H, int W, void* stream);
+                          int B, int C, int H, int W, int tf32, void* stream);
 
 /* ---------------------------------------------------------------- GEMM (model.py:155,161,162; :103,106) */
 enum { VU_ACT_NONE = 0, VU_ACT_GELU = 1, VU_ACT_GELU_BWD = 2 };

@@ -86,6 +86,39 @@ def test_patch_conv_fwd_bwd(ops, C, S, p, B, nconv):
     _close(db, torch.cat([d.reshape(B * N, C, p * p).sum((0, 2)) for d in dys]), rtol=1e-4, name="conv db")
 
 
+@pytest.mark.parametrize("C,S,p,B", [(3, 32, 16, 2), (1, 32, 8, 2), (3, 64, 32, 3), (3, 24, 8, 3), (3, 48, 16, 3), (2, 32, 8, 1),
+                                       (3, 224, 8, 2), (3, 224, 32, 3)])
+@pytest.mark.parametrize("nconv", [1, 2, 3])
+def test_patch_conv_tensor_core_class(ops, C, S, p, B, nconv):
+    """The q/k/v convs of the tf32 / bf16 modes: implicit GEMMs on TF32 warp MMAs (tf32=True) against F.conv2d in fp64
+    (operands rounded to 10 mantissa bits, fp32 accumulation: 27 / 81 products per output)."""
+    img = _rand(B, C, S, S)
+    x = O.patchify(img, p).contiguous()
+    N, D = x.shape[1], x.shape[2]
+    ws = [_rand(C, C, 3, 3, seed=10 + k, scale=0.5) for k in range(nconv)]
+    xr = x.double().clone().requires_grad_(True)
+    wr = [w.double().clone().requires_grad_(True) for w in ws]
+    ys = [F.conv2d(xr.reshape(B * N, C, p, p), w, padding=1).reshape(B, N, D) for w in wr]
+    outs = [torch.full((B, N, D), 7.0, device="cuda") for _ in range(nconv)]
+    wl = [w.cuda() for w in ws]
+    ops.conv3x3_fwd(x.cuda(), p, wl if nconv > 1 else wl[0], None, outs, p, p, B, C, S, S, tf32=True)
+    for o, y in zip(outs, ys):
+        _close(o, y, rtol=2e-3, atol_rel=2e-3, name="conv fwd (tf32 class)")
+    dys = [_rand(B, N, D, seed=20 + k) for k in range(nconv)]
+    sum((y * d.double()).sum() for y, d in zip(ys, dys)).backward()
+    dx = torch.full((B, N, D), 7.0, device="cuda")
+    ops.conv3x3_bwd_data([d.cuda() for d in dys], p, wl if nconv > 1 else wl[0], dx, p, p, B, C, S, S, tf32=True)
+    _close(dx, xr.grad, rtol=2e-3, atol_rel=2e-3, name="conv dx (tf32 class)")
+    base = _rand(B, N, D, seed=31)
+    dx2 = base.clone().cuda()
+    ops.conv3x3_bwd_data([d.cuda() for d in dys], p, wl if nconv > 1 else wl[0], dx2, p, p, B, C, S, S, accumulate=True, tf32=True)
+    _close(dx2, xr.grad + base.double(), rtol=2e-3, atol_rel=2e-3, name="conv dx accumulate (tf32 class)")
+    dws = [torch.zeros(C, C, 3, 3, device="cuda") for _ in range(nconv)]
+    ops.conv3x3_bwd_weight(x.cuda(), p, [d.cuda() for d in dys], p, dws if nconv > 1 else dws[0], None, p, B, C, S, S, tf32=True)
+    for dw, w in zip(dws, wr):
+        _close(dw, w.grad, rtol=2e-3, atol_rel=2e-3, name="conv dw (tf32 class)")
+
+
 @pytest.mark.parametrize("C,S,p", [(3, 32, 16), (1, 64, 32)])
 def test_image_conv_on_token_layout(ops, C, S, p):
     """Reconstruction head: un-patch + 3x3 'same' conv with bias (model.py:425-428), reading tokens directly."""

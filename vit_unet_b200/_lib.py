@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VU_LIB_PATH") or os.path.join(_HERE, "libvitunet_b200.so")     # VU_LIB_PATH: A/B builds of the kernels
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class VuError(RuntimeError):
@@ -42,9 +42,9 @@ SIGNATURES = {
     "vu_heads_transpose_bf16": [_p, _p, _i, _i, _i, _i, _i, _p],
     "vu_pe_fwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     "vu_pe_bwd_table": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
-    "vu_conv3x3_fwd": [_p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "vu_conv3x3_bwd_data": [_p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
-    "vu_conv3x3_bwd_weight": [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "vu_conv3x3_fwd": [_p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vu_conv3x3_bwd_data": [_p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vu_conv3x3_bwd_weight": [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "vu_gemm": [C.POINTER(GemmDesc), _p],
     "vu_colsum": [_p, _i, _l, _i, _l, _p, _i, _p],
     "vu_softmax_rows": [_p, _l, _i, _i, _f, _p],

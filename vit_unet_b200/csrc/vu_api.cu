@@ -30,7 +30,7 @@ int sm_count() {
 }
 }  // namespace vu
 
-extern "C" int vu_version(void) { return 8; }
+extern "C" int vu_version(void) { return 9; }
 extern "C" const char* vu_last_error(void) { return vu::g_err.c_str(); }
 extern "C" int vu_device_sm_count(int device) {
   int n = 0;

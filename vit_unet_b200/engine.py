@@ -29,6 +29,12 @@ _MAP_L2_BYTES = {"value": int(float(os.environ.get("VU_MAP_L2_MB", "0")) * (1 <<
 
 # bf16 storage of the mixed map A and the gradient map dA/dS (probabilities P stay fp32) on the tensor-core path:
 # halves the HBM bytes of the five map-consuming GEMMs and of the map kernels' A / dA traffic.
+# q/k/v convs as implicit GEMMs on TF32 warp MMAs (vu_conv.cu, tf32 / bf16 modes): OPT-IN (VU_CONV_MMA=1).  Measured on B200
+# (Base step, 256 images, ms per step, MMA vs FFMA kernels): forward 3.20 vs 2.15, data gradient 9.92 vs 3.10, weight gradient
+# 3.01 vs 3.03 -- the gathered fragments cost one LDS.32 per operand word and the accumulator layout scatters the stores into
+# 32-byte sectors, so the LSU, not the FMA pipe, is the limit; and the extra TF32 rounding of x / dy costs parity margin on the
+# tiny configs (7.8e-2 vs the 5e-2 asserted).  The FFMA patch kernels stay the default in every mode.
+_CONV_MMA = {"value": os.environ.get("VU_CONV_MMA", "0") == "1"}
 _BF16_MAPS = {"value": os.environ.get("VU_BF16_MAPS", "1") == "1"}      # on by default in the tf32 mode (1e-2 class)
 
 
@@ -207,11 +213,12 @@ class Engine:
         prec, b16 = self._prec(), self._b16()
         wq, wk, wv = P[pre + "qconv2d.weight"], P[pre + "kconv2d.weight"], P[pre + "vconv2d.weight"]
         q, k, v = _empty((B, N, D), xq), _empty((B, N, D), xq), _empty((B, N, D), xq)
+        tc = prec == ops.PREC_TF32 and _CONV_MMA["value"]     # tensor-core class: q/k/v convs as implicit GEMMs on warp MMAs
         if xq is xkv:         # the three filters are uploaded from their own parameter tensors (no concatenation pass)
-            ops.conv3x3_fwd(xq, p, [wq, wk, wv], None, [q, k, v], p, p, B, g.C, g.S, g.S)
+            ops.conv3x3_fwd(xq, p, [wq, wk, wv], None, [q, k, v], p, p, B, g.C, g.S, g.S, tf32=tc)
         else:
-            ops.conv3x3_fwd(xq, p, wq, None, [q], p, p, B, g.C, g.S, g.S)
-            ops.conv3x3_fwd(xkv, p, [wk, wv], None, [k, v], p, p, B, g.C, g.S, g.S)
+            ops.conv3x3_fwd(xq, p, wq, None, [q], p, p, B, g.C, g.S, g.S, tf32=tc)
+            ops.conv3x3_fwd(xkv, p, [wk, wv], None, [k, v], p, p, B, g.C, g.S, g.S, tf32=tc)
         # The (B,h,N,N) maps are processed in slices of `c` images sized so that the maps a kernel chain hands from
         # one launch to the next (S -> P -> A, ~2 live maps) stay resident in the 126 MB L2: HBM then sees P once on
         # the way out (it is saved for backward) and once on the way back in, instead of ~6 full passes.
@@ -497,14 +504,15 @@ class Engine:
         gq, gk, gv = G[pre + "qconv2d.weight"], G[pre + "kconv2d.weight"], G[pre + "vconv2d.weight"]
         xq, xkv = sv["xq"], sv["xkv"]
         C, S = g.C, g.S
+        tc = self._prec() == ops.PREC_TF32 and _CONV_MMA["value"]
         if xq is xkv:
-            ops.conv3x3_bwd_data([dq, dk, dv], p, [wq, wk, wv], dxq_acc, p, p, B, C, S, S, accumulate=acc_q)
-            ops.conv3x3_bwd_weight(xq, p, [dq, dk, dv], p, [gq, gk, gv], None, p, B, C, S, S)
+            ops.conv3x3_bwd_data([dq, dk, dv], p, [wq, wk, wv], dxq_acc, p, p, B, C, S, S, accumulate=acc_q, tf32=tc)
+            ops.conv3x3_bwd_weight(xq, p, [dq, dk, dv], p, [gq, gk, gv], None, p, B, C, S, S, tf32=tc)
         else:
-            ops.conv3x3_bwd_data([dq], p, wq, dxq_acc, p, p, B, C, S, S, accumulate=acc_q)
-            ops.conv3x3_bwd_data([dk, dv], p, [wk, wv], dxkv_acc, p, p, B, C, S, S, accumulate=acc_kv)
-            ops.conv3x3_bwd_weight(xq, p, [dq], p, gq, None, p, B, C, S, S)
-            ops.conv3x3_bwd_weight(xkv, p, [dk, dv], p, [gk, gv], None, p, B, C, S, S)
+            ops.conv3x3_bwd_data([dq], p, wq, dxq_acc, p, p, B, C, S, S, accumulate=acc_q, tf32=tc)
+            ops.conv3x3_bwd_data([dk, dv], p, [wk, wv], dxkv_acc, p, p, B, C, S, S, accumulate=acc_kv, tf32=tc)
+            ops.conv3x3_bwd_weight(xq, p, [dq], p, gq, None, p, B, C, S, S, tf32=tc)
+            ops.conv3x3_bwd_weight(xkv, p, [dk, dv], p, [gk, gv], None, p, B, C, S, S, tf32=tc)
 
     def _wgrad(self, dY, X, dW, M, N, K):
         """dW[N,K] += dY[M,N]^T @ X[M,K]; split over the (long) token dimension for parallelism."""

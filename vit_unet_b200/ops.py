@@ -146,32 +146,33 @@ def _filters(w, name):
     return _chk(w, name), None, None
 
 
-def conv3x3_fwd(x, p_x, w, bias, outs, p_out, border_p, B, Cc, H, W):
+def conv3x3_fwd(x, p_x, w, bias, outs, p_out, border_p, B, Cc, H, W, tf32=False):
+    """tf32: tensor-core precision class (the per-patch convs may run as implicit GEMMs on TF32 warp MMAs)"""
     n = len(outs)
     ptrs = [_chk(o, f"out{i}") for i, o in enumerate(outs)] + [None] * (3 - n)
     w0, w1, w2 = _filters(w, "w")
     _call("vu_conv3x3_fwd", _chk(x, "x"), p_x, w0, w1, w2, _opt(bias, "bias"), n, ptrs[0], ptrs[1], ptrs[2],
-          p_out, border_p, B, Cc, H, W, _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W, flops=18.0 * n * Cc * Cc * B * H * W)
+          p_out, border_p, B, Cc, H, W, int(tf32), _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W, flops=18.0 * n * Cc * Cc * B * H * W)
     return outs
 
 
-def conv3x3_bwd_data(dys, p_dy, w, dx, p_dx, border_p, B, Cc, H, W, accumulate=False):
+def conv3x3_bwd_data(dys, p_dy, w, dx, p_dx, border_p, B, Cc, H, W, accumulate=False, tf32=False):
     n = len(dys)
     ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
     w0, w1, w2 = _filters(w, "w")
     _call("vu_conv3x3_bwd_data", ptrs[0], ptrs[1], ptrs[2], p_dy, w0, w1, w2, n, _chk(dx, "dx"), p_dx,
-          border_p, B, Cc, H, W, int(accumulate), _stream(), nbytes=(1 + n + int(accumulate)) * 4.0 * B * Cc * H * W,
+          border_p, B, Cc, H, W, int(accumulate), int(tf32), _stream(), nbytes=(1 + n + int(accumulate)) * 4.0 * B * Cc * H * W,
           flops=18.0 * n * Cc * Cc * B * H * W)
     return dx
 
 
-def conv3x3_bwd_weight(x, p_x, dys, p_dy, dw, dbias, border_p, B, Cc, H, W):
+def conv3x3_bwd_weight(x, p_x, dys, p_dy, dw, dbias, border_p, B, Cc, H, W, tf32=False):
     """dw: one contiguous [nconv][C][C][3][3] tensor, or a list of per-conv gradient tensors (accumulated in place)"""
     n = len(dys)
     ptrs = [_chk(o, f"dy{i}") for i, o in enumerate(dys)] + [None] * (3 - n)
     d0, d1, d2 = _filters(dw, "dw")
     _call("vu_conv3x3_bwd_weight", _chk(x, "x"), p_x, ptrs[0], ptrs[1], ptrs[2], p_dy, n, d0, d1, d2,
-          _opt(dbias, "dbias"), border_p, B, Cc, H, W, _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W,
+          _opt(dbias, "dbias"), border_p, B, Cc, H, W, int(tf32), _stream(), nbytes=(1 + n) * 4.0 * B * Cc * H * W,
           flops=18.0 * n * Cc * Cc * B * H * W)
 
 
