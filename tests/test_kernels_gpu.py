@@ -86,6 +86,18 @@ def test_patch_conv_fwd_bwd(ops, C, S, p, B, nconv):
     _close(db, torch.cat([d.reshape(B * N, C, p * p).sum((0, 2)) for d in dys]), rtol=1e-4, name="conv db")
 
 
+@pytest.mark.parametrize("B,N,D,h", [(2, 784, 192, 8), (3, 196, 768, 8), (2, 49, 3072, 8), (2, 16, 64, 4), (2, 196, 48, 4),
+                                     (1, 100, 36, 3), (2, 3136, 48, 4), (1, 70, 200, 5), (2, 9, 30, 3)])
+def test_heads_transpose_bf16_bit_exact(ops, B, N, D, h):
+    """(B,N,D) fp32 -> per-head transposed bf16 copy (K-major B operand of the map-reading GEMMs; head split of model.py:152):
+    bit-equal to torch's round-to-nearest cast of the permuted tensor; the last shape (D % 4 != 0) takes the per-head kernel."""
+    x = _rand(B, N, D, seed=5).cuda()
+    out = ops.heads_transpose_bf16(x, B, N, D, h)
+    ref = x.view(B, N, h, D // h).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert out.shape[-1] == (N + 7) // 8 * 8
+    assert torch.equal(out[..., :N], ref)
+
+
 @pytest.mark.parametrize("C,S,p,B", [(3, 32, 16, 2), (1, 32, 8, 2), (3, 64, 32, 3), (3, 24, 8, 3), (3, 48, 16, 3), (2, 32, 8, 1),
                                        (3, 224, 8, 2), (3, 224, 32, 3)])
 @pytest.mark.parametrize("nconv", [1, 2, 3])

@@ -211,7 +211,8 @@ def test_tc_gemm_bf16_operands(ops, M, N, K, ta):
     assert torch.all(out[:, N:] == 7.0)
 
 
-@pytest.mark.parametrize("Nt,hd", [(100, 12), (70, 8), (65, 20), (130, 32), (784, 24), (264, 16), (196, 96), (72, 44), (200, 128)])
+@pytest.mark.parametrize("Nt,hd", [(100, 12), (70, 8), (65, 20), (130, 32), (784, 24), (264, 16), (196, 96), (72, 44), (200, 128),
+                                   (520, 24), (1024, 8), (1000, 30), (48, 24)])
 @pytest.mark.parametrize("out_bf16", [False, True])
 def test_scores_gemm_shapes(ops, Nt, hd, out_bf16):
     """S = alpha Q K^T with head_dim <= 32 runs on the warp-MMA write-stream kernel (vu_gemm_scores.cu): ragged token

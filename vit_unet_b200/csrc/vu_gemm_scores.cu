@@ -7,6 +7,9 @@
 // the B operand (N x K, 75 KB) is staged once in shared memory as TF32, every warp walks 16-row strips with
 // m16n8k8 warp MMAs whose accumulator fragments go straight from registers to global memory (full 32-byte sectors,
 // four consecutive n-tiles complete a 128-byte line), no TMEM, no epilogue hand-off: 11 instructions per 128 outputs.
+// Negative result (round 2, not in the tree): two row strips per work item, so that every B fragment (one LDS.64 per MMA) feeds
+// two MMAs -- 128 registers, and the Base step's scores launches went from 10.15 to 11.66 ms per step: the kernel is not bound by
+// the B-fragment loads; the second strip's accumulators only lengthen the dependent store phase of each item.
 #include <cuda_bf16.h>
 
 #include <algorithm>

@@ -106,6 +106,53 @@ heads_transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __rest
   }
 }
 
+// Wide variant (the default): one CTA moves 64 tokens x 64 columns of the (N, D) token matrix of one image, whatever the
+// head width -- the loads walk whole 256-byte row segments across head boundaries (the per-head kernel above reads 96-byte
+// head rows at hd = 24 and leaves a quarter of its lanes idle), the stores are 16-byte chunks of 8 tokens, eight lanes
+// completing a 128-byte line of one (head, e) row.  bf16 tile in shared memory, [column][token] with a pitch of 33 words:
+// both the transposing stores (lane = (token % 8, float4 of the row)) and the read-back (lane = (8-token group, column))
+// touch 32 distinct banks.  Tokens >= N load as zeros and land in the row padding (ldn = N rounded up to 8).
+__global__ void __launch_bounds__(256)
+heads_transpose_bf16_wide_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int D, int hd, int ldn) {
+  __shared__ __align__(16) uint32_t tile[64 * 33];               // tile[c][t / 2] packs tokens t, t + 1 of column c
+  const int b = blockIdx.z, n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __nv_bfloat16* th = reinterpret_cast<__nv_bfloat16*>(tile);
+  // loads: warp w, pass r -> tokens 8 (w + 8 r) .. + 7 (lane % 8), float4 column group lane / 8 + 4 q (q = 0..3)
+#pragma unroll
+  for (int r = 0; r < 1; ++r) {
+    const int t = 8 * warp + (lane & 7), n = n0 + t;
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + 4 * ((lane >> 3) + 4 * q);
+      v[q] = (n < N && c < D) ? __ldg(reinterpret_cast<const float4*>(src + ((int64_t)b * N + n) * D + c))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int cl = 4 * ((lane >> 3) + 4 * q);
+      th[(cl + 0) * 66 + t] = __float2bfloat16_rn(v[q].x);
+      th[(cl + 1) * 66 + t] = __float2bfloat16_rn(v[q].y);
+      th[(cl + 2) * 66 + t] = __float2bfloat16_rn(v[q].z);
+      th[(cl + 3) * 66 + t] = __float2bfloat16_rn(v[q].w);
+    }
+  }
+  __syncthreads();
+  // stores: lane -> 8-token group j = lane % 8 of column 4 (warp + 8 r) + lane / 8
+  const int j = lane & 7;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int cl = 4 * (warp + 8 * r) + (lane >> 3), c = c0 + cl, n = n0 + 8 * j;
+    if (c < D && n < N) {
+      const uint32_t* row = tile + cl * 33 + 4 * j;
+      uint4 o; o.x = row[0]; o.y = row[1]; o.z = row[2]; o.w = row[3];
+      const int hh = c / hd, e = c - hh * hd;
+      *reinterpret_cast<uint4*>(dst + (((int64_t)b * (D / hd) + hh) * hd + e) * ldn + n) = o;
+    }
+  }
+}
+
 static bool layout_ok(int H, int W, int p) { return p == 0 || (p > 0 && H % p == 0 && W % p == 0); }
 static bool vec_ok(int W, int p) { return p == 0 ? (W % 4 == 0) : (p % 4 == 0); }
 
@@ -166,6 +213,13 @@ extern "C" int vu_heads_transpose_bf16(const float* src, void* dst, int B, int N
   const char* fn = "vu_heads_transpose_bf16";
   VU_REQUIRE(src && dst && B > 0 && N > 0 && D > 0 && h > 0 && D % h == 0 && ldn >= N, fn, "bad arguments");
   const int hd = D / h;
+  static const bool wide_on = []() { const char* e = getenv("VU_TRANSPOSE_WIDE"); return !(e && e[0] == '0'); }();
+  if (wide_on && D % 4 == 0 && ldn % 8 == 0 && ldn >= ((N + 7) & ~7) && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0 &&
+      cdiv(D, 64) <= 65535 && B <= 65535) {
+    dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(D, 64), (unsigned)B);
+    heads_transpose_bf16_wide_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, N, D, hd, ldn);
+    return check_launch(fn);
+  }
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(hd, 32), (unsigned)(B * h));
   heads_transpose_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, N, D, hd, h, ldn);
   return check_launch(fn);

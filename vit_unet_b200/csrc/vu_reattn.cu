@@ -22,10 +22,10 @@ namespace vu {
 // vu_reattn_mma.cuh).  The kernels in THIS file are the exact fp32 FMA versions for any head count 1..8.
 __device__ __forceinline__ float4 map_ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 map_ld(const __nv_bfloat16* p) {
+  // bf16 -> fp32 is a 16-bit shift: one SHL / one AND per element (the cuda_bf16.h conversions compile to PRMT + shift pairs)
   const uint2 u = *reinterpret_cast<const uint2*>(p);
-  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
-  return make_float4(a.x, a.y, b.x, b.y);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
 }
 __device__ __forceinline__ void map_st(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void map_st(__nv_bfloat16* p, const float4& v) {

@@ -69,6 +69,24 @@ __device__ __forceinline__ uint32_t drop_quad(float4& v, uint32_t ctr, const Qua
   v.z = (m & 4u) ? v.z * q.dscale : 0.f; v.w = (m & 8u) ? v.w * q.dscale : 0.f;
   return m;
 }
+// Centred dropped probabilities (Pd - c) of one quad, the operand of the head mixing and of every moment.  fp32 map: v holds
+// P on entry.  Centred bf16 map: v holds d = P - c, and  keep ? (d + c) * s - c : -c  collapses into ONE FFMA + select per
+// element (kd = c * s - c) instead of add / multiply / select / subtract; without dropout d already is the result.
+// Returns the keep bits.  The last argument only selects the overload (the map's element type).
+__device__ __forceinline__ uint32_t pdc_quad(float4& v, uint32_t ctr, const QuadCtx& q, const float*) {
+  const uint32_t m = drop_quad(v, ctr, q);
+  v.x -= q.c; v.y -= q.c; v.z -= q.c; v.w -= q.c;
+  return m;
+}
+__device__ __forceinline__ uint32_t pdc_quad(float4& v, uint32_t ctr, const QuadCtx& q, const __nv_bfloat16*) {
+  if (!q.thresh) return 0xFu;
+  const uint4 rr = Philox::gen_k(q.key, ctr);
+  const float kd = fmaf(q.c, q.dscale, -q.c), nc = -q.c;
+  const bool k0 = rr.x >= q.thresh, k1 = rr.y >= q.thresh, k2 = rr.z >= q.thresh, k3 = rr.w >= q.thresh;
+  v.x = k0 ? fmaf(v.x, q.dscale, kd) : nc; v.y = k1 ? fmaf(v.y, q.dscale, kd) : nc;
+  v.z = k2 ? fmaf(v.z, q.dscale, kd) : nc; v.w = k3 ? fmaf(v.w, q.dscale, kd) : nc;
+  return (k0 ? 1u : 0u) | (k1 ? 2u : 0u) | (k2 ? 4u : 0u) | (k3 ? 8u : 0u);
+}
 // 2^x for x <= 0 as one MUFU (ex2() adds a denormal-range rescale around it; a softmax term below 2^-126 may flush)
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void sub4(float4& v, float c) { v.x -= c; v.y -= c; v.z -= c; v.w -= c; }
@@ -83,6 +101,9 @@ constexpr float4 kZero4 = {0.f, 0.f, 0.f, 0.f};
 // rounding is then relative to the deviation from the uniform row, which is what the head mixing + BatchNorm see.
 __device__ __forceinline__ float4 ldp(const float* p, float) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ldp(const __nv_bfloat16* p, float c) { float4 v = map_ld(p); add4(v, c); return v; }
+// what pdc_quad starts from: P (fp32 map) or d = P - c (centred bf16 map)
+__device__ __forceinline__ float4 ldraw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldraw(const __nv_bfloat16* p) { return map_ld(p); }
 
 __device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
   __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -90,21 +111,27 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
   return u;
 }
 __device__ __forceinline__ float4 unpack_bf16x4(const uint2& u) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
 }
-// write one quad of probabilities: fp32 in place over S, or centred bf16 into Pc (then continue with the ROUNDED
-// value, so the moments describe exactly the map the later kernels read back)
-__device__ __forceinline__ void emit_p(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, int off, float4& p, float c) {
+// softmax pass 3 of one quad: p = x * inv is written (fp32 over S, or centred bf16 into Pc) and turned into the centred
+// dropped value the moments are taken of -- for the bf16 map from the ROUNDED d, so the moments describe exactly the map the
+// later kernels read back: x * inv - c is one FFMA, pack, store, unpack (two shifts / masks), one FFMA + select.
+__device__ __forceinline__ float4 emit_pdc(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, int off, const float4& x,
+                                           float inv, uint32_t ctr, const QuadCtx& q) {
+  float4 v;
   if (Pc) {
-    float4 d = p; sub4(d, c);
-    const uint2 u = pack_bf16x4(d);
+    v = make_float4(fmaf(x.x, inv, -q.c), fmaf(x.y, inv, -q.c), fmaf(x.z, inv, -q.c), fmaf(x.w, inv, -q.c));
+    const uint2 u = pack_bf16x4(v);
     *reinterpret_cast<uint2*>(Pc + off) = u;
-    p = unpack_bf16x4(u); add4(p, c);
+    v = unpack_bf16x4(u);
+    pdc_quad(v, ctr, q, static_cast<const __nv_bfloat16*>(nullptr));
   } else {
-    *reinterpret_cast<float4*>(S + off) = p;
+    v = make_float4(x.x * inv, x.y * inv, x.z * inv, x.w * inv);
+    *reinterpret_cast<float4*>(S + off) = v;
+    pdc_quad(v, ctr, q, static_cast<const float*>(nullptr));
   }
+  return v;
 }
 // G'/X' style accumulation in the stats layout: C[e][2k4..2k4+1] += sum_keys A_e[key] * B_n[key] over this lane's 8 keys
 __device__ __forceinline__ void mma_keys(float (&c)[4], const float4& a_lo, const float4& a_hi, const float4& b_lo,
@@ -183,17 +210,13 @@ softmax_stats_mma_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, 
       float4 pa = kZero4, pb = kZero4;
       if (qa < ld4) {
         const float4 x = ldq(Sb + roff + 4 * qa);
-        pa = make_float4(ex2(fmaf(x.x, sl2, -m)) * inv, ex2(fmaf(x.y, sl2, -m)) * inv,
-                         ex2(fmaf(x.z, sl2, -m)) * inv, ex2(fmaf(x.w, sl2, -m)) * inv);
-        emit_p(Sb, Pb, roff + 4 * qa, pa, q.c);
-        drop_quad(pa, ctr0 + ((uint32_t)roff >> 2) + qa, q); sub4(pa, q.c);
+        const float4 ex = make_float4(ex2(fmaf(x.x, sl2, -m)), ex2(fmaf(x.y, sl2, -m)), ex2(fmaf(x.z, sl2, -m)), ex2(fmaf(x.w, sl2, -m)));
+        pa = emit_pdc(Sb, Pb, roff + 4 * qa, ex, inv, ctr0 + ((uint32_t)roff >> 2) + qa, q);
       }
       if (qb < ld4) {
         const float4 x = ldq(Sb + roff + 4 * qb);
-        pb = make_float4(ex2(fmaf(x.x, sl2, -m)) * inv, ex2(fmaf(x.y, sl2, -m)) * inv,
-                         ex2(fmaf(x.z, sl2, -m)) * inv, ex2(fmaf(x.w, sl2, -m)) * inv);
-        emit_p(Sb, Pb, roff + 4 * qb, pb, q.c);
-        drop_quad(pb, ctr0 + ((uint32_t)roff >> 2) + qb, q); sub4(pb, q.c);
+        const float4 ex = make_float4(ex2(fmaf(x.x, sl2, -m)), ex2(fmaf(x.y, sl2, -m)), ex2(fmaf(x.z, sl2, -m)), ex2(fmaf(x.w, sl2, -m)));
+        pb = emit_pdc(Sb, Pb, roff + 4 * qb, ex, inv, ctr0 + ((uint32_t)roff >> 2) + qb, q);
       }
       s += hsum4(pa) + hsum4(pb);
       mma_keys(cg, pa, pb, pa, pb);
@@ -226,14 +249,13 @@ reattn_mix_mma_kernel(const PT* __restrict__ P, MT* __restrict__ A, const float*
       const int tt = t + v * nw, quad = tt * 8 + e;
       ok[v] = tt < tiles && quad < quads;
       off[v] = k4 * hs + quad * 4;
-      x0[v] = ok[v] ? ldp(Pi + off[v], q.c) : kZero4;
-      x1[v] = ok[v] ? ldp(Pi + off[v] + 4 * hs, q.c) : kZero4;
+      x0[v] = ok[v] ? ldraw(Pi + off[v]) : kZero4;
+      x1[v] = ok[v] ? ldraw(Pi + off[v] + 4 * hs) : kZero4;
     }
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       if (t + v * nw >= tiles) break;                       // warp-uniform
-      drop_quad(x0[v], ctr0 + ((uint32_t)off[v] >> 2), q); drop_quad(x1[v], ctr0 + ((uint32_t)off[v] >> 2) + hs, q);
-      sub4(x0[v], q.c); sub4(x1[v], q.c);
+      pdc_quad(x0[v], ctr0 + ((uint32_t)off[v] >> 2), q, Pi); pdc_quad(x1[v], ctr0 + ((uint32_t)off[v] >> 2) + hs, q, Pi);
       float4 y0, y1; mix_pair(x0[v], x1[v], b0, b1, y0, y1);
       if (ok[v]) {
         add4(y0, sh0); add4(y1, sh1);
@@ -270,24 +292,23 @@ reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const MT* __restrict__ dA
     const int quad = t * 8 + e;
     const bool ok = mix && quad < quads;
     const int off = k4 * hs + quad * 4;
-    float4 x0 = ok ? ldp(Pi + off, q.c) : kZero4, x1 = ok ? ldp(Pi + off + 4 * hs, q.c) : kZero4;
+    float4 x0 = ok ? ldraw(Pi + off) : kZero4, x1 = ok ? ldraw(Pi + off + 4 * hs) : kZero4;
     // stats layout: head e, quads k4 and k4 + 4 of the tile
     const int qa = t * 8 + k4, qb = qa + 4;
     const bool va = qa < quads, vb = qb < quads;
     const int offa = e * hs + qa * 4, offb = offa + 16;
-    float4 pa = va ? ldp(Pi + offa, q.c) : kZero4, pb = vb ? ldp(Pi + offb, q.c) : kZero4;
+    float4 pa = va ? ldraw(Pi + offa) : kZero4, pb = vb ? ldraw(Pi + offb) : kZero4;
     const float4 da = va ? map_ld(Di + offa) : kZero4, db = vb ? map_ld(Di + offb) : kZero4;
     if (mix) {                                   // warp-uniform
-      drop_quad(x0, ctr0 + ((uint32_t)off >> 2), q); drop_quad(x1, ctr0 + ((uint32_t)off >> 2) + hs, q);
-      sub4(x0, q.c); sub4(x1, q.c);
+      pdc_quad(x0, ctr0 + ((uint32_t)off >> 2), q, Pi); pdc_quad(x1, ctr0 + ((uint32_t)off >> 2) + hs, q, Pi);
       float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1);
       if (ok) {
         add4(y0, sh0); add4(y1, sh1);
         map_st(Ai + off, y0); map_st(Ai + off + 4 * hs, y1);
       }
     }
-    if (va) { drop_quad(pa, ctr0 + ((uint32_t)offa >> 2), q); sub4(pa, q.c); }
-    if (vb) { drop_quad(pb, ctr0 + ((uint32_t)offb >> 2), q); sub4(pb, q.c); }
+    if (va) pdc_quad(pa, ctr0 + ((uint32_t)offa >> 2), q, Pi);
+    if (vb) pdc_quad(pb, ctr0 + ((uint32_t)offb >> 2), q, Pi);
     s1 += hsum4(da) + hsum4(db);
     mma_keys(cx, da, db, pa, pb);
   }
@@ -581,16 +602,8 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
       for (int t = w; t < ntiles; t += NW) {
         const int qa = t * 8 + k4, qb = qa + 4;
         float4 pa = kZero4, pb = kZero4;
-        if (qa < ld4) {
-          pa = ldq(rs + 4 * qa); mul4(pa, inv);
-          emit_p(Sb, Pb, roff + 4 * qa, pa, q.c);
-          drop_quad(pa, ctr0 + ((uint32_t)roff >> 2) + qa, q); sub4(pa, q.c);
-        }
-        if (qb < ld4) {
-          pb = ldq(rs + 4 * qb); mul4(pb, inv);
-          emit_p(Sb, Pb, roff + 4 * qb, pb, q.c);
-          drop_quad(pb, ctr0 + ((uint32_t)roff >> 2) + qb, q); sub4(pb, q.c);
-        }
+        if (qa < ld4) pa = emit_pdc(Sb, Pb, roff + 4 * qa, ldq(rs + 4 * qa), inv, ctr0 + ((uint32_t)roff >> 2) + qa, q);
+        if (qb < ld4) pb = emit_pdc(Sb, Pb, roff + 4 * qb, ldq(rs + 4 * qb), inv, ctr0 + ((uint32_t)roff >> 2) + qb, q);
         s += hsum4(pa) + hsum4(pb);
         mma_keys(cg, pa, pb, pa, pb);
       }
