@@ -766,11 +766,12 @@ extern "C" int vu_reattn_mix_reduce(const void* Pv, const void* dA, void* A, int
     const int64_t tiles = cdiv((int64_t)N * N / 4, 8);          // per image; grid = (x, B)
     const dim3 grid((unsigned)std::max<int64_t>(1, cdiv(tiles, 8 * 16)), B);      // 8 warps x ~16 iterations per CTA
     cudaStream_t st = as_stream(stream);
-    if (p_bf16) mma::reattn_mix_reduce_mma_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
-        (const __nv_bfloat16*)Pv, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
-    else if (map_bf16) mma::reattn_mix_reduce_mma_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(
-        P, (const __nv_bfloat16*)dA, (__nv_bfloat16*)A, fold, N, q, red);
-    else mma::reattn_mix_reduce_mma_kernel<float, float><<<grid, 256, 0, st>>>(P, (const float*)dA, (float*)A, fold, N, q, red);
+#define VU_MR(PTV, MTV, MIXV) mma::reattn_mix_reduce_mma_kernel<PTV, MTV, MIXV><<<grid, 256, 0, st>>>( \
+        (const PTV*)Pv, (const MTV*)dA, (MTV*)A, fold, N, q, red)
+    if (p_bf16) { if (A) VU_MR(__nv_bfloat16, __nv_bfloat16, true); else VU_MR(__nv_bfloat16, __nv_bfloat16, false); }
+    else if (map_bf16) { if (A) VU_MR(float, __nv_bfloat16, true); else VU_MR(float, __nv_bfloat16, false); }
+    else { if (A) VU_MR(float, float, true); else VU_MR(float, float, false); }
+#undef VU_MR
     return check_launch(fn);
   }
   int blocks = grid_for((int64_t)B * N * (ld / 4), 256 * 2, 4);

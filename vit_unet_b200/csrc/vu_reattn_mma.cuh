@@ -41,10 +41,11 @@ __device__ __forceinline__ int sigma(int n) { return (n >> 1) + ((n & 1) << 2); 
 // Pair layout: x0 / x1 = key quad of heads k4 / k4+4.  y_{k4}, y_{k4+4} = sum_g Bm[g][.] x_g, with (b0, b1) the
 // lane's fragment of the 8x8 weight matrix (see frag_fwd / frag_bwd).
 __device__ __forceinline__ void mix_pair(const float4& x0, const float4& x1, uint32_t b0, uint32_t b1,
-                                         float4& y0, float4& y1) {
+                                         float4& y0, float4& y1, float i0 = 0.f, float i1 = 0.f) {
   // data operands go in as raw fp32 bits: the tensor core reads the top 19 bits (truncation, 2^-11 mean relative
-  // shrink of CENTRED values -- far below the bf16 rounding of the stored result); only the weights are rounded (rna)
-  float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+  // shrink of CENTRED values -- far below the bf16 rounding of the stored result); only the weights are rounded (rna).
+  // (i0, i1): per-head constants of the two output heads, added by starting the accumulators from them
+  float c[4] = {i0, i1, i0, i1}, d[4] = {i0, i1, i0, i1};
   mma8(c, bits(x0.x), bits(x0.y), bits(x1.x), bits(x1.y), b0, b1);    // rows e / e+8 = components 0 / 1
   mma8(d, bits(x0.z), bits(x0.w), bits(x1.z), bits(x1.w), b0, b1);    // rows e / e+8 = components 2 / 3
   y0 = make_float4(c[0], c[2], d[0], d[2]);
@@ -227,6 +228,16 @@ softmax_stats_mma_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__ Pc, 
 
 // ------------------------------------------------------------------ forward: A = fold . (Pd - c) + shift'
 // grid (x, B): flat tiles of 32 consecutive positions of image blockIdx.y (rows are contiguous: ld == N), pair layout.
+// Whole tiles (all but possibly the last one of an image) take a predicate-free path whose four pointers simply walk the
+// map -- the general path's per-access 64-bit address arithmetic and zero fills were a third of the instructions issued.
+template <typename PT, typename MT>
+__device__ __forceinline__ void mix_tile(float4& x0, float4& x1, uint32_t ctr, int hs, const QuadCtx& q, uint32_t b0, uint32_t b1,
+                                         float sh0, float sh1, MT* a0, MT* a1, const PT* tag) {
+  pdc_quad(x0, ctr, q, tag); pdc_quad(x1, ctr + hs, q, tag);
+  float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1, sh0, sh1);
+  map_st(a0, y0); map_st(a1, y1);
+}
+
 template <typename PT, typename MT>
 __global__ void __launch_bounds__(256)
 reattn_mix_mma_kernel(const PT* __restrict__ P, MT* __restrict__ A, const float* __restrict__ fold,
@@ -237,78 +248,85 @@ reattn_mix_mma_kernel(const PT* __restrict__ P, MT* __restrict__ A, const float*
 #pragma unroll
   for (int g = 0; g < H; ++g) { sh0 += fold[k4 * H + g]; sh1 += fold[(k4 + 4) * H + g]; }
   sh0 = fmaf(sh0, q.c, fold[H * H + k4]); sh1 = fmaf(sh1, q.c, fold[H * H + k4 + 4]);
-  const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3;
+  const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3, full_tiles = quads >> 3;
   const int64_t base = (int64_t)blockIdx.y * hs * H;
   const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
   const PT* Pi = P + base; MT* Ai = A + base;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (int t = wid; t < tiles; t += 2 * nw) {
-    int off[2]; bool ok[2]; float4 x0[2], x1[2];
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int tt = t + v * nw, quad = tt * 8 + e;
-      ok[v] = tt < tiles && quad < quads;
-      off[v] = k4 * hs + quad * 4;
-      x0[v] = ok[v] ? ldraw(Pi + off[v]) : kZero4;
-      x1[v] = ok[v] ? ldraw(Pi + off[v] + 4 * hs) : kZero4;
-    }
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      if (t + v * nw >= tiles) break;                       // warp-uniform
-      pdc_quad(x0[v], ctr0 + ((uint32_t)off[v] >> 2), q, Pi); pdc_quad(x1[v], ctr0 + ((uint32_t)off[v] >> 2) + hs, q, Pi);
-      float4 y0, y1; mix_pair(x0[v], x1[v], b0, b1, y0, y1);
-      if (ok[v]) {
-        add4(y0, sh0); add4(y1, sh1);
-        map_st(Ai + off[v], y0); map_st(Ai + off[v] + 4 * hs, y1);
-      }
-    }
+  // this lane's walk: heads k4 / k4 + 4, quad t * 8 + e of tile t; consecutive tiles of the warp are `step` elements apart
+  const int lane_off = k4 * hs + (wid * 8 + e) * 4, step = 32 * nw;
+  const PT* p0 = Pi + lane_off; const PT* p1 = p0 + 4 * hs;
+  MT* a0 = Ai + lane_off; MT* a1 = a0 + 4 * hs;
+  uint32_t ctr = ctr0 + ((uint32_t)lane_off >> 2);
+  int t = wid;
+  for (; t + nw < full_tiles; t += 2 * nw) {                  // two whole tiles per iteration, four loads in flight
+    float4 x0 = ldraw(p0), x1 = ldraw(p1), z0 = ldraw(p0 + step), z1 = ldraw(p1 + step);
+    mix_tile(x0, x1, ctr, hs, q, b0, b1, sh0, sh1, a0, a1, Pi);
+    mix_tile(z0, z1, ctr + 8 * nw, hs, q, b0, b1, sh0, sh1, a0 + step, a1 + step, Pi);
+    p0 += 2 * step; p1 += 2 * step; a0 += 2 * step; a1 += 2 * step; ctr += 16 * nw;
+  }
+  for (; t < tiles; t += nw) {                                // what is left: one tile at a time, predicated
+    const int quad = t * 8 + e;
+    const bool ok = quad < quads;
+    const int off = k4 * hs + quad * 4;
+    float4 x0 = ok ? ldraw(Pi + off) : kZero4, x1 = ok ? ldraw(Pi + off + 4 * hs) : kZero4;
+    pdc_quad(x0, ctr0 + ((uint32_t)off >> 2), q, Pi); pdc_quad(x1, ctr0 + ((uint32_t)off >> 2) + hs, q, Pi);
+    float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1, sh0, sh1);
+    if (ok) { map_st(Ai + off, y0); map_st(Ai + off + 4 * hs, y1); }
   }
 }
 
 // ------------------------------------------------------------------ backward pass 1: A = mix(P) recomputed + reductions
-// red[h] += sum dA_h ;  red[H + h*H + g] += sum dA_h (Pd_g - c).  The mix runs in the pair layout, the reductions in
-// the stats layout (second read of the same P tile hits L1).  grid (x, B).
-template <typename PT, typename MT>
+// red[h] += sum dA_h ;  red[H + h*H + g] += sum dA_h (Pd_g - c).  The mix (MIX: the forward map was not kept) runs in the
+// pair layout, the reductions in the stats layout (second read of the same P tile hits L1).  grid (x, B).  Whole tiles take
+// a predicate-free path with walking pointers, as in the forward kernel.
+template <typename PT, typename MT, bool MIX>
 __global__ void __launch_bounds__(256)
 reattn_mix_reduce_mma_kernel(const PT* __restrict__ P, const MT* __restrict__ dA,
                              MT* __restrict__ A, const float* __restrict__ fold, int N, QuadCtx q,
                              double* __restrict__ out) {
   __shared__ float part[8][H + H * H];
   const int lane = threadIdx.x & 31, e = lane >> 2, k4 = lane & 3;
-  uint32_t b0, b1; frag_fwd(fold, e, k4, b0, b1);
+  uint32_t b0 = 0u, b1 = 0u;
   float sh0 = 0.f, sh1 = 0.f;
+  if (MIX) {
+    frag_fwd(fold, e, k4, b0, b1);
 #pragma unroll
-  for (int g = 0; g < H; ++g) { sh0 += fold[k4 * H + g]; sh1 += fold[(k4 + 4) * H + g]; }
-  sh0 = fmaf(sh0, q.c, fold[H * H + k4]); sh1 = fmaf(sh1, q.c, fold[H * H + k4 + 4]);
-  const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3;
+    for (int g = 0; g < H; ++g) { sh0 += fold[k4 * H + g]; sh1 += fold[(k4 + 4) * H + g]; }
+    sh0 = fmaf(sh0, q.c, fold[H * H + k4]); sh1 = fmaf(sh1, q.c, fold[H * H + k4 + 4]);
+  }
+  const int hs = N * N, quads = hs >> 2, tiles = (quads + 7) >> 3, full_tiles = quads >> 3;
   const int64_t base = (int64_t)blockIdx.y * hs * H;
   const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
-  const PT* Pi = P + base; const MT* Di = dA + base; MT* Ai = A ? A + base : nullptr;
+  const PT* Pi = P + base; const MT* Di = dA + base; MT* Ai = MIX ? A + base : nullptr;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   float cx[4] = {0.f, 0.f, 0.f, 0.f}, s1 = 0.f;
-  const bool mix = A != nullptr;                 // A == NULL: the forward map was kept, only the reductions are needed
-  for (int t = wid; t < tiles; t += nw) {
-    // pair layout: mixed map
-    const int quad = t * 8 + e;
-    const bool ok = mix && quad < quads;
-    const int off = k4 * hs + quad * 4;
-    float4 x0 = ok ? ldraw(Pi + off) : kZero4, x1 = ok ? ldraw(Pi + off + 4 * hs) : kZero4;
-    // stats layout: head e, quads k4 and k4 + 4 of the tile
-    const int qa = t * 8 + k4, qb = qa + 4;
-    const bool va = qa < quads, vb = qb < quads;
-    const int offa = e * hs + qa * 4, offb = offa + 16;
-    float4 pa = va ? ldraw(Pi + offa) : kZero4, pb = vb ? ldraw(Pi + offb) : kZero4;
-    const float4 da = va ? map_ld(Di + offa) : kZero4, db = vb ? map_ld(Di + offb) : kZero4;
-    if (mix) {                                   // warp-uniform
+  // stats-layout walk: head e, quads t * 8 + k4 and + 4 of tile t
+  const int lane_off = e * hs + (wid * 8 + k4) * 4, step = 32 * nw;
+  const PT* pp = Pi + lane_off; const MT* dp = Di + lane_off;
+  uint32_t ctr = ctr0 + ((uint32_t)lane_off >> 2);
+  for (int t = wid; t < tiles; t += nw, pp += step, dp += step, ctr += 8 * nw) {
+    if (MIX) {                                   // pair layout: mixed map
+      const int quad = t * 8 + e;
+      const bool ok = quad < quads;
+      const int off = k4 * hs + quad * 4;
+      float4 x0 = ok ? ldraw(Pi + off) : kZero4, x1 = ok ? ldraw(Pi + off + 4 * hs) : kZero4;
       pdc_quad(x0, ctr0 + ((uint32_t)off >> 2), q, Pi); pdc_quad(x1, ctr0 + ((uint32_t)off >> 2) + hs, q, Pi);
-      float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1);
-      if (ok) {
-        add4(y0, sh0); add4(y1, sh1);
-        map_st(Ai + off, y0); map_st(Ai + off + 4 * hs, y1);
-      }
+      float4 y0, y1; mix_pair(x0, x1, b0, b1, y0, y1, sh0, sh1);       // same accumulator start as the forward kernel: bit-equal maps
+      if (ok) { map_st(Ai + off, y0); map_st(Ai + off + 4 * hs, y1); }
     }
-    if (va) pdc_quad(pa, ctr0 + ((uint32_t)offa >> 2), q, Pi);
-    if (vb) pdc_quad(pb, ctr0 + ((uint32_t)offb >> 2), q, Pi);
+    float4 pa, pb, da, db;
+    if (t < full_tiles) {                        // warp-uniform: all eight quads of the tile exist
+      pa = ldraw(pp); pb = ldraw(pp + 16); da = map_ld(dp); db = map_ld(dp + 16);
+      pdc_quad(pa, ctr, q, Pi); pdc_quad(pb, ctr + 4, q, Pi);
+    } else {
+      const int qa = t * 8 + k4, qb = qa + 4;
+      const bool va = qa < quads, vb = qb < quads;
+      pa = va ? ldraw(pp) : kZero4; pb = vb ? ldraw(pp + 16) : kZero4;
+      da = va ? map_ld(dp) : kZero4; db = vb ? map_ld(dp + 16) : kZero4;
+      if (va) pdc_quad(pa, ctr, q, Pi);
+      if (vb) pdc_quad(pb, ctr + 4, q, Pi);
+    }
     s1 += hsum4(da) + hsum4(db);
     mma_keys(cx, da, db, pa, pb);
   }
@@ -323,16 +341,16 @@ struct RowsConst {
   uint32_t f0, f1, g0, g1;
   float offp[2], a1[2], a2[2];
 };
-// The per-head factor k_h = gamma_h invstd_h of dM, the keep scale 1/(1-p) of dP and the softmax scale of dS are all
-// folded into the backward weight fragment: the second MMA directly yields  scale * dPd_g / (1-p).
+// The per-head factor k_h = gamma_h invstd_h of dM and the softmax scale of dS are folded into the backward weight
+// fragment: the second MMA directly yields  scale * dPd_g;  the keep scale 1/(1-p) of dP rides on the keep factors of rows_tile.
 __device__ __forceinline__ RowsConst rows_const(const float* __restrict__ W, const float* __restrict__ bconv,
                                                 const float* __restrict__ gamma, const float* __restrict__ saved,
                                                 const float* __restrict__ coef, int train, const QuadCtx& q, float scale,
                                                 int e, int k4) {
   RowsConst k;
   frag_fwd(W, e, k4, k.f0, k.f1);           // M_h   = sum_g W[h][g] Pd_g
-  const float s0 = gamma[k4] * saved[H + k4] * q.dscale * scale, s1 = gamma[k4 + 4] * saved[H + k4 + 4] * q.dscale * scale;
-  k.g0 = tf32(W[k4 * H + sigma(e)] * s0);   // scale dPd_g/(1-p) = sum_h (k_h scale/(1-p) W[h][g]) (dA_h - m1_h - Ahat_h m2_h)
+  const float s0 = gamma[k4] * saved[H + k4] * scale, s1 = gamma[k4 + 4] * saved[H + k4 + 4] * scale;
+  k.g0 = tf32(W[k4 * H + sigma(e)] * s0);   // scale dPd_g = sum_h (k_h scale W[h][g]) (dA_h - m1_h - Ahat_h m2_h)
   k.g1 = tf32(W[(k4 + 4) * H + sigma(e)] * s1);
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
@@ -349,10 +367,23 @@ __device__ __forceinline__ RowsConst rows_const(const float* __restrict__ W, con
 // one tile of pass 1: (p0, p1) probabilities, (t0, t1) = dA in, dP out (before bf16 rounding)
 __device__ __forceinline__ void rows_tile(const RowsConst& k, const QuadCtx& q, int train, uint32_t ctr, int hs,
                                           const float4& p0, const float4& p1, float4& t0, float4& t1) {
-  float4 x0 = p0, x1 = p1;
-  const uint32_t m0 = drop_quad(x0, ctr, q), m1 = drop_quad(x1, ctr + hs, q);
+  // keep factors kf = keep ? 1/(1-p) : 0 as FLOATS: the centred dropped probabilities are one FFMA (P kf - c) and the
+  // masking of dP one FMUL, with no mask word to pack and to test again (that cost ~6 instructions per element)
+  float kf0[4], kf1[4];
+  if (q.thresh) {
+    const uint4 r0 = Philox::gen_k(q.key, ctr), r1 = Philox::gen_k(q.key, ctr + hs);
+    kf0[0] = r0.x >= q.thresh ? q.dscale : 0.f; kf0[1] = r0.y >= q.thresh ? q.dscale : 0.f;
+    kf0[2] = r0.z >= q.thresh ? q.dscale : 0.f; kf0[3] = r0.w >= q.thresh ? q.dscale : 0.f;
+    kf1[0] = r1.x >= q.thresh ? q.dscale : 0.f; kf1[1] = r1.y >= q.thresh ? q.dscale : 0.f;
+    kf1[2] = r1.z >= q.thresh ? q.dscale : 0.f; kf1[3] = r1.w >= q.thresh ? q.dscale : 0.f;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { kf0[u] = q.dscale; kf1[u] = q.dscale; }
+  }
   if (train) {
-    sub4(x0, q.c); sub4(x1, q.c);
+    const float nc = -q.c;
+    const float4 x0 = make_float4(fmaf(p0.x, kf0[0], nc), fmaf(p0.y, kf0[1], nc), fmaf(p0.z, kf0[2], nc), fmaf(p0.w, kf0[3], nc));
+    const float4 x1 = make_float4(fmaf(p1.x, kf1[0], nc), fmaf(p1.y, kf1[1], nc), fmaf(p1.z, kf1[2], nc), fmaf(p1.w, kf1[3], nc));
     float4 M0, M1; mix_pair(x0, x1, k.f0, k.f1, M0, M1);
     const float c0 = -k.a1[0] - k.offp[0] * k.a2[0], c1 = -k.a1[1] - k.offp[1] * k.a2[1];
     t0.x = fmaf(-M0.x, k.a2[0], t0.x + c0); t0.y = fmaf(-M0.y, k.a2[0], t0.y + c0);
@@ -360,9 +391,9 @@ __device__ __forceinline__ void rows_tile(const RowsConst& k, const QuadCtx& q, 
     t1.x = fmaf(-M1.x, k.a2[1], t1.x + c1); t1.y = fmaf(-M1.y, k.a2[1], t1.y + c1);
     t1.z = fmaf(-M1.z, k.a2[1], t1.z + c1); t1.w = fmaf(-M1.w, k.a2[1], t1.w + c1);
   }
-  float4 dp0, dp1; mix_pair(t0, t1, k.g0, k.g1, dp0, dp1);       // = scale * dPd / (1-p), see rows_const
-  t0.x = (m0 & 1u) ? dp0.x : 0.f; t0.y = (m0 & 2u) ? dp0.y : 0.f; t0.z = (m0 & 4u) ? dp0.z : 0.f; t0.w = (m0 & 8u) ? dp0.w : 0.f;
-  t1.x = (m1 & 1u) ? dp1.x : 0.f; t1.y = (m1 & 2u) ? dp1.y : 0.f; t1.z = (m1 & 4u) ? dp1.z : 0.f; t1.w = (m1 & 8u) ? dp1.w : 0.f;
+  float4 dp0, dp1; mix_pair(t0, t1, k.g0, k.g1, dp0, dp1);       // = scale * dPd (the keep factor carries 1/(1-p)), see rows_const
+  t0 = make_float4(dp0.x * kf0[0], dp0.y * kf0[1], dp0.z * kf0[2], dp0.w * kf0[3]);
+  t1 = make_float4(dp1.x * kf1[0], dp1.y * kf1[1], dp1.z * kf1[2], dp1.w * kf1[3]);
 }
 // dS = P (scale dP - scale r): dp and r already carry the softmax scale
 __device__ __forceinline__ float4 ds_quad(const float4& p, const float4& dp, float r) {
@@ -431,30 +462,41 @@ reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restri
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, e = lane >> 2, k4 = lane & 3;
   const RowsConst kc = rows_const(W, bconv, gamma, saved, coef, train, q, scale, e, k4);
   const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3, hs = N * N, rows = B * N;
+  // every quad of this warp's TPW tiles exists (warp-uniform, the same for all rows): predicate-free loads / stores at
+  // immediate offsets from four row pointers.  Only the warp that owns the ragged last tile takes the general path.
+  const bool allfull = (w + NW * (TPW - 1)) * 8 + 8 <= ld4;
+  constexpr int TS = 32 * NW;                                // elements between consecutive tiles of one warp
   int par = 0;
   for (int r = blockIdx.x; r < rows; r += gridDim.x, par ^= 1) {
     const int b = r / N, i = r - b * N;
     const int64_t base = (int64_t)b * hs * H;
-    const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
-    const PT* Pi = P + base; __nv_bfloat16* Di = dA + base;
-    const int roff = k4 * hs + i * N;
+    const int loff = k4 * hs + i * N + 4 * (w * 8 + e);      // heads k4 (and k4 + 4 at + 4 hs), quad w * 8 + e of the row
+    const uint32_t ctr = (uint32_t)((uint64_t)base >> 2) + ((uint32_t)loff >> 2);
+    const PT* pr = P + base + loff; const PT* pr1 = pr + 4 * hs;
+    __nv_bfloat16* dr = dA + base + loff; __nv_bfloat16* dr1 = dr + 4 * hs;
     float4 p0[TPW], p1[TPW]; uint2 k0[TPW], k1[TPW];      // k: dA on the way in, dP between the sweeps (bf16 x 4)
+    if (allfull) {
 #pragma unroll
-    for (int tt = 0; tt < TPW; ++tt) {
-      const int quad = (w + NW * tt) * 8 + e;
-      const bool ok = quad < ld4;
-      const int off = roff + 4 * quad;
-      p0[tt] = ok ? ldp(Pi + off, q.c) : kZero4; p1[tt] = ok ? ldp(Pi + off + 4 * hs, q.c) : kZero4;
-      k0[tt] = ok ? *reinterpret_cast<const uint2*>(Di + off) : make_uint2(0u, 0u);
-      k1[tt] = ok ? *reinterpret_cast<const uint2*>(Di + off + 4 * hs) : make_uint2(0u, 0u);
+      for (int tt = 0; tt < TPW; ++tt) {
+        p0[tt] = ldp(pr + tt * TS, q.c); p1[tt] = ldp(pr1 + tt * TS, q.c);
+        k0[tt] = *reinterpret_cast<const uint2*>(dr + tt * TS);
+        k1[tt] = *reinterpret_cast<const uint2*>(dr1 + tt * TS);
+      }
+    } else {
+#pragma unroll
+      for (int tt = 0; tt < TPW; ++tt) {
+        const bool ok = (w + NW * tt) * 8 + e < ld4;
+        p0[tt] = ok ? ldp(pr + tt * TS, q.c) : kZero4; p1[tt] = ok ? ldp(pr1 + tt * TS, q.c) : kZero4;
+        k0[tt] = ok ? *reinterpret_cast<const uint2*>(dr + tt * TS) : make_uint2(0u, 0u);
+        k1[tt] = ok ? *reinterpret_cast<const uint2*>(dr1 + tt * TS) : make_uint2(0u, 0u);
+      }
     }
     float rg0 = 0.f, rg1 = 0.f;
 #pragma unroll
     for (int tt = 0; tt < TPW; ++tt) {
-      if (w + NW * tt >= ntiles) break;                                   // warp-uniform
-      const int off = roff + 4 * ((w + NW * tt) * 8 + e);
+      if (!allfull && w + NW * tt >= ntiles) break;                       // warp-uniform
       float4 t0 = unpack_bf16x4(k0[tt]), t1 = unpack_bf16x4(k1[tt]);
-      rows_tile(kc, q, train, ctr0 + ((uint32_t)off >> 2), hs, p0[tt], p1[tt], t0, t1);
+      rows_tile(kc, q, train, ctr + 8 * NW * tt, hs, p0[tt], p1[tt], t0, t1);
       rg0 += dot4(t0, p0[tt]); rg1 += dot4(t1, p1[tt]);                   // invalid quads: P == 0
       k0[tt] = pack_bf16x4(t0); k1[tt] = pack_bf16x4(t1);
     }
@@ -467,13 +509,19 @@ reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restri
     rg0 = 0.f; rg1 = 0.f;
 #pragma unroll
     for (int ww = 0; ww < NW; ++ww) { rg0 += srg[par][ww][k4]; rg1 += srg[par][ww][k4 + 4]; }
+    if (allfull) {
 #pragma unroll
-    for (int tt = 0; tt < TPW; ++tt) {
-      const int quad = (w + NW * tt) * 8 + e;
-      if (quad < ld4) {
-        const int off = roff + 4 * quad;
-        map_st(Di + off, ds_quad(p0[tt], unpack_bf16x4(k0[tt]), rg0));
-        map_st(Di + off + 4 * hs, ds_quad(p1[tt], unpack_bf16x4(k1[tt]), rg1));
+      for (int tt = 0; tt < TPW; ++tt) {
+        map_st(dr + tt * TS, ds_quad(p0[tt], unpack_bf16x4(k0[tt]), rg0));
+        map_st(dr1 + tt * TS, ds_quad(p1[tt], unpack_bf16x4(k1[tt]), rg1));
+      }
+    } else {
+#pragma unroll
+      for (int tt = 0; tt < TPW; ++tt) {
+        if ((w + NW * tt) * 8 + e < ld4) {
+          map_st(dr + tt * TS, ds_quad(p0[tt], unpack_bf16x4(k0[tt]), rg0));
+          map_st(dr1 + tt * TS, ds_quad(p1[tt], unpack_bf16x4(k1[tt]), rg1));
+        }
       }
     }
   }
@@ -515,6 +563,15 @@ static inline size_t bulk_smem_bytes(int stages, int floats_per_stage) {
   return (size_t)stages * floats_per_stage * 4 + 2 * stages * sizeof(uint64_t);
 }
 
+// shared-memory accesses of the row ring by 32-bit shared-window address (computed once per row; the generic-pointer
+// form re-derived the window base -- S2UR + uniform adds -- in front of every access)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // NW consumer warps + 1 producer warp (8 by default, see the dispatcher).
 template <int STAGES, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32)
@@ -552,21 +609,22 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
   } else {
     const float sl2 = scale * 1.4426950408889634f;
     const int ld4 = N >> 2, ntiles = (ld4 + 7) >> 3;
+    const uint32_t ring_s = smem_addr(ring);
     int st = 0; uint32_t ph = 0;
     for (int k = 0; k < nmine; ++k) {
       const int par = k & 1;
       const int r = blockIdx.x + k * gridDim.x, b = r / N, i = r - b * N;
       const int64_t base = (int64_t)b * hs * H;
-      const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2);
-      float* Sb = S + base; __nv_bfloat16* Pb = Pc ? Pc + base : nullptr;
       const int roff = e * hs + i * N;
-      float* rs = ring + (st * H + e) * N;                          // this lane's head row in shared memory
+      const uint32_t ctr0 = (uint32_t)((uint64_t)base >> 2) + ((uint32_t)roff >> 2);
+      float* Srow = S + base + roff; __nv_bfloat16* Prow = Pc ? Pc + base + roff : nullptr;
+      const uint32_t rs = ring_s + (uint32_t)((st * H + e) * N) * 4u;  // this lane's head row in shared memory
       mbar_wait(full + st, ph);
       float m = -INFINITY;
       for (int t = w; t < ntiles; t += NW) {
         const int qa = t * 8 + k4, qb = qa + 4;
-        if (qa < ld4) m = fmaxf(m, hmax4(ldq(rs + 4 * qa)));
-        if (qb < ld4) m = fmaxf(m, hmax4(ldq(rs + 4 * qb)));
+        if (qa < ld4) m = fmaxf(m, hmax4(lds128(rs + 16 * qa)));
+        if (qb < ld4) m = fmaxf(m, hmax4(lds128(rs + 16 * qb)));
       }
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
@@ -579,15 +637,15 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
       for (int t = w; t < ntiles; t += NW) {
         const int qa = t * 8 + k4, qb = qa + 4;
         if (qa < ld4) {
-          float4 x = ldq(rs + 4 * qa);
+          float4 x = lds128(rs + 16 * qa);
           x.x = ex2(fmaf(x.x, sl2, -m)); x.y = ex2(fmaf(x.y, sl2, -m)); x.z = ex2(fmaf(x.z, sl2, -m)); x.w = ex2(fmaf(x.w, sl2, -m));
-          *reinterpret_cast<float4*>(rs + 4 * qa) = x;
+          sts128(rs + 16 * qa, x);
           l += hsum4(x);
         }
         if (qb < ld4) {
-          float4 x = ldq(rs + 4 * qb);
+          float4 x = lds128(rs + 16 * qb);
           x.x = ex2(fmaf(x.x, sl2, -m)); x.y = ex2(fmaf(x.y, sl2, -m)); x.z = ex2(fmaf(x.z, sl2, -m)); x.w = ex2(fmaf(x.w, sl2, -m));
-          *reinterpret_cast<float4*>(rs + 4 * qb) = x;
+          sts128(rs + 16 * qb, x);
           l += hsum4(x);
         }
       }
@@ -602,8 +660,8 @@ softmax_stats_mma_bulk_kernel(float* __restrict__ S, __nv_bfloat16* __restrict__
       for (int t = w; t < ntiles; t += NW) {
         const int qa = t * 8 + k4, qb = qa + 4;
         float4 pa = kZero4, pb = kZero4;
-        if (qa < ld4) pa = emit_pdc(Sb, Pb, roff + 4 * qa, ldq(rs + 4 * qa), inv, ctr0 + ((uint32_t)roff >> 2) + qa, q);
-        if (qb < ld4) pb = emit_pdc(Sb, Pb, roff + 4 * qb, ldq(rs + 4 * qb), inv, ctr0 + ((uint32_t)roff >> 2) + qb, q);
+        if (qa < ld4) pa = emit_pdc(Srow, Prow, 4 * qa, lds128(rs + 16 * qa), inv, ctr0 + qa, q);
+        if (qb < ld4) pb = emit_pdc(Srow, Prow, 4 * qb, lds128(rs + 16 * qb), inv, ctr0 + qb, q);
         s += hsum4(pa) + hsum4(pb);
         mma_keys(cg, pa, pb, pa, pb);
       }
