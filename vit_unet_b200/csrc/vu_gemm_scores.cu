@@ -10,6 +10,9 @@
 // Negative result (round 2, not in the tree): two row strips per work item, so that every B fragment (one LDS.64 per MMA) feeds
 // two MMAs -- 128 registers, and the Base step's scores launches went from 10.15 to 11.66 ms per step: the kernel is not bound by
 // the B-fragment loads; the second strip's accumulators only lengthen the dependent store phase of each item.
+// Second negative result: the staged 16-row tiles leaving shared memory as bulk (TMA) row copies (cp.async.bulk.global.shared::cta,
+// 16 rows of 128 / 256 bytes per instruction) instead of LDS.128 + STG.128 -- correct, but 12.47 vs 10.10 ms per step: 128-byte
+// bulk requests are bound by the copy engine's request rate, not by bytes.
 #include <cuda_bf16.h>
 
 #include <algorithm>
