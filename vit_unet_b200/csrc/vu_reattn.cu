@@ -680,6 +680,14 @@ extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int 
         const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<TPWV, NWV, PTV>, NWV * 32, (int64_t)B * N * NWV); \
         mma::reattn_bwd_rows_mma_cta_kernel<TPWV, NWV, PTV><<<grid, NWV * 32, 0, st>>>(PPTR, d, B, N, W, bconv, gamma, saved, coef, train, scale, q); \
       } while (0)
+      // centred bf16 probabilities, 5 x 5: four resident CTAs (96 registers, 8 bytes of spill) instead of three at 128
+      // registers -- the kernel is latency-bound: 8.90 vs 9.21 ms per Base step.  VU_ROWS_MINB=3 restores three.
+      static const bool minb3 = []() { const char* e = getenv("VU_ROWS_MINB"); return e && atoi(e) == 3; }();
+      if (p_bf16 && nw == 5 && !minb3) {
+        const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<5, 5, __nv_bfloat16, 4>, 5 * 32, (int64_t)B * N * 5);
+        mma::reattn_bwd_rows_mma_cta_kernel<5, 5, __nv_bfloat16, 4><<<grid, 5 * 32, 0, st>>>(Pb, d, B, N, W, bconv, gamma, saved, coef, train, scale, q);
+        return check_launch(fn);
+      }
       if (p_bf16) { if (nw == 5) VU_ROWS(5, 5, __nv_bfloat16, Pb); else if (nw == 7) VU_ROWS(4, 7, __nv_bfloat16, Pb); else VU_ROWS(4, 8, __nv_bfloat16, Pb); }
       else { if (nw == 5) VU_ROWS(5, 5, float, P); else if (nw == 7) VU_ROWS(4, 7, float, P); else VU_ROWS(4, 8, float, P); }
 #undef VU_ROWS
@@ -721,7 +729,8 @@ extern "C" int vu_softmax_stats(float* S, void* Pc, int B, int h, int N, int ld,
       constexpr int ST = 2;
       const size_t smem = mma::bulk_smem_bytes(ST, 8 * N);
       // consumer warps: 8 (measured at N = 784: 8.9 ms per step with 8 warps, 9.0 with 7, 9.7 with the evenly
-      // dividing 5 -- the shared-memory sweeps want the extra warps more than the balance); VU_SOFTMAX_NW overrides
+      // dividing 5 -- the shared-memory sweeps want the extra warps more than the balance; nine warps (three even rounds)
+      // at 48 registers / four CTAs per SM: 9.5 vs 8.6 ms); VU_SOFTMAX_NW overrides
       static const int nw_env = []() { const char* e = getenv("VU_SOFTMAX_NW"); return e ? atoi(e) : 0; }();
       int nw = 8;
       if (nw_env >= 5 && nw_env <= 8) nw = nw_env;

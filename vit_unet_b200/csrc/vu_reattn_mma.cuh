@@ -452,8 +452,8 @@ reattn_bwd_rows_mma_kernel(const PT* __restrict__ P, MT* __restrict__ dA, int B,
 // row over the NW warps of a CTA (TPW tiles per warp, NW * TPW >= tiles with as little slack as possible) and keeps
 // the row in registers between the sweeps: P and dA
 // cross HBM exactly once.  The row sums r_g are combined through shared memory.
-template <int TPW, int NW, typename PT>
-__global__ void __launch_bounds__(NW * 32, NW >= 7 ? 2 : 3)
+template <int TPW, int NW, typename PT, int MINB = (NW >= 7 ? 2 : 3)>
+__global__ void __launch_bounds__(NW * 32, MINB)
 reattn_bwd_rows_mma_cta_kernel(const PT* __restrict__ P, __nv_bfloat16* __restrict__ dA, int B, int N,
                                const float* __restrict__ W, const float* __restrict__ bconv,
                                const float* __restrict__ gamma, const float* __restrict__ saved,
