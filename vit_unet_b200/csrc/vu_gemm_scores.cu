@@ -13,6 +13,8 @@
 // Second negative result: the staged 16-row tiles leaving shared memory as bulk (TMA) row copies (cp.async.bulk.global.shared::cta,
 // 16 rows of 128 / 256 bytes per instruction) instead of LDS.128 + STG.128 -- correct, but 12.47 vs 10.10 ms per step: 128-byte
 // bulk requests are bound by the copy engine's request rate, not by bytes.
+// Third: 12 instead of 8 warps per CTA (24 instead of 16 resident warps per SM): 10.62 vs 10.20 ms -- not latency either; what is left
+// is the L1 / shared-memory pipe itself (B-fragment LDS.64 + the staging round trip, ~72 wavefronts per 512 outputs).
 #include <cuda_bf16.h>
 
 #include <algorithm>
