@@ -229,6 +229,27 @@ def test_scores_gemm_shapes(ops, Nt, hd, out_bf16):
     assert torch.all(S[..., Nt:].float() == 7.0)
 
 
+@pytest.mark.parametrize("Nt,hd", [(196, 96), (49, 384), (64, 8), (100, 24), (256, 40), (52, 104), (196, 88)])
+@pytest.mark.parametrize("trans_a", [False, True])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_map_reading_gemm_coarse_levels(ops, Nt, hd, trans_a, out_bf16):
+    """O = A V, dV = A^T dO, dQ = dS K, dK = dS^T Q on the coarse levels (tokens <= 256, fp32 maps with the leading dimension
+    padded to 4, model.py:161 and its backward): ragged token counts, head-strided token operands and outputs in the (B, N, D)
+    layout, fp32 and bf16 outputs, untouched neighbours."""
+    B, h, alpha = 8, 8, 0.75
+    D, ld = h * hd, (Nt + 3) // 4 * 4
+    A = torch.zeros(B, h, Nt, ld)
+    A[..., :Nt] = _rand(B, h, Nt, Nt, seed=11)
+    T = _rand(B, Nt, D, seed=12)
+    out = torch.full((B, Nt, D + 8), 7.0, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+    ops.gemm(A.cuda(), T.cuda(), out, Nt, hd, Nt, trans_a=trans_a, trans_b=False, lda=ld, ldb=D, ldc=D + 8, batch_outer=B,
+             batch_inner=h, sA=(h * Nt * ld, Nt * ld), sB=(Nt * D, hd), sC=(Nt * (D + 8), hd), alpha=alpha, precision=ops.PREC_TF32)
+    Ad = A[..., :Nt].double().transpose(-1, -2) if trans_a else A[..., :Nt].double()
+    exp = alpha * torch.einsum("bhij,bjhe->bihe", Ad, T.reshape(B, Nt, h, hd).double()).reshape(B, Nt, D)
+    _close(out[..., :D].float(), exp, 6e-3 if out_bf16 else TOL, "map-reading gemm")
+    assert torch.all(out[..., D:].float() == 7.0)
+
+
 def test_scores_gemm_unbatched_tall(ops):
     """K <= 32 without a batch (a token GEMM shape): the row strips are spread over many CTAs, not one."""
     M, N, K = 20000, 192, 32
