@@ -681,7 +681,8 @@ extern "C" int vu_reattn_bwd_rows(const void* Pv, void* dA_dS, int map_fmt, int 
         mma::reattn_bwd_rows_mma_cta_kernel<TPWV, NWV, PTV><<<grid, NWV * 32, 0, st>>>(PPTR, d, B, N, W, bconv, gamma, saved, coef, train, scale, q); \
       } while (0)
       // centred bf16 probabilities, 5 x 5: four resident CTAs (96 registers, 8 bytes of spill) instead of three at 128
-      // registers -- the kernel is latency-bound: 8.90 vs 9.21 ms per Base step.  VU_ROWS_MINB=3 restores three.
+      // registers -- the kernel is latency-bound: 8.90 vs 9.21 ms per Base step (five CTAs at 72 registers spill: 11.45 ms; 7 warps x 4
+      // tiles: 10.87).  VU_ROWS_MINB=3 restores three.
       static const bool minb3 = []() { const char* e = getenv("VU_ROWS_MINB"); return e && atoi(e) == 3; }();
       if (p_bf16 && nw == 5 && !minb3) {
         const int grid = resident_grid(mma::reattn_bwd_rows_mma_cta_kernel<5, 5, __nv_bfloat16, 4>, 5 * 32, (int64_t)B * N * 5);
